@@ -1,0 +1,186 @@
+/*
+ * bsplat.h -- C ABI of libbsplat.so, the B200 (sm_100a) backend of the MojoSplat forward path.
+ *
+ * Plain C: raw device pointers, sizes as runtime integers, a cudaStream_t passed as void*.
+ * No torch / C++ types cross this boundary, nothing is allocated inside (the caller owns every
+ * buffer and passes workspace), no global mutable state: calls are re-entrant and thread-safe,
+ * one stream per call.  Every entry point returns 0 (BSPLAT_OK) or a negative bsplat error /
+ * a positive cudaError_t; bsplat_error_string() explains either.
+ *
+ * Each entry point replaces one reference interface (paths relative to the reference checkout):
+ *
+ *   bsplat_project_fwd        mojosplat/projection.py:15-48 project_gaussians
+ *                             (= MAX op `project_gaussians`, kernels/projection.mojo:260-328,
+ *                              destination-passing call at projection.py:438-454; gsplat
+ *                              fully_fused_projection call at projection.py:381-397)
+ *   bsplat_bin_count_scan     mojosplat/binning.py:139-168   (tile rects, counts, total)
+ *   bsplat_bin_emit           mojosplat/binning.py:172-209   (emission loop; gsplat isect_tiles,
+ *                              binning.py:73-82)
+ *   bsplat_radix_sort_pairs   mojosplat/binning.py:223-231   (argsort depth + stable argsort tile)
+ *   bsplat_tile_ranges        mojosplat/binning.py:252-260   (searchsorted -> tile_ranges;
+ *                              gsplat isect_offset_encode, binning.py:84-100)
+ *   bsplat_rasterize_fwd      mojosplat/rasterization.py:13-57 rasterize_gaussians
+ *                             (= MAX op `rasterize_to_pixels_3dgs_fwd`,
+ *                              kernels/rasterization.mojo:169-240, call at rasterization.py:167-183)
+ *   bsplat_render_fwd         mojosplat/render.py:12-103 render_gaussians (the three stages chained
+ *                              on one stream with a single 16-byte read-back)
+ *   bsplat_render_fwd_host    same, host buffers in / host image out (end-to-end path)
+ *
+ * Array layouts are the reference's: row-major AoS, fp32 / int32, single camera per launch.
+ */
+#ifndef BSPLAT_H_
+#define BSPLAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSPLAT_VERSION 1
+
+/* error codes (negative; positive values are cudaError_t) */
+#define BSPLAT_OK 0
+#define BSPLAT_E_ARG (-1)        /* bad argument (null pointer, negative size, unsupported tile size ...) */
+#define BSPLAT_E_WORKSPACE (-2)  /* workspace too small; *needed_bytes tells how much is required */
+#define BSPLAT_E_OVERFLOW (-3)   /* more than 2^30-1 intersections */
+#define BSPLAT_E_NODEVICE (-4)   /* no CUDA device / wrong architecture */
+
+/* binning / projection rule sets */
+#define BSPLAT_SEM_TORCH 0   /* reference torch backend: projection.py:199-283, binning.py:139-162 */
+#define BSPLAT_SEM_GSPLAT 1  /* gsplat / Mojo rules: projection.mojo:59-87,213-244; isect_tiles */
+
+/* rasterizer arithmetic */
+#define BSPLAT_RASTER_FAST 0      /* folded exp2 form, sub-tile culling (default) */
+#define BSPLAT_RASTER_FAITHFUL 1  /* operation order of kernels/rasterization.mojo:138-157 */
+
+/* Pinhole camera, world->camera. Mirrors mojosplat/utils.py:5-31 (Camera.view_matrix, Ks, H, W,
+ * near, far) as a POD. viewmat is row-major 4x4. */
+typedef struct bsplat_camera {
+    float viewmat[16];
+    float fx, fy, cx, cy;
+    int32_t width, height;
+    float near_plane, far_plane;
+} bsplat_camera;
+
+/* Device-side summary written by bsplat_bin_count_scan (32 bytes). */
+typedef struct bsplat_bin_info {
+    uint64_t n_isect;        /* M: number of (gaussian, tile) intersections */
+    uint32_t min_depth_key;  /* min / max monotone depth key over Gaussians with >= 1 tile */
+    uint32_t max_depth_key;
+    uint32_t reserved[4];
+} bsplat_bin_info;
+
+/* Key layout chosen on the host from a bsplat_bin_info. */
+typedef struct bsplat_key_layout {
+    uint32_t depth_bias;  /* subtracted from every depth key (= min_depth_key) */
+    int32_t depth_bits;   /* live depth bits after the bias */
+    int32_t tile_bits;    /* ceil(log2(n_tiles)) */
+} bsplat_key_layout;
+
+int bsplat_version(void);
+const char* bsplat_error_string(int code);
+/* 0 when device `device` (or the current one if < 0) is an sm_100 part. */
+int bsplat_check_device(int device);
+
+/* ---- stage 1: projection ------------------------------------------------------------------- */
+/* Projects N Gaussians through n_cams cameras; outputs are [n_cams, N, ...] contiguous.
+ * opacities may be NULL for BSPLAT_SEM_TORCH (the torch backend ignores them). */
+int bsplat_project_fwd(int64_t N, const float* means3d, const float* log_scales, const float* quats,
+                       const float* opacities, const bsplat_camera* cams_host, int32_t n_cams,
+                       float eps2d, int32_t semantics, float* means2d, float* conics, float* depths,
+                       int32_t* radii, void* stream);
+
+/* ---- stage 2: binning ---------------------------------------------------------------------- */
+size_t bsplat_bin_scan_workspace_bytes(int64_t N);
+/* Tile rect per Gaussian -> exclusive prefix sum offsets[N+1] (uint32) and *info (device).
+ * radii is int32 [N,2] (projection output) or float [N,2] when radii_is_float != 0
+ * (the reference's tests pass float radii, tests/test_binning.py:23).
+ * tile_row_begin/end restrict emission to a band of tile rows (row-band multi-GPU split);
+ * pass 0 and tiles_h for the whole image. */
+int bsplat_bin_count_scan(int64_t N, const float* means2d, const void* radii, int32_t radii_is_float,
+                          const float* depths, int32_t width, int32_t height, int32_t tile_size,
+                          int32_t tile_row_begin, int32_t tile_row_end, int32_t semantics,
+                          uint32_t* offsets, bsplat_bin_info* info, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* Host helper: key layout (depth bias / live bits) from a read-back info. */
+bsplat_key_layout bsplat_make_key_layout(const bsplat_bin_info* info_host, int32_t width,
+                                         int32_t height, int32_t tile_size);
+/* Writes keys[M] = (tile_id << depth_bits) | (depth_key - depth_bias) and gaussian ids[M] in
+ * emission order (gaussian, tile row, tile column ascending). */
+int bsplat_bin_emit(int64_t N, const float* means2d, const void* radii, int32_t radii_is_float,
+                    const float* depths, int32_t width, int32_t height, int32_t tile_size,
+                    int32_t tile_row_begin, int32_t tile_row_end, int32_t semantics,
+                    const uint32_t* offsets, bsplat_key_layout layout, uint64_t* keys, int32_t* ids,
+                    void* stream);
+size_t bsplat_radix_sort_workspace_bytes(int64_t M, int32_t begin_bit, int32_t end_bit);
+/* Stable LSD onesweep radix sort of (uint64 key, int32 value) pairs on key bits
+ * [begin_bit, end_bit). Ping-pongs between the two buffer pairs; *result_in_alt tells where the
+ * sorted data ended up (0: keys/vals, 1: keys_alt/vals_alt). */
+int bsplat_radix_sort_pairs(int64_t M, uint64_t* keys, uint64_t* keys_alt, int32_t* vals,
+                            int32_t* vals_alt, int32_t begin_bit, int32_t end_bit, void* workspace,
+                            size_t workspace_bytes, int32_t* result_in_alt, void* stream);
+/* tile_ranges[n_tiles, 2] int32 = [first, past-last) index of each tile in the sorted keys
+ * (searchsorted-left semantics for empty tiles, binning.py:252-260). */
+int bsplat_tile_ranges(int64_t M, const uint64_t* sorted_keys, int32_t tile_shift, int32_t n_tiles,
+                       int32_t* tile_ranges, void* stream);
+
+/* ---- stage 3: rasterization ---------------------------------------------------------------- */
+/* image[height, width, channels]. opacities are used raw (no sigmoid), like the reference. */
+int bsplat_rasterize_fwd(int64_t N, int32_t channels, const float* means2d, const float* conics,
+                         const float* colors, const float* opacities, const float* background,
+                         const int32_t* tile_ranges, const int32_t* sorted_ids, int64_t M,
+                         int32_t width, int32_t height, int32_t tile_size, int32_t mode,
+                         float* image, void* stream);
+
+/* Faithful kernel + counters: stats[0] += evaluated (pixel, Gaussian) pairs, stats[1] += contributing
+ * pairs (device uint64[2], caller-zeroed) -- the algorithmic work E_all / E_pass of SURVEY.md 8d. */
+int bsplat_rasterize_stats(int64_t N, int32_t channels, const float* means2d, const float* conics,
+                           const float* colors, const float* opacities, const float* background,
+                           const int32_t* tile_ranges, const int32_t* sorted_ids, int64_t M,
+                           int32_t width, int32_t height, int32_t tile_size, float* image,
+                           uint64_t* stats, void* stream);
+
+/* ---- fused forward ------------------------------------------------------------------------- */
+/* Optional outputs of the fused path (any pointer may be NULL). */
+typedef struct bsplat_render_aux {
+    float* means2d;        /* [N,2] */
+    float* conics;         /* [N,3] */
+    float* depths;         /* [N]   */
+    int32_t* radii;        /* [N,2] */
+    int32_t* tile_ranges;  /* [tiles_h, tiles_w, 2] */
+    int32_t* sorted_ids;   /* [sorted_ids_capacity]; filled when M <= capacity */
+    int64_t sorted_ids_capacity;
+    int64_t n_isect;       /* out: M */
+    int32_t timing;        /* in: record per-stage CUDA-event times (adds a final sync) */
+    float stage_ms[4];     /* out when timing != 0: projection, count+scan+emit, sort+ranges, raster */
+} bsplat_render_aux;
+
+size_t bsplat_render_workspace_bytes(int64_t N, int64_t M_capacity, int32_t width, int32_t height,
+                                     int32_t tile_size);
+/* render.py:63-101 on one stream. Returns BSPLAT_E_WORKSPACE and sets *needed_bytes when the
+ * workspace cannot hold the M this frame produced (call again with a larger one).
+ * M == 0 gives an all-zero image (render.py:73-76), not the background. */
+int bsplat_render_fwd(int64_t N, const float* means3d, const float* log_scales, const float* quats,
+                      const float* opacities, const float* colors, int32_t channels,
+                      const bsplat_camera* cam_host, const float* background, int32_t tile_size,
+                      int32_t semantics, int32_t raster_mode, float* image, void* workspace,
+                      size_t workspace_bytes, size_t* needed_bytes, bsplat_render_aux* aux,
+                      void* stream);
+/* Same with HOST buffers (pinned or pageable): copies the Gaussians in, renders, copies the
+ * image out and synchronises the stream. device_scratch must hold
+ * bsplat_render_host_scratch_bytes() in addition to the render workspace. */
+size_t bsplat_render_host_scratch_bytes(int64_t N, int32_t channels, int32_t width, int32_t height);
+int bsplat_render_fwd_host(int64_t N, const float* means3d, const float* log_scales,
+                           const float* quats, const float* opacities, const float* colors,
+                           int32_t channels, const bsplat_camera* cam_host, const float* background,
+                           int32_t tile_size, int32_t semantics, int32_t raster_mode,
+                           float* image_host, void* device_scratch, size_t scratch_bytes,
+                           void* workspace, size_t workspace_bytes, size_t* needed_bytes,
+                           bsplat_render_aux* aux, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSPLAT_H_ */

@@ -1,0 +1,270 @@
+// C-ABI glue of libbsplat.so: utility entry points, the rasterizer entry and the fused
+// render path (render.py:63-101 of the reference chained on one stream).
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace bsplat {
+int project_fwd_launch(int64_t N, const float* means3d, const float* log_scales, const float* quats,
+                       const float* opacities, const bsplat_camera& cam, float eps2d, int semantics,
+                       float* means2d, float* conics, float* depths, int32_t* radii, cudaStream_t stream);
+int rasterize_launch(int64_t N, int channels, const float* means2d, const float* conics, const float* colors,
+                     const float* opacities, const float* background_dev, const int32_t* tile_ranges,
+                     const int32_t* sorted_ids, int W, int H, int tile_size, int mode, float* image,
+                     unsigned long long* stats, cudaStream_t stream);
+}  // namespace bsplat
+
+using namespace bsplat;
+
+extern "C" int bsplat_version(void) { return BSPLAT_VERSION; }
+
+extern "C" const char* bsplat_error_string(int code) {
+    switch (code) {
+        case BSPLAT_OK: return "ok";
+        case BSPLAT_E_ARG: return "bsplat: invalid argument";
+        case BSPLAT_E_WORKSPACE: return "bsplat: workspace too small";
+        case BSPLAT_E_OVERFLOW: return "bsplat: too many tile intersections (>= 2^30)";
+        case BSPLAT_E_NODEVICE: return "bsplat: no sm_100 CUDA device";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    return "bsplat: unknown error";
+}
+
+extern "C" int bsplat_check_device(int device) {
+    int dev = device;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) return BSPLAT_E_NODEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return BSPLAT_E_NODEVICE;
+    return (prop.major == 10) ? BSPLAT_OK : BSPLAT_E_NODEVICE;
+}
+
+extern "C" int bsplat_rasterize_fwd(int64_t N, int32_t channels, const float* means2d, const float* conics,
+                                    const float* colors, const float* opacities, const float* background,
+                                    const int32_t* tile_ranges, const int32_t* sorted_ids, int64_t M,
+                                    int32_t width, int32_t height, int32_t tile_size, int32_t mode,
+                                    float* image, void* stream) {
+    if (N < 0 || M < 0 || !tile_ranges || !image || !background) return BSPLAT_E_ARG;
+    if (M > 0 && (!sorted_ids || !means2d || !conics || !colors || !opacities)) return BSPLAT_E_ARG;
+    return rasterize_launch(N, channels, means2d, conics, colors, opacities, background, tile_ranges,
+                            sorted_ids, width, height, tile_size, mode, image, nullptr, (cudaStream_t)stream);
+}
+
+// Same as bsplat_rasterize_fwd but always the faithful kernel, and counts the evaluated /
+// contributing (pixel, Gaussian) pairs into stats[2] (device, uint64, caller-zeroed): the
+// algorithmic work figures E_all / E_pass of SURVEY.md 8d.
+extern "C" int bsplat_rasterize_stats(int64_t N, int32_t channels, const float* means2d, const float* conics,
+                                      const float* colors, const float* opacities, const float* background,
+                                      const int32_t* tile_ranges, const int32_t* sorted_ids, int64_t M,
+                                      int32_t width, int32_t height, int32_t tile_size, float* image,
+                                      uint64_t* stats, void* stream) {
+    if (N < 0 || M < 0 || !tile_ranges || !image || !background || !stats) return BSPLAT_E_ARG;
+    return rasterize_launch(N, channels, means2d, conics, colors, opacities, background, tile_ranges,
+                            sorted_ids, width, height, tile_size, BSPLAT_RASTER_FAITHFUL, image,
+                            reinterpret_cast<unsigned long long*>(stats), (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// fused render
+// ------------------------------------------------------------------------------------------
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+struct RenderWs {
+    float* means2d; float* conics; float* depths; int32_t* radii;
+    uint32_t* offsets; bsplat_bin_info* info; void* scan_ws; size_t scan_bytes;
+    int32_t* tile_ranges;
+    uint64_t* keys; uint64_t* keys_alt; int32_t* ids; int32_t* ids_alt;
+    void* sort_ws; size_t sort_bytes;
+    size_t total;
+};
+
+RenderWs carve_render(void* base, int64_t N, int64_t M, int W, int H, int tile_size) {
+    RenderWs w;
+    char* p = static_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
+    const int64_t n = N > 0 ? N : 1;
+    const int64_t m = M > 0 ? M : 1;
+    const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
+    w.means2d = (float*)take(n * 2 * sizeof(float));
+    w.conics = (float*)take(n * 3 * sizeof(float));
+    w.depths = (float*)take(n * sizeof(float));
+    w.radii = (int32_t*)take(n * 2 * sizeof(int32_t));
+    w.offsets = (uint32_t*)take((n + 1) * sizeof(uint32_t));
+    w.info = (bsplat_bin_info*)take(sizeof(bsplat_bin_info));
+    w.scan_bytes = bsplat_bin_scan_workspace_bytes(N);
+    w.scan_ws = take(w.scan_bytes);
+    w.tile_ranges = (int32_t*)take((size_t)tiles_w * tiles_h * 2 * sizeof(int32_t));
+    w.keys = (uint64_t*)take(m * sizeof(uint64_t));
+    w.keys_alt = (uint64_t*)take(m * sizeof(uint64_t));
+    w.ids = (int32_t*)take(m * sizeof(int32_t));
+    w.ids_alt = (int32_t*)take(m * sizeof(int32_t));
+    w.sort_bytes = bsplat_radix_sort_workspace_bytes(M, 0, 64);
+    w.sort_ws = take(w.sort_bytes);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" size_t bsplat_render_workspace_bytes(int64_t N, int64_t M_capacity, int32_t width, int32_t height,
+                                                int32_t tile_size) {
+    if (N < 0 || M_capacity < 0 || width <= 0 || height <= 0 || tile_size <= 0) return 0;
+    return carve_render(nullptr, N, M_capacity, width, height, tile_size).total;
+}
+
+extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* log_scales, const float* quats,
+                                 const float* opacities, const float* colors, int32_t channels,
+                                 const bsplat_camera* cam, const float* background, int32_t tile_size,
+                                 int32_t semantics, int32_t raster_mode, float* image, void* workspace,
+                                 size_t workspace_bytes, size_t* needed_bytes, bsplat_render_aux* aux,
+                                 void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!cam || !image || !background || N < 0 || channels <= 0 || tile_size <= 0 || tile_size > 32)
+        return BSPLAT_E_ARG;
+    if (N > 0 && (!means3d || !log_scales || !quats || !opacities || !colors)) return BSPLAT_E_ARG;
+    const int W = cam->width, H = cam->height;
+    if (W <= 0 || H <= 0) return BSPLAT_E_ARG;
+    const size_t image_bytes = (size_t)W * H * channels * sizeof(float);
+    if (aux) aux->n_isect = 0;
+
+    // fixed (N-dependent) part must fit before anything runs
+    RenderWs w = carve_render(workspace, N, 0, W, H, tile_size);
+    if (!workspace || workspace_bytes < w.total) {
+        if (needed_bytes) *needed_bytes = carve_render(nullptr, N, 4 * N + 1024, W, H, tile_size).total;
+        return BSPLAT_E_WORKSPACE;
+    }
+    if (N == 0) {
+        BSPLAT_CUDA_TRY(cudaMemsetAsync(image, 0, image_bytes, stream));
+        return BSPLAT_OK;
+    }
+    const bool timing = aux && aux->timing;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (timing) {
+        for (auto& e : ev) BSPLAT_CUDA_TRY(cudaEventCreate(&e));
+        BSPLAT_CUDA_TRY(cudaEventRecord(ev[0], stream));
+    }
+    float* d_means2d = (aux && aux->means2d) ? aux->means2d : w.means2d;
+    float* d_conics = (aux && aux->conics) ? aux->conics : w.conics;
+    float* d_depths = (aux && aux->depths) ? aux->depths : w.depths;
+    int32_t* d_radii = (aux && aux->radii) ? aux->radii : w.radii;
+
+    int rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, *cam, 0.3f, semantics, d_means2d,
+                                d_conics, d_depths, d_radii, stream);
+    if (rc != BSPLAT_OK) return rc;
+    if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[1], stream));
+
+    const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
+    rc = bsplat_bin_count_scan(N, d_means2d, d_radii, 0, d_depths, W, H, tile_size, 0, tiles_h, semantics,
+                               w.offsets, w.info, w.scan_ws, w.scan_bytes, stream);
+    if (rc != BSPLAT_OK) return rc;
+    bsplat_bin_info info;
+    BSPLAT_CUDA_TRY(cudaMemcpyAsync(&info, w.info, sizeof(info), cudaMemcpyDeviceToHost, stream));
+    BSPLAT_CUDA_TRY(cudaStreamSynchronize(stream));  // the single read-back of the frame (M, key range)
+    const int64_t M = (int64_t)info.n_isect;
+    if (aux) aux->n_isect = M;
+    if (M >= (1ll << 30)) return BSPLAT_E_OVERFLOW;
+    if (M == 0) {
+        // render.py:73-76: no overlaps => black image (not the background)
+        BSPLAT_CUDA_TRY(cudaMemsetAsync(image, 0, image_bytes, stream));
+        if (aux && aux->tile_ranges)
+            BSPLAT_CUDA_TRY(cudaMemsetAsync(aux->tile_ranges, 0, (size_t)tiles_w * tiles_h * 2 * sizeof(int32_t), stream));
+        if (timing) for (auto& e : ev) cudaEventDestroy(e);
+        return BSPLAT_OK;
+    }
+    w = carve_render(workspace, N, M, W, H, tile_size);
+    if (workspace_bytes < w.total) {
+        if (needed_bytes) *needed_bytes = w.total;
+        if (timing) for (auto& e : ev) cudaEventDestroy(e);
+        return BSPLAT_E_WORKSPACE;
+    }
+    const bsplat_key_layout layout = bsplat_make_key_layout(&info, W, H, tile_size);
+    rc = bsplat_bin_emit(N, d_means2d, d_radii, 0, d_depths, W, H, tile_size, 0, tiles_h, semantics, w.offsets,
+                         layout, w.keys, w.ids, stream);
+    if (rc != BSPLAT_OK) return rc;
+    if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[2], stream));
+    int in_alt = 0;
+    rc = bsplat_radix_sort_pairs(M, w.keys, w.keys_alt, w.ids, w.ids_alt, 0, layout.depth_bits + layout.tile_bits,
+                                 w.sort_ws, w.sort_bytes, &in_alt, stream);
+    if (rc != BSPLAT_OK) return rc;
+    const uint64_t* sorted_keys = in_alt ? w.keys_alt : w.keys;
+    const int32_t* sorted_ids = in_alt ? w.ids_alt : w.ids;
+    int32_t* d_ranges = (aux && aux->tile_ranges) ? aux->tile_ranges : w.tile_ranges;
+    rc = bsplat_tile_ranges(M, sorted_keys, layout.depth_bits, tiles_w * tiles_h, d_ranges, stream);
+    if (rc != BSPLAT_OK) return rc;
+    if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[3], stream));
+    rc = rasterize_launch(N, channels, d_means2d, d_conics, colors, opacities, background, d_ranges, sorted_ids,
+                          W, H, tile_size, raster_mode, image, nullptr, stream);
+    if (rc != BSPLAT_OK) return rc;
+    if (aux && aux->sorted_ids && aux->sorted_ids_capacity >= M)
+        BSPLAT_CUDA_TRY(cudaMemcpyAsync(aux->sorted_ids, sorted_ids, (size_t)M * sizeof(int32_t),
+                                        cudaMemcpyDeviceToDevice, stream));
+    if (timing) {
+        BSPLAT_CUDA_TRY(cudaEventRecord(ev[4], stream));
+        BSPLAT_CUDA_TRY(cudaEventSynchronize(ev[4]));
+        for (int s = 0; s < 4; ++s) cudaEventElapsedTime(&aux->stage_ms[s], ev[s], ev[s + 1]);
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+    return BSPLAT_OK;
+}
+
+extern "C" size_t bsplat_render_host_scratch_bytes(int64_t N, int32_t channels, int32_t width, int32_t height) {
+    const size_t n = (size_t)(N > 0 ? N : 1);
+    size_t off = 0;
+    off += align_up(n * 3 * sizeof(float)) * 2;        // means3d, log_scales
+    off += align_up(n * 4 * sizeof(float));            // quats
+    off += align_up(n * sizeof(float));                // opacities
+    off += align_up(n * (size_t)channels * sizeof(float));
+    off += align_up((size_t)channels * sizeof(float)); // background
+    off += align_up((size_t)width * height * channels * sizeof(float));
+    return off;
+}
+
+extern "C" int bsplat_render_fwd_host(int64_t N, const float* means3d, const float* log_scales,
+                                      const float* quats, const float* opacities, const float* colors,
+                                      int32_t channels, const bsplat_camera* cam, const float* background,
+                                      int32_t tile_size, int32_t semantics, int32_t raster_mode,
+                                      float* image_host, void* device_scratch, size_t scratch_bytes,
+                                      void* workspace, size_t workspace_bytes, size_t* needed_bytes,
+                                      bsplat_render_aux* aux, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!cam || !image_host || !background || N < 0 || channels <= 0) return BSPLAT_E_ARG;
+    const int W = cam->width, H = cam->height;
+    const size_t need = bsplat_render_host_scratch_bytes(N, channels, W, H);
+    if (!device_scratch || scratch_bytes < need) {
+        if (needed_bytes) *needed_bytes = need;
+        return BSPLAT_E_WORKSPACE;
+    }
+    const size_t n = (size_t)(N > 0 ? N : 1);
+    char* p = static_cast<char*>(device_scratch);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* r = p + off; off += align_up(bytes); return r; };
+    float* d_means = (float*)take(n * 3 * sizeof(float));
+    float* d_scales = (float*)take(n * 3 * sizeof(float));
+    float* d_quats = (float*)take(n * 4 * sizeof(float));
+    float* d_opac = (float*)take(n * sizeof(float));
+    float* d_colors = (float*)take(n * (size_t)channels * sizeof(float));
+    float* d_bg = (float*)take((size_t)channels * sizeof(float));
+    float* d_image = (float*)take((size_t)W * H * channels * sizeof(float));
+    if (N > 0) {
+        BSPLAT_CUDA_TRY(cudaMemcpyAsync(d_means, means3d, (size_t)N * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        BSPLAT_CUDA_TRY(cudaMemcpyAsync(d_scales, log_scales, (size_t)N * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        BSPLAT_CUDA_TRY(cudaMemcpyAsync(d_quats, quats, (size_t)N * 4 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        BSPLAT_CUDA_TRY(cudaMemcpyAsync(d_opac, opacities, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, stream));
+        BSPLAT_CUDA_TRY(cudaMemcpyAsync(d_colors, colors, (size_t)N * channels * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
+    BSPLAT_CUDA_TRY(cudaMemcpyAsync(d_bg, background, (size_t)channels * sizeof(float), cudaMemcpyHostToDevice, stream));
+    int rc = bsplat_render_fwd(N, d_means, d_scales, d_quats, d_opac, d_colors, channels, cam, d_bg, tile_size,
+                               semantics, raster_mode, d_image, workspace, workspace_bytes, needed_bytes, aux, stream);
+    if (rc != BSPLAT_OK) return rc;
+    BSPLAT_CUDA_TRY(cudaMemcpyAsync(image_host, d_image, (size_t)W * H * channels * sizeof(float),
+                                    cudaMemcpyDeviceToHost, stream));
+    BSPLAT_CUDA_TRY(cudaStreamSynchronize(stream));
+    return BSPLAT_OK;
+}

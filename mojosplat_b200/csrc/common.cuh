@@ -1,0 +1,124 @@
+// Shared device/host helpers for libbsplat (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bsplat.h"
+
+#define BSPLAT_CUDA_TRY(expr)                                  \
+    do {                                                       \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) return static_cast<int>(_e);    \
+    } while (0)
+
+#define BSPLAT_LAUNCH_CHECK()                                  \
+    do {                                                       \
+        cudaError_t _e = cudaGetLastError();                   \
+        if (_e != cudaSuccess) return static_cast<int>(_e);    \
+    } while (0)
+
+namespace bsplat {
+
+constexpr int kWarp = 32;
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Monotone float -> uint32 map: ascending float order, -0.0 == +0.0, NaN last.
+// Canonical depth order of the binning stage (reference: torch.argsort of float depths,
+// binning.py:223).
+__host__ __device__ inline uint32_t depth_key(float d) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(d);
+#else
+    union { float f; uint32_t u; } cv; cv.f = d; uint32_t b = cv.u;
+#endif
+    if ((b & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;
+    if (b == 0x80000000u) b = 0u;
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+struct TileRect {
+    int x0, y0, x1, y1;  // exclusive ends, in tiles
+};
+
+// torch.clamp(v, lo, hi) for finite bounds: NaN propagates.
+__device__ inline float clamp_torch(float v, float lo, float hi) {
+    if (v != v) return v;
+    v = v < lo ? lo : v;
+    v = v > hi ? hi : v;
+    return v;
+}
+
+__device__ inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Tile rectangle of one Gaussian.
+//   BSPLAT_SEM_TORCH : binning.py:139-155,181-184 -- pixel-space clamp to [0, W-1] x [0, H-1] in
+//     fp32, IEEE division by tile_size, truncation to int32, both ends inclusive; every Gaussian
+//     (radii == 0 included) yields >= 1 tile.
+//   BSPLAT_SEM_GSPLAT: floor / ceil in tile space, exclusive max, nothing for radii <= 0.
+// row_begin/row_end clip the rectangle to a band of tile rows (multi-GPU row-band split).
+__device__ inline TileRect tile_rect(float mx, float my, float rx, float ry, int W, int H,
+                                     float tile_size_f, int tiles_w, int tiles_h, int semantics,
+                                     int row_begin, int row_end) {
+    TileRect r;
+    if (semantics == BSPLAT_SEM_TORCH) {
+        const float ax = clamp_torch(mx - rx, 0.0f, (float)(W - 1));
+        const float bx = clamp_torch(mx + rx, 0.0f, (float)(W - 1));
+        const float ay = clamp_torch(my - ry, 0.0f, (float)(H - 1));
+        const float by = clamp_torch(my + ry, 0.0f, (float)(H - 1));
+        // NaN -> int conversion: torch (x86 cvttss2si) gives INT_MIN, which the tile-space clamp
+        // maps to 0; __float2int_rz(NaN) is 0 on the GPU -- same tile.
+        r.x0 = clampi(__float2int_rz(__fdiv_rn(ax, tile_size_f)), 0, tiles_w - 1);
+        r.x1 = clampi(__float2int_rz(__fdiv_rn(bx, tile_size_f)), 0, tiles_w - 1) + 1;
+        r.y0 = clampi(__float2int_rz(__fdiv_rn(ay, tile_size_f)), 0, tiles_h - 1);
+        r.y1 = clampi(__float2int_rz(__fdiv_rn(by, tile_size_f)), 0, tiles_h - 1) + 1;
+    } else {
+        if (!(rx > 0.0f) || !(ry > 0.0f)) {
+            r.x0 = r.x1 = r.y0 = r.y1 = 0;
+            return r;
+        }
+        const float fx0 = floorf(__fdiv_rn(mx - rx, tile_size_f));
+        const float fx1 = ceilf(__fdiv_rn(mx + rx, tile_size_f));
+        const float fy0 = floorf(__fdiv_rn(my - ry, tile_size_f));
+        const float fy1 = ceilf(__fdiv_rn(my + ry, tile_size_f));
+        r.x0 = (int)fminf(fmaxf(fx0, 0.0f), (float)tiles_w);
+        r.x1 = (int)fminf(fmaxf(fx1, 0.0f), (float)tiles_w);
+        r.y0 = (int)fminf(fmaxf(fy0, 0.0f), (float)tiles_h);
+        r.y1 = (int)fminf(fmaxf(fy1, 0.0f), (float)tiles_h);
+    }
+    // band clip
+    r.y0 = r.y0 < row_begin ? row_begin : r.y0;
+    r.y1 = r.y1 > row_end ? row_end : r.y1;
+    if (r.y1 < r.y0) r.y1 = r.y0;
+    if (r.x1 < r.x0) r.x1 = r.x0;
+    return r;
+}
+
+__device__ inline uint32_t lane_id() { return threadIdx.x & 31u; }
+
+__device__ inline uint32_t lanemask_lt() {
+    uint32_t m;
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// volatile / relaxed accesses used by the decoupled look-back chains
+__device__ inline uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ inline void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ inline unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ inline void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+}  // namespace bsplat

@@ -1,0 +1,360 @@
+// Stage 3 -- tile rasterizer: front-to-back alpha compositing of the per-tile sorted lists.
+//
+// Replaces the MAX op `rasterize_to_pixels_3dgs_fwd` (mojosplat/kernels/rasterization.mojo:16-162,
+// called from mojosplat/rasterization.py:127-186) and gsplat's rasterize_to_pixels
+// (rasterization.py:81-124).  Per pixel p = (j+0.5, i+0.5), for the tile's Gaussians front to back:
+//   sigma = 0.5 (a dx^2 + c dy^2) + b dx dy ; alpha = min(0.999, o exp(-sigma))
+//   skip if sigma < 0 or alpha < 1/255 ; stop if T (1-alpha) <= 1e-4 ; out += colour alpha T ; T *= 1-alpha
+//   image = out + T background                                   (rasterization.mojo:138-162)
+//
+// Two kernels:
+//   raster_faithful_kernel  any tile size <= 32 and any channel count; arithmetic in the exact
+//       operation order of the Mojo kernel (separately rounded products, expf).  Parity anchor
+//       and fallback for non-default shapes.
+//   raster_fast_kernel      16x16 tiles, RGB.  One warp owns an 8x4 pixel block; staged Gaussians
+//       carry log2-folded conics so a pixel costs 2 FADD + 2 FMUL + 3 FFMA + 1 MUFU.EX2; each warp
+//       first tests 32 staged Gaussians at once (one per lane) against its 8x4 block with an exact
+//       conservative ellipse/rectangle bound and then only walks the survivors (warp ballot),
+//       warps retire when all 32 pixels are saturated, the CTA retires on __syncthreads_count,
+//       the tile is written with 128-bit stores.  Skipping is exact: a skipped Gaussian has
+//       alpha < 1/255 on every pixel of the block, so the composited result is unchanged.
+// No tensor cores: no stage of this path is a dense contraction.
+#include "common.cuh"
+
+namespace bsplat {
+
+constexpr float kAlphaThreshold = 1.0f / 255.0f;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLog2AlphaThreshold = -7.994353436858858f;  // log2(1/255)
+
+// ------------------------------------------------------------------------------------------
+// faithful kernel
+// ------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(1024) raster_faithful_kernel(const int64_t N, const int cdim, const int c0,
+                                       const float* __restrict__ means2d, const float* __restrict__ conics,
+                                       const float* __restrict__ colors, const float* __restrict__ opacities,
+                                       const float* __restrict__ background,
+                                       const int32_t* __restrict__ tile_ranges,
+                                       const int32_t* __restrict__ sorted_ids, const int W, const int H,
+                                       const int ts, const int tiles_w, float* __restrict__ image,
+                                       unsigned long long* __restrict__ stats) {
+    extern __shared__ float s_buf[];
+    const int nthreads = ts * ts;
+    float* s_mx = s_buf;
+    float* s_my = s_mx + nthreads;
+    float* s_a = s_my + nthreads;
+    float* s_b = s_a + nthreads;
+    float* s_c = s_b + nthreads;
+    float* s_o = s_c + nthreads;
+    float* s_col = s_o + nthreads;  // [nthreads][CH]
+
+    const int tid = threadIdx.y * ts + threadIdx.x;
+    const int tile = blockIdx.y * tiles_w + blockIdx.x;
+    const int i = blockIdx.y * ts + threadIdx.y;
+    const int j = blockIdx.x * ts + threadIdx.x;
+    const bool inside = (i < H) && (j < W);
+    bool done = !inside;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+
+    const int32_t r0 = tile_ranges[2 * tile], r1 = tile_ranges[2 * tile + 1];
+    float T = 1.0f;
+    float acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = 0.0f;
+    unsigned int n_eval = 0, n_pass = 0;
+
+    for (int32_t b0 = r0; b0 < r1; b0 += nthreads) {
+        // barrier before the staging buffers are overwritten; also the whole-tile early exit
+        if (__syncthreads_count(done) >= nthreads) break;
+        const int32_t idx = b0 + tid;
+        if (idx < r1) {
+            const int32_t g = sorted_ids[idx];
+            if (g >= 0 && (int64_t)g < N) {
+                s_mx[tid] = means2d[2 * (int64_t)g];
+                s_my[tid] = means2d[2 * (int64_t)g + 1];
+                s_a[tid] = conics[3 * (int64_t)g];
+                s_b[tid] = conics[3 * (int64_t)g + 1];
+                s_c[tid] = conics[3 * (int64_t)g + 2];
+                s_o[tid] = opacities[g];
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+                    s_col[tid * CH + c] = (c0 + c < cdim) ? colors[(int64_t)g * cdim + c0 + c] : 0.0f;
+            } else {
+                // out-of-range id: the Mojo staging guard (rasterization.mojo:109) skips it
+                s_mx[tid] = s_my[tid] = s_a[tid] = s_b[tid] = s_c[tid] = 0.0f;
+                s_o[tid] = __int_as_float(0x7fc00000);  // NaN marks "not a Gaussian"
+            }
+        }
+        __syncthreads();
+        if (!done) {
+            const int bs = min(nthreads, (int)(r1 - b0));
+            for (int t = 0; t < bs; ++t) {
+                const float op = s_o[t];
+                if (op != op) continue;
+                ++n_eval;
+                const float dx = __fsub_rn(s_mx[t], px), dy = __fsub_rn(s_my[t], py);
+                const float a = s_a[t], b = s_b[t], c = s_c[t];
+                // 0.5 * (a*dx*dx + c*dy*dy) + b*dx*dy, every operation rounded separately
+                const float q = __fadd_rn(__fmul_rn(__fmul_rn(a, dx), dx), __fmul_rn(__fmul_rn(c, dy), dy));
+                const float sigma = __fadd_rn(__fmul_rn(0.5f, q), __fmul_rn(__fmul_rn(b, dx), dy));
+                float alpha = __fmul_rn(op, expf(-sigma));
+                alpha = fminf(alpha, 0.999f);
+                if (sigma < 0.0f || alpha < kAlphaThreshold) continue;
+                const float next_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                if (next_T <= 1e-4f) { done = true; break; }
+                const float vis = __fmul_rn(alpha, T);
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) acc[ch] = __fadd_rn(acc[ch], __fmul_rn(s_col[t * CH + ch], vis));
+                T = next_T;
+                ++n_pass;
+            }
+        }
+    }
+    if (inside) {
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch)
+            if (c0 + ch < cdim)
+                image[((int64_t)i * W + j) * cdim + c0 + ch] =
+                    __fadd_rn(acc[ch], __fmul_rn(T, background[c0 + ch]));
+    }
+    if (stats != nullptr) {
+        // blocks may end in a partial warp (tile sizes like 10): plain per-thread atomics
+        if (n_eval) atomicAdd(stats, (unsigned long long)n_eval);
+        if (n_pass) atomicAdd(stats + 1, (unsigned long long)n_pass);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fast kernel (tile 16, RGB)
+// ------------------------------------------------------------------------------------------
+constexpr int kFastTile = 16;
+constexpr int kFastThreads = 256;
+constexpr int kFastBatch = 256;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct __align__(16) StagedA { float mx, my, A, B; };       // A = 0.5 a log2e, B = b log2e
+struct __align__(16) StagedB { float C, L, hy, hx; };       // C = 0.5 c log2e, L = log2(o), hy = -B/(2C), hx = -B/(2A)
+struct __align__(16) StagedC { float r, g, b, tau; };       // tau = L - log2(1/255) (+inf: never cull)
+
+template <bool kCull>
+__global__ void __launch_bounds__(kFastThreads)
+raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
+                   const float* __restrict__ colors, const float* __restrict__ opacities,
+                   const float* __restrict__ background, const int32_t* __restrict__ tile_ranges,
+                   const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
+                   float* __restrict__ image, const int vec_store) {
+    __shared__ StagedA s_a[kFastBatch];
+    __shared__ StagedB s_b[kFastBatch];
+    __shared__ StagedC s_c[kFastBatch];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.y * tiles_w + blockIdx.x;
+    // warp -> 8x4 pixel block inside the tile; lane -> pixel inside the block
+    const int bx = blockIdx.x * kFastTile + (warp & 1) * 8;
+    const int by = blockIdx.y * kFastTile + (warp >> 1) * 4;
+    const int j = bx + (lane & 7);
+    const int i = by + (lane >> 3);
+    const bool inside = (i < H) && (j < W);
+    bool done = !inside;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    // pixel-centre extent of this warp's block (clipped blocks only get more conservative)
+    const float X0 = (float)bx + 0.5f, X1 = (float)bx + 7.5f;
+    const float Y0 = (float)by + 0.5f, Y1 = (float)by + 3.5f;
+
+    const int32_t r0 = tile_ranges[2 * tile], r1 = tile_ranges[2 * tile + 1];
+    float T = 1.0f, accr = 0.0f, accg = 0.0f, accb = 0.0f;
+
+    for (int32_t b0 = r0; b0 < r1; b0 += kFastBatch) {
+        if (__syncthreads_count(done) >= kFastThreads) break;
+        const int32_t idx = b0 + tid;
+        if (idx < r1) {
+            const int32_t g = __ldg(sorted_ids + idx);
+            StagedA sa; StagedB sb; StagedC sc;
+            if (g >= 0 && (int64_t)g < N) {
+                const float2 m = __ldg(reinterpret_cast<const float2*>(means2d) + g);
+                const float ca = __ldg(conics + 3 * (int64_t)g), cb = __ldg(conics + 3 * (int64_t)g + 1),
+                            cc = __ldg(conics + 3 * (int64_t)g + 2);
+                const float op = __ldg(opacities + g);
+                sa.mx = m.x; sa.my = m.y;
+                sa.A = 0.5f * kLog2e * ca; sa.B = kLog2e * cb;
+                sb.C = 0.5f * kLog2e * cc;
+                // accurate log2 keeps alpha = 2^(L - q) within a few ulp of o*exp(-sigma)
+                sb.L = (op > 0.0f) ? log2f(op) : -INFINITY;
+                const bool pd = (sa.A > 0.0f) && (sb.C > 0.0f) && (4.0f * sa.A * sb.C - sa.B * sa.B > 0.0f);
+                sb.hy = pd ? -sa.B / (2.0f * sb.C) : 0.0f;
+                sb.hx = pd ? -sa.B / (2.0f * sa.A) : 0.0f;
+                sc.r = __ldg(colors + 3 * (int64_t)g); sc.g = __ldg(colors + 3 * (int64_t)g + 1);
+                sc.b = __ldg(colors + 3 * (int64_t)g + 2);
+                sc.tau = pd ? (sb.L - kLog2AlphaThreshold) : INFINITY;
+                if (!(op == op)) sc.tau = INFINITY;  // NaN opacity: evaluate, never cull
+            } else {
+                sa.mx = sa.my = sa.A = sa.B = 0.0f;
+                sb.C = 0.0f; sb.L = -INFINITY; sb.hy = sb.hx = 0.0f;
+                sc.r = sc.g = sc.b = 0.0f; sc.tau = -INFINITY;
+            }
+            s_a[tid] = sa; s_b[tid] = sb; s_c[tid] = sc;
+        }
+        __syncthreads();
+
+        const int bs = min(kFastBatch, (int)(r1 - b0));
+        // warp-uniform loop; a warp whose 32 pixels are all saturated just falls through
+        for (int c0 = 0; c0 < bs; c0 += 32) {
+            if (__all_sync(0xffffffffu, done)) break;
+            unsigned int mask;
+            if (kCull) {
+                bool hit = false;
+                const int gi = c0 + lane;
+                if (gi < bs) {
+                    const StagedA a = s_a[gi];
+                    const StagedB b = s_b[gi];
+                    const float tau = s_c[gi].tau;
+                    // u = mx - x over the block, v = my - y
+                    const float u0 = a.mx - X1, u1 = a.mx - X0;
+                    const float v0 = a.my - Y1, v1 = a.my - Y0;
+                    const bool zu = (u0 <= 0.0f) && (u1 >= 0.0f);
+                    const bool zv = (v0 <= 0.0f) && (v1 >= 0.0f);
+                    float qmin;
+                    if (zu && zv) {
+                        qmin = 0.0f;
+                    } else {
+                        float q1 = INFINITY, q2 = INFINITY;
+                        if (!zu) {  // vertical edge nearest to the mean
+                            const float ue = (u0 > 0.0f) ? u0 : u1;
+                            const float vs = fminf(fmaxf(b.hy * ue, v0), v1);
+                            q1 = a.A * ue * ue + a.B * ue * vs + b.C * vs * vs;
+                        }
+                        if (!zv) {  // horizontal edge nearest to the mean
+                            const float ve = (v0 > 0.0f) ? v0 : v1;
+                            const float us = fminf(fmaxf(b.hx * ve, u0), u1);
+                            q2 = a.A * us * us + a.B * us * ve + b.C * ve * ve;
+                        }
+                        qmin = fminf(q1, q2);
+                    }
+                    const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
+                    const float slack = 4e-6f * (a.A * um * um + b.C * vm * vm) + 1e-3f;
+                    hit = !(qmin > tau + slack);  // NaN-safe: anything odd counts as a hit
+                }
+                mask = __ballot_sync(0xffffffffu, hit);
+            } else {
+                const int rem = bs - c0;
+                mask = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+            }
+            while (mask) {
+                const int t = c0 + (__ffs(mask) - 1);
+                mask &= mask - 1;
+                if (done) continue;
+                const StagedA a = s_a[t];
+                const StagedB b = s_b[t];
+                const float dx = a.mx - px, dy = a.my - py;
+                const float t1 = fmaf(a.B, dy, a.A * dx);
+                float q = t1 * dx;
+                q = fmaf(b.C * dy, dy, q);
+                const float power = b.L - q;
+                if (q < 0.0f || !(power >= kLog2AlphaThreshold)) continue;
+                const float alpha = fminf(0.999f, ex2_approx(power));
+                const float next_T = T * (1.0f - alpha);
+                if (next_T <= 1e-4f) { done = true; continue; }
+                const float vis = alpha * T;
+                const StagedC c = s_c[t];
+                accr = fmaf(c.r, vis, accr);
+                accg = fmaf(c.g, vis, accg);
+                accb = fmaf(c.b, vis, accb);
+                T = next_T;
+            }
+        }
+    }
+
+    // ---- write the tile: through shared memory as 128-bit rows when the layout allows ----
+    const float outr = fmaf(T, __ldg(background), accr), outg = fmaf(T, __ldg(background + 1), accg),
+                outb = fmaf(T, __ldg(background + 2), accb);
+    const bool full_tile = (blockIdx.x * kFastTile + kFastTile <= W) && (blockIdx.y * kFastTile + kFastTile <= H);
+    if (vec_store && full_tile) {
+        __syncthreads();  // staging buffers are dead from here on
+        float* s_out = reinterpret_cast<float*>(s_a);  // 16 rows x 48 floats = 3 KB
+        const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+        s_out[(ly * kFastTile + lx) * 3 + 0] = outr;
+        s_out[(ly * kFastTile + lx) * 3 + 1] = outg;
+        s_out[(ly * kFastTile + lx) * 3 + 2] = outb;
+        __syncthreads();
+        if (tid < 16 * 12) {
+            const int row = tid / 12, c4 = tid % 12;
+            const float4 v = reinterpret_cast<const float4*>(s_out)[row * 12 + c4];
+            float* dst = image + ((int64_t)(blockIdx.y * kFastTile + row) * W + blockIdx.x * kFastTile) * 3;
+            reinterpret_cast<float4*>(dst)[c4] = v;
+        }
+    } else if (inside) {
+        float* dst = image + ((int64_t)i * W + j) * 3;
+        dst[0] = outr; dst[1] = outg; dst[2] = outb;
+    }
+}
+
+}  // namespace bsplat
+
+using namespace bsplat;
+
+template <int CH>
+static int launch_faithful(int64_t N, int cdim, int c0, const float* means2d, const float* conics,
+                           const float* colors, const float* opacities, const float* background,
+                           const int32_t* tile_ranges, const int32_t* sorted_ids, int W, int H, int ts,
+                           float* image, unsigned long long* stats, cudaStream_t stream) {
+    const int tiles_w = (W + ts - 1) / ts, tiles_h = (H + ts - 1) / ts;
+    const dim3 grid(tiles_w, tiles_h), block(ts, ts);
+    const size_t smem = (size_t)ts * ts * (6 + CH) * sizeof(float);
+    raster_faithful_kernel<CH><<<grid, block, smem, stream>>>(N, cdim, c0, means2d, conics, colors, opacities,
+                                                              background, tile_ranges, sorted_ids, W, H, ts,
+                                                              tiles_w, image, stats);
+    BSPLAT_LAUNCH_CHECK();
+    return BSPLAT_OK;
+}
+
+namespace bsplat {
+// shared with capi.cu; mode 2 = fast arithmetic without sub-tile culling (A/B testing)
+int rasterize_launch(int64_t N, int channels, const float* means2d, const float* conics, const float* colors,
+                     const float* opacities, const float* background_dev,
+                     const int32_t* tile_ranges, const int32_t* sorted_ids, int W, int H, int tile_size,
+                     int mode, float* image, unsigned long long* stats, cudaStream_t stream) {
+    if (W <= 0 || H <= 0 || tile_size <= 0 || tile_size > 32 || channels <= 0 || !background_dev)
+        return BSPLAT_E_ARG;
+    const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
+    if (tiles_h > 65535) return BSPLAT_E_ARG;
+    const bool fast_ok = (mode == BSPLAT_RASTER_FAST || mode == 2) && tile_size == kFastTile &&
+                         channels == 3 && stats == nullptr &&
+                         (reinterpret_cast<uintptr_t>(means2d) & 7u) == 0;
+    if (fast_ok) {
+        const float* bg = background_dev;
+        const int vec = ((reinterpret_cast<uintptr_t>(image) & 15u) == 0 && (W % 4) == 0) ? 1 : 0;
+        const dim3 grid(tiles_w, tiles_h);
+        if (mode == 2)
+            raster_fast_kernel<false><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
+                                                                         tile_ranges, sorted_ids, W, H, tiles_w,
+                                                                         image, vec);
+        else
+            raster_fast_kernel<true><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
+                                                                        tile_ranges, sorted_ids, W, H, tiles_w,
+                                                                        image, vec);
+        BSPLAT_LAUNCH_CHECK();
+        return BSPLAT_OK;
+    }
+    // faithful path: channels in chunks of <= 4 (alpha is recomputed per chunk; RGB is one chunk)
+    for (int c0 = 0; c0 < channels; c0 += 4) {
+        const int ch = channels - c0 < 4 ? channels - c0 : 4;
+        int rc;
+        unsigned long long* st = (c0 == 0) ? stats : nullptr;
+        switch (ch) {
+            case 1: rc = launch_faithful<1>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, image, st, stream); break;
+            case 2: rc = launch_faithful<2>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, image, st, stream); break;
+            case 3: rc = launch_faithful<3>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, image, st, stream); break;
+            default: rc = launch_faithful<4>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, image, st, stream); break;
+        }
+        if (rc != BSPLAT_OK) return rc;
+    }
+    return BSPLAT_OK;
+}
+}  // namespace bsplat

@@ -1,0 +1,93 @@
+"""Stage 3 -- rasterization dispatcher (mirrors the reference's mojosplat/rasterization.py:13-57).
+
+``rasterize_gaussians(means2d, conics, colors, opacities, background_color, tile_ranges,
+sorted_gaussian_indices, camera, tile_size=16, backend)`` -> ``image[H, W, C]`` float32.
+Opacities are used raw (no sigmoid), tile_ranges may be int64 (cast like rasterization.py:163).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .projection import CUDA_BACKENDS, _reference_module
+from .utils import Camera
+
+RASTER_MODES = {"fast": _lib.RASTER_FAST, "faithful": _lib.RASTER_FAITHFUL,
+                "fast_nocull": _lib.RASTER_FAST_NOCULL}
+
+
+def rasterize_gaussians(
+    means2d: torch.Tensor,  # (N, 2)
+    conics: torch.Tensor,  # (N, 3)
+    colors: torch.Tensor,  # (N, C)
+    opacities: torch.Tensor,  # (N,) or (N, 1)
+    background_color: torch.Tensor,  # (C,)
+    tile_ranges: torch.Tensor,  # (tile_height, tile_width, 2)
+    sorted_gaussian_indices: torch.Tensor,  # (M,)
+    camera: Camera,
+    tile_size: int = 16,
+    backend: str = "cuda",
+) -> torch.Tensor:
+    """Rasterizes 2D Gaussians to pixels (reference: rasterization.py:13-57)."""
+    if backend in CUDA_BACKENDS:
+        return rasterize_gaussians_cuda(means2d, conics, colors, opacities, background_color, tile_ranges,
+                                        sorted_gaussian_indices, camera, tile_size)
+    if backend in ("torch", "gsplat", "mojo"):
+        return _reference_module("rasterization").rasterize_gaussians(
+            means2d, conics, colors, opacities, background_color, tile_ranges, sorted_gaussian_indices,
+            camera, tile_size=tile_size, backend=backend)
+    raise ValueError(f"Invalid backend: {backend}")
+
+
+def _prep(means2d, conics, colors, opacities, background_color, tile_ranges, sorted_ids):
+    dev = means2d.device
+    means2d = _lib.as_f32(means2d, "means2d")
+    conics = _lib.as_f32(conics, "conics")
+    colors = _lib.as_f32(colors, "colors")
+    opacities = _lib.as_f32(opacities, "opacities").reshape(-1)
+    background = _lib.as_f32(background_color, "background_color").reshape(-1).to(dev)
+    tile_ranges = tile_ranges.to(torch.int32).contiguous()
+    sorted_ids = sorted_ids.reshape(-1).to(torch.int32).contiguous()
+    N, C = colors.shape
+    if means2d.shape != (N, 2) or conics.shape != (N, 3) or opacities.shape != (N,):
+        raise ValueError("expected means2d (N,2), conics (N,3), colors (N,C), opacities (N,)")
+    if background.shape[0] != C:
+        raise ValueError(f"Background color channels ({background.shape[0]}) must match gaussian color channels ({C})")
+    return dev, means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, N, C
+
+
+def rasterize_gaussians_cuda(means2d, conics, colors, opacities, background_color, tile_ranges,
+                             sorted_gaussian_indices, camera, tile_size=16, mode="fast"):
+    """sm_100a tile rasterizer behind the C ABI (include/bsplat.h: bsplat_rasterize_fwd)."""
+    L = _lib.require_device(means2d.device)
+    dev, means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, N, C = _prep(
+        means2d, conics, colors, opacities, background_color, tile_ranges, sorted_gaussian_indices)
+    H, W = int(camera.H), int(camera.W)
+    image = torch.empty((H, W, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.bsplat_rasterize_fwd(N, C, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
+                                    _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
+                                    _lib.ptr(sorted_ids), sorted_ids.numel(), W, H, int(tile_size),
+                                    RASTER_MODES[mode], _lib.ptr(image), _lib.stream_ptr(dev))
+    _lib.check(rc, "bsplat_rasterize_fwd")
+    return image
+
+
+def rasterize_gaussians_stats(means2d, conics, colors, opacities, background_color, tile_ranges,
+                              sorted_gaussian_indices, camera, tile_size=16):
+    """Faithful kernel + work counters: returns (image, E_all, E_pass) -- the evaluated and the
+    contributing (pixel, Gaussian) pairs of the reference algorithm."""
+    L = _lib.require_device(means2d.device)
+    dev, means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, N, C = _prep(
+        means2d, conics, colors, opacities, background_color, tile_ranges, sorted_gaussian_indices)
+    H, W = int(camera.H), int(camera.W)
+    image = torch.empty((H, W, C), dtype=torch.float32, device=dev)
+    stats = torch.zeros((2,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.bsplat_rasterize_stats(N, C, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
+                                      _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
+                                      _lib.ptr(sorted_ids), sorted_ids.numel(), W, H, int(tile_size),
+                                      _lib.ptr(image), _lib.ptr(stats), _lib.stream_ptr(dev))
+    _lib.check(rc, "bsplat_rasterize_stats")
+    e_all, e_pass = stats.tolist()
+    return image, int(e_all), int(e_pass)

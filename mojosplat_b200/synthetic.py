@@ -1,7 +1,7 @@
 """Synthetic scenes of BASELINE.json's configs.
 
 Everything is drawn on the CPU with ``torch.Generator().manual_seed(seed)`` so that the CPU
-oracle and the CUDA kernels see bit-identical inputs (the reference seeds the CUDA generator,
+CPU checker and the CUDA kernels see bit-identical inputs (the reference seeds the CUDA generator,
 tests/test_rasterization.py:26-27, which is not reproducible without a GPU).  Distribution
 and draw order follow the reference's render_sample.py:86-102.
 """
