@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the forward render (projection -> binning -> rasterization).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Workload (BASELINE.json `metric`: frames/s, 1 M Gaussians @1920x1080): the config-3 "garden-sized"
+synthetic scene of SURVEY.md 8d, seen from a 64-view orbit whose view 0 is the config-3 pose.  A step
+is one frame per rank; ranks render different views (Gaussians are NCCL-broadcast once, no data-path
+collective afterwards) -> weak scaling, value = frames of all ranks / max-over-ranks device time.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: `roofline` (dominant kernel = the
+rasterizer, bound by FP32 issue rate -- no stage of this path is HBM- or tensor-bound at this size;
+SURVEY.md 8d), `stages` (per-stage device times and HBM GB/s for projection / binning), `cpu_baseline`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "frames/s, 1M Gaussians @1920x1080"
+WORKLOAD = "config3_1m_1080p"
+N_VIEWS = 64
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--n-gaussians", type=int, default=None, help="override N (debug only; marks the line)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--semantics", default="torch", choices=["torch", "gsplat"])
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_frame(sc_np, cam, background, semantics=0):
+    from oracle import oracle
+    return oracle.render(*sc_np, cam.view_matrix.numpy(), cam.fx, cam.fy, cam.cx, cam.cy, cam.W, cam.H,
+                         cam.near, cam.far, background=background, semantics=semantics, return_all=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference algorithm on the host cores: oracle port (C, OpenMP) of projection.py:285-346,
+    binning.py:108-262 and kernels/rasterization.mojo:75-162.  The reference itself is Python + Mojo
+    and has no compilable C sources (no oracle/_ref); its own torch binning is a Python loop
+    (~3.5 min per frame at this size), so the port is the generous baseline."""
+    if rank != 0:
+        return
+    from mojosplat_b200 import synthetic
+    from oracle import oracle
+    sc = synthetic.make_scene(args.workload, N=args.n_gaussians)
+    cams = synthetic.orbit_cameras(N_VIEWS, sc.camera.W, sc.camera.H, sc.camera.fx)
+    sc_np = [t.numpy() for t in sc.gaussians()]
+    bg = sc.background.numpy()
+    cores = oracle.num_threads()
+    for k in range(min(args.warmup, 1)):
+        oracle_frame(sc_np, cams[k % N_VIEWS], bg)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        oracle_frame(sc_np, cams[k % N_VIEWS], bg)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    sample = f"{args.steps} full frames ({sc.N} Gaussians @{sc.camera.W}x{sc.camera.H}, all three stages)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, sc), "host": "CPU only, rank 0"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args, sc):
+    s = (f"{args.workload}: {sc.N} Gaussians (garden-sized synthetic, SH0 RGB) @{sc.camera.W}x{sc.camera.H}, "
+         f"{N_VIEWS}-view orbit (view 0 = config-3 pose)")
+    if args.n_gaussians is not None:
+        s += " [DEBUG: N overridden, not the BASELINE size]"
+    return s
+
+
+# --------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    import mojosplat_b200 as ms
+    from mojosplat_b200 import _lib, rasterization, synthetic
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    L = _lib.require_device(dev)  # fails loudly without the .so / an sm_100 device
+    sem = _lib.SEM_TORCH if args.semantics == "torch" else _lib.SEM_GSPLAT
+
+    # ---- scene: rank 0 draws it, everyone else receives it over NCCL (one broadcast, at load) ----
+    ref_scene = synthetic.make_scene(args.workload, N=1 if rank != 0 else args.n_gaussians)
+    N = synthetic.CONFIGS[args.workload][0] if args.n_gaussians is None else args.n_gaussians
+    cam0 = ref_scene.camera
+    W, H = cam0.W, cam0.H
+    if rank == 0:
+        host = [t.pin_memory() for t in ref_scene.gaussians()]
+        g = [t.to(dev, non_blocking=True) for t in host]
+    else:
+        shapes = [(N, 3), (N, 3), (N, 4), (N,), (N, 3)]
+        g = [torch.empty(s, dtype=torch.float32, device=dev) for s in shapes]
+        host = None
+    if world > 1:
+        for t in g:
+            dist.broadcast(t, src=0)
+    bg = ref_scene.background.to(dev)
+    cams = synthetic.orbit_cameras(N_VIEWS, W, H, cam0.fx)
+    for c in cams:
+        _lib.camera_struct(c)  # host-side POD cached: no device read-back inside the timed loop
+    view_of = lambda k: cams[(k * world + rank) % N_VIEWS]
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def frame(k, **kw):
+        return ms.render_fused(*g, view_of(k), bg, 16, semantics=sem, **kw)
+
+    # ---- warm-up ----
+    for k in range(max(args.warmup, 3)):
+        frame(k)
+    torch.cuda.synchronize(dev)
+
+    # ---- timed region: K frames, device-timed per step, L2 flushed between steps ----
+    K = args.steps
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler.start()
+    wall0 = time.perf_counter()
+    launches = 0
+    for k in range(K):
+        flush.zero_()
+        ev_s[k].record()
+        frame(k)
+        ev_e[k].record()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    if world > 1:
+        dist.barrier()
+    step_ms = [s.elapsed_time(e) for s, e in zip(ev_s, ev_e)]
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * K / (total_ms_max * 1e-3)
+
+    # ---- end-to-end through the public host-buffer API (pinned host in, host image out) ----
+    host_all = host if host is not None else [x.cpu().pin_memory() for x in g]
+    out_img = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
+    bg_host = ref_scene.background
+    for k in range(2):
+        ms.render_gaussians_host(*host_all, view_of(k), background_color=bg_host, out=out_img, device=dev)
+    Ke = max(3, min(K, 10))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(Ke):
+        ms.render_gaussians_host(*host_all, view_of(k), background_color=bg_host, out=out_img, device=dev)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * Ke / (float(te.item()) * 1e-3)
+    h2d = N * (3 + 3 + 4 + 1 + 3) * 4 + 3 * 4
+    d2h = H * W * 3 * 4
+
+    if rank != 0:
+        return
+
+    # ---- per-stage device times (view 0, L2 flushed) and the work counters of that frame ----
+    stage = np.zeros(4)
+    Ks = 10
+    info = None
+    for k in range(Ks + 2):
+        flush.zero_()
+        _, info = ms.render_fused(*g, cams[0], bg, 16, semantics=sem, return_aux=True, timing=True)
+        if k >= 2:
+            stage += np.array(info["stage_ms"])
+    stage /= Ks
+    M, P = info["n_isect"], info["sort_passes"]
+    launches = K * info["n_launches"]
+    _, e_all, e_pass = rasterization.rasterize_gaussians_stats(
+        info["means2d"], info["conics"], g[4], g[3], bg, info["tile_ranges"], info["sorted_ids"], cams[0], 16)
+
+    # measured FP32 / SFU issue peaks (roofline denominators of the rasterizer)
+    def micro(kind):
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        blocks, iters = 148 * 8, 8192
+        best = 1e9
+        for _ in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(L.bsplat_microbench(kind, blocks, iters, _lib.ptr(out), _lib.stream_ptr(dev)), "microbench")
+            b.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, a.elapsed_time(b))
+        return blocks * 256 * 8 * iters / (best * 1e-3)
+    ffma_per_s, ex2_per_s = micro(0), micro(1)
+    fp32_peak_tflops = 2 * ffma_per_s / 1e12
+
+    hbm_peak, hbm_src = measured_peaks()
+    raster_s = stage[3] * 1e-3
+    flops = 14 * e_all + 10 * e_pass
+    achieved = flops / raster_s / 1e12
+    n_tiles = math.ceil(H / 16) * math.ceil(W / 16)
+    proj_bytes = 72 * N
+    bin_bytes = 52 * N + (28 + 24 * P) * M + 8 * n_tiles
+    stages = {
+        "projection": {"ms": stage[0], "GB/s": proj_bytes / (stage[0] * 1e-3) / 1e9,
+                       "frac_hbm": proj_bytes / (stage[0] * 1e-3) / 1e9 / hbm_peak, "bytes": proj_bytes},
+        "binning": {"ms": stage[1] + stage[2], "count_scan_emit_ms": stage[1], "sort_ranges_ms": stage[2],
+                    "GB/s": bin_bytes / ((stage[1] + stage[2]) * 1e-3) / 1e9,
+                    "frac_hbm": bin_bytes / ((stage[1] + stage[2]) * 1e-3) / 1e9 / hbm_peak,
+                    "bytes": bin_bytes, "M": M, "sort_passes": P, "key_bits": info["key_bits"]},
+        "raster": {"ms": stage[3], "E_all": e_all, "E_pass": e_pass, "nominal_256M": 256 * M,
+                   "G_splat_px_per_s": e_all / raster_s / 1e9,
+                   "sfu_frac": (e_all / raster_s) / ex2_per_s},
+        "hbm_peak_GB/s": hbm_peak, "hbm_peak_source": hbm_src,
+        "ffma_peak_T/s": ffma_per_s / 1e12, "ex2_peak_T/s": ex2_per_s / 1e12,
+    }
+    roofline = {"kernel": "raster_fast_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak_tflops,
+                "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": None,
+                "peak_source": "measured in this run (FFMA chain micro-benchmark, bsplat_microbench)",
+                "work": "14*E_all + 10*E_pass flop per launch (SURVEY.md 8d)", "share_of_step": stage[3] / stage.sum()}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle
+        sc_np = [x.numpy() for x in ref_scene.gaussians()]
+        t0 = time.perf_counter()
+        reps = 3
+        for k in range(reps):
+            ref = oracle_frame(sc_np, cams[k], bg_host.numpy(), 0 if args.semantics == "torch" else 1)
+        dt = (time.perf_counter() - t0) / reps
+        cpu_baseline = {"value": 1.0 / dt, "unit": "frames/s", "cores": oracle.num_threads(), "kind": "port",
+                        "sample": f"{reps} full frames of the same workload (oracle C port, all three stages)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, ref_scene), "tile_size": 16, "semantics": args.semantics,
+                   "l2": "flushed between timed steps (512 MiB memset outside the per-step event pair)",
+                   "parallelism": f"views split across {world} rank(s); Gaussians NCCL-broadcast once at load",
+                   "timing": "sum of per-step CUDA-event times, max over ranks", "wall_ms_per_step": 1e3 * wall / K},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "api": "mojosplat_b200.render_gaussians_host (pinned host tensors in, host image out)"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "stages": stages,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line, default=float), flush=True)
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -154,6 +154,9 @@ typedef struct bsplat_render_aux {
     int64_t sorted_ids_capacity;
     int64_t n_isect;       /* out: M */
     int32_t timing;        /* in: record per-stage CUDA-event times (adds a final sync) */
+    int32_t n_launches;    /* out: kernels launched by this call */
+    int32_t sort_passes;   /* out: onesweep passes (= ceil(live key bits / 8)) */
+    int32_t key_bits;      /* out: live key bits (depth_bits + tile_bits) */
     float stage_ms[4];     /* out when timing != 0: projection, count+scan+emit, sort+ranges, raster */
 } bsplat_render_aux;
 
@@ -179,6 +182,12 @@ int bsplat_render_fwd_host(int64_t N, const float* means3d, const float* log_sca
                            float* image_host, void* device_scratch, size_t scratch_bytes,
                            void* workspace, size_t workspace_bytes, size_t* needed_bytes,
                            bsplat_render_aux* aux, void* stream);
+
+/* ---- measurement helper (not on the product path) ------------------------------------------ */
+/* Issue-rate micro-benchmark: kind 0 = FP32 FFMA chains, kind 1 = MUFU.EX2 chains; blocks x 256
+ * threads x 8 x iters operations. Timed by the caller with CUDA events; gives the measured
+ * FP32 / SFU denominators of the rasterizer roofline. */
+int bsplat_microbench(int32_t kind, int32_t blocks, int32_t iters, float* out, void* stream);
 
 #ifdef __cplusplus
 }

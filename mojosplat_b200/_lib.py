@@ -31,7 +31,7 @@ SYMBOLS = [
     "bsplat_bin_emit", "bsplat_radix_sort_workspace_bytes", "bsplat_radix_sort_pairs",
     "bsplat_tile_ranges", "bsplat_rasterize_fwd", "bsplat_rasterize_stats",
     "bsplat_render_workspace_bytes", "bsplat_render_fwd", "bsplat_render_host_scratch_bytes",
-    "bsplat_render_fwd_host",
+    "bsplat_render_fwd_host", "bsplat_microbench",
 ]
 
 
@@ -53,7 +53,8 @@ class BsplatKeyLayout(Structure):
 class BsplatRenderAux(Structure):
     _fields_ = [("means2d", c_void_p), ("conics", c_void_p), ("depths", c_void_p), ("radii", c_void_p),
                 ("tile_ranges", c_void_p), ("sorted_ids", c_void_p), ("sorted_ids_capacity", c_int64),
-                ("n_isect", c_int64), ("timing", c_int32), ("stage_ms", c_float * 4)]
+                ("n_isect", c_int64), ("timing", c_int32), ("n_launches", c_int32), ("sort_passes", c_int32),
+                ("key_bits", c_int32), ("stage_ms", c_float * 4)]
 
 
 class BsplatError(RuntimeError):
@@ -131,6 +132,7 @@ def load() -> ctypes.CDLL:
                                              c_int32, POINTER(BsplatCamera), c_void_p, c_int32, c_int32,
                                              c_int32, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
                                              POINTER(c_size_t), POINTER(BsplatRenderAux), c_void_p]
+        L.bsplat_microbench.argtypes = [c_int32, c_int32, c_int32, c_void_p, c_void_p]
         _lib = L
     return _lib
 

@@ -132,7 +132,7 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     const int W = cam->width, H = cam->height;
     if (W <= 0 || H <= 0) return BSPLAT_E_ARG;
     const size_t image_bytes = (size_t)W * H * channels * sizeof(float);
-    if (aux) aux->n_isect = 0;
+    if (aux) { aux->n_isect = 0; aux->n_launches = 0; aux->sort_passes = 0; aux->key_bits = 0; }
 
     // fixed (N-dependent) part must fit before anything runs
     RenderWs w = carve_render(workspace, N, 0, W, H, tile_size);
@@ -168,7 +168,7 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     BSPLAT_CUDA_TRY(cudaMemcpyAsync(&info, w.info, sizeof(info), cudaMemcpyDeviceToHost, stream));
     BSPLAT_CUDA_TRY(cudaStreamSynchronize(stream));  // the single read-back of the frame (M, key range)
     const int64_t M = (int64_t)info.n_isect;
-    if (aux) aux->n_isect = M;
+    if (aux) { aux->n_isect = M; aux->n_launches = 3; }  // project, count_scan, finalize_info
     if (M >= (1ll << 30)) return BSPLAT_E_OVERFLOW;
     if (M == 0) {
         // render.py:73-76: no overlaps => black image (not the background)
@@ -205,6 +205,12 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     if (aux && aux->sorted_ids && aux->sorted_ids_capacity >= M)
         BSPLAT_CUDA_TRY(cudaMemcpyAsync(aux->sorted_ids, sorted_ids, (size_t)M * sizeof(int32_t),
                                         cudaMemcpyDeviceToDevice, stream));
+    if (aux) {
+        aux->key_bits = layout.depth_bits + layout.tile_bits;
+        aux->sort_passes = (aux->key_bits + 7) / 8;
+        // + emit, histogram, scan, P x onesweep, tile_ranges, raster
+        aux->n_launches = 3 + 1 + 2 + aux->sort_passes + 1 + 1;
+    }
     if (timing) {
         BSPLAT_CUDA_TRY(cudaEventRecord(ev[4], stream));
         BSPLAT_CUDA_TRY(cudaEventSynchronize(ev[4]));

@@ -115,6 +115,7 @@ def render_fused(means3d, scales, quats, opacities, colors, camera, background, 
         aux.depths, aux.radii = outs["depths"].data_ptr(), outs["radii"].data_ptr()
         aux.tile_ranges = outs["tile_ranges"].data_ptr()
         cap = _last_M.get(key, 0)
+        cap = int(cap * 1.3) + 4096 if cap else 0
         if cap:
             outs["sorted_ids"] = torch.empty((cap,), dtype=torch.int32, device=dev)
             aux.sorted_ids, aux.sorted_ids_capacity = outs["sorted_ids"].data_ptr(), cap
@@ -137,6 +138,9 @@ def render_fused(means3d, scales, quats, opacities, colors, camera, background, 
         warnings.warn("No Gaussian overlaps found; returning a black image (render.py:73-76)")
     if return_aux:
         outs["n_isect"] = M
+        outs["n_launches"] = int(aux.n_launches)
+        outs["sort_passes"] = int(aux.sort_passes)
+        outs["key_bits"] = int(aux.key_bits)
         if "sorted_ids" in outs:
             outs["sorted_ids"] = outs["sorted_ids"][:M] if outs["sorted_ids"].numel() >= M else None
         if timing:
