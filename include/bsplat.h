@@ -19,6 +19,7 @@
  *   bsplat_radix_sort_pairs   mojosplat/binning.py:223-231   (argsort depth + stable argsort tile)
  *   bsplat_tile_ranges        mojosplat/binning.py:252-260   (searchsorted -> tile_ranges;
  *                              gsplat isect_offset_encode, binning.py:84-100)
+ *   bsplat_bin2_prepare/finish mojosplat/binning.py:108-262 as a whole (two-level sort, default path)
  *   bsplat_rasterize_fwd      mojosplat/rasterization.py:13-57 rasterize_gaussians
  *                             (= MAX op `rasterize_to_pixels_3dgs_fwd`,
  *                              kernels/rasterization.mojo:169-240, call at rasterization.py:167-183)
@@ -54,6 +55,9 @@ extern "C" {
 /* rasterizer arithmetic */
 #define BSPLAT_RASTER_FAST 0      /* folded exp2 form, sub-tile culling (default) */
 #define BSPLAT_RASTER_FAITHFUL 1  /* operation order of kernels/rasterization.mojo:138-157 */
+
+/* bsplat_render_fwd `flags`: low byte = rasterizer mode, plus */
+#define BSPLAT_FLAG_BIN_SINGLE_LEVEL 0x100  /* one sort of packed 64-bit keys instead of the two-level sort */
 
 /* Pinhole camera, world->camera. Mirrors mojosplat/utils.py:5-31 (Camera.view_matrix, Ks, H, W,
  * near, far) as a POD. viewmat is row-major 4x4. */
@@ -126,6 +130,22 @@ int bsplat_radix_sort_pairs(int64_t M, uint64_t* keys, uint64_t* keys_alt, int32
 int bsplat_tile_ranges(int64_t M, const uint64_t* sorted_keys, int32_t tile_shift, int32_t n_tiles,
                        int32_t* tile_ranges, void* stream);
 
+/* Two-level binning (default path; same results, ~4x less sort traffic): depth-sort the N
+ * Gaussians (4 onesweep passes over uint32 depth keys), count + scan and emit in depth order, then a
+ * stable sort by tile id only (ceil(log2 n_tiles) bits, 2 passes over the M pairs) -- the structure
+ * of the reference's argsort(depth) + stable argsort(tile) (binning.py:223-231).
+ * prepare: writes M to *info_out (device); the caller reads it back, sizes sorted_ids[M] and calls
+ * finish with the same workspace (>= bsplat_bin2_workspace_bytes(N, M)). */
+size_t bsplat_bin2_workspace_bytes(int64_t N, int64_t M_capacity);
+int bsplat_bin2_prepare(int64_t N, const float* means2d, const void* radii, int32_t radii_is_float,
+                        const float* depths, int32_t width, int32_t height, int32_t tile_size,
+                        int32_t tile_row_begin, int32_t tile_row_end, int32_t semantics, void* workspace,
+                        size_t workspace_bytes, bsplat_bin_info* info_out, void* stream);
+int bsplat_bin2_finish(int64_t N, int64_t M, const float* means2d, const void* radii,
+                       int32_t radii_is_float, int32_t width, int32_t height, int32_t tile_size,
+                       int32_t tile_row_begin, int32_t tile_row_end, int32_t semantics, void* workspace,
+                       size_t workspace_bytes, int32_t* sorted_ids, int32_t* tile_ranges, void* stream);
+
 /* ---- stage 3: rasterization ---------------------------------------------------------------- */
 /* image[height, width, channels]. opacities are used raw (no sigmoid), like the reference. */
 int bsplat_rasterize_fwd(int64_t N, int32_t channels, const float* means2d, const float* conics,
@@ -168,7 +188,7 @@ size_t bsplat_render_workspace_bytes(int64_t N, int64_t M_capacity, int32_t widt
 int bsplat_render_fwd(int64_t N, const float* means3d, const float* log_scales, const float* quats,
                       const float* opacities, const float* colors, int32_t channels,
                       const bsplat_camera* cam_host, const float* background, int32_t tile_size,
-                      int32_t semantics, int32_t raster_mode, float* image, void* workspace,
+                      int32_t semantics, int32_t flags, float* image, void* workspace,
                       size_t workspace_bytes, size_t* needed_bytes, bsplat_render_aux* aux,
                       void* stream);
 /* Same with HOST buffers (pinned or pageable): copies the Gaussians in, renders, copies the
@@ -178,7 +198,7 @@ size_t bsplat_render_host_scratch_bytes(int64_t N, int32_t channels, int32_t wid
 int bsplat_render_fwd_host(int64_t N, const float* means3d, const float* log_scales,
                            const float* quats, const float* opacities, const float* colors,
                            int32_t channels, const bsplat_camera* cam_host, const float* background,
-                           int32_t tile_size, int32_t semantics, int32_t raster_mode,
+                           int32_t tile_size, int32_t semantics, int32_t flags,
                            float* image_host, void* device_scratch, size_t scratch_bytes,
                            void* workspace, size_t workspace_bytes, size_t* needed_bytes,
                            bsplat_render_aux* aux, void* stream);

@@ -23,6 +23,7 @@ OK = 0
 E_ARG, E_WORKSPACE, E_OVERFLOW, E_NODEVICE = -1, -2, -3, -4
 SEM_TORCH, SEM_GSPLAT = 0, 1
 RASTER_FAST, RASTER_FAITHFUL, RASTER_FAST_NOCULL = 0, 1, 2
+FLAG_BIN_SINGLE_LEVEL = 0x100
 
 # every symbol include/bsplat.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
@@ -31,7 +32,8 @@ SYMBOLS = [
     "bsplat_bin_emit", "bsplat_radix_sort_workspace_bytes", "bsplat_radix_sort_pairs",
     "bsplat_tile_ranges", "bsplat_rasterize_fwd", "bsplat_rasterize_stats",
     "bsplat_render_workspace_bytes", "bsplat_render_fwd", "bsplat_render_host_scratch_bytes",
-    "bsplat_render_fwd_host", "bsplat_microbench",
+    "bsplat_render_fwd_host", "bsplat_microbench", "bsplat_bin2_workspace_bytes", "bsplat_bin2_prepare",
+    "bsplat_bin2_finish",
 ]
 
 
@@ -133,6 +135,14 @@ def load() -> ctypes.CDLL:
                                              c_int32, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
                                              POINTER(c_size_t), POINTER(BsplatRenderAux), c_void_p]
         L.bsplat_microbench.argtypes = [c_int32, c_int32, c_int32, c_void_p, c_void_p]
+        L.bsplat_bin2_workspace_bytes.restype = c_size_t
+        L.bsplat_bin2_workspace_bytes.argtypes = [c_int64, c_int64]
+        L.bsplat_bin2_prepare.argtypes = [c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32,
+                                          c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p,
+                                          c_void_p]
+        L.bsplat_bin2_finish.argtypes = [c_int64, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                         c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p,
+                                         c_void_p, c_void_p]
         _lib = L
     return _lib
 

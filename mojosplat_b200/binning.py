@@ -43,12 +43,20 @@ def read_bin_info(info_dev: torch.Tensor) -> _lib.BsplatBinInfo:
 
 
 def bin_gaussians_to_tiles_cuda(means2d, radii, depths, img_height, img_width, tile_size,
-                                semantics=_lib.SEM_TORCH, tile_rows=None, return_keys=False):
-    """count+scan -> emit -> onesweep radix sort on the live key bits -> tile ranges.
+                                semantics=_lib.SEM_TORCH, tile_rows=None, return_keys=False,
+                                algo="two_level"):
+    """Binning on the GPU, two algorithms with bit-identical results:
+
+    ``algo="two_level"`` (default): depth-sort the N Gaussians, count+scan and emit in depth order,
+    stable-sort the M pairs by tile id only (bsplat_bin2_prepare / bsplat_bin2_finish).
+    ``algo="single"``: count+scan -> emit packed (tile << depth_bits | depth) keys -> one onesweep
+    sort over the live key bits -> tile ranges (needed for ``return_keys``).
 
     ``tile_rows=(begin, end)`` restricts emission to a band of tile rows (row-band multi-GPU split);
     per-tile lists inside the band are identical to the full-frame ones.
     """
+    if algo == "two_level" and not return_keys:
+        return _bin_two_level(means2d, radii, depths, img_height, img_width, tile_size, semantics, tile_rows)
     dev = means2d.device
     L = _lib.require_device(dev)
     means2d = _lib.as_f32(means2d, "means2d")
@@ -99,4 +107,45 @@ def bin_gaussians_to_tiles_cuda(means2d, radii, depths, img_height, img_width, t
                                         _lib.ptr(tile_ranges), stream), "bsplat_tile_ranges")
     if return_keys:
         return sorted_ids, tile_ranges, sorted_keys, layout
+    return sorted_ids, tile_ranges
+
+
+def _bin_two_level(means2d, radii, depths, img_height, img_width, tile_size, semantics, tile_rows):
+    dev = means2d.device
+    L = _lib.require_device(dev)
+    means2d = _lib.as_f32(means2d, "means2d")
+    depths = _lib.as_f32(depths, "depths").reshape(-1)
+    N = means2d.shape[0]
+    if radii.dtype == torch.int32:
+        radii_c, radii_is_float = radii.contiguous(), 0
+    else:
+        radii_c, radii_is_float = radii.to(torch.float32).contiguous(), 1
+    if means2d.shape != (N, 2) or radii_c.shape != (N, 2) or depths.shape != (N,):
+        raise ValueError("expected means2d (N,2), radii (N,2), depths (N,)")
+    H, W, ts = int(img_height), int(img_width), int(tile_size)
+    th, tw = math.ceil(H / ts), math.ceil(W / ts)
+    r0, r1 = (0, th) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
+    stream = _lib.stream_ptr(dev)
+    info = torch.empty((32,), dtype=torch.uint8, device=dev)
+    tile_ranges = torch.empty((th, tw, 2), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _lib.workspace.get(dev, "bin2", L.bsplat_bin2_workspace_bytes(N, 4 * N + 1024))
+        _lib.check(L.bsplat_bin2_prepare(N, _lib.ptr(means2d), _lib.ptr(radii_c), radii_is_float, _lib.ptr(depths),
+                                         W, H, ts, r0, r1, semantics, _lib.ptr(ws), ws.numel(), _lib.ptr(info),
+                                         stream), "bsplat_bin2_prepare")
+        M = int(read_bin_info(info).n_isect)
+        if M >= (1 << 30):
+            raise _lib.BsplatError(_lib.E_OVERFLOW, "bin_gaussians_to_tiles")
+        need = L.bsplat_bin2_workspace_bytes(N, M)
+        if ws.numel() < need:
+            # grow, keeping the N-part (perm, offsets) that prepare just produced
+            old = ws
+            ws = torch.empty(int(need * 1.25), dtype=torch.uint8, device=dev)
+            n_part = L.bsplat_bin2_workspace_bytes(N, 0)
+            ws[:n_part].copy_(old[:n_part])
+            _lib.workspace._bufs[(dev.index if dev.index is not None else torch.cuda.current_device(), "bin2")] = ws
+        sorted_ids = torch.empty((M,), dtype=torch.int32, device=dev)
+        _lib.check(L.bsplat_bin2_finish(N, M, _lib.ptr(means2d), _lib.ptr(radii_c), radii_is_float, W, H, ts, r0, r1,
+                                        semantics, _lib.ptr(ws), ws.numel(), _lib.ptr(sorted_ids),
+                                        _lib.ptr(tile_ranges), stream), "bsplat_bin2_finish")
     return sorted_ids, tile_ranges

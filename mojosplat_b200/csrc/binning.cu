@@ -11,43 +11,14 @@
 //   3. tile_ranges_kernel     turns the sorted keys into [start, end) per tile, with
 //      searchsorted-left semantics for empty tiles.
 // Key = (tile_id << depth_bits) | (depth_key - depth_bias): only live bits are ever sorted.
-#include "common.cuh"
+#include "binning.cuh"
 
 namespace bsplat {
 
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 4;
-constexpr int kScanChunk = kScanThreads * kScanItems;  // Gaussians per block
-
-// workspace layout of the scan: [0] chunk ticket, [1..] one 64-bit status word per chunk
-constexpr unsigned long long kFlagAgg = 1ull << 62;
-constexpr unsigned long long kFlagPrefix = 2ull << 62;
-constexpr unsigned long long kValueMask = (1ull << 62) - 1;
-
-struct BinParams {
-    int W, H, tiles_w, tiles_h, semantics, row_begin, row_end;
-    float tile_size_f;
-};
-
-__device__ inline void load_mean_radii(const float* __restrict__ means2d, const void* __restrict__ radii,
-                                       int radii_is_float, int64_t i, float& mx, float& my, float& rx,
-                                       float& ry) {
-    mx = __ldg(means2d + 2 * i);
-    my = __ldg(means2d + 2 * i + 1);
-    if (radii_is_float) {
-        const float* r = static_cast<const float*>(radii);
-        rx = __ldg(r + 2 * i);
-        ry = __ldg(r + 2 * i + 1);
-    } else {
-        const int32_t* r = static_cast<const int32_t*>(radii);
-        rx = (float)__ldg(r + 2 * i);  // int32 -> float promotion of `means2d - radii`
-        ry = (float)__ldg(r + 2 * i + 1);
-    }
-}
-
 __global__ void __launch_bounds__(kScanThreads)
-bin_count_scan_kernel(const int64_t N, const float* __restrict__ means2d, const void* __restrict__ radii,
-                      const int radii_is_float, const float* __restrict__ depths, const BinParams p,
+bin_count_scan_kernel(const int64_t N, const int32_t* __restrict__ perm, const float* __restrict__ means2d,
+                      const void* __restrict__ radii, const int radii_is_float,
+                      const float* __restrict__ depths, const BinParams p,
                       uint32_t* __restrict__ offsets, bsplat_bin_info* __restrict__ info,
                       unsigned long long* __restrict__ ws) {
     __shared__ unsigned int s_chunk;
@@ -68,9 +39,11 @@ bin_count_scan_kernel(const int64_t N, const float* __restrict__ means2d, const 
     uint32_t thread_sum = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        const int64_t i = base + (int64_t)tid * kScanItems + k;
+        const int64_t jj = base + (int64_t)tid * kScanItems + k;
         uint32_t c = 0;
-        if (i < N) {
+        if (jj < N) {
+            // two-level path: slot jj of the depth-sorted order holds Gaussian perm[jj]
+            const int64_t i = perm ? (int64_t)__ldg(perm + jj) : jj;
             float mx, my, rx, ry;
             load_mean_radii(means2d, radii, radii_is_float, i, mx, my, rx, ry);
             const TileRect r = tile_rect(mx, my, rx, ry, p.W, p.H, p.tile_size_f, p.tiles_w, p.tiles_h,
@@ -213,7 +186,8 @@ bin_emit_kernel(const int64_t N, const float* __restrict__ means2d, const void* 
 
 // ------------------------------------------------------------------------------------------
 // tile_ranges[t] = [first index with tile >= t, first index with tile >= t+1)
-__global__ void tile_ranges_kernel(const int64_t M, const uint64_t* __restrict__ keys, const int tile_shift,
+template <typename KeyT>
+__global__ void tile_ranges_kernel(const int64_t M, const KeyT* __restrict__ keys, const int tile_shift,
                                    const int n_tiles, int32_t* __restrict__ ranges) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > M) return;
@@ -225,7 +199,30 @@ __global__ void tile_ranges_kernel(const int64_t M, const uint64_t* __restrict__
     }
 }
 
-static int make_params(int32_t width, int32_t height, int32_t tile_size, int32_t row_begin,
+// workspace and info must be zeroed by the caller (stream-ordered memset)
+int bin_count_scan_launch(int64_t N, const int32_t* perm, const float* means2d, const void* radii,
+                          int radii_is_float, const float* depths, const BinParams& p, uint32_t* offsets,
+                          bsplat_bin_info* info, void* workspace, cudaStream_t stream) {
+    const unsigned grid = (unsigned)ceil_div(N, kScanChunk);
+    bin_count_scan_kernel<<<grid, kScanThreads, 0, stream>>>(N, perm, means2d, radii, radii_is_float, depths, p,
+                                                             offsets, info,
+                                                             static_cast<unsigned long long*>(workspace));
+    BSPLAT_LAUNCH_CHECK();
+    bin_finalize_info_kernel<<<1, 1, 0, stream>>>(info);
+    BSPLAT_LAUNCH_CHECK();
+    return BSPLAT_OK;
+}
+
+int tile_ranges_u32_launch(int64_t M, const uint32_t* sorted_tile_ids, int n_tiles, int32_t* tile_ranges,
+                           cudaStream_t stream) {
+    const int threads = 256;
+    const unsigned grid = (unsigned)ceil_div(M + 1, threads);
+    tile_ranges_kernel<uint32_t><<<grid, threads, 0, stream>>>(M, sorted_tile_ids, 0, n_tiles, tile_ranges);
+    BSPLAT_LAUNCH_CHECK();
+    return BSPLAT_OK;
+}
+
+int make_bin_params(int32_t width, int32_t height, int32_t tile_size, int32_t row_begin,
                        int32_t row_end, int32_t semantics, BinParams* p) {
     if (width <= 0 || height <= 0 || tile_size <= 0) return BSPLAT_E_ARG;
     if (semantics != BSPLAT_SEM_TORCH && semantics != BSPLAT_SEM_GSPLAT) return BSPLAT_E_ARG;
@@ -258,7 +255,7 @@ extern "C" int bsplat_bin_count_scan(int64_t N, const float* means2d, const void
                                      void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     BinParams p;
-    int rc = make_params(width, height, tile_size, tile_row_begin, tile_row_end, semantics, &p);
+    int rc = make_bin_params(width, height, tile_size, tile_row_begin, tile_row_end, semantics, &p);
     if (rc != BSPLAT_OK) return rc;
     if (N < 0 || !offsets || !info) return BSPLAT_E_ARG;
     if (N > 0 && (!means2d || !radii || !depths)) return BSPLAT_E_ARG;
@@ -271,13 +268,8 @@ extern "C" int bsplat_bin_count_scan(int64_t N, const float* means2d, const void
         return BSPLAT_OK;
     }
     const unsigned grid = (unsigned)ceil_div(N, kScanChunk);
-    bin_count_scan_kernel<<<grid, kScanThreads, 0, stream>>>(
-        N, means2d, radii, radii_is_float, depths, p, offsets, info,
-        static_cast<unsigned long long*>(workspace));
-    BSPLAT_LAUNCH_CHECK();
-    bin_finalize_info_kernel<<<1, 1, 0, stream>>>(info);
-    BSPLAT_LAUNCH_CHECK();
-    return BSPLAT_OK;
+    return bin_count_scan_launch(N, nullptr, means2d, radii, radii_is_float, depths, p, offsets, info, workspace,
+                                 stream);
 }
 
 extern "C" bsplat_key_layout bsplat_make_key_layout(const bsplat_bin_info* info_host, int32_t width,
@@ -304,7 +296,7 @@ extern "C" int bsplat_bin_emit(int64_t N, const float* means2d, const void* radi
                                bsplat_key_layout layout, uint64_t* keys, int32_t* ids, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     BinParams p;
-    int rc = make_params(width, height, tile_size, tile_row_begin, tile_row_end, semantics, &p);
+    int rc = make_bin_params(width, height, tile_size, tile_row_begin, tile_row_end, semantics, &p);
     if (rc != BSPLAT_OK) return rc;
     if (N < 0 || !offsets) return BSPLAT_E_ARG;
     if (layout.depth_bits < 1 || layout.depth_bits > 32 || layout.tile_bits < 1 ||
@@ -327,7 +319,7 @@ extern "C" int bsplat_tile_ranges(int64_t M, const uint64_t* sorted_keys, int32_
     if (M > 0 && !sorted_keys) return BSPLAT_E_ARG;
     const int threads = 256;
     const unsigned grid = (unsigned)ceil_div(M + 1, threads);
-    tile_ranges_kernel<<<grid, threads, 0, stream>>>(M, sorted_keys, tile_shift, n_tiles, tile_ranges);
+    tile_ranges_kernel<uint64_t><<<grid, threads, 0, stream>>>(M, sorted_keys, tile_shift, n_tiles, tile_ranges);
     BSPLAT_LAUNCH_CHECK();
     return BSPLAT_OK;
 }

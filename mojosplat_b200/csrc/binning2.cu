@@ -1,0 +1,288 @@
+// Stage 2 (default path) -- two-level binning.
+//
+// The reference sorts the (gaussian, tile) pairs twice: argsort by depth, then a STABLE argsort by
+// tile id (mojosplat/binning.py:223-231).  This path keeps that structure but moves the depth sort to
+// where it is cheap:
+//   1. depth-sort the N Gaussians          4 onesweep passes over (uint32 depth key, index) -- N items
+//   2. count + scan in depth order         tile rects of Gaussian perm[j], exclusive prefix sum, M
+//   3. emit in depth order                 (tile id, gaussian id) pairs; tile-digit histograms on the fly
+//   4. stable sort by tile id only         ceil(log2(n_tiles)) bits -> 2 onesweep passes over M items
+//   5. tile ranges                         from the sorted tile ids
+// Result = ascending (tile, depth, gaussian index): bit-identical to the single-level sort of
+// (tile << depth_bits | depth_key) keys and to the reference's lists (canonical tie order),
+// with ~4x less sort traffic: M-scale data is moved by 2 passes of 8 B pairs instead of 6 passes of 12 B.
+#include "binning.cuh"
+#include "radix_sort.cuh"
+
+namespace bsplat {
+
+// ---- 1. depth keys + digit histograms of the 4 depth passes ---------------------------------
+__global__ void __launch_bounds__(256)
+depth_key_hist_kernel(const int64_t N, const float* __restrict__ depths, uint32_t* __restrict__ keys,
+                      uint32_t* __restrict__ hist /* [4][256] */) {
+    __shared__ uint32_t s_hist[4][kRadix];
+    for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t warp_start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane;
+    for (int64_t wi = warp_start; wi < N; wi += stride) {  // warp-uniform trip count
+        const int64_t i = wi + lane;
+        const bool valid = i < N;
+        uint32_t k = 0;
+        if (valid) {
+            k = depth_key(__ldg(depths + i));
+            keys[i] = k;
+            atomicAdd(&s_hist[0][k & 0xffu], 1u);
+            atomicAdd(&s_hist[1][(k >> 8) & 0xffu], 1u);
+            atomicAdd(&s_hist[2][(k >> 16) & 0xffu], 1u);
+        }
+        // sign + exponent bits: a handful of distinct values per warp -> aggregate before the atomic
+        const uint32_t top = valid ? (k >> 24) : 0x100u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, top);
+        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[3][top], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) {
+        const uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(hist + i, v);
+    }
+}
+
+// ---- 3. emission in depth order ------------------------------------------------------------
+constexpr int kEmit2Threads = 256;
+
+__global__ void __launch_bounds__(kEmit2Threads)
+bin_emit2_kernel(const int64_t N, const int32_t* __restrict__ perm, const float* __restrict__ means2d,
+                 const void* __restrict__ radii, const int radii_is_float, const BinParams p,
+                 const uint32_t* __restrict__ offsets, const int lo_bits, uint32_t* __restrict__ tile_keys,
+                 int32_t* __restrict__ ids, uint32_t* __restrict__ hist /* [2][256] */) {
+    __shared__ uint32_t s_off[kEmit2Threads + 1];
+    __shared__ uint32_t s_xy[kEmit2Threads];  // x0 | y0 << 16
+    __shared__ uint32_t s_w[kEmit2Threads];   // rect width in tiles
+    __shared__ int32_t s_id[kEmit2Threads];
+    __shared__ uint32_t s_hist[2][kRadix];
+
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const int64_t base = (int64_t)blockIdx.x * kEmit2Threads;
+    const int n_here = (int)min((int64_t)kEmit2Threads, N - base);
+    for (int i = tid; i < 2 * kRadix; i += kEmit2Threads) (&s_hist[0][0])[i] = 0;
+    if (tid < n_here) {
+        const int32_t g = __ldg(perm + base + tid);
+        float mx, my, rx, ry;
+        load_mean_radii(means2d, radii, radii_is_float, g, mx, my, rx, ry);
+        const TileRect r = tile_rect(mx, my, rx, ry, p.W, p.H, p.tile_size_f, p.tiles_w, p.tiles_h,
+                                     p.semantics, p.row_begin, p.row_end);
+        s_xy[tid] = (uint32_t)r.x0 | ((uint32_t)r.y0 << 16);
+        s_w[tid] = (uint32_t)(r.x1 - r.x0);
+        s_id[tid] = g;
+        s_off[tid] = __ldg(offsets + base + tid);
+    }
+    if (tid == 0) s_off[n_here] = __ldg(offsets + base + n_here);
+    __syncthreads();
+
+    const uint32_t begin = s_off[0], end = s_off[n_here];
+    const uint32_t lo_mask = (1u << lo_bits) - 1u;
+    for (uint32_t wpos = begin + (uint32_t)(tid - (int)lane); wpos < end; wpos += kEmit2Threads) {
+        const uint32_t pos = wpos + lane;
+        const bool valid = pos < end;
+        uint32_t tile = 0;
+        if (valid) {
+            int lo = 0, hi = n_here;  // invariant: s_off[lo] <= pos < s_off[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= pos) lo = mid; else hi = mid;
+            }
+            const uint32_t k = pos - s_off[lo];
+            const uint32_t w = s_w[lo];
+            const uint32_t dy = k / w, dx = k - dy * w;
+            const uint32_t xy = s_xy[lo];
+            tile = ((xy >> 16) + dy) * (uint32_t)p.tiles_w + (xy & 0xffffu) + dx;
+            tile_keys[pos] = tile;
+            ids[pos] = s_id[lo];
+            atomicAdd(&s_hist[0][tile & lo_mask], 1u);  // neighbouring lanes hold neighbouring tiles
+        }
+        // high digit: lanes of one Gaussian's row share it -> aggregate
+        const uint32_t top = valid ? (tile >> lo_bits) : 0x100u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, top);
+        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[1][top], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * kRadix; i += kEmit2Threads) {
+        const uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(hist + i, v);
+    }
+}
+
+// ---- workspace ------------------------------------------------------------------------------
+constexpr size_t kBinAlign = 256;
+static inline size_t bin_align(size_t v) { return (v + kBinAlign - 1) / kBinAlign * kBinAlign; }
+
+struct Bin2Ws {
+    // N part (lives from prepare to finish)
+    uint32_t* dkeys; uint32_t* dkeys_alt; int32_t* perm; int32_t* perm_alt;
+    uint32_t* offsets; bsplat_bin_info* info; void* scan_ws; size_t scan_bytes;
+    uint32_t* hist;      // [6][256]: 4 depth passes + 2 tile passes
+    uint32_t* tickets;   // [8]
+    uint32_t* status_n;  // [4][tilesN][256]
+    size_t zero_begin, zero_end_n;  // byte range zeroed by prepare
+    size_t n_bytes;
+    // M part
+    uint32_t* tkeys; uint32_t* tkeys_alt; int32_t* ids; int32_t* ids_alt;
+    uint32_t* status_m;  // [2][tilesM][256]
+    size_t status_m_off, status_m_bytes;
+    size_t total;
+};
+
+static Bin2Ws carve_bin2(void* base, int64_t N, int64_t M) {
+    Bin2Ws w;
+    char* p = static_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += bin_align(bytes); return r; };
+    const size_t n = (size_t)(N > 0 ? N : 1), m = (size_t)(M > 0 ? M : 1);
+    w.dkeys = (uint32_t*)take(n * 4); w.dkeys_alt = (uint32_t*)take(n * 4);
+    w.perm = (int32_t*)take(n * 4); w.perm_alt = (int32_t*)take(n * 4);
+    w.offsets = (uint32_t*)take((n + 1) * 4);
+    w.zero_begin = off;
+    w.info = (bsplat_bin_info*)take(sizeof(bsplat_bin_info));
+    w.scan_bytes = bsplat_bin_scan_workspace_bytes(N);
+    w.scan_ws = take(w.scan_bytes);
+    w.hist = (uint32_t*)take(6 * kRadix * 4);
+    w.tickets = (uint32_t*)take(8 * 4);
+    w.status_n = (uint32_t*)take(sort_status_words(sort_tiles_u32(N), 4) * 4);
+    w.zero_end_n = off;
+    w.n_bytes = off;
+    w.tkeys = (uint32_t*)take(m * 4); w.tkeys_alt = (uint32_t*)take(m * 4);
+    w.ids = (int32_t*)take(m * 4); w.ids_alt = (int32_t*)take(m * 4);
+    w.status_m_off = off;
+    w.status_m_bytes = sort_status_words(sort_tiles_u32(M), 2) * 4;
+    w.status_m = (uint32_t*)take(w.status_m_bytes);
+    w.total = off;
+    return w;
+}
+
+static int tile_bits_of(const BinParams& p) {
+    const int64_t n_tiles = (int64_t)p.tiles_w * p.tiles_h;
+    int tb = 1;
+    while (((int64_t)1 << tb) < n_tiles) ++tb;
+    return tb;
+}
+
+int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_is_float, const float* depths,
+                 const BinParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    Bin2Ws w = carve_bin2(workspace, N, 0);
+    if (!workspace || workspace_bytes < w.n_bytes) return BSPLAT_E_WORKSPACE;
+    char* base = static_cast<char*>(workspace);
+    BSPLAT_CUDA_TRY(cudaMemsetAsync(base + w.zero_begin, 0, w.zero_end_n - w.zero_begin, stream));
+    if (N == 0) {
+        BSPLAT_CUDA_TRY(cudaMemsetAsync(w.offsets, 0, sizeof(uint32_t), stream));
+        return BSPLAT_OK;
+    }
+    int64_t hb = ceil_div(N, 256 * 4);
+    depth_key_hist_kernel<<<(unsigned)(hb < 148 * 8 ? hb : 148 * 8), 256, 0, stream>>>(N, depths, w.dkeys, w.hist);
+    BSPLAT_LAUNCH_CHECK();
+    int rc = radix_scan_launch(w.hist, 4, stream);
+    if (rc != BSPLAT_OK) return rc;
+    const int64_t tn = sort_tiles_u32(N);
+    const uint32_t* ksrc = w.dkeys; uint32_t* kdst = w.dkeys_alt;
+    const int32_t* vsrc = nullptr; int32_t* vdst = w.perm_alt;
+    for (int pass = 0; pass < 4; ++pass) {
+        rc = onesweep_pass_u32(N, nullptr, ksrc, pass == 3 ? nullptr : kdst, vsrc, vdst, 8 * pass, 8,
+                               w.hist + (size_t)pass * kRadix, w.tickets + pass,
+                               w.status_n + (size_t)pass * tn * kRadix, stream);
+        if (rc != BSPLAT_OK) return rc;
+        // ping-pong: pass 0 writes (dkeys_alt, perm_alt), pass 1 (dkeys, perm), ...; pass 3 ends in perm
+        ksrc = kdst; kdst = (kdst == w.dkeys_alt) ? w.dkeys : w.dkeys_alt;
+        vsrc = vdst; vdst = (vdst == w.perm_alt) ? w.perm : w.perm_alt;
+    }
+    // after 4 passes the sorted permutation is in w.perm (passes 1 and 3 write w.perm)
+    return bin_count_scan_launch(N, w.perm, means2d, radii, radii_is_float, depths, p, w.offsets, w.info,
+                                 w.scan_ws, stream);
+}
+
+int bin2_finish(int64_t N, int64_t M, const float* means2d, const void* radii, int radii_is_float,
+                const BinParams& p, void* workspace, size_t workspace_bytes, int32_t* sorted_ids,
+                int32_t* tile_ranges, cudaStream_t stream) {
+    const int n_tiles = p.tiles_w * p.tiles_h;
+    Bin2Ws w = carve_bin2(workspace, N, M);
+    if (!workspace || workspace_bytes < w.total) return BSPLAT_E_WORKSPACE;
+    if (M == 0) {
+        BSPLAT_CUDA_TRY(cudaMemsetAsync(tile_ranges, 0, (size_t)n_tiles * 2 * sizeof(int32_t), stream));
+        return BSPLAT_OK;
+    }
+    BSPLAT_CUDA_TRY(cudaMemsetAsync(w.status_m, 0, w.status_m_bytes, stream));
+    const int tb = tile_bits_of(p);
+    const int lo_bits = tb > 8 ? (tb + 1) / 2 : tb;  // split the tile id evenly over <= 2 passes
+    const int hi_bits = tb - lo_bits;
+    bin_emit2_kernel<<<(unsigned)ceil_div(N, kEmit2Threads), kEmit2Threads, 0, stream>>>(
+        N, w.perm, means2d, radii, radii_is_float, p, w.offsets, lo_bits, w.tkeys, w.ids, w.hist + 4 * kRadix);
+    BSPLAT_LAUNCH_CHECK();
+    int rc = radix_scan_launch(w.hist + 4 * kRadix, 2, stream);
+    if (rc != BSPLAT_OK) return rc;
+    const int64_t tm = sort_tiles_u32(M);
+    if (hi_bits > 0) {
+        rc = onesweep_pass_u32(M, nullptr, w.tkeys, w.tkeys_alt, w.ids, w.ids_alt, 0, lo_bits, w.hist + 4 * kRadix,
+                               w.tickets + 4, w.status_m, stream);
+        if (rc != BSPLAT_OK) return rc;
+        rc = onesweep_pass_u32(M, nullptr, w.tkeys_alt, w.tkeys, w.ids_alt, sorted_ids, lo_bits, hi_bits,
+                               w.hist + 5 * kRadix, w.tickets + 5, w.status_m + (size_t)tm * kRadix, stream);
+    } else {
+        rc = onesweep_pass_u32(M, nullptr, w.tkeys, w.tkeys_alt, w.ids, sorted_ids, 0, lo_bits, w.hist + 4 * kRadix,
+                               w.tickets + 4, w.status_m, stream);
+    }
+    if (rc != BSPLAT_OK) return rc;
+    const uint32_t* sorted_tiles = hi_bits > 0 ? w.tkeys : w.tkeys_alt;
+    return tile_ranges_u32_launch(M, sorted_tiles, n_tiles, tile_ranges, stream);
+}
+
+size_t bin2_workspace_bytes(int64_t N, int64_t M) { return carve_bin2(nullptr, N, M).total; }
+bsplat_bin_info* bin2_info_ptr(void* workspace, int64_t N) { return carve_bin2(workspace, N, 0).info; }
+
+}  // namespace bsplat
+
+using namespace bsplat;
+
+extern "C" size_t bsplat_bin2_workspace_bytes(int64_t N, int64_t M_capacity) {
+    if (N < 0 || M_capacity < 0) return 0;
+    return bin2_workspace_bytes(N, M_capacity);
+}
+
+// Phase 1: depth-sort the Gaussians, tile rects + prefix sum in depth order. Afterwards *info_out
+// (device, 32 bytes) holds M; the caller reads it back (the stage's single read-back), sizes
+// sorted_ids and calls phase 2 with the same workspace.
+extern "C" int bsplat_bin2_prepare(int64_t N, const float* means2d, const void* radii, int32_t radii_is_float,
+                                   const float* depths, int32_t width, int32_t height, int32_t tile_size,
+                                   int32_t tile_row_begin, int32_t tile_row_end, int32_t semantics,
+                                   void* workspace, size_t workspace_bytes, bsplat_bin_info* info_out,
+                                   void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BinParams p;
+    int rc = make_bin_params(width, height, tile_size, tile_row_begin, tile_row_end, semantics, &p);
+    if (rc != BSPLAT_OK) return rc;
+    if (N < 0 || !info_out) return BSPLAT_E_ARG;
+    if (N > 0 && (!means2d || !radii || !depths)) return BSPLAT_E_ARG;
+    rc = bin2_prepare(N, means2d, radii, radii_is_float, depths, p, workspace, workspace_bytes, stream);
+    if (rc != BSPLAT_OK) return rc;
+    const bsplat_bin_info* src = bin2_info_ptr(workspace, N);
+    if (info_out != src)
+        BSPLAT_CUDA_TRY(cudaMemcpyAsync(info_out, src, sizeof(bsplat_bin_info), cudaMemcpyDeviceToDevice, stream));
+    return BSPLAT_OK;
+}
+
+// Phase 2: emit in depth order, stable sort by tile id, tile ranges.
+extern "C" int bsplat_bin2_finish(int64_t N, int64_t M, const float* means2d, const void* radii,
+                                  int32_t radii_is_float, int32_t width, int32_t height, int32_t tile_size,
+                                  int32_t tile_row_begin, int32_t tile_row_end, int32_t semantics,
+                                  void* workspace, size_t workspace_bytes, int32_t* sorted_ids,
+                                  int32_t* tile_ranges, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BinParams p;
+    int rc = make_bin_params(width, height, tile_size, tile_row_begin, tile_row_end, semantics, &p);
+    if (rc != BSPLAT_OK) return rc;
+    if (N < 0 || M < 0 || !tile_ranges) return BSPLAT_E_ARG;
+    if (M >= (int64_t)kStatMask) return BSPLAT_E_OVERFLOW;
+    if (M > 0 && (!means2d || !radii || !sorted_ids)) return BSPLAT_E_ARG;
+    return bin2_finish(N, M, means2d, radii, radii_is_float, p, workspace, workspace_bytes, sorted_ids,
+                       tile_ranges, stream);
+}

@@ -70,37 +70,34 @@ extern "C" int bsplat_rasterize_stats(int64_t N, int32_t channels, const float* 
 // ------------------------------------------------------------------------------------------
 // fused render
 // ------------------------------------------------------------------------------------------
+namespace bsplat {
+size_t bin2_workspace_bytes(int64_t N, int64_t M);
+bsplat_bin_info* bin2_info_ptr(void* workspace, int64_t N);
+}  // namespace bsplat
+
 namespace {
 
 constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
-struct RenderWs {
-    float* means2d; float* conics; float* depths; int32_t* radii;
+// single-level binning scratch (BSPLAT_FLAG_BIN_SINGLE_LEVEL)
+struct Bin1Ws {
     uint32_t* offsets; bsplat_bin_info* info; void* scan_ws; size_t scan_bytes;
-    int32_t* tile_ranges;
     uint64_t* keys; uint64_t* keys_alt; int32_t* ids; int32_t* ids_alt;
     void* sort_ws; size_t sort_bytes;
     size_t total;
 };
 
-RenderWs carve_render(void* base, int64_t N, int64_t M, int W, int H, int tile_size) {
-    RenderWs w;
+Bin1Ws carve_bin1(void* base, int64_t N, int64_t M) {
+    Bin1Ws w;
     char* p = static_cast<char*>(base);
     size_t off = 0;
     auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
-    const int64_t n = N > 0 ? N : 1;
-    const int64_t m = M > 0 ? M : 1;
-    const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
-    w.means2d = (float*)take(n * 2 * sizeof(float));
-    w.conics = (float*)take(n * 3 * sizeof(float));
-    w.depths = (float*)take(n * sizeof(float));
-    w.radii = (int32_t*)take(n * 2 * sizeof(int32_t));
+    const size_t n = (size_t)(N > 0 ? N : 1), m = (size_t)(M > 0 ? M : 1);
     w.offsets = (uint32_t*)take((n + 1) * sizeof(uint32_t));
     w.info = (bsplat_bin_info*)take(sizeof(bsplat_bin_info));
     w.scan_bytes = bsplat_bin_scan_workspace_bytes(N);
     w.scan_ws = take(w.scan_bytes);
-    w.tile_ranges = (int32_t*)take((size_t)tiles_w * tiles_h * 2 * sizeof(int32_t));
     w.keys = (uint64_t*)take(m * sizeof(uint64_t));
     w.keys_alt = (uint64_t*)take(m * sizeof(uint64_t));
     w.ids = (int32_t*)take(m * sizeof(int32_t));
@@ -111,18 +108,47 @@ RenderWs carve_render(void* base, int64_t N, int64_t M, int W, int H, int tile_s
     return w;
 }
 
+struct RenderWs {
+    float* means2d; float* conics; float* depths; int32_t* radii;
+    int32_t* tile_ranges; int32_t* sorted_ids;
+    void* bin_ws; size_t bin_bytes;
+    size_t total;
+};
+
+RenderWs carve_render(void* base, int64_t N, int64_t M, int W, int H, int tile_size, bool single_level) {
+    RenderWs w;
+    char* p = static_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
+    const size_t n = (size_t)(N > 0 ? N : 1), m = (size_t)(M > 0 ? M : 1);
+    const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
+    w.means2d = (float*)take(n * 2 * sizeof(float));
+    w.conics = (float*)take(n * 3 * sizeof(float));
+    w.depths = (float*)take(n * sizeof(float));
+    w.radii = (int32_t*)take(n * 2 * sizeof(int32_t));
+    w.tile_ranges = (int32_t*)take((size_t)tiles_w * tiles_h * 2 * sizeof(int32_t));
+    // the N-dependent part of the binning scratch comes first so that it survives the re-carve with M
+    w.bin_bytes = single_level ? carve_bin1(nullptr, N, M).total : bin2_workspace_bytes(N, M);
+    w.bin_ws = take(w.bin_bytes);
+    w.sorted_ids = (int32_t*)take(m * sizeof(int32_t));
+    w.total = off;
+    return w;
+}
+
 }  // namespace
 
 extern "C" size_t bsplat_render_workspace_bytes(int64_t N, int64_t M_capacity, int32_t width, int32_t height,
                                                 int32_t tile_size) {
     if (N < 0 || M_capacity < 0 || width <= 0 || height <= 0 || tile_size <= 0) return 0;
-    return carve_render(nullptr, N, M_capacity, width, height, tile_size).total;
+    const size_t a = carve_render(nullptr, N, M_capacity, width, height, tile_size, false).total;
+    const size_t b = carve_render(nullptr, N, M_capacity, width, height, tile_size, true).total;
+    return a > b ? a : b;
 }
 
 extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* log_scales, const float* quats,
                                  const float* opacities, const float* colors, int32_t channels,
                                  const bsplat_camera* cam, const float* background, int32_t tile_size,
-                                 int32_t semantics, int32_t raster_mode, float* image, void* workspace,
+                                 int32_t semantics, int32_t flags, float* image, void* workspace,
                                  size_t workspace_bytes, size_t* needed_bytes, bsplat_render_aux* aux,
                                  void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -131,13 +157,15 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     if (N > 0 && (!means3d || !log_scales || !quats || !opacities || !colors)) return BSPLAT_E_ARG;
     const int W = cam->width, H = cam->height;
     if (W <= 0 || H <= 0) return BSPLAT_E_ARG;
+    const int raster_mode = flags & 0xff;
+    const bool single_level = (flags & BSPLAT_FLAG_BIN_SINGLE_LEVEL) != 0;
     const size_t image_bytes = (size_t)W * H * channels * sizeof(float);
     if (aux) { aux->n_isect = 0; aux->n_launches = 0; aux->sort_passes = 0; aux->key_bits = 0; }
 
     // fixed (N-dependent) part must fit before anything runs
-    RenderWs w = carve_render(workspace, N, 0, W, H, tile_size);
+    RenderWs w = carve_render(workspace, N, 0, W, H, tile_size, single_level);
     if (!workspace || workspace_bytes < w.total) {
-        if (needed_bytes) *needed_bytes = carve_render(nullptr, N, 4 * N + 1024, W, H, tile_size).total;
+        if (needed_bytes) *needed_bytes = bsplat_render_workspace_bytes(N, 4 * N + 1024, W, H, tile_size);
         return BSPLAT_E_WORKSPACE;
     }
     if (N == 0) {
@@ -146,6 +174,7 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     }
     const bool timing = aux && aux->timing;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    auto drop_events = [&]() { if (timing) for (auto& e : ev) if (e) cudaEventDestroy(e); };
     if (timing) {
         for (auto& e : ev) BSPLAT_CUDA_TRY(cudaEventCreate(&e));
         BSPLAT_CUDA_TRY(cudaEventRecord(ev[0], stream));
@@ -154,68 +183,93 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     float* d_conics = (aux && aux->conics) ? aux->conics : w.conics;
     float* d_depths = (aux && aux->depths) ? aux->depths : w.depths;
     int32_t* d_radii = (aux && aux->radii) ? aux->radii : w.radii;
+    int32_t* d_ranges = (aux && aux->tile_ranges) ? aux->tile_ranges : w.tile_ranges;
 
     int rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, *cam, 0.3f, semantics, d_means2d,
                                 d_conics, d_depths, d_radii, stream);
-    if (rc != BSPLAT_OK) return rc;
+    if (rc != BSPLAT_OK) { drop_events(); return rc; }
     if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[1], stream));
 
     const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
-    rc = bsplat_bin_count_scan(N, d_means2d, d_radii, 0, d_depths, W, H, tile_size, 0, tiles_h, semantics,
-                               w.offsets, w.info, w.scan_ws, w.scan_bytes, stream);
-    if (rc != BSPLAT_OK) return rc;
+    bsplat_bin_info* d_info;
+    Bin1Ws b1 = carve_bin1(w.bin_ws, N, 0);
+    if (single_level) {
+        rc = bsplat_bin_count_scan(N, d_means2d, d_radii, 0, d_depths, W, H, tile_size, 0, tiles_h, semantics,
+                                   b1.offsets, b1.info, b1.scan_ws, b1.scan_bytes, stream);
+        d_info = b1.info;
+    } else {
+        d_info = bin2_info_ptr(w.bin_ws, N);
+        rc = bsplat_bin2_prepare(N, d_means2d, d_radii, 0, d_depths, W, H, tile_size, 0, tiles_h, semantics,
+                                 w.bin_ws, w.bin_bytes, d_info, stream);
+    }
+    if (rc != BSPLAT_OK) { drop_events(); return rc; }
     bsplat_bin_info info;
-    BSPLAT_CUDA_TRY(cudaMemcpyAsync(&info, w.info, sizeof(info), cudaMemcpyDeviceToHost, stream));
+    BSPLAT_CUDA_TRY(cudaMemcpyAsync(&info, d_info, sizeof(info), cudaMemcpyDeviceToHost, stream));
     BSPLAT_CUDA_TRY(cudaStreamSynchronize(stream));  // the single read-back of the frame (M, key range)
     const int64_t M = (int64_t)info.n_isect;
-    if (aux) { aux->n_isect = M; aux->n_launches = 3; }  // project, count_scan, finalize_info
-    if (M >= (1ll << 30)) return BSPLAT_E_OVERFLOW;
+    if (aux) { aux->n_isect = M; aux->n_launches = single_level ? 3 : 9; }
+    if (M >= (1ll << 30)) { drop_events(); return BSPLAT_E_OVERFLOW; }
     if (M == 0) {
         // render.py:73-76: no overlaps => black image (not the background)
         BSPLAT_CUDA_TRY(cudaMemsetAsync(image, 0, image_bytes, stream));
-        if (aux && aux->tile_ranges)
-            BSPLAT_CUDA_TRY(cudaMemsetAsync(aux->tile_ranges, 0, (size_t)tiles_w * tiles_h * 2 * sizeof(int32_t), stream));
-        if (timing) for (auto& e : ev) cudaEventDestroy(e);
+        BSPLAT_CUDA_TRY(cudaMemsetAsync(d_ranges, 0, (size_t)tiles_w * tiles_h * 2 * sizeof(int32_t), stream));
+        drop_events();
         return BSPLAT_OK;
     }
-    w = carve_render(workspace, N, M, W, H, tile_size);
+    w = carve_render(workspace, N, M, W, H, tile_size, single_level);
     if (workspace_bytes < w.total) {
-        if (needed_bytes) *needed_bytes = w.total;
-        if (timing) for (auto& e : ev) cudaEventDestroy(e);
+        if (needed_bytes) *needed_bytes = bsplat_render_workspace_bytes(N, M + M / 4, W, H, tile_size);
+        drop_events();
         return BSPLAT_E_WORKSPACE;
     }
-    const bsplat_key_layout layout = bsplat_make_key_layout(&info, W, H, tile_size);
-    rc = bsplat_bin_emit(N, d_means2d, d_radii, 0, d_depths, W, H, tile_size, 0, tiles_h, semantics, w.offsets,
-                         layout, w.keys, w.ids, stream);
-    if (rc != BSPLAT_OK) return rc;
-    if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[2], stream));
-    int in_alt = 0;
-    rc = bsplat_radix_sort_pairs(M, w.keys, w.keys_alt, w.ids, w.ids_alt, 0, layout.depth_bits + layout.tile_bits,
-                                 w.sort_ws, w.sort_bytes, &in_alt, stream);
-    if (rc != BSPLAT_OK) return rc;
-    const uint64_t* sorted_keys = in_alt ? w.keys_alt : w.keys;
-    const int32_t* sorted_ids = in_alt ? w.ids_alt : w.ids;
-    int32_t* d_ranges = (aux && aux->tile_ranges) ? aux->tile_ranges : w.tile_ranges;
-    rc = bsplat_tile_ranges(M, sorted_keys, layout.depth_bits, tiles_w * tiles_h, d_ranges, stream);
-    if (rc != BSPLAT_OK) return rc;
+    const int32_t* sorted_ids = nullptr;
+    if (single_level) {
+        b1 = carve_bin1(w.bin_ws, N, M);
+        const bsplat_key_layout layout = bsplat_make_key_layout(&info, W, H, tile_size);
+        rc = bsplat_bin_emit(N, d_means2d, d_radii, 0, d_depths, W, H, tile_size, 0, tiles_h, semantics,
+                             b1.offsets, layout, b1.keys, b1.ids, stream);
+        if (rc != BSPLAT_OK) { drop_events(); return rc; }
+        if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[2], stream));
+        int in_alt = 0;
+        rc = bsplat_radix_sort_pairs(M, b1.keys, b1.keys_alt, b1.ids, b1.ids_alt, 0,
+                                     layout.depth_bits + layout.tile_bits, b1.sort_ws, b1.sort_bytes, &in_alt, stream);
+        if (rc != BSPLAT_OK) { drop_events(); return rc; }
+        sorted_ids = in_alt ? b1.ids_alt : b1.ids;
+        rc = bsplat_tile_ranges(M, in_alt ? b1.keys_alt : b1.keys, layout.depth_bits, tiles_w * tiles_h, d_ranges,
+                                stream);
+        if (rc != BSPLAT_OK) { drop_events(); return rc; }
+        if (aux) {
+            aux->key_bits = layout.depth_bits + layout.tile_bits;
+            aux->sort_passes = (aux->key_bits + 7) / 8;
+            aux->n_launches = 3 + 1 + 2 + aux->sort_passes + 1 + 1;
+        }
+    } else {
+        if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[2], stream));
+        rc = bsplat_bin2_finish(N, M, d_means2d, d_radii, 0, W, H, tile_size, 0, tiles_h, semantics, w.bin_ws,
+                                w.bin_bytes, w.sorted_ids, d_ranges, stream);
+        if (rc != BSPLAT_OK) { drop_events(); return rc; }
+        sorted_ids = w.sorted_ids;
+        if (aux) {
+            int tb = 1;
+            while ((1 << tb) < tiles_w * tiles_h) ++tb;
+            aux->key_bits = 32 + tb;
+            aux->sort_passes = 4 + (tb > 8 ? 2 : 1);  // 4 over N items, the rest over M items
+            // project, depth hist, scan, 4 passes, count_scan, finalize | emit, scan, passes, ranges, raster
+            aux->n_launches = 9 + 1 + 1 + (tb > 8 ? 2 : 1) + 1 + 1;
+        }
+    }
     if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[3], stream));
     rc = rasterize_launch(N, channels, d_means2d, d_conics, colors, opacities, background, d_ranges, sorted_ids,
                           W, H, tile_size, raster_mode, image, nullptr, stream);
-    if (rc != BSPLAT_OK) return rc;
+    if (rc != BSPLAT_OK) { drop_events(); return rc; }
     if (aux && aux->sorted_ids && aux->sorted_ids_capacity >= M)
         BSPLAT_CUDA_TRY(cudaMemcpyAsync(aux->sorted_ids, sorted_ids, (size_t)M * sizeof(int32_t),
                                         cudaMemcpyDeviceToDevice, stream));
-    if (aux) {
-        aux->key_bits = layout.depth_bits + layout.tile_bits;
-        aux->sort_passes = (aux->key_bits + 7) / 8;
-        // + emit, histogram, scan, P x onesweep, tile_ranges, raster
-        aux->n_launches = 3 + 1 + 2 + aux->sort_passes + 1 + 1;
-    }
     if (timing) {
         BSPLAT_CUDA_TRY(cudaEventRecord(ev[4], stream));
         BSPLAT_CUDA_TRY(cudaEventSynchronize(ev[4]));
         for (int s = 0; s < 4; ++s) cudaEventElapsedTime(&aux->stage_ms[s], ev[s], ev[s + 1]);
-        for (auto& e : ev) cudaEventDestroy(e);
+        drop_events();
     }
     return BSPLAT_OK;
 }
@@ -235,7 +289,7 @@ extern "C" size_t bsplat_render_host_scratch_bytes(int64_t N, int32_t channels, 
 extern "C" int bsplat_render_fwd_host(int64_t N, const float* means3d, const float* log_scales,
                                       const float* quats, const float* opacities, const float* colors,
                                       int32_t channels, const bsplat_camera* cam, const float* background,
-                                      int32_t tile_size, int32_t semantics, int32_t raster_mode,
+                                      int32_t tile_size, int32_t semantics, int32_t flags,
                                       float* image_host, void* device_scratch, size_t scratch_bytes,
                                       void* workspace, size_t workspace_bytes, size_t* needed_bytes,
                                       bsplat_render_aux* aux, void* stream_) {
@@ -267,7 +321,7 @@ extern "C" int bsplat_render_fwd_host(int64_t N, const float* means3d, const flo
     }
     BSPLAT_CUDA_TRY(cudaMemcpyAsync(d_bg, background, (size_t)channels * sizeof(float), cudaMemcpyHostToDevice, stream));
     int rc = bsplat_render_fwd(N, d_means, d_scales, d_quats, d_opac, d_colors, channels, cam, d_bg, tile_size,
-                               semantics, raster_mode, d_image, workspace, workspace_bytes, needed_bytes, aux, stream);
+                               semantics, flags, d_image, workspace, workspace_bytes, needed_bytes, aux, stream);
     if (rc != BSPLAT_OK) return rc;
     BSPLAT_CUDA_TRY(cudaMemcpyAsync(image_host, d_image, (size_t)W * H * channels * sizeof(float),
                                     cudaMemcpyDeviceToHost, stream));

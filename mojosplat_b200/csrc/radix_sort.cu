@@ -1,75 +1,38 @@
-// Stage 2b -- onesweep least-significant-digit radix sort of (uint64 key, int32 id) pairs.
+// Stage 2b -- onesweep least-significant-digit radix sort (stable), uint32 or uint64 keys with
+// int32 payloads.
 //
 // Replaces the two sorts of the reference's binning (mojosplat/binning.py:223-231: argsort by
 // depth, then stable argsort by tile id) -- and gsplat's cub::DeviceRadixSort inside isect_tiles
-// (binning.py:73-82) -- with one stable sort over the packed key
-// (tile_id << depth_bits) | depth_key, restricted to the live bits [begin_bit, end_bit).
+// (binning.py:73-82).  Only live key bits [begin_bit, end_bit) are ever sorted.
 //
 // Structure (Adinets & Merrill, "Onesweep"):
 //   radix_histogram_kernel  one read of the keys builds the digit histograms of ALL passes
+//                           (the two-level binning path gets them from its producers instead)
 //   radix_scan_kernel       exclusive scan of each 256-bin histogram
-//   onesweep_kernel         per pass: each CTA takes a tile of 3072 pairs in ticket order, ranks
-//                           them stably by digit (warp match-any multisplit), resolves its global
-//                           digit offsets with a decoupled look-back chain (one chain per digit,
-//                           one thread per digit) and scatters through shared memory so that
-//                           global stores are contiguous runs per digit.
-// Per pass the kernel moves 12 B in + 12 B out per pair; nothing else touches HBM.
-#include "common.cuh"
+//   onesweep_kernel         per pass: each CTA takes a tile of pairs in ticket order, ranks them
+//                           stably by digit (warp match-any multisplit), resolves its global digit
+//                           offsets with a decoupled look-back chain (one chain per digit, one
+//                           thread per digit, 8 predecessors fetched per round trip) and scatters
+//                           through shared memory so that global stores are contiguous runs per digit.
+// Per pass the kernel moves key+payload in and out once; nothing else touches HBM.
+#include "radix_sort.cuh"
 
 namespace bsplat {
 
-constexpr int kSortThreads = 256;
-constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems = 12;
-constexpr int kSortTile = kSortThreads * kSortItems;  // 3072 pairs per CTA
-constexpr int kRadixBits = 8;
-constexpr int kRadix = 1 << kRadixBits;
-constexpr int kMaxPasses = 8;
-
-constexpr uint32_t kStatAgg = 1u << 30;
-constexpr uint32_t kStatPrefix = 2u << 30;
-constexpr uint32_t kStatMask = (1u << 30) - 1;
-
-struct SortWs {
-    uint32_t* hist;     // [P][256]
-    uint32_t* tickets;  // [256] (P used)
-    uint32_t* status;   // [P][n_tiles][256]
-    size_t bytes;
-};
-
-static SortWs carve_ws(void* ws, int64_t M, int passes) {
-    const int64_t n_tiles = ceil_div(M > 0 ? M : 1, kSortTile);
-    SortWs w;
-    uint32_t* p = static_cast<uint32_t*>(ws);
-    w.hist = p;
-    w.tickets = p + (size_t)kMaxPasses * kRadix;
-    w.status = w.tickets + kRadix;
-    w.bytes = ((size_t)kMaxPasses * kRadix + kRadix + (size_t)passes * n_tiles * kRadix) * sizeof(uint32_t);
-    return w;
-}
-
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
-radix_histogram_kernel(const int64_t M, const uint64_t* __restrict__ keys, const int begin_bit,
+radix_histogram_kernel(const int64_t M, const KeyT* __restrict__ keys, const int begin_bit,
                        const int end_bit, const int passes, uint32_t* __restrict__ hist) {
     __shared__ uint32_t s_hist[kMaxPasses][kRadix];
     for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += blockDim.x) (&s_hist[0][0])[i] = 0;
     __syncthreads();
-    const uint32_t lane = lane_id();
-    // warp-uniform trip count so that match.any sees full warps
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t warp_start = start - lane;
-    for (int64_t wi = warp_start; wi < M; wi += stride) {
-        const int64_t i = wi + lane;
-        const bool valid = i < M;
-        const uint64_t key = valid ? __ldg(keys + i) : 0ull;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
+        const KeyT key = keys[i];
         for (int p = 0; p < passes; ++p) {
             const int shift = begin_bit + p * kRadixBits;
             const int bits = min(kRadixBits, end_bit - shift);
-            const uint32_t d = (uint32_t)(key >> shift) & ((1u << bits) - 1u);
-            const uint32_t dm = valid ? d : 0x100u;
-            const uint32_t peers = __match_any_sync(0xffffffffu, dm);
-            if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[p][d], __popc(peers));
+            atomicAdd(&s_hist[p][(uint32_t)(key >> shift) & ((1u << bits) - 1u)], 1u);
         }
     }
     __syncthreads();
@@ -97,21 +60,28 @@ __global__ void __launch_bounds__(kRadix) radix_scan_kernel(uint32_t* __restrict
     h[tid] = off + incl - v;
 }
 
-__global__ void __launch_bounds__(kSortThreads)
-onesweep_kernel(const int64_t M, const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
-                const int32_t* __restrict__ vals_in, int32_t* __restrict__ vals_out, const int shift,
-                const int bits, const uint32_t* __restrict__ bins, uint32_t* __restrict__ ticket,
+// keys_out may be null on a final pass whose keys are not needed; vals_in may be null: the payload
+// is then the element's own index (first pass of an argsort).
+// m_dev (optional) overrides M with a device-side count (launches sized by a capacity).
+template <typename KeyT, int ITEMS>
+__global__ void __launch_bounds__(kSortThreads, 3)
+onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const KeyT* __restrict__ keys_in,
+                KeyT* __restrict__ keys_out, const int32_t* __restrict__ vals_in,
+                int32_t* __restrict__ vals_out, const int shift, const int bits,
+                const uint32_t* __restrict__ bins, uint32_t* __restrict__ ticket,
                 uint32_t* __restrict__ status) {
+    constexpr int TILE = kSortThreads * ITEMS;
     __shared__ uint32_t s_whist[kSortWarps][kRadix];
     __shared__ union {
-        uint64_t keys[kSortTile];
-        uint32_t vals[kSortTile];
+        KeyT keys[TILE];
+        uint32_t vals[TILE];
     } s_x;
     __shared__ uint32_t s_local_off[kRadix];
     __shared__ uint32_t s_gbase[kRadix];
     __shared__ uint32_t s_warp_tot[kSortWarps];
     __shared__ uint32_t s_tile;
 
+    const int64_t M = m_dev ? (int64_t)(*m_dev) : M_host;
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const int warp = tid >> 5;
@@ -119,31 +89,33 @@ onesweep_kernel(const int64_t M, const uint64_t* __restrict__ keys_in, uint64_t*
     for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&s_whist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
-    const int64_t tile_base = (int64_t)tile * kSortTile;
-    const int n_valid = (int)min((int64_t)kSortTile, M - tile_base);
+    const int64_t tile_base = (int64_t)tile * TILE;
+    if (tile_base >= M) return;  // launches sized by capacity: surplus CTAs retire (uniform per CTA)
+    const int n_valid = (int)min((int64_t)TILE, M - tile_base);
     const uint32_t digit_mask = (1u << bits) - 1u;
+    const int n_digits = 1 << bits;
 
     // ---- load (warp-striped: memory order == (warp, item, lane) order) ----
-    uint64_t key[kSortItems];
-    int32_t val[kSortItems];
-    const int warp_off = warp * (kSortItems * 32);
+    KeyT key[ITEMS];
+    int32_t val[ITEMS];
+    const int warp_off = warp * (ITEMS * 32);
 #pragma unroll
-    for (int it = 0; it < kSortItems; ++it) {
+    for (int it = 0; it < ITEMS; ++it) {
         const int local = warp_off + it * 32 + (int)lane;
         if (local < n_valid) {
-            key[it] = __ldg(keys_in + tile_base + local);
-            val[it] = __ldg(vals_in + tile_base + local);
+            key[it] = keys_in[tile_base + local];
+            val[it] = vals_in ? vals_in[tile_base + local] : (int32_t)(tile_base + local);
         } else {
-            key[it] = ~0ull;
+            key[it] = (KeyT)~(KeyT)0;
             val[it] = 0;
         }
     }
 
     // ---- stable rank inside the warp ----
-    uint32_t rank[kSortItems];
+    uint32_t rank[ITEMS];
     const uint32_t lt = lanemask_lt();
 #pragma unroll
-    for (int it = 0; it < kSortItems; ++it) {
+    for (int it = 0; it < ITEMS; ++it) {
         const int local = warp_off + it * 32 + (int)lane;
         const bool valid = local < n_valid;
         const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
@@ -171,7 +143,6 @@ onesweep_kernel(const int64_t M, const uint64_t* __restrict__ keys_in, uint64_t*
             run += c;
         }
         const uint32_t count = run;
-        // block exclusive scan of `count` over the 256 digit-threads
         uint32_t incl = count;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -184,70 +155,124 @@ onesweep_kernel(const int64_t M, const uint64_t* __restrict__ keys_in, uint64_t*
         for (int w = 0; w < warp; ++w) excl += s_warp_tot[w];
         s_local_off[tid] = excl;
 
-        // decoupled look-back for digit `tid`
-        uint32_t prev = 0;
-        uint32_t* my = status + (size_t)tile * kRadix + tid;
-        if (tile == 0) {
-            st_relaxed_u32(my, kStatPrefix | count);
-        } else {
-            st_relaxed_u32(my, kStatAgg | count);
-            int64_t j = (int64_t)tile - 1;
-            while (true) {
-                const uint32_t v = ld_relaxed_u32(status + (size_t)j * kRadix + tid);
-                if ((v & ~kStatMask) == 0) continue;
-                prev += v & kStatMask;
-                if (v & kStatPrefix) break;
-                --j;
+        if (tid < n_digits) {
+            // decoupled look-back for digit `tid`, kLookback predecessors per round trip
+            uint32_t prev = 0;
+            uint32_t* my = status + (size_t)tile * kRadix + tid;
+            if (tile == 0) {
+                st_relaxed_u32(my, kStatPrefix | count);
+            } else {
+                st_relaxed_u32(my, kStatAgg | count);
+                int64_t j = (int64_t)tile - 1;
+                bool found = false;
+                while (!found) {
+                    uint32_t v[kLookback];
+#pragma unroll
+                    for (int w = 0; w < kLookback; ++w)
+                        v[w] = (j - w >= 0) ? ld_relaxed_u32(status + (size_t)(j - w) * kRadix + tid) : kStatPrefix;
+                    int consumed = 0;
+#pragma unroll
+                    for (int w = 0; w < kLookback; ++w) {
+                        if (!found && consumed == w) {
+                            if ((v[w] & ~kStatMask) != 0) {
+                                prev += v[w] & kStatMask;
+                                ++consumed;
+                                if (v[w] & kStatPrefix) found = true;
+                            }
+                        }
+                    }
+                    j -= consumed;
+                }
+                st_relaxed_u32(my, kStatPrefix | (prev + count));
             }
-            st_relaxed_u32(my, kStatPrefix | (prev + count));
+            s_gbase[tid] = bins[tid] + prev - excl;
         }
-        s_gbase[tid] = bins[tid] + prev - excl;
     }
     __syncthreads();
 
     // ---- keys: scatter to shared in tile-sorted order, then contiguous runs to global ----
-    uint32_t pos[kSortItems];
+    uint32_t pos[ITEMS];
 #pragma unroll
-    for (int it = 0; it < kSortItems; ++it) {
+    for (int it = 0; it < ITEMS; ++it) {
         const int local = warp_off + it * 32 + (int)lane;
         const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
         pos[it] = s_local_off[d] + s_whist[warp][d] + rank[it];
         if (local < n_valid) s_x.keys[pos[it]] = key[it];
     }
     __syncthreads();
-    uint32_t dst[kSortItems];
+    uint32_t dst[ITEMS];
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const int j = tid + k * kSortThreads;
         if (j < n_valid) {
-            const uint64_t kk = s_x.keys[j];
+            const KeyT kk = s_x.keys[j];
             const uint32_t d = (uint32_t)(kk >> shift) & digit_mask;
             dst[k] = s_gbase[d] + (uint32_t)j;
-            keys_out[dst[k]] = kk;
+            if (keys_out) keys_out[dst[k]] = kk;
         }
     }
     __syncthreads();
-    // ---- values ride the same permutation ----
+    // ---- payloads ride the same permutation ----
 #pragma unroll
-    for (int it = 0; it < kSortItems; ++it) {
+    for (int it = 0; it < ITEMS; ++it) {
         const int local = warp_off + it * 32 + (int)lane;
         if (local < n_valid) s_x.vals[pos[it]] = (uint32_t)val[it];
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const int j = tid + k * kSortThreads;
         if (j < n_valid) vals_out[dst[k]] = (int32_t)s_x.vals[j];
     }
+}
+
+// ------------------------------------------------------------------------------------------
+int64_t sort_tiles_u32(int64_t M) { return ceil_div(M > 0 ? M : 1, kSortThreads * kSortItems32); }
+int64_t sort_tiles_u64(int64_t M) { return ceil_div(M > 0 ? M : 1, kSortThreads * kSortItems64); }
+
+size_t sort_status_words(int64_t n_tiles, int passes) { return (size_t)passes * n_tiles * kRadix; }
+
+int onesweep_pass_u32(int64_t M, const uint64_t* m_dev, const uint32_t* keys_in, uint32_t* keys_out,
+                      const int32_t* vals_in, int32_t* vals_out, int shift, int bits, const uint32_t* bins,
+                      uint32_t* ticket, uint32_t* status, cudaStream_t stream) {
+    const int64_t n_tiles = sort_tiles_u32(M);
+    onesweep_kernel<uint32_t, kSortItems32><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
+        M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, bins, ticket, status);
+    BSPLAT_LAUNCH_CHECK();
+    return BSPLAT_OK;
+}
+
+int radix_scan_launch(uint32_t* hist, int passes, cudaStream_t stream) {
+    radix_scan_kernel<<<passes, kRadix, 0, stream>>>(hist);
+    BSPLAT_LAUNCH_CHECK();
+    return BSPLAT_OK;
 }
 
 }  // namespace bsplat
 
 using namespace bsplat;
 
-static int sort_passes(int begin_bit, int end_bit) {
-    return (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
+namespace {
+struct SortWs {
+    uint32_t* hist;     // [kMaxPasses][256]
+    uint32_t* tickets;  // [256]
+    uint32_t* status;   // [P][n_tiles][256]
+    size_t bytes;
+};
+
+SortWs carve_ws(void* ws, int64_t M, int passes) {
+    const int64_t n_tiles = sort_tiles_u64(M);
+    SortWs w;
+    uint32_t* p = static_cast<uint32_t*>(ws);
+    w.hist = p;
+    w.tickets = p + (size_t)kMaxPasses * kRadix;
+    w.status = w.tickets + kRadix;
+    w.bytes = ((size_t)kMaxPasses * kRadix + kRadix + sort_status_words(n_tiles, passes)) * sizeof(uint32_t);
+    return w;
 }
+
+int sort_passes(int begin_bit, int end_bit) { return (end_bit - begin_bit + kRadixBits - 1) / kRadixBits; }
+}  // namespace
 
 extern "C" size_t bsplat_radix_sort_workspace_bytes(int64_t M, int32_t begin_bit, int32_t end_bit) {
     if (M < 0 || end_bit < begin_bit) return 0;
@@ -267,23 +292,23 @@ extern "C" int bsplat_radix_sort_pairs(int64_t M, uint64_t* keys, uint64_t* keys
     if (!keys || !keys_alt || !vals || !vals_alt) return BSPLAT_E_ARG;
     SortWs w = carve_ws(workspace, M, passes);
     if (!workspace || workspace_bytes < w.bytes) return BSPLAT_E_WORKSPACE;
-    const int64_t n_tiles = ceil_div(M, kSortTile);
+    const int64_t n_tiles = sort_tiles_u64(M);
 
     BSPLAT_CUDA_TRY(cudaMemsetAsync(workspace, 0, w.bytes, stream));
-    int64_t hist_blocks = ceil_div(M, 256 * 8);
+    int64_t hist_blocks = ceil_div(M, 256 * 4);
     const int hist_grid = (int)(hist_blocks < 148 * 8 ? hist_blocks : 148 * 8);
-    radix_histogram_kernel<<<hist_grid, 256, 0, stream>>>(M, keys, begin_bit, end_bit, passes, w.hist);
+    radix_histogram_kernel<uint64_t><<<hist_grid, 256, 0, stream>>>(M, keys, begin_bit, end_bit, passes, w.hist);
     BSPLAT_LAUNCH_CHECK();
-    radix_scan_kernel<<<passes, kRadix, 0, stream>>>(w.hist);
-    BSPLAT_LAUNCH_CHECK();
+    int rc = radix_scan_launch(w.hist, passes, stream);
+    if (rc != BSPLAT_OK) return rc;
 
     uint64_t* ksrc = keys; uint64_t* kdst = keys_alt;
     int32_t* vsrc = vals; int32_t* vdst = vals_alt;
     for (int p = 0; p < passes; ++p) {
         const int shift = begin_bit + p * kRadixBits;
         const int bits = (end_bit - shift) < kRadixBits ? (end_bit - shift) : kRadixBits;
-        onesweep_kernel<<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
-            M, ksrc, kdst, vsrc, vdst, shift, bits, w.hist + (size_t)p * kRadix, w.tickets + p,
+        onesweep_kernel<uint64_t, kSortItems64><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
+            M, nullptr, ksrc, kdst, vsrc, vdst, shift, bits, w.hist + (size_t)p * kRadix, w.tickets + p,
             w.status + (size_t)p * n_tiles * kRadix);
         BSPLAT_LAUNCH_CHECK();
         uint64_t* tk = ksrc; ksrc = kdst; kdst = tk;

@@ -88,7 +88,8 @@ _last_M: dict = {}
 
 
 def render_fused(means3d, scales, quats, opacities, colors, camera, background, tile_size=TILE_SIZE,
-                 semantics=_lib.SEM_TORCH, raster_mode="fast", return_aux=False, timing=False):
+                 semantics=_lib.SEM_TORCH, raster_mode="fast", return_aux=False, timing=False,
+                 bin_algo="two_level"):
     """One C call per frame (include/bsplat.h: bsplat_render_fwd). Device tensors in, image out."""
     dev = means3d.device
     L = _lib.require_device(dev)
@@ -120,11 +121,12 @@ def render_fused(means3d, scales, quats, opacities, colors, camera, background, 
             outs["sorted_ids"] = torch.empty((cap,), dtype=torch.int32, device=dev)
             aux.sorted_ids, aux.sorted_ids_capacity = outs["sorted_ids"].data_ptr(), cap
     needed = c_size_t(0)
+    flags = RASTER_MODES[raster_mode] | (_lib.FLAG_BIN_SINGLE_LEVEL if bin_algo == "single" else 0)
     with torch.cuda.device(dev):
         for _attempt in range(3):
             rc = L.bsplat_render_fwd(N, _lib.ptr(means3d), _lib.ptr(scales), _lib.ptr(quats),
                                      _lib.ptr(opacities), _lib.ptr(colors), C, byref(cam),
-                                     _lib.ptr(background), ts, semantics, RASTER_MODES[raster_mode],
+                                     _lib.ptr(background), ts, semantics, flags,
                                      _lib.ptr(image), _lib.ptr(ws), ws.numel(), byref(needed), byref(aux),
                                      _lib.stream_ptr(dev))
             if rc == _lib.E_WORKSPACE:

@@ -15,13 +15,18 @@ CASES = ["config1_1k_256", "garden_6k_1080p", "dense_300_1080p", "teststyle_500_
          "bin_50_ts16", "bin_50_ts32", "bin_ties_400", "bin_empty"]
 
 
+@pytest.mark.parametrize("algo", ["two_level", "single"])
 @pytest.mark.parametrize("name", CASES)
-def test_binning_vs_reference_golden(cuda_device, name):
+def test_binning_vs_reference_golden(cuda_device, name, algo):
     g = load_golden(name)
     W, H = [int(v) for v in g["size"]]
     ts = int(g["tile_size"])
-    ids, ranges = ms.bin_gaussians_to_tiles(dev(g["means2d"], cuda_device), dev(g["radii"], cuda_device),
-                                            dev(g["depths"], cuda_device), H, W, ts, backend="cuda")
+    if algo == "two_level":  # the public dispatcher (default algorithm)
+        ids, ranges = ms.bin_gaussians_to_tiles(dev(g["means2d"], cuda_device), dev(g["radii"], cuda_device),
+                                                dev(g["depths"], cuda_device), H, W, ts, backend="cuda")
+    else:
+        ids, ranges = binning.bin_gaussians_to_tiles_cuda(dev(g["means2d"], cuda_device), dev(g["radii"], cuda_device),
+                                                          dev(g["depths"], cuda_device), H, W, ts, algo="single")
     assert ids.dtype == torch.int32 and ranges.dtype == torch.int32
     assert tuple(ranges.shape) == g["tile_ranges"].shape
     ids, ranges = ids.cpu().numpy(), ranges.cpu().numpy()
@@ -46,6 +51,10 @@ def test_binning_full_size_bit_exact_vs_oracle(cuda_device, cfg, N, sem):
     assert ids.numel() == o_ids.shape[0]
     assert np.array_equal(ranges.cpu().numpy(), o_ranges)
     assert np.array_equal(ids.cpu().numpy(), o_ids)
+    # the default two-level algorithm gives the same lists, bit for bit
+    ids2, ranges2 = binning.bin_gaussians_to_tiles_cuda(
+        dev(m2, cuda_device), dev(rad, cuda_device), dev(dep, cuda_device), cam.H, cam.W, 16, semantics=sem)
+    assert torch.equal(ids2, ids) and torch.equal(ranges2, ranges)
     # size-independent properties: keys sorted, tile field consistent with the ranges
     k = keys.cpu().numpy().astype(np.uint64)
     assert (np.diff(k.astype(np.int64)) >= 0).all()
@@ -60,7 +69,7 @@ def test_binning_row_bands_match_full_frame(cuda_device):
     m2, con, dep, rad = oracle_project_scene(sc)
     cam = sc.camera
     a = [dev(x, cuda_device) for x in (m2, rad, dep)]
-    ids, ranges = binning.bin_gaussians_to_tiles_cuda(*a, cam.H, cam.W, 16)
+    ids, ranges = binning.bin_gaussians_to_tiles_cuda(*a, cam.H, cam.W, 16, algo="single")
     ids, ranges = ids.cpu().numpy(), ranges.cpu().numpy()
     th = ranges.shape[0]
     for r0, r1 in [(0, 17), (17, 40), (40, th)]:

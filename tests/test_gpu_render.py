@@ -31,6 +31,10 @@ def test_render_end_to_end_vs_oracle(cuda_device, cfg, N):
     # stage outputs of the fused path: binning must be bit-exact when the projected inputs agree
     img2, aux = ms.render_fused(m, s, q, o, c, cam, sc.background.to(cuda_device), return_aux=True)
     assert torch.equal(img, img2)
+    img3, aux3 = ms.render_fused(m, s, q, o, c, cam, sc.background.to(cuda_device), return_aux=True, bin_algo="single")
+    assert torch.equal(img, img3) and torch.equal(aux["tile_ranges"], aux3["tile_ranges"])
+    if aux.get("sorted_ids") is not None and aux3.get("sorted_ids") is not None:
+        assert torch.equal(aux["sorted_ids"], aux3["sorted_ids"])
     assert aux["n_isect"] == ref["sorted_ids"].shape[0] or abs(aux["n_isect"] - ref["sorted_ids"].shape[0]) <= 8
     if np.array_equal(aux["radii"].cpu().numpy(), ref["radii"]) and \
             np.array_equal(aux["means2d"].cpu().numpy(), ref["means2d"]):
