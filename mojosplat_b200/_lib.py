@@ -33,7 +33,7 @@ SYMBOLS = [
     "bsplat_tile_ranges", "bsplat_rasterize_fwd", "bsplat_rasterize_stats",
     "bsplat_render_workspace_bytes", "bsplat_render_fwd", "bsplat_render_host_scratch_bytes",
     "bsplat_render_fwd_host", "bsplat_microbench", "bsplat_bin2_workspace_bytes", "bsplat_bin2_prepare",
-    "bsplat_bin2_finish",
+    "bsplat_bin2_finish", "bsplat_tile_order",
 ]
 
 
@@ -117,8 +117,9 @@ def load() -> ctypes.CDLL:
                                               c_int32, c_void_p, c_size_t, POINTER(c_int32), c_void_p]
         L.bsplat_tile_ranges.argtypes = [c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
         L.bsplat_rasterize_fwd.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
-                                           c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                            c_int32, c_int32, c_void_p, c_void_p]
+        L.bsplat_tile_order.argtypes = [c_int32, c_void_p, c_void_p, c_void_p]
         L.bsplat_rasterize_stats.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                              c_int32, c_void_p, c_void_p, c_void_p]

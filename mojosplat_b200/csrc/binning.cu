@@ -86,33 +86,43 @@ bin_count_scan_kernel(const int64_t N, const int32_t* __restrict__ perm, const f
     }
     const unsigned long long thread_excl = warp_excl + incl - thread_sum;
 
-    // decoupled look-back over previous chunks (thread 0 walks the chain)
-    if (tid == 0) {
+    // decoupled look-back over previous chunks: warp 0 inspects 32 predecessors per round trip
+    if (warp == 0) {
         unsigned long long prefix = 0;
         if (chunk == 0) {
-            st_relaxed_u64(status + 0, kFlagPrefix | block_total);
+            if (lane == 0) st_relaxed_u64(status + 0, kFlagPrefix | block_total);
         } else {
-            st_relaxed_u64(status + chunk, kFlagAgg | block_total);
+            if (lane == 0) st_relaxed_u64(status + chunk, kFlagAgg | block_total);
             int64_t j = (int64_t)chunk - 1;
             while (true) {
-                const unsigned long long v = ld_relaxed_u64(status + j);
-                if ((v & ~kValueMask) == 0) continue;  // not published yet
-                prefix += v & kValueMask;
-                if (v & kFlagPrefix) break;
-                --j;
-            }
-            st_relaxed_u64(status + chunk, kFlagPrefix | (prefix + block_total));
-        }
-        s_prefix = prefix;
-        uint32_t bmax = 0, bmin_inv = 0;
+                const int64_t idx = j - lane;  // lane 0 = nearest predecessor
+                const unsigned long long v = idx >= 0 ? ld_relaxed_u64(status + idx) : kFlagPrefix;
+                const unsigned ready = __ballot_sync(0xffffffffu, (v & ~kValueMask) != 0);
+                const unsigned pref = __ballot_sync(0xffffffffu, (v & kFlagPrefix) != 0);
+                const unsigned first_pref = pref ? (unsigned)(__ffs(pref) - 1) : 32u;
+                const unsigned need = first_pref == 32u ? 0xffffffffu : ((2u << first_pref) - 1u);
+                if ((ready & need) != need) { __nanosleep(64); continue; }  // not published yet: polite re-poll
+                unsigned long long contrib = ((unsigned)lane <= first_pref) ? (v & kValueMask) : 0ull;
 #pragma unroll
-        for (int w = 0; w < kScanThreads / 32; ++w) {
-            bmax = max(bmax, s_red[0][w]);
-            bmin_inv = max(bmin_inv, s_red[1][w]);
+                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                prefix += contrib;
+                if (first_pref != 32u) break;
+                j -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(status + chunk, kFlagPrefix | (prefix + block_total));
         }
-        if (block_total > 0) {
-            atomicMax(&info->max_depth_key, bmax);
-            atomicMax(&info->reserved[0], bmin_inv);  // ~min, finalised by the last chunk
+        if (lane == 0) {
+            s_prefix = prefix;
+            uint32_t bmax = 0, bmin_inv = 0;
+#pragma unroll
+            for (int w = 0; w < kScanThreads / 32; ++w) {
+                bmax = max(bmax, s_red[0][w]);
+                bmin_inv = max(bmin_inv, s_red[1][w]);
+            }
+            if (block_total > 0) {
+                atomicMax(&info->max_depth_key, bmax);
+                atomicMax(&info->reserved[0], bmin_inv);  // ~min, finalised after the scan
+            }
         }
     }
     __syncthreads();

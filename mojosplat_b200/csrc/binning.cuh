@@ -5,7 +5,7 @@
 namespace bsplat {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 4;
+constexpr int kScanItems = 8;
 constexpr int kScanChunk = kScanThreads * kScanItems;  // Gaussians per block
 
 // workspace layout of the scan: [0] chunk ticket, [1..] one 64-bit status word per chunk

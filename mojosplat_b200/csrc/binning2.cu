@@ -179,8 +179,8 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
         BSPLAT_CUDA_TRY(cudaMemsetAsync(w.offsets, 0, sizeof(uint32_t), stream));
         return BSPLAT_OK;
     }
-    int64_t hb = ceil_div(N, 256 * 4);
-    depth_key_hist_kernel<<<(unsigned)(hb < 148 * 8 ? hb : 148 * 8), 256, 0, stream>>>(N, depths, w.dkeys, w.hist);
+    int64_t hb = ceil_div(N, 256 * 8);
+    depth_key_hist_kernel<<<(unsigned)(hb < 148 * 2 ? hb : 148 * 2), 256, 0, stream>>>(N, depths, w.dkeys, w.hist);
     BSPLAT_LAUNCH_CHECK();
     int rc = radix_scan_launch(w.hist, 4, stream);
     if (rc != BSPLAT_OK) return rc;

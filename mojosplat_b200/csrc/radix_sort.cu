@@ -63,8 +63,13 @@ __global__ void __launch_bounds__(kRadix) radix_scan_kernel(uint32_t* __restrict
 // keys_out may be null on a final pass whose keys are not needed; vals_in may be null: the payload
 // is then the element's own index (first pass of an argsort).
 // m_dev (optional) overrides M with a device-side count (launches sized by a capacity).
+//
+// Phases: load -> stable rank (warp match-any multisplit) -> per-digit counts, published at once as
+// the tile's aggregate -> scatter key/payload into shared memory in tile-sorted order (registers are
+// free from here on) -> decoupled look-back, kLookback predecessors in flight per round trip ->
+// contiguous per-digit runs to global.
 template <typename KeyT, int ITEMS>
-__global__ void __launch_bounds__(kSortThreads, 3)
+__global__ void __launch_bounds__(kSortThreads, 4)
 onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const KeyT* __restrict__ keys_in,
                 KeyT* __restrict__ keys_out, const int32_t* __restrict__ vals_in,
                 int32_t* __restrict__ vals_out, const int shift, const int bits,
@@ -72,10 +77,8 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
                 uint32_t* __restrict__ status) {
     constexpr int TILE = kSortThreads * ITEMS;
     __shared__ uint32_t s_whist[kSortWarps][kRadix];
-    __shared__ union {
-        KeyT keys[TILE];
-        uint32_t vals[TILE];
-    } s_x;
+    __shared__ KeyT s_keys[TILE];
+    __shared__ int32_t s_vals[TILE];
     __shared__ uint32_t s_local_off[kRadix];
     __shared__ uint32_t s_gbase[kRadix];
     __shared__ uint32_t s_warp_tot[kSortWarps];
@@ -94,47 +97,65 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
     const int n_valid = (int)min((int64_t)TILE, M - tile_base);
     const uint32_t digit_mask = (1u << bits) - 1u;
     const int n_digits = 1 << bits;
+    uint32_t* my_status = status + (size_t)tile * kRadix + tid;
 
-    // ---- load (warp-striped: memory order == (warp, item, lane) order) ----
-    KeyT key[ITEMS];
-    int32_t val[ITEMS];
-    const int warp_off = warp * (ITEMS * 32);
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-        const int local = warp_off + it * 32 + (int)lane;
-        if (local < n_valid) {
-            key[it] = keys_in[tile_base + local];
-            val[it] = vals_in ? vals_in[tile_base + local] : (int32_t)(tile_base + local);
-        } else {
-            key[it] = (KeyT)~(KeyT)0;
-            val[it] = 0;
-        }
-    }
-
-    // ---- stable rank inside the warp ----
-    uint32_t rank[ITEMS];
-    const uint32_t lt = lanemask_lt();
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-        const int local = warp_off + it * 32 + (int)lane;
-        const bool valid = local < n_valid;
-        const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
-        const uint32_t dm = valid ? d : 0x100u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, dm);
-        const int leader = __ffs(peers) - 1;
-        uint32_t pre = 0;
-        if (valid && (int)lane == leader) {
-            pre = s_whist[warp][d];
-            s_whist[warp][d] = pre + __popc(peers);
-        }
-        pre = __shfl_sync(0xffffffffu, pre, leader);
-        rank[it] = pre + __popc(peers & lt);
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // ---- per-digit: exclusive scan over warps, tile count, look-back ----
     {
+        // ---- load (warp-striped: memory order == (warp, item, lane) order) ----
+        KeyT key[ITEMS];
+        int32_t val[ITEMS];
+        const int warp_off = warp * (ITEMS * 32);
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            const int local = warp_off + it * 32 + (int)lane;
+            if (local < n_valid) {
+                key[it] = keys_in[tile_base + local];
+                val[it] = vals_in ? vals_in[tile_base + local] : (int32_t)(tile_base + local);
+            } else {
+                key[it] = (KeyT)~(KeyT)0;
+                val[it] = 0;
+            }
+        }
+
+        // ---- stable rank inside the warp ----
+        // peers[it] = lanes of this warp holding the same digit.  Built from one ballot per digit bit
+        // (fixed cost); match.any was measured ~3x slower here: its cost grows with the number of
+        // distinct values in the warp, which is ~30 for high-entropy digits.
+        uint32_t rank[ITEMS];
+        uint32_t peers[ITEMS];
+        const uint32_t lt = lanemask_lt();
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            const int local = warp_off + it * 32 + (int)lane;
+            const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
+            uint32_t p = __ballot_sync(0xffffffffu, local < n_valid);
+#pragma unroll
+            for (int b = 0; b < kRadixBits; ++b) {
+                if (b < bits) {
+                    const bool bit = (d >> b) & 1u;
+                    const uint32_t m = __ballot_sync(0xffffffffu, bit);
+                    p &= bit ? m : ~m;
+                }
+            }
+            peers[it] = p;
+        }
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            const int local = warp_off + it * 32 + (int)lane;
+            const bool valid = local < n_valid;
+            const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
+            const int leader = __ffs(peers[it]) - 1;
+            uint32_t pre = 0;
+            if (valid && (int)lane == leader) {
+                pre = s_whist[warp][d];
+                s_whist[warp][d] = pre + __popc(peers[it]);
+            }
+            pre = __shfl_sync(0xffffffffu, pre, leader);
+            rank[it] = pre + __popc(peers[it] & lt);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---- per-digit: exclusive scan over warps, tile count -> aggregate published immediately ----
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
@@ -143,6 +164,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
             run += c;
         }
         const uint32_t count = run;
+        if (tid < n_digits) st_relaxed_u32(my_status, (tile == 0 ? kStatPrefix : kStatAgg) | count);
         uint32_t incl = count;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -154,75 +176,78 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
         uint32_t excl = incl - count;
         for (int w = 0; w < warp; ++w) excl += s_warp_tot[w];
         s_local_off[tid] = excl;
+        // s_gbase holds (count, excl) needs: keep count in s_gbase until the look-back rewrites it
+        s_gbase[tid] = count;
+        __syncthreads();
 
-        if (tid < n_digits) {
-            // decoupled look-back for digit `tid`, kLookback predecessors per round trip
-            uint32_t prev = 0;
-            uint32_t* my = status + (size_t)tile * kRadix + tid;
-            if (tile == 0) {
-                st_relaxed_u32(my, kStatPrefix | count);
-            } else {
-                st_relaxed_u32(my, kStatAgg | count);
-                int64_t j = (int64_t)tile - 1;
-                bool found = false;
-                while (!found) {
-                    uint32_t v[kLookback];
+        // ---- scatter key / payload into shared memory in tile-sorted order ----
 #pragma unroll
-                    for (int w = 0; w < kLookback; ++w)
-                        v[w] = (j - w >= 0) ? ld_relaxed_u32(status + (size_t)(j - w) * kRadix + tid) : kStatPrefix;
-                    int consumed = 0;
-#pragma unroll
-                    for (int w = 0; w < kLookback; ++w) {
-                        if (!found && consumed == w) {
-                            if ((v[w] & ~kStatMask) != 0) {
-                                prev += v[w] & kStatMask;
-                                ++consumed;
-                                if (v[w] & kStatPrefix) found = true;
-                            }
-                        }
-                    }
-                    j -= consumed;
-                }
-                st_relaxed_u32(my, kStatPrefix | (prev + count));
+        for (int it = 0; it < ITEMS; ++it) {
+            const int local = warp_off + it * 32 + (int)lane;
+            if (local < n_valid) {
+                const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
+                const uint32_t pos = s_local_off[d] + s_whist[warp][d] + rank[it];
+                s_keys[pos] = key[it];
+                s_vals[pos] = val[it];
             }
-            s_gbase[tid] = bins[tid] + prev - excl;
         }
     }
-    __syncthreads();
 
-    // ---- keys: scatter to shared in tile-sorted order, then contiguous runs to global ----
-    uint32_t pos[ITEMS];
+    // ---- decoupled look-back for digit `tid` (registers are free: wide window) ----
+    if (tid < n_digits) {
+        const uint32_t count = s_gbase[tid];
+        uint32_t prev = 0;
+        if (tile != 0) {
+            int64_t j = (int64_t)tile - 1;
+            bool found = false;
+            while (!found) {
+                // polite wait on the nearest unread predecessor: one word, exponential back-off, so that
+                // waiting warps do not take issue slots from CTAs that still have to rank and publish
+                const uint32_t* near = status + (size_t)j * kRadix + tid;
+                uint32_t v0 = ld_relaxed_u32(near);
+                unsigned ns = 32;
+                while ((v0 & ~kStatMask) == 0) {
+                    __nanosleep(ns);
+                    if (ns < 512) ns <<= 1;
+                    v0 = ld_relaxed_u32(near);
+                }
+                prev += v0 & kStatMask;
+                if (v0 & kStatPrefix) break;
+                --j;
+                if (j < 0) break;
+                // the ones behind it are older and almost surely published: fetch a window at once
+                uint32_t v[kLookback];
 #pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-        const int local = warp_off + it * 32 + (int)lane;
-        const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
-        pos[it] = s_local_off[d] + s_whist[warp][d] + rank[it];
-        if (local < n_valid) s_x.keys[pos[it]] = key[it];
+                for (int w = 0; w < kLookback; ++w)
+                    v[w] = (j - w >= 0) ? ld_relaxed_u32(status + (size_t)(j - w) * kRadix + tid) : kStatPrefix;
+                int consumed = 0;
+#pragma unroll
+                for (int w = 0; w < kLookback; ++w) {
+                    if ((v[w] & ~kStatMask) == 0) break;  // not published yet: go back to the polite wait
+                    prev += v[w] & kStatMask;
+                    ++consumed;
+                    if (v[w] & kStatPrefix) { found = true; break; }
+                }
+                j -= consumed;
+                if (j < 0) break;
+            }
+            st_relaxed_u32(my_status, kStatPrefix | (prev + count));
+        }
+        s_gbase[tid] = bins[tid] + prev - s_local_off[tid];
     }
     __syncthreads();
-    uint32_t dst[ITEMS];
+
+    // ---- contiguous per-digit runs to global ----
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const int j = tid + k * kSortThreads;
         if (j < n_valid) {
-            const KeyT kk = s_x.keys[j];
+            const KeyT kk = s_keys[j];
             const uint32_t d = (uint32_t)(kk >> shift) & digit_mask;
-            dst[k] = s_gbase[d] + (uint32_t)j;
-            if (keys_out) keys_out[dst[k]] = kk;
+            const uint32_t dst = s_gbase[d] + (uint32_t)j;
+            if (keys_out) keys_out[dst] = kk;
+            vals_out[dst] = s_vals[j];
         }
-    }
-    __syncthreads();
-    // ---- payloads ride the same permutation ----
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-        const int local = warp_off + it * 32 + (int)lane;
-        if (local < n_valid) s_x.vals[pos[it]] = (uint32_t)val[it];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const int j = tid + k * kSortThreads;
-        if (j < n_valid) vals_out[dst[k]] = (int32_t)s_x.vals[j];
     }
 }
 

@@ -6,12 +6,12 @@ namespace bsplat {
 
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortItems64 = 12;  // 3072 (uint64 key, int32) pairs per CTA
-constexpr int kSortItems32 = 16;  // 4096 (uint32 key, int32) pairs per CTA
+constexpr int kSortItems64 = 10;  // 2560 (uint64 key, int32) pairs per CTA
+constexpr int kSortItems32 = 8;   // 2048 (uint32 key, int32) pairs per CTA
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
-constexpr int kLookback = 8;  // predecessors fetched per look-back round trip
+constexpr int kLookback = 16;  // predecessors fetched per look-back round trip
 
 constexpr uint32_t kStatAgg = 1u << 30;
 constexpr uint32_t kStatPrefix = 2u << 30;

@@ -138,32 +138,34 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-struct __align__(16) StagedA { float mx, my, A, B; };       // A = 0.5 a log2e, B = b log2e
-struct __align__(16) StagedB { float C, L, hy, hx; };       // C = 0.5 c log2e, L = log2(o), hy = -B/(2C), hx = -B/(2A)
-struct __align__(16) StagedC { float r, g, b, tau; };       // tau = L - log2(1/255) (+inf: never cull)
-
+// Staged Gaussian t (log2-folded, 48 B): s_g[3t] = {mx, my, A, B}, s_g[3t+1] = {C, L, hy, hx},
+// s_g[3t+2] = {r, g, b, tau} with A = 0.5 a log2e, B = b log2e, C = 0.5 c log2e, L = log2(opacity),
+// hy = -B/(2C), hx = -B/(2A) (edge minimisers of the quadratic), tau = L - log2(1/255)
+// (+inf: never cull, -inf: not a Gaussian).  alpha = 2^(L - (A dx^2 + B dx dy + C dy^2)).
 template <bool kCull>
 __global__ void __launch_bounds__(kFastThreads)
 raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
                    const float* __restrict__ colors, const float* __restrict__ opacities,
                    const float* __restrict__ background, const int32_t* __restrict__ tile_ranges,
-                   const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
-                   float* __restrict__ image, const int vec_store) {
-    __shared__ StagedA s_a[kFastBatch];
-    __shared__ StagedB s_b[kFastBatch];
-    __shared__ StagedC s_c[kFastBatch];
+                   const int32_t* __restrict__ tile_order, const int32_t* __restrict__ sorted_ids, const int W,
+                   const int H, const int tiles_w, float* __restrict__ image, const int vec_store) {
+    __shared__ float4 s_g[kFastBatch * 3];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.y * tiles_w + blockIdx.x;
+    // heavy tiles first (tile_order, longest lists first) so that no long list starts at the tail
+    const int tile = tile_order ? __ldg(tile_order + blockIdx.x) : (int)blockIdx.x;
+    const int tile_y = tile / tiles_w, tile_x = tile - tile_y * tiles_w;
     // warp -> 8x4 pixel block inside the tile; lane -> pixel inside the block
-    const int bx = blockIdx.x * kFastTile + (warp & 1) * 8;
-    const int by = blockIdx.y * kFastTile + (warp >> 1) * 4;
+    const int bx = tile_x * kFastTile + (warp & 1) * 8;
+    const int by = tile_y * kFastTile + (warp >> 1) * 4;
     const int j = bx + (lane & 7);
     const int i = by + (lane >> 3);
     const bool inside = (i < H) && (j < W);
-    bool done = !inside;
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    // a finished pixel gets an infinite x: every later Gaussian then fails the alpha test by itself,
+    // and "done" is simply px == inf (no separate flag to maintain in the inner loop)
+    float px = inside ? (float)j + 0.5f : INFINITY;
+    const float py = (float)i + 0.5f;
     // pixel-centre extent of this warp's block (clipped blocks only get more conservative)
     const float X0 = (float)bx + 0.5f, X1 = (float)bx + 7.5f;
     const float Y0 = (float)by + 0.5f, Y1 = (float)by + 3.5f;
@@ -172,52 +174,50 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
     float T = 1.0f, accr = 0.0f, accg = 0.0f, accb = 0.0f;
 
     for (int32_t b0 = r0; b0 < r1; b0 += kFastBatch) {
-        if (__syncthreads_count(done) >= kFastThreads) break;
+        if (__syncthreads_count(!(px < INFINITY)) >= kFastThreads) break;
         const int32_t idx = b0 + tid;
         if (idx < r1) {
             const int32_t g = __ldg(sorted_ids + idx);
-            StagedA sa; StagedB sb; StagedC sc;
+            float4 ga, gb, gc;
             if (g >= 0 && (int64_t)g < N) {
                 const float2 m = __ldg(reinterpret_cast<const float2*>(means2d) + g);
                 const float ca = __ldg(conics + 3 * (int64_t)g), cb = __ldg(conics + 3 * (int64_t)g + 1),
                             cc = __ldg(conics + 3 * (int64_t)g + 2);
                 const float op = __ldg(opacities + g);
-                sa.mx = m.x; sa.my = m.y;
-                sa.A = 0.5f * kLog2e * ca; sa.B = kLog2e * cb;
-                sb.C = 0.5f * kLog2e * cc;
+                const float A = 0.5f * kLog2e * ca, B = kLog2e * cb, C = 0.5f * kLog2e * cc;
                 // accurate log2 keeps alpha = 2^(L - q) within a few ulp of o*exp(-sigma)
-                sb.L = (op > 0.0f) ? log2f(op) : -INFINITY;
-                const bool pd = (sa.A > 0.0f) && (sb.C > 0.0f) && (4.0f * sa.A * sb.C - sa.B * sa.B > 0.0f);
-                sb.hy = pd ? -sa.B / (2.0f * sb.C) : 0.0f;
-                sb.hx = pd ? -sa.B / (2.0f * sa.A) : 0.0f;
-                sc.r = __ldg(colors + 3 * (int64_t)g); sc.g = __ldg(colors + 3 * (int64_t)g + 1);
-                sc.b = __ldg(colors + 3 * (int64_t)g + 2);
-                sc.tau = pd ? (sb.L - kLog2AlphaThreshold) : INFINITY;
-                if (!(op == op)) sc.tau = INFINITY;  // NaN opacity: evaluate, never cull
+                const float L = (op > 0.0f) ? log2f(op) : -INFINITY;
+                const bool pd = (A > 0.0f) && (C > 0.0f) && (4.0f * A * C - B * B > 0.0f);
+                ga = make_float4(m.x, m.y, A, B);
+                gb = make_float4(C, L, pd ? -B / (2.0f * C) : 0.0f, pd ? -B / (2.0f * A) : 0.0f);
+                float tau = pd ? (L - kLog2AlphaThreshold) : INFINITY;
+                if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
+                gc = make_float4(__ldg(colors + 3 * (int64_t)g), __ldg(colors + 3 * (int64_t)g + 1),
+                                 __ldg(colors + 3 * (int64_t)g + 2), tau);
             } else {
-                sa.mx = sa.my = sa.A = sa.B = 0.0f;
-                sb.C = 0.0f; sb.L = -INFINITY; sb.hy = sb.hx = 0.0f;
-                sc.r = sc.g = sc.b = 0.0f; sc.tau = -INFINITY;
+                ga = make_float4(0.f, 0.f, 0.f, 0.f);
+                gb = make_float4(0.f, -INFINITY, 0.f, 0.f);
+                gc = make_float4(0.f, 0.f, 0.f, -INFINITY);
             }
-            s_a[tid] = sa; s_b[tid] = sb; s_c[tid] = sc;
+            s_g[3 * tid] = ga; s_g[3 * tid + 1] = gb; s_g[3 * tid + 2] = gc;
         }
         __syncthreads();
 
         const int bs = min(kFastBatch, (int)(r1 - b0));
         // warp-uniform loop; a warp whose 32 pixels are all saturated just falls through
         for (int c0 = 0; c0 < bs; c0 += 32) {
-            if (__all_sync(0xffffffffu, done)) break;
+            if (__all_sync(0xffffffffu, !(px < INFINITY))) break;
             unsigned int mask;
             if (kCull) {
                 bool hit = false;
                 const int gi = c0 + lane;
                 if (gi < bs) {
-                    const StagedA a = s_a[gi];
-                    const StagedB b = s_b[gi];
-                    const float tau = s_c[gi].tau;
+                    const float4 a = s_g[3 * gi];
+                    const float4 b = s_g[3 * gi + 1];
+                    const float tau = s_g[3 * gi + 2].w;
                     // u = mx - x over the block, v = my - y
-                    const float u0 = a.mx - X1, u1 = a.mx - X0;
-                    const float v0 = a.my - Y1, v1 = a.my - Y0;
+                    const float u0 = a.x - X1, u1 = a.x - X0;
+                    const float v0 = a.y - Y1, v1 = a.y - Y0;
                     const bool zu = (u0 <= 0.0f) && (u1 >= 0.0f);
                     const bool zv = (v0 <= 0.0f) && (v1 >= 0.0f);
                     float qmin;
@@ -227,18 +227,18 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                         float q1 = INFINITY, q2 = INFINITY;
                         if (!zu) {  // vertical edge nearest to the mean
                             const float ue = (u0 > 0.0f) ? u0 : u1;
-                            const float vs = fminf(fmaxf(b.hy * ue, v0), v1);
-                            q1 = a.A * ue * ue + a.B * ue * vs + b.C * vs * vs;
+                            const float vs = fminf(fmaxf(b.z * ue, v0), v1);
+                            q1 = a.z * ue * ue + a.w * ue * vs + b.x * vs * vs;
                         }
                         if (!zv) {  // horizontal edge nearest to the mean
                             const float ve = (v0 > 0.0f) ? v0 : v1;
-                            const float us = fminf(fmaxf(b.hx * ve, u0), u1);
-                            q2 = a.A * us * us + a.B * us * ve + b.C * ve * ve;
+                            const float us = fminf(fmaxf(b.w * ve, u0), u1);
+                            q2 = a.z * us * us + a.w * us * ve + b.x * ve * ve;
                         }
                         qmin = fminf(q1, q2);
                     }
                     const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
-                    const float slack = 4e-6f * (a.A * um * um + b.C * vm * vm) + 1e-3f;
+                    const float slack = 4e-6f * (a.z * um * um + b.x * vm * vm) + 1e-3f;
                     hit = !(qmin > tau + slack);  // NaN-safe: anything odd counts as a hit
                 }
                 mask = __ballot_sync(0xffffffffu, hit);
@@ -246,27 +246,31 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                 const int rem = bs - c0;
                 mask = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
             }
+            const float4* rec = s_g + 3 * c0;
             while (mask) {
-                const int t = c0 + (__ffs(mask) - 1);
+                const int t = __ffs(mask) - 1;
                 mask &= mask - 1;
-                if (done) continue;
-                const StagedA a = s_a[t];
-                const StagedB b = s_b[t];
-                const float dx = a.mx - px, dy = a.my - py;
-                const float t1 = fmaf(a.B, dy, a.A * dx);
-                float q = t1 * dx;
-                q = fmaf(b.C * dy, dy, q);
-                const float power = b.L - q;
-                if (q < 0.0f || !(power >= kLog2AlphaThreshold)) continue;
-                const float alpha = fminf(0.999f, ex2_approx(power));
-                const float next_T = T * (1.0f - alpha);
-                if (next_T <= 1e-4f) { done = true; continue; }
-                const float vis = alpha * T;
-                const StagedC c = s_c[t];
-                accr = fmaf(c.r, vis, accr);
-                accg = fmaf(c.g, vis, accg);
-                accb = fmaf(c.b, vis, accb);
-                T = next_T;
+                const float4* r = rec + 3 * t;
+                const float4 a = r[0];
+                const float2 b = *reinterpret_cast<const float2*>(r + 1);
+                const float dx = a.x - px, dy = a.y - py;
+                const float t1 = fmaf(a.w, dy, a.z * dx);
+                const float q = fmaf(b.x * dy, dy, t1 * dx);
+                const float power = b.y - q;
+                if (q >= 0.0f && power >= kLog2AlphaThreshold) {
+                    const float alpha = fminf(0.999f, ex2_approx(power));
+                    const float next_T = T * (1.0f - alpha);
+                    if (next_T <= 1e-4f) {
+                        px = INFINITY;  // saturated: this Gaussian is not added (rasterization.mojo:146-150)
+                    } else {
+                        const float vis = alpha * T;
+                        const float4 c = r[2];
+                        accr = fmaf(c.x, vis, accr);
+                        accg = fmaf(c.y, vis, accg);
+                        accb = fmaf(c.z, vis, accb);
+                        T = next_T;
+                    }
+                }
             }
         }
     }
@@ -274,10 +278,10 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
     // ---- write the tile: through shared memory as 128-bit rows when the layout allows ----
     const float outr = fmaf(T, __ldg(background), accr), outg = fmaf(T, __ldg(background + 1), accg),
                 outb = fmaf(T, __ldg(background + 2), accb);
-    const bool full_tile = (blockIdx.x * kFastTile + kFastTile <= W) && (blockIdx.y * kFastTile + kFastTile <= H);
+    const bool full_tile = (tile_x * kFastTile + kFastTile <= W) && (tile_y * kFastTile + kFastTile <= H);
     if (vec_store && full_tile) {
         __syncthreads();  // staging buffers are dead from here on
-        float* s_out = reinterpret_cast<float*>(s_a);  // 16 rows x 48 floats = 3 KB
+        float* s_out = reinterpret_cast<float*>(s_g);  // 16 rows x 48 floats = 3 KB
         const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
         s_out[(ly * kFastTile + lx) * 3 + 0] = outr;
         s_out[(ly * kFastTile + lx) * 3 + 1] = outg;
@@ -286,12 +290,39 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
         if (tid < 16 * 12) {
             const int row = tid / 12, c4 = tid % 12;
             const float4 v = reinterpret_cast<const float4*>(s_out)[row * 12 + c4];
-            float* dst = image + ((int64_t)(blockIdx.y * kFastTile + row) * W + blockIdx.x * kFastTile) * 3;
+            float* dst = image + ((int64_t)(tile_y * kFastTile + row) * W + tile_x * kFastTile) * 3;
             reinterpret_cast<float4*>(dst)[c4] = v;
         }
     } else if (inside) {
         float* dst = image + ((int64_t)i * W + j) * 3;
         dst[0] = outr; dst[1] = outg; dst[2] = outb;
+    }
+}
+
+// Tiles sorted by list length, longest first (counting sort on len/32 capped to 255 buckets; order
+// inside a bucket is arbitrary and does not affect results).  One CTA, n_tiles is small.
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(const int n_tiles, const int32_t* __restrict__ tile_ranges, int32_t* __restrict__ order) {
+    __shared__ int s_cnt[256];
+    __shared__ int s_base[256];
+    const int tid = threadIdx.x;
+    if (tid < 256) s_cnt[tid] = 0;
+    __syncthreads();
+    for (int t = tid; t < n_tiles; t += blockDim.x) {
+        const int len = tile_ranges[2 * t + 1] - tile_ranges[2 * t];
+        const int b = 255 - min(255, (len + 31) >> 5);  // bucket 0 = longest
+        atomicAdd(&s_cnt[b], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int b = 0; b < 256; ++b) { s_base[b] = acc; acc += s_cnt[b]; }
+    }
+    __syncthreads();
+    for (int t = tid; t < n_tiles; t += blockDim.x) {
+        const int len = tile_ranges[2 * t + 1] - tile_ranges[2 * t];
+        const int b = 255 - min(255, (len + 31) >> 5);
+        order[atomicAdd(&s_base[b], 1)] = t;
     }
 }
 
@@ -318,8 +349,9 @@ namespace bsplat {
 // shared with capi.cu; mode 2 = fast arithmetic without sub-tile culling (A/B testing)
 int rasterize_launch(int64_t N, int channels, const float* means2d, const float* conics, const float* colors,
                      const float* opacities, const float* background_dev,
-                     const int32_t* tile_ranges, const int32_t* sorted_ids, int W, int H, int tile_size,
-                     int mode, float* image, unsigned long long* stats, cudaStream_t stream) {
+                     const int32_t* tile_ranges, const int32_t* tile_order, const int32_t* sorted_ids, int W,
+                     int H, int tile_size, int mode, float* image, unsigned long long* stats,
+                     cudaStream_t stream) {
     if (W <= 0 || H <= 0 || tile_size <= 0 || tile_size > 32 || channels <= 0 || !background_dev)
         return BSPLAT_E_ARG;
     const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
@@ -330,15 +362,15 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
     if (fast_ok) {
         const float* bg = background_dev;
         const int vec = ((reinterpret_cast<uintptr_t>(image) & 15u) == 0 && (W % 4) == 0) ? 1 : 0;
-        const dim3 grid(tiles_w, tiles_h);
+        const unsigned grid = (unsigned)(tiles_w * tiles_h);
         if (mode == 2)
             raster_fast_kernel<false><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
-                                                                         tile_ranges, sorted_ids, W, H, tiles_w,
-                                                                         image, vec);
+                                                                         tile_ranges, tile_order, sorted_ids, W, H,
+                                                                         tiles_w, image, vec);
         else
             raster_fast_kernel<true><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
-                                                                        tile_ranges, sorted_ids, W, H, tiles_w,
-                                                                        image, vec);
+                                                                        tile_ranges, tile_order, sorted_ids, W, H,
+                                                                        tiles_w, image, vec);
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
     }
@@ -355,6 +387,12 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         }
         if (rc != BSPLAT_OK) return rc;
     }
+    return BSPLAT_OK;
+}
+
+int tile_order_launch(int n_tiles, const int32_t* tile_ranges, int32_t* order, cudaStream_t stream) {
+    tile_order_kernel<<<1, 1024, 0, stream>>>(n_tiles, tile_ranges, order);
+    BSPLAT_LAUNCH_CHECK();
     return BSPLAT_OK;
 }
 }  // namespace bsplat

@@ -65,9 +65,15 @@ def rasterize_gaussians_cuda(means2d, conics, colors, opacities, background_colo
     H, W = int(camera.H), int(camera.W)
     image = torch.empty((H, W, C), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
+        order = None
+        if mode != "faithful" and int(tile_size) == 16 and C == 3:
+            # heavy tiles first: a scheduling hint only, results do not depend on it
+            order = torch.empty((tile_ranges.shape[0] * tile_ranges.shape[1],), dtype=torch.int32, device=dev)
+            _lib.check(L.bsplat_tile_order(order.numel(), _lib.ptr(tile_ranges), _lib.ptr(order),
+                                           _lib.stream_ptr(dev)), "bsplat_tile_order")
         rc = L.bsplat_rasterize_fwd(N, C, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
                                     _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
-                                    _lib.ptr(sorted_ids), sorted_ids.numel(), W, H, int(tile_size),
+                                    _lib.ptr(order), _lib.ptr(sorted_ids), sorted_ids.numel(), W, H, int(tile_size),
                                     RASTER_MODES[mode], _lib.ptr(image), _lib.stream_ptr(dev))
     _lib.check(rc, "bsplat_rasterize_fwd")
     return image
