@@ -149,14 +149,18 @@ int bsplat_bin2_finish(int64_t N, int64_t M, const float* means2d, const void* r
 /* ---- stage 3: rasterization ---------------------------------------------------------------- */
 /* tile_order[n_tiles]: tile ids sorted by list length, longest first (scheduling hint for the
  * rasterizer: under the torch binning rules the culled Gaussians pile up in the corner tiles). */
-int bsplat_tile_order(int32_t n_tiles, const int32_t* tile_ranges, int32_t* tile_order, void* stream);
+int bsplat_tile_order(int32_t first_tile, int32_t n_tiles, const int32_t* tile_ranges,
+                      int32_t* tile_order, void* stream);
 /* image[height, width, channels]. opacities are used raw (no sigmoid), like the reference.
- * tile_order may be NULL (row-major tile order). */
+ * tile_order may be NULL (row-major tile order). Only tile rows [tile_row_begin, tile_row_end) are
+ * rasterized and written (pass 0 and tiles_h for the whole frame; a row band for the multi-GPU split --
+ * tile_order, if given, must then list exactly the band's tiles). */
 int bsplat_rasterize_fwd(int64_t N, int32_t channels, const float* means2d, const float* conics,
                          const float* colors, const float* opacities, const float* background,
                          const int32_t* tile_ranges, const int32_t* tile_order,
                          const int32_t* sorted_ids, int64_t M, int32_t width, int32_t height,
-                         int32_t tile_size, int32_t mode, float* image, void* stream);
+                         int32_t tile_size, int32_t tile_row_begin, int32_t tile_row_end, int32_t mode,
+                         float* image, void* stream);
 
 /* Faithful kernel + counters: stats[0] += evaluated (pixel, Gaussian) pairs, stats[1] += contributing
  * pairs (device uint64[2], caller-zeroed) -- the algorithmic work E_all / E_pass of SURVEY.md 8d. */

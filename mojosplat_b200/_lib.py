@@ -118,8 +118,8 @@ def load() -> ctypes.CDLL:
         L.bsplat_tile_ranges.argtypes = [c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
         L.bsplat_rasterize_fwd.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
-                                           c_int32, c_int32, c_void_p, c_void_p]
-        L.bsplat_tile_order.argtypes = [c_int32, c_void_p, c_void_p, c_void_p]
+                                           c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+        L.bsplat_tile_order.argtypes = [c_int32, c_int32, c_void_p, c_void_p, c_void_p]
         L.bsplat_rasterize_stats.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                              c_int32, c_void_p, c_void_p, c_void_p]

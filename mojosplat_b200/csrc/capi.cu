@@ -11,9 +11,11 @@ int project_fwd_launch(int64_t N, const float* means3d, const float* log_scales,
                        float* means2d, float* conics, float* depths, int32_t* radii, cudaStream_t stream);
 int rasterize_launch(int64_t N, int channels, const float* means2d, const float* conics, const float* colors,
                      const float* opacities, const float* background_dev, const int32_t* tile_ranges,
-                     const int32_t* tile_order, const int32_t* sorted_ids, int W, int H, int tile_size, int mode,
-                     float* image, unsigned long long* stats, cudaStream_t stream);
-int tile_order_launch(int n_tiles, const int32_t* tile_ranges, int32_t* order, cudaStream_t stream);
+                     const int32_t* tile_order, const int32_t* sorted_ids, int W, int H, int tile_size,
+                     int row_begin, int row_end, int mode, float* image, unsigned long long* stats,
+                     cudaStream_t stream);
+int tile_order_launch(int first_tile, int n_tiles, const int32_t* tile_ranges, int32_t* order,
+                      cudaStream_t stream);
 }  // namespace bsplat
 
 using namespace bsplat;
@@ -47,16 +49,19 @@ extern "C" int bsplat_rasterize_fwd(int64_t N, int32_t channels, const float* me
                                     const float* colors, const float* opacities, const float* background,
                                     const int32_t* tile_ranges, const int32_t* tile_order,
                                     const int32_t* sorted_ids, int64_t M, int32_t width, int32_t height,
-                                    int32_t tile_size, int32_t mode, float* image, void* stream) {
+                                    int32_t tile_size, int32_t tile_row_begin, int32_t tile_row_end,
+                                    int32_t mode, float* image, void* stream) {
     if (N < 0 || M < 0 || !tile_ranges || !image || !background) return BSPLAT_E_ARG;
     if (M > 0 && (!sorted_ids || !means2d || !conics || !colors || !opacities)) return BSPLAT_E_ARG;
     return rasterize_launch(N, channels, means2d, conics, colors, opacities, background, tile_ranges, tile_order,
-                            sorted_ids, width, height, tile_size, mode, image, nullptr, (cudaStream_t)stream);
+                            sorted_ids, width, height, tile_size, tile_row_begin, tile_row_end, mode, image,
+                            nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int bsplat_tile_order(int32_t n_tiles, const int32_t* tile_ranges, int32_t* tile_order, void* stream) {
-    if (n_tiles <= 0 || !tile_ranges || !tile_order) return BSPLAT_E_ARG;
-    return tile_order_launch(n_tiles, tile_ranges, tile_order, (cudaStream_t)stream);
+extern "C" int bsplat_tile_order(int32_t first_tile, int32_t n_tiles, const int32_t* tile_ranges,
+                                 int32_t* tile_order, void* stream) {
+    if (first_tile < 0 || n_tiles < 0 || !tile_ranges || !tile_order) return BSPLAT_E_ARG;
+    return tile_order_launch(first_tile, n_tiles, tile_ranges, tile_order, (cudaStream_t)stream);
 }
 
 // Same as bsplat_rasterize_fwd but always the faithful kernel, and counts the evaluated /
@@ -69,7 +74,7 @@ extern "C" int bsplat_rasterize_stats(int64_t N, int32_t channels, const float* 
                                       uint64_t* stats, void* stream) {
     if (N < 0 || M < 0 || !tile_ranges || !image || !background || !stats) return BSPLAT_E_ARG;
     return rasterize_launch(N, channels, means2d, conics, colors, opacities, background, tile_ranges, nullptr,
-                            sorted_ids, width, height, tile_size, BSPLAT_RASTER_FAITHFUL, image,
+                            sorted_ids, width, height, tile_size, 0, 1 << 30, BSPLAT_RASTER_FAITHFUL, image,
                             reinterpret_cast<unsigned long long*>(stats), (cudaStream_t)stream);
 }
 
@@ -267,14 +272,14 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     }
     const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
     if (fast_raster) {
-        rc = tile_order_launch(tiles_w * tiles_h, d_ranges, w.tile_order, stream);
+        rc = tile_order_launch(0, tiles_w * tiles_h, d_ranges, w.tile_order, stream);
         if (rc != BSPLAT_OK) { drop_events(); return rc; }
         if (aux) aux->n_launches += 1;
     }
     if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[3], stream));
     rc = rasterize_launch(N, channels, d_means2d, d_conics, colors, opacities, background, d_ranges,
-                          fast_raster ? w.tile_order : nullptr, sorted_ids, W, H, tile_size, raster_mode, image,
-                          nullptr, stream);
+                          fast_raster ? w.tile_order : nullptr, sorted_ids, W, H, tile_size, 0, tiles_h, raster_mode,
+                          image, nullptr, stream);
     if (rc != BSPLAT_OK) { drop_events(); return rc; }
     if (aux && aux->sorted_ids && aux->sorted_ids_capacity >= M)
         BSPLAT_CUDA_TRY(cudaMemcpyAsync(aux->sorted_ids, sorted_ids, (size_t)M * sizeof(int32_t),

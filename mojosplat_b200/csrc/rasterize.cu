@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(1024) raster_faithful_kernel(const int64_t N, 
                                        const float* __restrict__ background,
                                        const int32_t* __restrict__ tile_ranges,
                                        const int32_t* __restrict__ sorted_ids, const int W, const int H,
-                                       const int ts, const int tiles_w, float* __restrict__ image,
-                                       unsigned long long* __restrict__ stats) {
+                                       const int ts, const int tiles_w, const int row_begin,
+                                       float* __restrict__ image, unsigned long long* __restrict__ stats) {
     extern __shared__ float s_buf[];
     const int nthreads = ts * ts;
     float* s_mx = s_buf;
@@ -50,8 +50,9 @@ __global__ void __launch_bounds__(1024) raster_faithful_kernel(const int64_t N, 
     float* s_col = s_o + nthreads;  // [nthreads][CH]
 
     const int tid = threadIdx.y * ts + threadIdx.x;
-    const int tile = blockIdx.y * tiles_w + blockIdx.x;
-    const int i = blockIdx.y * ts + threadIdx.y;
+    const int tile_row = row_begin + (int)blockIdx.y;
+    const int tile = tile_row * tiles_w + blockIdx.x;
+    const int i = tile_row * ts + threadIdx.y;
     const int j = blockIdx.x * ts + threadIdx.x;
     const bool inside = (i < H) && (j < W);
     bool done = !inside;
@@ -147,14 +148,15 @@ __global__ void __launch_bounds__(kFastThreads)
 raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
                    const float* __restrict__ colors, const float* __restrict__ opacities,
                    const float* __restrict__ background, const int32_t* __restrict__ tile_ranges,
-                   const int32_t* __restrict__ tile_order, const int32_t* __restrict__ sorted_ids, const int W,
-                   const int H, const int tiles_w, float* __restrict__ image, const int vec_store) {
+                   const int32_t* __restrict__ tile_order, const int first_tile,
+                   const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
+                   float* __restrict__ image, const int vec_store) {
     __shared__ float4 s_g[kFastBatch * 3];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     // heavy tiles first (tile_order, longest lists first) so that no long list starts at the tail
-    const int tile = tile_order ? __ldg(tile_order + blockIdx.x) : (int)blockIdx.x;
+    const int tile = tile_order ? __ldg(tile_order + blockIdx.x) : first_tile + (int)blockIdx.x;
     const int tile_y = tile / tiles_w, tile_x = tile - tile_y * tiles_w;
     // warp -> 8x4 pixel block inside the tile; lane -> pixel inside the block
     const int bx = tile_x * kFastTile + (warp & 1) * 8;
@@ -302,7 +304,9 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
 // Tiles sorted by list length, longest first (counting sort on len/32 capped to 255 buckets; order
 // inside a bucket is arbitrary and does not affect results).  One CTA, n_tiles is small.
 __global__ void __launch_bounds__(1024)
-tile_order_kernel(const int n_tiles, const int32_t* __restrict__ tile_ranges, int32_t* __restrict__ order) {
+tile_order_kernel(const int first_tile, const int n_tiles, const int32_t* __restrict__ tile_ranges_all,
+                  int32_t* __restrict__ order) {
+    const int32_t* tile_ranges = tile_ranges_all + 2 * (int64_t)first_tile;
     __shared__ int s_cnt[256];
     __shared__ int s_base[256];
     const int tid = threadIdx.x;
@@ -322,7 +326,7 @@ tile_order_kernel(const int n_tiles, const int32_t* __restrict__ tile_ranges, in
     for (int t = tid; t < n_tiles; t += blockDim.x) {
         const int len = tile_ranges[2 * t + 1] - tile_ranges[2 * t];
         const int b = 255 - min(255, (len + 31) >> 5);
-        order[atomicAdd(&s_base[b], 1)] = t;
+        order[atomicAdd(&s_base[b], 1)] = first_tile + t;
     }
 }
 
@@ -334,13 +338,14 @@ template <int CH>
 static int launch_faithful(int64_t N, int cdim, int c0, const float* means2d, const float* conics,
                            const float* colors, const float* opacities, const float* background,
                            const int32_t* tile_ranges, const int32_t* sorted_ids, int W, int H, int ts,
-                           float* image, unsigned long long* stats, cudaStream_t stream) {
-    const int tiles_w = (W + ts - 1) / ts, tiles_h = (H + ts - 1) / ts;
-    const dim3 grid(tiles_w, tiles_h), block(ts, ts);
+                           int row_begin, int row_end, float* image, unsigned long long* stats,
+                           cudaStream_t stream) {
+    const int tiles_w = (W + ts - 1) / ts;
+    const dim3 grid(tiles_w, row_end - row_begin), block(ts, ts);
     const size_t smem = (size_t)ts * ts * (6 + CH) * sizeof(float);
     raster_faithful_kernel<CH><<<grid, block, smem, stream>>>(N, cdim, c0, means2d, conics, colors, opacities,
                                                               background, tile_ranges, sorted_ids, W, H, ts,
-                                                              tiles_w, image, stats);
+                                                              tiles_w, row_begin, image, stats);
     BSPLAT_LAUNCH_CHECK();
     return BSPLAT_OK;
 }
@@ -350,27 +355,31 @@ namespace bsplat {
 int rasterize_launch(int64_t N, int channels, const float* means2d, const float* conics, const float* colors,
                      const float* opacities, const float* background_dev,
                      const int32_t* tile_ranges, const int32_t* tile_order, const int32_t* sorted_ids, int W,
-                     int H, int tile_size, int mode, float* image, unsigned long long* stats,
-                     cudaStream_t stream) {
+                     int H, int tile_size, int row_begin, int row_end, int mode, float* image,
+                     unsigned long long* stats, cudaStream_t stream) {
     if (W <= 0 || H <= 0 || tile_size <= 0 || tile_size > 32 || channels <= 0 || !background_dev)
         return BSPLAT_E_ARG;
     const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
     if (tiles_h > 65535) return BSPLAT_E_ARG;
+    if (row_begin < 0) row_begin = 0;
+    if (row_end > tiles_h) row_end = tiles_h;
+    if (row_end <= row_begin) return BSPLAT_OK;  // empty band
     const bool fast_ok = (mode == BSPLAT_RASTER_FAST || mode == 2) && tile_size == kFastTile &&
                          channels == 3 && stats == nullptr &&
                          (reinterpret_cast<uintptr_t>(means2d) & 7u) == 0;
     if (fast_ok) {
         const float* bg = background_dev;
         const int vec = ((reinterpret_cast<uintptr_t>(image) & 15u) == 0 && (W % 4) == 0) ? 1 : 0;
-        const unsigned grid = (unsigned)(tiles_w * tiles_h);
+        const unsigned grid = (unsigned)(tiles_w * (row_end - row_begin));
+        const int first_tile = row_begin * tiles_w;
         if (mode == 2)
             raster_fast_kernel<false><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
-                                                                         tile_ranges, tile_order, sorted_ids, W, H,
-                                                                         tiles_w, image, vec);
+                                                                         tile_ranges, tile_order, first_tile, sorted_ids,
+                                                                         W, H, tiles_w, image, vec);
         else
             raster_fast_kernel<true><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
-                                                                        tile_ranges, tile_order, sorted_ids, W, H,
-                                                                        tiles_w, image, vec);
+                                                                        tile_ranges, tile_order, first_tile, sorted_ids,
+                                                                        W, H, tiles_w, image, vec);
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
     }
@@ -380,18 +389,20 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         int rc;
         unsigned long long* st = (c0 == 0) ? stats : nullptr;
         switch (ch) {
-            case 1: rc = launch_faithful<1>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, image, st, stream); break;
-            case 2: rc = launch_faithful<2>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, image, st, stream); break;
-            case 3: rc = launch_faithful<3>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, image, st, stream); break;
-            default: rc = launch_faithful<4>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, image, st, stream); break;
+            case 1: rc = launch_faithful<1>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, stream); break;
+            case 2: rc = launch_faithful<2>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, stream); break;
+            case 3: rc = launch_faithful<3>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, stream); break;
+            default: rc = launch_faithful<4>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, stream); break;
         }
         if (rc != BSPLAT_OK) return rc;
     }
     return BSPLAT_OK;
 }
 
-int tile_order_launch(int n_tiles, const int32_t* tile_ranges, int32_t* order, cudaStream_t stream) {
-    tile_order_kernel<<<1, 1024, 0, stream>>>(n_tiles, tile_ranges, order);
+int tile_order_launch(int first_tile, int n_tiles, const int32_t* tile_ranges, int32_t* order,
+                      cudaStream_t stream) {
+    if (n_tiles <= 0) return BSPLAT_OK;
+    tile_order_kernel<<<1, 1024, 0, stream>>>(first_tile, n_tiles, tile_ranges, order);
     BSPLAT_LAUNCH_CHECK();
     return BSPLAT_OK;
 }

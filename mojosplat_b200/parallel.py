@@ -1,0 +1,197 @@
+"""Multi-camera and multi-GPU entry points (additive; the reference is single-camera, single-GPU:
+``"C": 1`` at mojosplat/projection.py:431 and rasterization.py:175, ``I = 1`` at binning.py:72).
+
+The forward path shards in exactly two ways:
+
+* **by view** -- every rank holds the whole Gaussian set (one NCCL broadcast at load), ranks render
+  disjoint subsets of the cameras, no data-path collective (``render_views``); images are only
+  gathered if a consumer asks for them.
+* **by tile-row band** -- one very large frame: every rank projects all Gaussians (HBM-bound, cheap),
+  bins and rasterizes only its band of tile rows (bands balanced by intersection count), then one
+  all-gather of the bands (``render_frame_row_split``).  Per-tile lists are those of the
+  single-GPU run, so the assembled image is bit-identical to it.
+
+One process per GPU (torchrun); ``torch.distributed`` is plumbing (NCCL on GPUs, gloo in the CPU
+tests of this host logic).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .binning import bin_gaussians_to_tiles_cuda
+from .projection import project_gaussians_cuda
+from .rasterization import rasterize_gaussians_cuda
+from .render import TILE_SIZE, render_fused
+from .utils import Camera
+
+
+# ----------------------------------------------------------------------------------------------
+# partitioning (pure host logic, tested on CPU with gloo)
+# ----------------------------------------------------------------------------------------------
+def split_views(n_views: int, rank: int, world: int) -> list:
+    """Round-robin view assignment: rank r renders views r, r+world, ... (orbit neighbours have similar
+    cost, so round-robin balances better than contiguous blocks)."""
+    return list(range(rank, n_views, world))
+
+
+def balanced_row_bands(row_cost: Sequence[float], world: int) -> list:
+    """Split tile rows 0..R-1 into ``world`` contiguous bands with near-equal summed cost.
+    Returns [(begin, end)] * world; bands may be empty (when world > R or the cost is concentrated)."""
+    import bisect
+    R = len(row_cost)
+    cum = [0.0]
+    for c in row_cost:
+        cum.append(cum[-1] + float(c))
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        e = bisect.bisect_left(cum, target)          # first e with cost(rows[0:e]) >= target
+        if e > 0 and abs(cum[e - 1] - target) <= abs(cum[min(e, R)] - target):
+            e -= 1                                     # the cut just before is at least as close
+        cuts.append(min(max(e, cuts[-1]), R))
+    cuts.append(R)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def tile_row_cost(means2d: torch.Tensor, radii: torch.Tensor, H: int, W: int, tile_size: int) -> torch.Tensor:
+    """Approximate number of (gaussian, tile) intersections per tile row -- only used to balance the
+    bands, never to decide what is rendered."""
+    ts = float(tile_size)
+    th, tw = math.ceil(H / tile_size), math.ceil(W / tile_size)
+    r = radii.to(torch.float32)
+    x0 = ((means2d[:, 0] - r[:, 0]).clamp(0, W - 1) / ts).floor()
+    x1 = ((means2d[:, 0] + r[:, 0]).clamp(0, W - 1) / ts).floor()
+    y0 = ((means2d[:, 1] - r[:, 1]).clamp(0, H - 1) / ts).floor().long().clamp(0, th - 1)
+    y1 = ((means2d[:, 1] + r[:, 1]).clamp(0, H - 1) / ts).floor().long().clamp(0, th - 1)
+    width = (x1 - x0 + 1).clamp(min=0)
+    # difference array over rows: +width at y0, -width after y1
+    diff = torch.zeros(th + 1, dtype=torch.float32, device=means2d.device)
+    diff.index_add_(0, y0, width)
+    diff.index_add_(0, y1 + 1, -width)
+    return diff.cumsum(0)[:th]
+
+
+def broadcast_gaussians(tensors: Sequence[torch.Tensor], src: int = 0, group=None) -> None:
+    """The one exchange of the view-split path: rank ``src``'s Gaussian arrays to everyone
+    (56 B per Gaussian for RGB: 168 MB at 3 M).  In place."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for t in tensors:
+        dist.broadcast(t, src=src, group=group)
+
+
+# ----------------------------------------------------------------------------------------------
+# rendering
+# ----------------------------------------------------------------------------------------------
+def render_gaussians_batched(means3d, scales, quats, opacities, features, cameras: Sequence[Camera],
+                             background_color=None, tile_size: int = TILE_SIZE, backend: str = "cuda",
+                             out: torch.Tensor | None = None) -> torch.Tensor:
+    """All cameras on this GPU: images [C, H, W, 3].  Views are independent; each is one fused C call
+    on the current stream, workspace reused."""
+    from .projection import CUDA_BACKENDS
+    from .render import _background_tensor
+    if backend not in CUDA_BACKENDS:
+        raise ValueError(f"Invalid backend: {backend}")
+    C = features.shape[-1]
+    bg = _background_tensor(background_color, C, means3d.device, torch.float32)
+    cam0 = cameras[0]
+    if out is None:
+        out = torch.empty((len(cameras), cam0.H, cam0.W, C), dtype=torch.float32, device=means3d.device)
+    for k, cam in enumerate(cameras):
+        out[k] = render_fused(means3d, scales, quats, opacities, features, cam, bg, tile_size,
+                              semantics=CUDA_BACKENDS[backend])
+    return out
+
+
+def render_views(means3d, scales, quats, opacities, features, cameras: Sequence[Camera], background_color=None,
+                 tile_size: int = TILE_SIZE, backend: str = "cuda", gather: bool = False, group=None,
+                 render_fn: Callable | None = None):
+    """View-split multi-GPU render.  Returns ``(view_ids, images)`` of this rank, or -- with
+    ``gather=True`` -- all images ``[n_views, H, W, C]`` on every rank (one all_gather)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = split_views(len(cameras), rank, world)
+    fn = render_fn or (lambda cams: render_gaussians_batched(means3d, scales, quats, opacities, features, cams,
+                                                             background_color, tile_size, backend))
+    images = fn([cameras[v] for v in mine]) if mine else None
+    if not gather or world == 1:
+        return mine, images
+    n_max = math.ceil(len(cameras) / world)
+    cam0 = cameras[0]
+    C = features.shape[-1]
+    dev = features.device
+    pad = torch.zeros((n_max, cam0.H, cam0.W, C), dtype=torch.float32, device=dev)
+    if images is not None:
+        pad[: images.shape[0]] = images
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    full = torch.empty((len(cameras), cam0.H, cam0.W, C), dtype=torch.float32, device=dev)
+    for r in range(world):
+        ids = split_views(len(cameras), r, world)
+        if ids:
+            full[ids] = parts[r][: len(ids)]
+    return list(range(len(cameras))), full
+
+
+def render_band(means3d, scales, quats, opacities, features, camera: Camera, background, band, tile_size=TILE_SIZE,
+                semantics=_lib.SEM_TORCH, out: torch.Tensor | None = None, projected=None):
+    """Project everything, bin + rasterize only tile rows [band[0], band[1]).  Returns the full-size image
+    buffer with only the band rows written."""
+    H, W = camera.H, camera.W
+    if projected is None:
+        projected = project_gaussians_cuda(means3d, scales, quats, opacities, camera, semantics=semantics)
+    means2d, conics, depths, radii = projected
+    ids, ranges = bin_gaussians_to_tiles_cuda(means2d, radii, depths, H, W, tile_size, semantics=semantics,
+                                              tile_rows=band)
+    if out is None:
+        out = torch.zeros((H, W, features.shape[-1]), dtype=torch.float32, device=means3d.device)
+    rasterize_gaussians_cuda(means2d, conics, features, opacities, background, ranges, ids, camera, tile_size,
+                             tile_rows=band, out=out)
+    return out
+
+
+def render_frame_row_split(means3d, scales, quats, opacities, features, camera: Camera, background_color=None,
+                           tile_size: int = TILE_SIZE, semantics=_lib.SEM_TORCH, group=None, bands=None):
+    """One frame split into tile-row bands across the ranks, then one all-gather of the bands.
+    The result equals the single-GPU image bit for bit (per-tile lists are unchanged)."""
+    from .render import _background_tensor
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    H, W = camera.H, camera.W
+    C = features.shape[-1]
+    th = math.ceil(H / tile_size)
+    bg = _background_tensor(background_color, C, means3d.device, torch.float32)
+    projected = project_gaussians_cuda(means3d, scales, quats, opacities, camera, semantics=semantics)
+    if bands is None:
+        cost = tile_row_cost(projected[0], projected[3], H, W, tile_size)
+        if world > 1:
+            dist.broadcast(cost, src=0, group=group)  # identical inputs give identical costs; be explicit
+        bands = balanced_row_bands(cost.tolist(), world)
+    image = torch.zeros((H, W, C), dtype=torch.float32, device=means3d.device)
+    render_band(means3d, scales, quats, opacities, features, camera, bg, bands[rank], tile_size, semantics,
+                out=image, projected=projected)
+    if world == 1:
+        return image
+    return assemble_bands(image, bands, tile_size, rank, world, group)
+
+
+def assemble_bands(image: torch.Tensor, bands, tile_size: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """All-gather of the row bands (each rank contributes rows [b0*ts, min(b1*ts, H)) of its buffer)."""
+    H = image.shape[0]
+    rows = [(min(b0 * tile_size, H), min(b1 * tile_size, H)) for b0, b1 in bands]
+    n_max = max(e - s for s, e in rows)
+    pad = torch.zeros((n_max,) + tuple(image.shape[1:]), dtype=image.dtype, device=image.device)
+    s, e = rows[rank]
+    pad[: e - s] = image[s:e]
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    full = torch.empty_like(image)
+    for r, (s, e) in enumerate(rows):
+        full[s:e] = parts[r][: e - s]
+    return full

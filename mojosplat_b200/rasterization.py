@@ -57,23 +57,30 @@ def _prep(means2d, conics, colors, opacities, background_color, tile_ranges, sor
 
 
 def rasterize_gaussians_cuda(means2d, conics, colors, opacities, background_color, tile_ranges,
-                             sorted_gaussian_indices, camera, tile_size=16, mode="fast"):
-    """sm_100a tile rasterizer behind the C ABI (include/bsplat.h: bsplat_rasterize_fwd)."""
+                             sorted_gaussian_indices, camera, tile_size=16, mode="fast", tile_rows=None,
+                             out=None):
+    """sm_100a tile rasterizer behind the C ABI (include/bsplat.h: bsplat_rasterize_fwd).
+
+    ``tile_rows=(begin, end)`` rasterizes only that band of tile rows into ``out`` (the other rows of
+    the image are left untouched): the per-rank step of the row-band multi-GPU split."""
     L = _lib.require_device(means2d.device)
     dev, means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, N, C = _prep(
         means2d, conics, colors, opacities, background_color, tile_ranges, sorted_gaussian_indices)
     H, W = int(camera.H), int(camera.W)
-    image = torch.empty((H, W, C), dtype=torch.float32, device=dev)
+    image = torch.empty((H, W, C), dtype=torch.float32, device=dev) if out is None else out
+    th, tw = tile_ranges.shape[0], tile_ranges.shape[1]
+    r0, r1 = (0, th) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
     with torch.cuda.device(dev):
         order = None
-        if mode != "faithful" and int(tile_size) == 16 and C == 3:
+        if mode != "faithful" and int(tile_size) == 16 and C == 3 and r1 > r0:
             # heavy tiles first: a scheduling hint only, results do not depend on it
-            order = torch.empty((tile_ranges.shape[0] * tile_ranges.shape[1],), dtype=torch.int32, device=dev)
-            _lib.check(L.bsplat_tile_order(order.numel(), _lib.ptr(tile_ranges), _lib.ptr(order),
+            order = torch.empty(((r1 - r0) * tw,), dtype=torch.int32, device=dev)
+            _lib.check(L.bsplat_tile_order(r0 * tw, order.numel(), _lib.ptr(tile_ranges), _lib.ptr(order),
                                            _lib.stream_ptr(dev)), "bsplat_tile_order")
         rc = L.bsplat_rasterize_fwd(N, C, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
                                     _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
                                     _lib.ptr(order), _lib.ptr(sorted_ids), sorted_ids.numel(), W, H, int(tile_size),
+                                    r0, r1,
                                     RASTER_MODES[mode], _lib.ptr(image), _lib.stream_ptr(dev))
     _lib.check(rc, "bsplat_rasterize_fwd")
     return image
