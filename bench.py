@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--n-gaussians", type=int, default=None, help="override N (debug only; marks the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--semantics", default="torch", choices=["torch", "gsplat"])
+    ap.add_argument("--pipeline-depth", type=int, default=2, help="frames in flight per GPU")
     return ap.parse_args()
 
 
@@ -194,40 +195,57 @@ def run_b200(args, rank, world, local_rank):
     def frame(k, **kw):
         return ms.render_fused(*g, view_of(k), bg, 16, semantics=sem, **kw)
 
+    from mojosplat_b200.pipeline import FramePipeline
+    pipe = FramePipeline(dev, N, W, H, semantics=sem, depth=args.pipeline_depth)
+    ring = torch.empty((4, H, W, 3), dtype=torch.float32, device=dev)
+
     # clocks are sampled from the first warm-up frame to the end of the e2e loop (the GPU is under this
     # workload the whole time; the device-timed region alone lasts only tens of milliseconds)
     sampler = ClockSampler(local_rank)
     sampler.start()
     # ---- warm-up ----
-    for k in range(max(args.warmup, 3)):
+    Wm = max(args.warmup, 3)
+    for k in range(Wm):
         frame(k)
+    pipe.render(*g, [view_of(k) for k in range(Wm)], bg, out=ring)
     torch.cuda.synchronize(dev)
 
-    # ---- timed region: K frames, device-timed per step, L2 flushed between steps ----
+    # ---- timed region: K frames (steps) through the 2-deep frame pipeline, one device-timed region ----
+    # No explicit flush here: every step streams ~290 MB (56 MB inputs + ~230 MB intermediates + image)
+    # through a 126 MB L2 and two frames are in flight, so nothing survives from one step to the next
+    # except part of the (read-only) Gaussian arrays, as in any multi-view render of one scene.
     K = args.steps
-    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    views = [view_of(k) for k in range(K)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
-    launches = 0
-    for k in range(K):
-        flush.zero_()
-        ev_s[k].record()
-        frame(k)
-        ev_e[k].record()
+    e_beg.record()
+    pipe.render(*g, views, bg, out=ring)
+    e_end.record()
     torch.cuda.synchronize(dev)
     wall = time.perf_counter() - wall0
     if world > 1:
         dist.barrier()
-    step_ms = [s.elapsed_time(e) for s, e in zip(ev_s, ev_e)]
-    total_ms = float(sum(step_ms))
+    total_ms = float(e_beg.elapsed_time(e_end))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = world * K / (total_ms_max * 1e-3)
+
+    # ---- single-frame latency: frame-by-frame, L2 flushed (512 MiB memset) between frames ----
+    Kl = min(K, 20)
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(Kl)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(Kl)]
+    for k in range(Kl):
+        flush.zero_()
+        ev_s[k].record()
+        frame(k)
+        ev_e[k].record()
+    torch.cuda.synchronize(dev)
+    latency_ms = float(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))) / Kl
 
     # ---- end-to-end through the public host-buffer API (pinned host in, host image out) ----
     host_all = host if host is not None else [x.cpu().pin_memory() for x in g]
@@ -330,9 +348,13 @@ def run_b200(args, rank, world, local_rank):
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, ref_scene), "tile_size": 16, "semantics": args.semantics,
-                   "l2": "flushed between timed steps (512 MiB memset outside the per-step event pair)",
-                   "parallelism": f"views split across {world} rank(s); Gaussians NCCL-broadcast once at load",
-                   "timing": "sum of per-step CUDA-event times, max over ranks", "wall_ms_per_step": 1e3 * wall / K},
+                   "l2": "no explicit flush in the timed region: inputs + intermediates per step (~290 MB) exceed the "
+                         "126 MB L2 and 2 frames are in flight; single_frame_latency_ms is measured with a 512 MiB "
+                         "flush between frames",
+                   "parallelism": f"views split across {world} rank(s); Gaussians NCCL-broadcast once at load; "
+                                  f"{args.pipeline_depth} frames in flight per GPU (begin(k+1) overlaps end(k), FramePipeline)",
+                   "timing": "one CUDA-event pair around the K steps, max over ranks",
+                   "wall_ms_per_step": 1e3 * wall / K, "single_frame_latency_ms": latency_ms},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "api": "mojosplat_b200.render_gaussians_host (pinned host tensors in, host image out)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "stages": stages,

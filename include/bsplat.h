@@ -199,6 +199,19 @@ int bsplat_render_fwd(int64_t N, const float* means3d, const float* log_scales, 
                       int32_t semantics, int32_t flags, float* image, void* workspace,
                       size_t workspace_bytes, size_t* needed_bytes, bsplat_render_aux* aux,
                       void* stream);
+/* Split-phase frame for pipelined multi-view rendering. begin: projection + depth sort + count/scan
+ * and an ASYNC copy of the bin info (M) into pinned host memory -- no sync. The caller waits for the
+ * stream (event), reads M, then calls end (emit + tile sort + ranges + raster) with the same workspace,
+ * which must hold bsplat_render_workspace_bytes(N, M, ...). Two streams with one workspace each overlap
+ * begin(k+1) with end(k). Two-level binning only. */
+int bsplat_render_begin(int64_t N, const float* means3d, const float* log_scales, const float* quats,
+                        const float* opacities, const bsplat_camera* cam_host, int32_t tile_size,
+                        int32_t semantics, void* workspace, size_t workspace_bytes,
+                        bsplat_bin_info* info_host_pinned, void* stream);
+int bsplat_render_end(int64_t N, int64_t M, const float* colors, const float* opacities, int32_t channels,
+                      const bsplat_camera* cam_host, const float* background, int32_t tile_size,
+                      int32_t semantics, int32_t flags, float* image, void* workspace,
+                      size_t workspace_bytes, size_t* needed_bytes, void* stream);
 /* Same with HOST buffers (pinned or pageable): copies the Gaussians in, renders, copies the
  * image out and synchronises the stream. device_scratch must hold
  * bsplat_render_host_scratch_bytes() in addition to the render workspace. */

@@ -33,7 +33,7 @@ SYMBOLS = [
     "bsplat_tile_ranges", "bsplat_rasterize_fwd", "bsplat_rasterize_stats",
     "bsplat_render_workspace_bytes", "bsplat_render_fwd", "bsplat_render_host_scratch_bytes",
     "bsplat_render_fwd_host", "bsplat_microbench", "bsplat_bin2_workspace_bytes", "bsplat_bin2_prepare",
-    "bsplat_bin2_finish", "bsplat_tile_order",
+    "bsplat_bin2_finish", "bsplat_tile_order", "bsplat_render_begin", "bsplat_render_end",
 ]
 
 
@@ -120,6 +120,11 @@ def load() -> ctypes.CDLL:
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                            c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
         L.bsplat_tile_order.argtypes = [c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+        L.bsplat_render_begin.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(BsplatCamera),
+                                          c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_void_p]
+        L.bsplat_render_end.argtypes = [c_int64, c_int64, c_void_p, c_void_p, c_int32, POINTER(BsplatCamera),
+                                        c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
+                                        POINTER(c_size_t), c_void_p]
         L.bsplat_rasterize_stats.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                              c_int32, c_void_p, c_void_p, c_void_p]

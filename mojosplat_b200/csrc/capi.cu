@@ -293,6 +293,67 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     return BSPLAT_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// split-phase frame: begin = project + depth sort + count/scan (N-scale, latency-bound) and an async
+// copy of M into pinned host memory; end = emit + tile sort + ranges + order + raster (M-scale).
+// A two-stream pipeline overlaps begin(k+1) with end(k) (mojosplat_b200/parallel.py).
+// ------------------------------------------------------------------------------------------
+extern "C" int bsplat_render_begin(int64_t N, const float* means3d, const float* log_scales, const float* quats,
+                                   const float* opacities, const bsplat_camera* cam, int32_t tile_size,
+                                   int32_t semantics, void* workspace, size_t workspace_bytes,
+                                   bsplat_bin_info* info_host_pinned, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!cam || !info_host_pinned || N <= 0 || tile_size <= 0 || tile_size > 32) return BSPLAT_E_ARG;
+    if (!means3d || !log_scales || !quats) return BSPLAT_E_ARG;
+    const int W = cam->width, H = cam->height;
+    if (W <= 0 || H <= 0) return BSPLAT_E_ARG;
+    RenderWs w = carve_render(workspace, N, 0, W, H, tile_size, false);
+    if (!workspace || workspace_bytes < w.total) return BSPLAT_E_WORKSPACE;
+    int rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, *cam, 0.3f, semantics, w.means2d, w.conics,
+                                w.depths, w.radii, stream);
+    if (rc != BSPLAT_OK) return rc;
+    const int tiles_h = (H + tile_size - 1) / tile_size;
+    bsplat_bin_info* d_info = bin2_info_ptr(w.bin_ws, N);
+    rc = bsplat_bin2_prepare(N, w.means2d, w.radii, 0, w.depths, W, H, tile_size, 0, tiles_h, semantics, w.bin_ws,
+                             w.bin_bytes, d_info, stream);
+    if (rc != BSPLAT_OK) return rc;
+    BSPLAT_CUDA_TRY(cudaMemcpyAsync(info_host_pinned, d_info, sizeof(bsplat_bin_info), cudaMemcpyDeviceToHost, stream));
+    return BSPLAT_OK;
+}
+
+extern "C" int bsplat_render_end(int64_t N, int64_t M, const float* colors, const float* opacities, int32_t channels,
+                                 const bsplat_camera* cam, const float* background, int32_t tile_size,
+                                 int32_t semantics, int32_t flags, float* image, void* workspace,
+                                 size_t workspace_bytes, size_t* needed_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!cam || !image || !background || N <= 0 || M < 0 || channels <= 0) return BSPLAT_E_ARG;
+    if (!colors || !opacities) return BSPLAT_E_ARG;
+    if (M >= (1ll << 30)) return BSPLAT_E_OVERFLOW;
+    const int W = cam->width, H = cam->height;
+    const int raster_mode = flags & 0xff;
+    const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
+    if (M == 0) {
+        BSPLAT_CUDA_TRY(cudaMemsetAsync(image, 0, (size_t)W * H * channels * sizeof(float), stream));
+        return BSPLAT_OK;
+    }
+    RenderWs w = carve_render(workspace, N, M, W, H, tile_size, false);
+    if (!workspace || workspace_bytes < w.total) {
+        if (needed_bytes) *needed_bytes = w.total;
+        return BSPLAT_E_WORKSPACE;
+    }
+    int rc = bsplat_bin2_finish(N, M, w.means2d, w.radii, 0, W, H, tile_size, 0, tiles_h, semantics, w.bin_ws,
+                                w.bin_bytes, w.sorted_ids, w.tile_ranges, stream);
+    if (rc != BSPLAT_OK) return rc;
+    const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
+    if (fast_raster) {
+        rc = tile_order_launch(0, tiles_w * tiles_h, w.tile_ranges, w.tile_order, stream);
+        if (rc != BSPLAT_OK) return rc;
+    }
+    return rasterize_launch(N, channels, w.means2d, w.conics, colors, opacities, background, w.tile_ranges,
+                            fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, 0, tiles_h,
+                            raster_mode, image, nullptr, stream);
+}
+
 extern "C" size_t bsplat_render_host_scratch_bytes(int64_t N, int32_t channels, int32_t width, int32_t height) {
     const size_t n = (size_t)(N > 0 ? N : 1);
     size_t off = 0;

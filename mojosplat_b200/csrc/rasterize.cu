@@ -212,7 +212,9 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
             unsigned int mask;
             if (kCull) {
                 bool hit = false;
-                const int gi = c0 + lane;
+                // lane l tests Gaussian c0 + 31 - l: the earliest Gaussian is the HIGHEST ballot bit, so the
+                // walk below needs a single FLO (clz) per survivor instead of BREV + FLO
+                const int gi = c0 + 31 - lane;
                 if (gi < bs) {
                     const float4 a = s_g[3 * gi];
                     const float4 b = s_g[3 * gi + 1];
@@ -222,20 +224,23 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                     const float v0 = a.y - Y1, v1 = a.y - Y0;
                     const bool zu = (u0 <= 0.0f) && (u1 >= 0.0f);
                     const bool zv = (v0 <= 0.0f) && (v1 >= 0.0f);
-                    float qmin;
-                    if (zu && zv) {
-                        qmin = 0.0f;
-                    } else {
+                    // min of q over the block = min over the (<= 2) edges facing the mean; along the edge
+                    // u = ue the quadratic is D ue^2 + C (v - hy ue)^2 with D = A - B^2/(4C) = A + B hy / 2
+                    // (and symmetrically E = C + B hx / 2), so each edge costs a clamp and two FMAs.
+                    float qmin = 0.0f;
+                    if (!(zu && zv)) {
                         float q1 = INFINITY, q2 = INFINITY;
-                        if (!zu) {  // vertical edge nearest to the mean
+                        if (!zu) {
                             const float ue = (u0 > 0.0f) ? u0 : u1;
-                            const float vs = fminf(fmaxf(b.z * ue, v0), v1);
-                            q1 = a.z * ue * ue + a.w * ue * vs + b.x * vs * vs;
+                            const float vstar = b.z * ue;
+                            const float dv = vstar - fminf(fmaxf(vstar, v0), v1);
+                            q1 = fmaf(fmaf(0.5f * a.w, b.z, a.z) * ue, ue, b.x * dv * dv);
                         }
-                        if (!zv) {  // horizontal edge nearest to the mean
+                        if (!zv) {
                             const float ve = (v0 > 0.0f) ? v0 : v1;
-                            const float us = fminf(fmaxf(b.w * ve, u0), u1);
-                            q2 = a.z * us * us + a.w * us * ve + b.x * ve * ve;
+                            const float ustar = b.w * ve;
+                            const float du = ustar - fminf(fmaxf(ustar, u0), u1);
+                            q2 = fmaf(fmaf(0.5f * a.w, b.w, b.x) * ve, ve, a.z * du * du);
                         }
                         qmin = fminf(q1, q2);
                     }
@@ -246,33 +251,36 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                 mask = __ballot_sync(0xffffffffu, hit);
             } else {
                 const int rem = bs - c0;
-                mask = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+                mask = rem >= 32 ? 0xffffffffu : ~(0xffffffffu >> rem);  // Gaussian c0+k <-> bit 31-k
             }
-            const float4* rec = s_g + 3 * c0;
+            const float4* rec_hi = s_g + 3 * (c0 + 31);  // record of ballot bit 0; bit b is 3*b records earlier
             while (mask) {
-                const int t = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float4* r = rec + 3 * t;
+                // highest set bit = next Gaussian, front to back (bfind -> a single FLO; written in PTX
+                // because nvcc rewrites 31 - clz(x) into a longer clz-based sequence)
+                unsigned int b_hi;
+                asm("bfind.u32 %0, %1;" : "=r"(b_hi) : "r"(mask));
+                mask ^= 1u << b_hi;
+                const float4* r = rec_hi - 3 * (int)b_hi;
                 const float4 a = r[0];
                 const float2 b = *reinterpret_cast<const float2*>(r + 1);
+                const float4 c = r[2];
                 const float dx = a.x - px, dy = a.y - py;
                 const float t1 = fmaf(a.w, dy, a.z * dx);
                 const float q = fmaf(b.x * dy, dy, t1 * dx);
                 const float power = b.y - q;
-                if (q >= 0.0f && power >= kLog2AlphaThreshold) {
-                    const float alpha = fminf(0.999f, ex2_approx(power));
-                    const float next_T = T * (1.0f - alpha);
-                    if (next_T <= 1e-4f) {
-                        px = INFINITY;  // saturated: this Gaussian is not added (rasterization.mojo:146-150)
-                    } else {
-                        const float vis = alpha * T;
-                        const float4 c = r[2];
-                        accr = fmaf(c.x, vis, accr);
-                        accg = fmaf(c.y, vis, accg);
-                        accb = fmaf(c.z, vis, accb);
-                        T = next_T;
-                    }
-                }
+                // branch-free body: selects instead of divergent paths (90 % of the walked Gaussians
+                // contribute to at least one pixel of the block, so a skip branch saves nothing)
+                const bool pass = (q >= 0.0f) && (power >= kLog2AlphaThreshold);
+                const float alpha = fminf(0.999f, ex2_approx(power));
+                const float next_T = T * (1.0f - alpha);
+                const bool live = next_T > 1e-4f;
+                const float vis = (pass && live) ? alpha * T : 0.0f;
+                accr = fmaf(c.x, vis, accr);
+                accg = fmaf(c.y, vis, accg);
+                accb = fmaf(c.z, vis, accb);
+                T = (pass && live) ? next_T : T;
+                // saturated: this Gaussian is not added (rasterization.mojo:146-150) and the pixel retires
+                px = (pass && !live) ? INFINITY : px;
             }
         }
     }

@@ -45,3 +45,22 @@ def test_batched_views_equal_single_renders(cuda_device):
     ids, mine = parallel.render_views(m, s, q, o, c, cams, bg)  # world size 1: everything is mine
     assert ids == [0, 1, 2, 3] and torch.equal(mine, imgs)
     assert not torch.equal(imgs[0], imgs[1])
+
+
+def test_pipelined_views_equal_sequential(cuda_device):
+    from mojosplat_b200.pipeline import FramePipeline
+    sc = synthetic.make_scene("config3_1m_1080p", N=200_000)
+    (m, s, q, o, c), _ = scene_on(sc, cuda_device)
+    cams = synthetic.orbit_cameras(7, 960, 540, 500.0)
+    bg = sc.background.to(cuda_device)
+    # tiny initial capacity: exercises the grow-and-redo path as well
+    pipe = FramePipeline(cuda_device, sc.N, 960, 540, m_capacity=1000)
+    imgs = pipe.render(m, s, q, o, c, cams, bg)
+    torch.cuda.synchronize()
+    for k, cam in enumerate(cams):
+        assert torch.equal(imgs[k], ms.render_fused(m, s, q, o, c, cam, bg)), k
+    # second run with warm workspaces, ring output of 2 slots
+    ring = torch.empty((2, 540, 960, 3), device=cuda_device)
+    pipe.render(m, s, q, o, c, cams, bg, out=ring)
+    torch.cuda.synchronize()
+    assert torch.equal(ring[0], imgs[6]) and torch.equal(ring[1], imgs[5])
