@@ -212,14 +212,16 @@ __global__ void tile_ranges_kernel(const int64_t M, const KeyT* __restrict__ key
 // workspace and info must be zeroed by the caller (stream-ordered memset)
 int bin_count_scan_launch(int64_t N, const int32_t* perm, const float* means2d, const void* radii,
                           int radii_is_float, const float* depths, const BinParams& p, uint32_t* offsets,
-                          bsplat_bin_info* info, void* workspace, cudaStream_t stream) {
+                          bsplat_bin_info* info, void* workspace, bool finalize_key_range, cudaStream_t stream) {
     const unsigned grid = (unsigned)ceil_div(N, kScanChunk);
     bin_count_scan_kernel<<<grid, kScanThreads, 0, stream>>>(N, perm, means2d, radii, radii_is_float, depths, p,
                                                              offsets, info,
                                                              static_cast<unsigned long long*>(workspace));
     BSPLAT_LAUNCH_CHECK();
-    bin_finalize_info_kernel<<<1, 1, 0, stream>>>(info);
-    BSPLAT_LAUNCH_CHECK();
+    if (finalize_key_range) {  // only the single-level path needs min/max depth keys
+        bin_finalize_info_kernel<<<1, 1, 0, stream>>>(info);
+        BSPLAT_LAUNCH_CHECK();
+    }
     return BSPLAT_OK;
 }
 
@@ -279,7 +281,7 @@ extern "C" int bsplat_bin_count_scan(int64_t N, const float* means2d, const void
     }
     const unsigned grid = (unsigned)ceil_div(N, kScanChunk);
     return bin_count_scan_launch(N, nullptr, means2d, radii, radii_is_float, depths, p, offsets, info, workspace,
-                                 stream);
+                                 true, stream);
 }
 
 extern "C" bsplat_key_layout bsplat_make_key_layout(const bsplat_bin_info* info_host, int32_t width,

@@ -182,14 +182,13 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
     int64_t hb = ceil_div(N, 256 * 8);
     depth_key_hist_kernel<<<(unsigned)(hb < 148 * 2 ? hb : 148 * 2), 256, 0, stream>>>(N, depths, w.dkeys, w.hist);
     BSPLAT_LAUNCH_CHECK();
-    int rc = radix_scan_launch(w.hist, 4, stream);
-    if (rc != BSPLAT_OK) return rc;
+    int rc = BSPLAT_OK;
     const int64_t tn = sort_tiles_u32(N);
     const uint32_t* ksrc = w.dkeys; uint32_t* kdst = w.dkeys_alt;
     const int32_t* vsrc = nullptr; int32_t* vdst = w.perm_alt;
     for (int pass = 0; pass < 4; ++pass) {
         rc = onesweep_pass_u32(N, nullptr, ksrc, pass == 3 ? nullptr : kdst, vsrc, vdst, 8 * pass, 8,
-                               w.hist + (size_t)pass * kRadix, w.tickets + pass,
+                               w.hist + (size_t)pass * kRadix, 0, w.tickets + pass,
                                w.status_n + (size_t)pass * tn * kRadix, stream);
         if (rc != BSPLAT_OK) return rc;
         // ping-pong: pass 0 writes (dkeys_alt, perm_alt), pass 1 (dkeys, perm), ...; pass 3 ends in perm
@@ -198,7 +197,7 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
     }
     // after 4 passes the sorted permutation is in w.perm (passes 1 and 3 write w.perm)
     return bin_count_scan_launch(N, w.perm, means2d, radii, radii_is_float, depths, p, w.offsets, w.info,
-                                 w.scan_ws, stream);
+                                 w.scan_ws, /*finalize_key_range=*/false, stream);
 }
 
 int bin2_finish(int64_t N, int64_t M, const float* means2d, const void* radii, int radii_is_float,
@@ -218,18 +217,17 @@ int bin2_finish(int64_t N, int64_t M, const float* means2d, const void* radii, i
     bin_emit2_kernel<<<(unsigned)ceil_div(N, kEmit2Threads), kEmit2Threads, 0, stream>>>(
         N, w.perm, means2d, radii, radii_is_float, p, w.offsets, lo_bits, w.tkeys, w.ids, w.hist + 4 * kRadix);
     BSPLAT_LAUNCH_CHECK();
-    int rc = radix_scan_launch(w.hist + 4 * kRadix, 2, stream);
-    if (rc != BSPLAT_OK) return rc;
+    int rc = BSPLAT_OK;
     const int64_t tm = sort_tiles_u32(M);
     if (hi_bits > 0) {
         rc = onesweep_pass_u32(M, nullptr, w.tkeys, w.tkeys_alt, w.ids, w.ids_alt, 0, lo_bits, w.hist + 4 * kRadix,
-                               w.tickets + 4, w.status_m, stream);
+                               0, w.tickets + 4, w.status_m, stream);
         if (rc != BSPLAT_OK) return rc;
         rc = onesweep_pass_u32(M, nullptr, w.tkeys_alt, w.tkeys, w.ids_alt, sorted_ids, lo_bits, hi_bits,
-                               w.hist + 5 * kRadix, w.tickets + 5, w.status_m + (size_t)tm * kRadix, stream);
+                               w.hist + 5 * kRadix, 0, w.tickets + 5, w.status_m + (size_t)tm * kRadix, stream);
     } else {
         rc = onesweep_pass_u32(M, nullptr, w.tkeys, w.tkeys_alt, w.ids, sorted_ids, 0, lo_bits, w.hist + 4 * kRadix,
-                               w.tickets + 4, w.status_m, stream);
+                               0, w.tickets + 4, w.status_m, stream);
     }
     if (rc != BSPLAT_OK) return rc;
     const uint32_t* sorted_tiles = hi_bits > 0 ? w.tkeys : w.tkeys_alt;

@@ -68,19 +68,22 @@ __global__ void __launch_bounds__(kRadix) radix_scan_kernel(uint32_t* __restrict
 // the tile's aggregate -> scatter key/payload into shared memory in tile-sorted order (registers are
 // free from here on) -> decoupled look-back, kLookback predecessors in flight per round trip ->
 // contiguous per-digit runs to global.
-template <typename KeyT, int ITEMS>
+template <typename KeyT, int ITEMS, int BITS>
 __global__ void __launch_bounds__(kSortThreads, 4)
 onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const KeyT* __restrict__ keys_in,
                 KeyT* __restrict__ keys_out, const int32_t* __restrict__ vals_in,
-                int32_t* __restrict__ vals_out, const int shift, const int bits,
-                const uint32_t* __restrict__ bins, uint32_t* __restrict__ ticket,
+                int32_t* __restrict__ vals_out, const int shift, const int bits_rt,
+                const uint32_t* __restrict__ hist, const int hist_is_scanned, uint32_t* __restrict__ ticket,
                 uint32_t* __restrict__ status) {
     constexpr int TILE = kSortThreads * ITEMS;
+    // BITS > 0: digit width known at compile time (branch-free ballot loop with constant masks)
+    const int bits = BITS > 0 ? BITS : bits_rt;
     __shared__ uint32_t s_whist[kSortWarps][kRadix];
     __shared__ KeyT s_keys[TILE];
     __shared__ int32_t s_vals[TILE];
     __shared__ uint32_t s_local_off[kRadix];
     __shared__ uint32_t s_gbase[kRadix];
+    __shared__ uint32_t s_bins[kRadix];
     __shared__ uint32_t s_warp_tot[kSortWarps];
     __shared__ uint32_t s_tile;
 
@@ -98,6 +101,28 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
     const uint32_t digit_mask = (1u << bits) - 1u;
     const int n_digits = 1 << bits;
     uint32_t* my_status = status + (size_t)tile * kRadix + tid;
+    // global digit offsets: either already exclusive-scanned, or a raw histogram scanned here
+    // (256-wide block scan; saves a kernel launch per sort)
+    {
+        const uint32_t h = hist[tid];
+        uint32_t incl = h;
+        if (!hist_is_scanned) {
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += t;
+            }
+            if (lane == 31) s_warp_tot[warp] = incl;
+        }
+        __syncthreads();
+        uint32_t excl = h;
+        if (!hist_is_scanned) {
+            excl = incl - h;
+            for (int w = 0; w < warp; ++w) excl += s_warp_tot[w];
+        }
+        s_bins[tid] = excl;
+        __syncthreads();  // s_warp_tot is reused below
+    }
 
     {
         // ---- load (warp-striped: memory order == (warp, item, lane) order) ----
@@ -131,7 +156,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
 #pragma unroll
             for (int b = 0; b < kRadixBits; ++b) {
                 if (b < bits) {
-                    const bool bit = (d >> b) & 1u;
+                    const bool bit = (d & (1u << b)) != 0u;
                     const uint32_t m = __ballot_sync(0xffffffffu, bit);
                     p &= bit ? m : ~m;
                 }
@@ -233,7 +258,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
             }
             st_relaxed_u32(my_status, kStatPrefix | (prev + count));
         }
-        s_gbase[tid] = bins[tid] + prev - s_local_off[tid];
+        s_gbase[tid] = s_bins[tid] + prev - s_local_off[tid];
     }
     __syncthreads();
 
@@ -257,12 +282,20 @@ int64_t sort_tiles_u64(int64_t M) { return ceil_div(M > 0 ? M : 1, kSortThreads 
 
 size_t sort_status_words(int64_t n_tiles, int passes) { return (size_t)passes * n_tiles * kRadix; }
 
+#define BSPLAT_ONESWEEP32(B)                                                                              \
+    onesweep_kernel<uint32_t, kSortItems32, B><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(               \
+        M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status)
+
 int onesweep_pass_u32(int64_t M, const uint64_t* m_dev, const uint32_t* keys_in, uint32_t* keys_out,
-                      const int32_t* vals_in, int32_t* vals_out, int shift, int bits, const uint32_t* bins,
-                      uint32_t* ticket, uint32_t* status, cudaStream_t stream) {
+                      const int32_t* vals_in, int32_t* vals_out, int shift, int bits, const uint32_t* hist,
+                      int hist_is_scanned, uint32_t* ticket, uint32_t* status, cudaStream_t stream) {
     const int64_t n_tiles = sort_tiles_u32(M);
-    onesweep_kernel<uint32_t, kSortItems32><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
-        M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, bins, ticket, status);
+    switch (bits) {
+        case 8: BSPLAT_ONESWEEP32(8); break;
+        case 7: BSPLAT_ONESWEEP32(7); break;
+        case 6: BSPLAT_ONESWEEP32(6); break;
+        default: BSPLAT_ONESWEEP32(0); break;
+    }
     BSPLAT_LAUNCH_CHECK();
     return BSPLAT_OK;
 }
@@ -332,8 +365,8 @@ extern "C" int bsplat_radix_sort_pairs(int64_t M, uint64_t* keys, uint64_t* keys
     for (int p = 0; p < passes; ++p) {
         const int shift = begin_bit + p * kRadixBits;
         const int bits = (end_bit - shift) < kRadixBits ? (end_bit - shift) : kRadixBits;
-        onesweep_kernel<uint64_t, kSortItems64><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
-            M, nullptr, ksrc, kdst, vsrc, vdst, shift, bits, w.hist + (size_t)p * kRadix, w.tickets + p,
+        onesweep_kernel<uint64_t, kSortItems64, 0><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
+            M, nullptr, ksrc, kdst, vsrc, vdst, shift, bits, w.hist + (size_t)p * kRadix, 1, w.tickets + p,
             w.status + (size_t)p * n_tiles * kRadix);
         BSPLAT_LAUNCH_CHECK();
         uint64_t* tk = ksrc; ksrc = kdst; kdst = tk;

@@ -22,13 +22,14 @@ int64_t sort_tiles_u64(int64_t M);
 size_t sort_status_words(int64_t n_tiles, int passes);
 
 // One pass over (uint32 key, int32 payload) pairs on key bits [shift, shift+bits).
-//   bins    256 exclusive-scanned digit counts of this pass
+//   hist    256 digit counts of this pass: exclusive-scanned (hist_is_scanned != 0) or raw (the kernel
+//           then scans them itself -- saves the separate scan launch)
 //   ticket  one zeroed uint32; status: zeroed [sort_tiles_u32(M)][256] uint32
 //   m_dev   optional device-side element count (grid still sized by M)
 //   vals_in == nullptr: payload = element index; keys_out == nullptr: keys are not written
 int onesweep_pass_u32(int64_t M, const uint64_t* m_dev, const uint32_t* keys_in, uint32_t* keys_out,
-                      const int32_t* vals_in, int32_t* vals_out, int shift, int bits, const uint32_t* bins,
-                      uint32_t* ticket, uint32_t* status, cudaStream_t stream);
+                      const int32_t* vals_in, int32_t* vals_out, int shift, int bits, const uint32_t* hist,
+                      int hist_is_scanned, uint32_t* ticket, uint32_t* status, cudaStream_t stream);
 // In-place exclusive scan of `passes` consecutive 256-bin histograms.
 int radix_scan_launch(uint32_t* hist, int passes, cudaStream_t stream);
 
