@@ -135,8 +135,9 @@ int bsplat_tile_ranges(int64_t M, const uint64_t* sorted_keys, int32_t tile_shif
  * stable sort by tile id only (ceil(log2 n_tiles) bits, 2 passes over the M pairs) -- the structure
  * of the reference's argsort(depth) + stable argsort(tile) (binning.py:223-231).
  * prepare: writes M to *info_out (device); the caller reads it back, sizes sorted_ids[M] and calls
- * finish with the same workspace (>= bsplat_bin2_workspace_bytes(N, M)). */
-size_t bsplat_bin2_workspace_bytes(int64_t N, int64_t M_capacity);
+ * finish with the same workspace (>= bsplat_bin2_workspace_bytes(N, M, n_tiles)). The last sort pass
+ * also yields the per-tile counts, so tile_ranges (and the rasterizer's tile_order) cost one tiny kernel. */
+size_t bsplat_bin2_workspace_bytes(int64_t N, int64_t M_capacity, int64_t n_tiles);
 int bsplat_bin2_prepare(int64_t N, const float* means2d, const void* radii, int32_t radii_is_float,
                         const float* depths, int32_t width, int32_t height, int32_t tile_size,
                         int32_t tile_row_begin, int32_t tile_row_end, int32_t semantics, void* workspace,
@@ -144,7 +145,9 @@ int bsplat_bin2_prepare(int64_t N, const float* means2d, const void* radii, int3
 int bsplat_bin2_finish(int64_t N, int64_t M, const float* means2d, const void* radii,
                        int32_t radii_is_float, int32_t width, int32_t height, int32_t tile_size,
                        int32_t tile_row_begin, int32_t tile_row_end, int32_t semantics, void* workspace,
-                       size_t workspace_bytes, int32_t* sorted_ids, int32_t* tile_ranges, void* stream);
+                       size_t workspace_bytes, int32_t* sorted_ids, int32_t* tile_ranges,
+                       int32_t* tile_order /* nullable: [tiles of the band], longest list first */,
+                       void* stream);
 
 /* ---- stage 3: rasterization ---------------------------------------------------------------- */
 /* tile_order[n_tiles]: tile ids sorted by list length, longest first (scheduling hint for the

@@ -142,13 +142,13 @@ def load() -> ctypes.CDLL:
                                              POINTER(c_size_t), POINTER(BsplatRenderAux), c_void_p]
         L.bsplat_microbench.argtypes = [c_int32, c_int32, c_int32, c_void_p, c_void_p]
         L.bsplat_bin2_workspace_bytes.restype = c_size_t
-        L.bsplat_bin2_workspace_bytes.argtypes = [c_int64, c_int64]
+        L.bsplat_bin2_workspace_bytes.argtypes = [c_int64, c_int64, c_int64]
         L.bsplat_bin2_prepare.argtypes = [c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                           c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p,
                                           c_void_p]
         L.bsplat_bin2_finish.argtypes = [c_int64, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p,
-                                         c_void_p, c_void_p]
+                                         c_void_p, c_void_p, c_void_p]
         _lib = L
     return _lib
 

@@ -129,23 +129,23 @@ def _bin_two_level(means2d, radii, depths, img_height, img_width, tile_size, sem
     info = torch.empty((32,), dtype=torch.uint8, device=dev)
     tile_ranges = torch.empty((th, tw, 2), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        ws = _lib.workspace.get(dev, "bin2", L.bsplat_bin2_workspace_bytes(N, 4 * N + 1024))
+        ws = _lib.workspace.get(dev, "bin2", L.bsplat_bin2_workspace_bytes(N, 4 * N + 1024, th * tw))
         _lib.check(L.bsplat_bin2_prepare(N, _lib.ptr(means2d), _lib.ptr(radii_c), radii_is_float, _lib.ptr(depths),
                                          W, H, ts, r0, r1, semantics, _lib.ptr(ws), ws.numel(), _lib.ptr(info),
                                          stream), "bsplat_bin2_prepare")
         M = int(read_bin_info(info).n_isect)
         if M >= (1 << 30):
             raise _lib.BsplatError(_lib.E_OVERFLOW, "bin_gaussians_to_tiles")
-        need = L.bsplat_bin2_workspace_bytes(N, M)
+        need = L.bsplat_bin2_workspace_bytes(N, M, th * tw)
         if ws.numel() < need:
             # grow, keeping the N-part (perm, offsets) that prepare just produced
             old = ws
             ws = torch.empty(int(need * 1.25), dtype=torch.uint8, device=dev)
-            n_part = L.bsplat_bin2_workspace_bytes(N, 0)
+            n_part = L.bsplat_bin2_workspace_bytes(N, 0, 0)
             ws[:n_part].copy_(old[:n_part])
             _lib.workspace._bufs[(dev.index if dev.index is not None else torch.cuda.current_device(), "bin2")] = ws
         sorted_ids = torch.empty((M,), dtype=torch.int32, device=dev)
         _lib.check(L.bsplat_bin2_finish(N, M, _lib.ptr(means2d), _lib.ptr(radii_c), radii_is_float, W, H, ts, r0, r1,
                                         semantics, _lib.ptr(ws), ws.numel(), _lib.ptr(sorted_ids),
-                                        _lib.ptr(tile_ranges), stream), "bsplat_bin2_finish")
+                                        _lib.ptr(tile_ranges), None, stream), "bsplat_bin2_finish")
     return sorted_ids, tile_ranges

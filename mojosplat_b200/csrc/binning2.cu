@@ -115,6 +115,80 @@ bin_emit2_kernel(const int64_t N, const int32_t* __restrict__ perm, const float*
     }
 }
 
+// ---- 5. per-tile counts -> tile ranges (+ heavy-first tile order), one CTA ---------------------
+// ranges[t] = [exclusive prefix of counts, + count) -- searchsorted-left semantics for empty tiles
+// (binning.py:252-260).  order (optional) lists the tiles [first, first + n_order) by list length,
+// longest first (counting sort on len/32, 256 buckets; order inside a bucket is arbitrary).
+constexpr int kFinishThreads = 1024;
+
+__global__ void __launch_bounds__(kFinishThreads)
+tile_finish_kernel(const int n_tiles, const int first, const int n_order, const uint32_t* __restrict__ counts,
+                   int32_t* __restrict__ ranges, int32_t* __restrict__ order) {
+    __shared__ uint32_t s_warp[kFinishThreads / 32];
+    __shared__ int s_cnt[256];
+    __shared__ int s_base[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 256) s_cnt[tid] = 0;
+    const int per = (n_tiles + kFinishThreads - 1) / kFinishThreads;  // consecutive tiles per thread
+    const int t0 = tid * per, t1 = min(t0 + per, n_tiles);
+    uint32_t sum = 0;
+    for (int t = t0; t < t1; ++t) sum += counts ? counts[t] : 0u;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += v;
+        }
+        s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + incl - sum;
+    for (int t = t0; t < t1; ++t) {
+        const uint32_t c = counts ? counts[t] : 0u;
+        ranges[2 * t] = (int32_t)run;
+        ranges[2 * t + 1] = (int32_t)(run + c);
+        run += c;
+        if (order && t >= first && t < first + n_order) atomicAdd(&s_cnt[255 - min(255u, (c + 31u) >> 5)], 1);
+    }
+    if (!order) return;
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 256 bucket sizes, 8 per lane
+        int local[8], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { local[k] = tot; tot += s_cnt[lane * 8 + k]; }
+        int wi = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += v;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_base[lane * 8 + k] = wi - tot + local[k];
+    }
+    __syncthreads();
+    for (int t = max(t0, first); t < min(t1, first + n_order); ++t) {
+        const uint32_t c = counts ? counts[t] : 0u;
+        order[atomicAdd(&s_base[255 - min(255u, (c + 31u) >> 5)], 1)] = t;
+    }
+}
+
+int tile_finish_launch(int n_tiles, int first, int n_order, const uint32_t* counts, int32_t* ranges,
+                       int32_t* order, cudaStream_t stream) {
+    tile_finish_kernel<<<1, kFinishThreads, 0, stream>>>(n_tiles, first, n_order, counts, ranges, order);
+    BSPLAT_LAUNCH_CHECK();
+    return BSPLAT_OK;
+}
+
 // ---- workspace ------------------------------------------------------------------------------
 constexpr size_t kBinAlign = 256;
 static inline size_t bin_align(size_t v) { return (v + kBinAlign - 1) / kBinAlign * kBinAlign; }
@@ -131,11 +205,12 @@ struct Bin2Ws {
     // M part
     uint32_t* tkeys; uint32_t* tkeys_alt; int32_t* ids; int32_t* ids_alt;
     uint32_t* status_m;  // [2][tilesM][256]
+    uint32_t* tile_counts;  // [n_tiles], directly behind status_m (zeroed together)
     size_t status_m_off, status_m_bytes;
     size_t total;
 };
 
-static Bin2Ws carve_bin2(void* base, int64_t N, int64_t M) {
+static Bin2Ws carve_bin2(void* base, int64_t N, int64_t M, int64_t n_tiles) {
     Bin2Ws w;
     char* p = static_cast<char*>(base);
     size_t off = 0;
@@ -157,7 +232,9 @@ static Bin2Ws carve_bin2(void* base, int64_t N, int64_t M) {
     w.ids = (int32_t*)take(m * 4); w.ids_alt = (int32_t*)take(m * 4);
     w.status_m_off = off;
     w.status_m_bytes = sort_status_words(sort_tiles_u32(M), 2) * 4;
-    w.status_m = (uint32_t*)take(w.status_m_bytes);
+    // status_m and tile_counts must be contiguous (single memset): take them as one block
+    w.status_m = (uint32_t*)take(w.status_m_bytes + (size_t)(n_tiles > 0 ? n_tiles : 1) * sizeof(uint32_t));
+    w.tile_counts = w.status_m ? w.status_m + w.status_m_bytes / sizeof(uint32_t) : nullptr;
     w.total = off;
     return w;
 }
@@ -171,7 +248,7 @@ static int tile_bits_of(const BinParams& p) {
 
 int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_is_float, const float* depths,
                  const BinParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    Bin2Ws w = carve_bin2(workspace, N, 0);
+    Bin2Ws w = carve_bin2(workspace, N, 0, 0);
     if (!workspace || workspace_bytes < w.n_bytes) return BSPLAT_E_WORKSPACE;
     char* base = static_cast<char*>(workspace);
     BSPLAT_CUDA_TRY(cudaMemsetAsync(base + w.zero_begin, 0, w.zero_end_n - w.zero_begin, stream));
@@ -189,7 +266,7 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
     for (int pass = 0; pass < 4; ++pass) {
         rc = onesweep_pass_u32(N, nullptr, ksrc, pass == 3 ? nullptr : kdst, vsrc, vdst, 8 * pass, 8,
                                w.hist + (size_t)pass * kRadix, 0, w.tickets + pass,
-                               w.status_n + (size_t)pass * tn * kRadix, stream);
+                               w.status_n + (size_t)pass * tn * kRadix, nullptr, stream);
         if (rc != BSPLAT_OK) return rc;
         // ping-pong: pass 0 writes (dkeys_alt, perm_alt), pass 1 (dkeys, perm), ...; pass 3 ends in perm
         ksrc = kdst; kdst = (kdst == w.dkeys_alt) ? w.dkeys : w.dkeys_alt;
@@ -202,15 +279,19 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
 
 int bin2_finish(int64_t N, int64_t M, const float* means2d, const void* radii, int radii_is_float,
                 const BinParams& p, void* workspace, size_t workspace_bytes, int32_t* sorted_ids,
-                int32_t* tile_ranges, cudaStream_t stream) {
+                int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream) {
     const int n_tiles = p.tiles_w * p.tiles_h;
-    Bin2Ws w = carve_bin2(workspace, N, M);
+    Bin2Ws w = carve_bin2(workspace, N, M, n_tiles);
     if (!workspace || workspace_bytes < w.total) return BSPLAT_E_WORKSPACE;
     if (M == 0) {
         BSPLAT_CUDA_TRY(cudaMemsetAsync(tile_ranges, 0, (size_t)n_tiles * 2 * sizeof(int32_t), stream));
+        if (tile_order)
+            return tile_finish_launch(n_tiles, p.row_begin * p.tiles_w, (p.row_end - p.row_begin) * p.tiles_w,
+                                      nullptr, tile_ranges, tile_order, stream);
         return BSPLAT_OK;
     }
-    BSPLAT_CUDA_TRY(cudaMemsetAsync(w.status_m, 0, w.status_m_bytes, stream));
+    // status words of the two passes and the per-tile counters are contiguous: one memset
+    BSPLAT_CUDA_TRY(cudaMemsetAsync(w.status_m, 0, w.status_m_bytes + (size_t)n_tiles * sizeof(uint32_t), stream));
     const int tb = tile_bits_of(p);
     const int lo_bits = tb > 8 ? (tb + 1) / 2 : tb;  // split the tile id evenly over <= 2 passes
     const int hi_bits = tb - lo_bits;
@@ -221,29 +302,31 @@ int bin2_finish(int64_t N, int64_t M, const float* means2d, const void* radii, i
     const int64_t tm = sort_tiles_u32(M);
     if (hi_bits > 0) {
         rc = onesweep_pass_u32(M, nullptr, w.tkeys, w.tkeys_alt, w.ids, w.ids_alt, 0, lo_bits, w.hist + 4 * kRadix,
-                               0, w.tickets + 4, w.status_m, stream);
+                               0, w.tickets + 4, w.status_m, nullptr, stream);
         if (rc != BSPLAT_OK) return rc;
-        rc = onesweep_pass_u32(M, nullptr, w.tkeys_alt, w.tkeys, w.ids_alt, sorted_ids, lo_bits, hi_bits,
-                               w.hist + 5 * kRadix, 0, w.tickets + 5, w.status_m + (size_t)tm * kRadix, stream);
+        // last pass: sorted tile ids are not written; per-tile counts come out of the pass instead
+        rc = onesweep_pass_u32(M, nullptr, w.tkeys_alt, nullptr, w.ids_alt, sorted_ids, lo_bits, hi_bits,
+                               w.hist + 5 * kRadix, 0, w.tickets + 5, w.status_m + (size_t)tm * kRadix,
+                               w.tile_counts, stream);
     } else {
-        rc = onesweep_pass_u32(M, nullptr, w.tkeys, w.tkeys_alt, w.ids, sorted_ids, 0, lo_bits, w.hist + 4 * kRadix,
-                               0, w.tickets + 4, w.status_m, stream);
+        rc = onesweep_pass_u32(M, nullptr, w.tkeys, nullptr, w.ids, sorted_ids, 0, lo_bits, w.hist + 4 * kRadix,
+                               0, w.tickets + 4, w.status_m, w.tile_counts, stream);
     }
     if (rc != BSPLAT_OK) return rc;
-    const uint32_t* sorted_tiles = hi_bits > 0 ? w.tkeys : w.tkeys_alt;
-    return tile_ranges_u32_launch(M, sorted_tiles, n_tiles, tile_ranges, stream);
+    return tile_finish_launch(n_tiles, p.row_begin * p.tiles_w, (p.row_end - p.row_begin) * p.tiles_w,
+                              w.tile_counts, tile_ranges, tile_order, stream);
 }
 
-size_t bin2_workspace_bytes(int64_t N, int64_t M) { return carve_bin2(nullptr, N, M).total; }
-bsplat_bin_info* bin2_info_ptr(void* workspace, int64_t N) { return carve_bin2(workspace, N, 0).info; }
+size_t bin2_workspace_bytes(int64_t N, int64_t M, int64_t n_tiles) { return carve_bin2(nullptr, N, M, n_tiles).total; }
+bsplat_bin_info* bin2_info_ptr(void* workspace, int64_t N) { return carve_bin2(workspace, N, 0, 0).info; }
 
 }  // namespace bsplat
 
 using namespace bsplat;
 
-extern "C" size_t bsplat_bin2_workspace_bytes(int64_t N, int64_t M_capacity) {
-    if (N < 0 || M_capacity < 0) return 0;
-    return bin2_workspace_bytes(N, M_capacity);
+extern "C" size_t bsplat_bin2_workspace_bytes(int64_t N, int64_t M_capacity, int64_t n_tiles) {
+    if (N < 0 || M_capacity < 0 || n_tiles < 0) return 0;
+    return bin2_workspace_bytes(N, M_capacity, n_tiles);
 }
 
 // Phase 1: depth-sort the Gaussians, tile rects + prefix sum in depth order. Afterwards *info_out
@@ -273,7 +356,7 @@ extern "C" int bsplat_bin2_finish(int64_t N, int64_t M, const float* means2d, co
                                   int32_t radii_is_float, int32_t width, int32_t height, int32_t tile_size,
                                   int32_t tile_row_begin, int32_t tile_row_end, int32_t semantics,
                                   void* workspace, size_t workspace_bytes, int32_t* sorted_ids,
-                                  int32_t* tile_ranges, void* stream_) {
+                                  int32_t* tile_ranges, int32_t* tile_order, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     BinParams p;
     int rc = make_bin_params(width, height, tile_size, tile_row_begin, tile_row_end, semantics, &p);
@@ -282,5 +365,5 @@ extern "C" int bsplat_bin2_finish(int64_t N, int64_t M, const float* means2d, co
     if (M >= (int64_t)kStatMask) return BSPLAT_E_OVERFLOW;
     if (M > 0 && (!means2d || !radii || !sorted_ids)) return BSPLAT_E_ARG;
     return bin2_finish(N, M, means2d, radii, radii_is_float, p, workspace, workspace_bytes, sorted_ids,
-                       tile_ranges, stream);
+                       tile_ranges, tile_order, stream);
 }

@@ -82,7 +82,7 @@ extern "C" int bsplat_rasterize_stats(int64_t N, int32_t channels, const float* 
 // fused render
 // ------------------------------------------------------------------------------------------
 namespace bsplat {
-size_t bin2_workspace_bytes(int64_t N, int64_t M);
+size_t bin2_workspace_bytes(int64_t N, int64_t M, int64_t n_tiles);
 bsplat_bin_info* bin2_info_ptr(void* workspace, int64_t N);
 }  // namespace bsplat
 
@@ -140,7 +140,7 @@ RenderWs carve_render(void* base, int64_t N, int64_t M, int W, int H, int tile_s
     w.tile_ranges = (int32_t*)take((size_t)tiles_w * tiles_h * 2 * sizeof(int32_t));
     w.tile_order = (int32_t*)take((size_t)tiles_w * tiles_h * sizeof(int32_t));
     // the N-dependent part of the binning scratch comes first so that it survives the re-carve with M
-    w.bin_bytes = single_level ? carve_bin1(nullptr, N, M).total : bin2_workspace_bytes(N, M);
+    w.bin_bytes = single_level ? carve_bin1(nullptr, N, M).total : bin2_workspace_bytes(N, M, (int64_t)tiles_w * tiles_h);
     w.bin_ws = take(w.bin_bytes);
     w.sorted_ids = (int32_t*)take(m * sizeof(int32_t));
     w.total = off;
@@ -219,7 +219,7 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     BSPLAT_CUDA_TRY(cudaMemcpyAsync(&info, d_info, sizeof(info), cudaMemcpyDeviceToHost, stream));
     BSPLAT_CUDA_TRY(cudaStreamSynchronize(stream));  // the single read-back of the frame (M, key range)
     const int64_t M = (int64_t)info.n_isect;
-    if (aux) { aux->n_isect = M; aux->n_launches = single_level ? 3 : 9; }
+    if (aux) { aux->n_isect = M; aux->n_launches = single_level ? 3 : 7; }
     if (M >= (1ll << 30)) { drop_events(); return BSPLAT_E_OVERFLOW; }
     if (M == 0) {
         // render.py:73-76: no overlaps => black image (not the background)
@@ -235,6 +235,7 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
         return BSPLAT_E_WORKSPACE;
     }
     const int32_t* sorted_ids = nullptr;
+    bool have_order = false;
     if (single_level) {
         b1 = carve_bin1(w.bin_ws, N, M);
         const bsplat_key_layout layout = bsplat_make_key_layout(&info, W, H, tile_size);
@@ -258,20 +259,21 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     } else {
         if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[2], stream));
         rc = bsplat_bin2_finish(N, M, d_means2d, d_radii, 0, W, H, tile_size, 0, tiles_h, semantics, w.bin_ws,
-                                w.bin_bytes, w.sorted_ids, d_ranges, stream);
+                                w.bin_bytes, w.sorted_ids, d_ranges, w.tile_order, stream);
         if (rc != BSPLAT_OK) { drop_events(); return rc; }
         sorted_ids = w.sorted_ids;
+        have_order = true;
         if (aux) {
             int tb = 1;
             while ((1 << tb) < tiles_w * tiles_h) ++tb;
             aux->key_bits = 32 + tb;
             aux->sort_passes = 4 + (tb > 8 ? 2 : 1);  // 4 over N items, the rest over M items
-            // project, depth hist, scan, 4 passes, count_scan, finalize | emit, scan, passes, ranges, raster
-            aux->n_launches = 9 + 1 + 1 + (tb > 8 ? 2 : 1) + 1 + 1;
+            // project, depth hist, 4 passes, count_scan | emit, 1-2 passes, tile_finish, raster
+            aux->n_launches = 7 + 1 + (tb > 8 ? 2 : 1) + 1 + 1;
         }
     }
     const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
-    if (fast_raster) {
+    if (fast_raster && !have_order) {
         rc = tile_order_launch(0, tiles_w * tiles_h, d_ranges, w.tile_order, stream);
         if (rc != BSPLAT_OK) { drop_events(); return rc; }
         if (aux) aux->n_launches += 1;
@@ -342,13 +344,9 @@ extern "C" int bsplat_render_end(int64_t N, int64_t M, const float* colors, cons
         return BSPLAT_E_WORKSPACE;
     }
     int rc = bsplat_bin2_finish(N, M, w.means2d, w.radii, 0, W, H, tile_size, 0, tiles_h, semantics, w.bin_ws,
-                                w.bin_bytes, w.sorted_ids, w.tile_ranges, stream);
+                                w.bin_bytes, w.sorted_ids, w.tile_ranges, w.tile_order, stream);
     if (rc != BSPLAT_OK) return rc;
     const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
-    if (fast_raster) {
-        rc = tile_order_launch(0, tiles_w * tiles_h, w.tile_ranges, w.tile_order, stream);
-        if (rc != BSPLAT_OK) return rc;
-    }
     return rasterize_launch(N, channels, w.means2d, w.conics, colors, opacities, background, w.tile_ranges,
                             fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, 0, tiles_h,
                             raster_mode, image, nullptr, stream);

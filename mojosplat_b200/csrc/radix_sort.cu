@@ -74,7 +74,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
                 KeyT* __restrict__ keys_out, const int32_t* __restrict__ vals_in,
                 int32_t* __restrict__ vals_out, const int shift, const int bits_rt,
                 const uint32_t* __restrict__ hist, const int hist_is_scanned, uint32_t* __restrict__ ticket,
-                uint32_t* __restrict__ status) {
+                uint32_t* __restrict__ status, uint32_t* __restrict__ key_counts) {
     constexpr int TILE = kSortThreads * ITEMS;
     // BITS > 0: digit width known at compile time (branch-free ballot loop with constant masks)
     const int bits = BITS > 0 ? BITS : bits_rt;
@@ -272,6 +272,17 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
             const uint32_t dst = s_gbase[d] + (uint32_t)j;
             if (keys_out) keys_out[dst] = kk;
             vals_out[dst] = s_vals[j];
+            if (key_counts) {
+                // Final pass of the tile sort: the CTA's elements are now fully sorted by key (globally
+                // sorted by the low digit on input, stably re-sorted by the high digit here), so equal keys
+                // form runs.  Run start j adds -j, run end j adds j+1: two atomics per run give
+                // key_counts[key] += run length (uint32 wrap-around arithmetic).
+                const bool first = (j == 0) || (s_keys[j - 1] != kk);
+                const bool last = (j == n_valid - 1) || (s_keys[j + 1] != kk);
+                if (first && last) atomicAdd(key_counts + kk, 1u);
+                else if (first) atomicAdd(key_counts + kk, (uint32_t)(0 - j));
+                else if (last) atomicAdd(key_counts + kk, (uint32_t)(j + 1));
+            }
         }
     }
 }
@@ -284,11 +295,13 @@ size_t sort_status_words(int64_t n_tiles, int passes) { return (size_t)passes * 
 
 #define BSPLAT_ONESWEEP32(B)                                                                              \
     onesweep_kernel<uint32_t, kSortItems32, B><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(               \
-        M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status)
+        M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,    \
+        key_counts)
 
 int onesweep_pass_u32(int64_t M, const uint64_t* m_dev, const uint32_t* keys_in, uint32_t* keys_out,
                       const int32_t* vals_in, int32_t* vals_out, int shift, int bits, const uint32_t* hist,
-                      int hist_is_scanned, uint32_t* ticket, uint32_t* status, cudaStream_t stream) {
+                      int hist_is_scanned, uint32_t* ticket, uint32_t* status, uint32_t* key_counts,
+                      cudaStream_t stream) {
     const int64_t n_tiles = sort_tiles_u32(M);
     switch (bits) {
         case 8: BSPLAT_ONESWEEP32(8); break;
@@ -367,7 +380,7 @@ extern "C" int bsplat_radix_sort_pairs(int64_t M, uint64_t* keys, uint64_t* keys
         const int bits = (end_bit - shift) < kRadixBits ? (end_bit - shift) : kRadixBits;
         onesweep_kernel<uint64_t, kSortItems64, 0><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
             M, nullptr, ksrc, kdst, vsrc, vdst, shift, bits, w.hist + (size_t)p * kRadix, 1, w.tickets + p,
-            w.status + (size_t)p * n_tiles * kRadix);
+            w.status + (size_t)p * n_tiles * kRadix, nullptr);
         BSPLAT_LAUNCH_CHECK();
         uint64_t* tk = ksrc; ksrc = kdst; kdst = tk;
         int32_t* tv = vsrc; vsrc = vdst; vdst = tv;
