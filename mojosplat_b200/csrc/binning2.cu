@@ -50,64 +50,121 @@ depth_key_hist_kernel(const int64_t N, const float* __restrict__ depths, uint32_
 }
 
 // ---- 3. emission in depth order ------------------------------------------------------------
+// CTA = 256 consecutive Gaussians of the depth-sorted order.  Small rectangles (<= kEmitSmall tiles,
+// the common case: ~4 tiles per Gaussian in garden-sized scenes) are written by their own thread
+// with a running (row, column) counter -- no search, no division; large rectangles are queued in shared
+// memory and written by whole warps with coalesced stores.  The digit histograms of the two tile-sort
+// passes are accumulated on the fly (shared-memory atomics, run-length aggregated for the high digit).
 constexpr int kEmit2Threads = 256;
+constexpr int kEmitSmall = 16;
+constexpr int kEmitStage = 2048;  // pairs staged in shared memory per CTA (coalesced copy-out)
 
 __global__ void __launch_bounds__(kEmit2Threads)
 bin_emit2_kernel(const int64_t N, const int32_t* __restrict__ perm, const float* __restrict__ means2d,
                  const void* __restrict__ radii, const int radii_is_float, const BinParams p,
                  const uint32_t* __restrict__ offsets, const int lo_bits, uint32_t* __restrict__ tile_keys,
                  int32_t* __restrict__ ids, uint32_t* __restrict__ hist /* [2][256] */) {
-    __shared__ uint32_t s_off[kEmit2Threads + 1];
-    __shared__ uint32_t s_xy[kEmit2Threads];  // x0 | y0 << 16
-    __shared__ uint32_t s_w[kEmit2Threads];   // rect width in tiles
-    __shared__ int32_t s_id[kEmit2Threads];
     __shared__ uint32_t s_hist[2][kRadix];
+    __shared__ int s_queue[kEmit2Threads];
+    __shared__ int s_nqueue;
+    __shared__ uint32_t s_off[kEmit2Threads];
+    __shared__ uint32_t s_xy[kEmit2Threads];   // x0 | y0 << 16
+    __shared__ uint32_t s_wh[kEmit2Threads];   // w | h << 16
+    __shared__ int32_t s_id[kEmit2Threads];
+    __shared__ uint32_t s_keys[kEmitStage];
+    __shared__ int32_t s_ids[kEmitStage];
 
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
-    const int64_t base = (int64_t)blockIdx.x * kEmit2Threads;
-    const int n_here = (int)min((int64_t)kEmit2Threads, N - base);
+    const int warp = tid >> 5;
     for (int i = tid; i < 2 * kRadix; i += kEmit2Threads) (&s_hist[0][0])[i] = 0;
+    const uint32_t lo_mask = (1u << lo_bits) - 1u;
+    const uint32_t tw = (uint32_t)p.tiles_w;
+    // persistent CTAs: each walks several 256-Gaussian chunks and flushes its histograms ONCE -- the
+    // flush is ~190 same-address global atomics per CTA, which dominated the kernel with one CTA per chunk
+    const int64_t n_chunks = ceil_div(N, kEmit2Threads);
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int64_t base = chunk * kEmit2Threads;
+    const int n_here = (int)min((int64_t)kEmit2Threads, N - base);
+    __syncthreads();  // previous chunk's staging buffers and queue are fully consumed
+    if (tid == 0) s_nqueue = 0;
+    __syncthreads();
+    // the CTA's pairs are one contiguous output range; when it fits, build it in shared memory and copy it
+    // out with coalesced stores (per-thread runs of ~4 pairs would otherwise cost ~4 partial-sector writes each)
+    const uint32_t cta_begin = __ldg(offsets + base), cta_end = __ldg(offsets + base + n_here);
+    const bool staged = (cta_end - cta_begin) <= (uint32_t)kEmitStage;
+    uint32_t* const okeys = staged ? s_keys : tile_keys + cta_begin;
+    int32_t* const oids = staged ? s_ids : ids + cta_begin;
+
     if (tid < n_here) {
         const int32_t g = __ldg(perm + base + tid);
         float mx, my, rx, ry;
         load_mean_radii(means2d, radii, radii_is_float, g, mx, my, rx, ry);
         const TileRect r = tile_rect(mx, my, rx, ry, p.W, p.H, p.tile_size_f, p.tiles_w, p.tiles_h,
                                      p.semantics, p.row_begin, p.row_end);
-        s_xy[tid] = (uint32_t)r.x0 | ((uint32_t)r.y0 << 16);
-        s_w[tid] = (uint32_t)(r.x1 - r.x0);
-        s_id[tid] = g;
-        s_off[tid] = __ldg(offsets + base + tid);
+        const uint32_t w = (uint32_t)(r.x1 - r.x0), h = (uint32_t)(r.y1 - r.y0);
+        const uint32_t off = __ldg(offsets + base + tid);
+        const uint32_t count = w * h;
+        if (count > (uint32_t)kEmitSmall) {
+            const int q = atomicAdd(&s_nqueue, 1);
+            s_queue[q] = tid;
+            s_off[tid] = off; s_xy[tid] = (uint32_t)r.x0 | ((uint32_t)r.y0 << 16);
+            s_wh[tid] = w | (h << 16); s_id[tid] = g;
+        } else if (count > 0) {
+            uint32_t pos = off - cta_begin;
+            uint32_t run_top = 0xffffffffu, run_len = 0;
+            for (uint32_t dy = 0; dy < h; ++dy) {
+                uint32_t tile = ((uint32_t)r.y0 + dy) * tw + (uint32_t)r.x0;
+                for (uint32_t dx = 0; dx < w; ++dx, ++tile, ++pos) {
+                    okeys[pos] = tile;
+                    oids[pos] = g;
+                    atomicAdd(&s_hist[0][tile & lo_mask], 1u);
+                    const uint32_t top = tile >> lo_bits;
+                    if (top != run_top) {
+                        if (run_len) atomicAdd(&s_hist[1][run_top], run_len);
+                        run_top = top; run_len = 0;
+                    }
+                    ++run_len;
+                }
+            }
+            if (run_len) atomicAdd(&s_hist[1][run_top], run_len);
+        }
     }
-    if (tid == 0) s_off[n_here] = __ldg(offsets + base + n_here);
     __syncthreads();
 
-    const uint32_t begin = s_off[0], end = s_off[n_here];
-    const uint32_t lo_mask = (1u << lo_bits) - 1u;
-    for (uint32_t wpos = begin + (uint32_t)(tid - (int)lane); wpos < end; wpos += kEmit2Threads) {
-        const uint32_t pos = wpos + lane;
-        const bool valid = pos < end;
-        uint32_t tile = 0;
-        if (valid) {
-            int lo = 0, hi = n_here;  // invariant: s_off[lo] <= pos < s_off[hi]
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s_off[mid] <= pos) lo = mid; else hi = mid;
+    // large rectangles: one warp per queued Gaussian, lanes stride over its tiles (coalesced stores)
+    const int nq = s_nqueue;
+    for (int q = warp; q < nq; q += kEmit2Threads / 32) {
+        const int j = s_queue[q];
+        const uint32_t off = s_off[j], xy = s_xy[j], wh = s_wh[j];
+        const uint32_t w = wh & 0xffffu, count = w * (wh >> 16);
+        const int32_t g = s_id[j];
+        for (uint32_t k0 = 0; k0 < count; k0 += 32) {  // warp-uniform trip count
+            const uint32_t k = k0 + lane;
+            const bool valid = k < count;
+            uint32_t tile = 0;
+            if (valid) {
+                const uint32_t dy = k / w, dx = k - dy * w;
+                tile = ((xy >> 16) + dy) * tw + (xy & 0xffffu) + dx;
+                okeys[off - cta_begin + k] = tile;
+                oids[off - cta_begin + k] = g;
+                atomicAdd(&s_hist[0][tile & lo_mask], 1u);
             }
-            const uint32_t k = pos - s_off[lo];
-            const uint32_t w = s_w[lo];
-            const uint32_t dy = k / w, dx = k - dy * w;
-            const uint32_t xy = s_xy[lo];
-            tile = ((xy >> 16) + dy) * (uint32_t)p.tiles_w + (xy & 0xffffu) + dx;
-            tile_keys[pos] = tile;
-            ids[pos] = s_id[lo];
-            atomicAdd(&s_hist[0][tile & lo_mask], 1u);  // neighbouring lanes hold neighbouring tiles
+            // high digit: the lanes of a row share it -> aggregate (few distinct values: match.any is cheap)
+            const uint32_t top = valid ? (tile >> lo_bits) : 0x100u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, top);
+            if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[1][top], (uint32_t)__popc(peers));
         }
-        // high digit: lanes of one Gaussian's row share it -> aggregate
-        const uint32_t top = valid ? (tile >> lo_bits) : 0x100u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, top);
-        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[1][top], (uint32_t)__popc(peers));
     }
+    __syncthreads();
+    if (staged) {
+        const uint32_t total = cta_end - cta_begin;
+        for (uint32_t i = tid; i < total; i += kEmit2Threads) {
+            tile_keys[cta_begin + i] = s_keys[i];
+            ids[cta_begin + i] = s_ids[i];
+        }
+    }
+    }  // chunk loop
     __syncthreads();
     for (int i = tid; i < 2 * kRadix; i += kEmit2Threads) {
         const uint32_t v = (&s_hist[0][0])[i];
@@ -295,7 +352,8 @@ int bin2_finish(int64_t N, int64_t M, const float* means2d, const void* radii, i
     const int tb = tile_bits_of(p);
     const int lo_bits = tb > 8 ? (tb + 1) / 2 : tb;  // split the tile id evenly over <= 2 passes
     const int hi_bits = tb - lo_bits;
-    bin_emit2_kernel<<<(unsigned)ceil_div(N, kEmit2Threads), kEmit2Threads, 0, stream>>>(
+    const int64_t emit_chunks = ceil_div(N, kEmit2Threads);
+    bin_emit2_kernel<<<(unsigned)(emit_chunks < 148 * 6 ? emit_chunks : 148 * 6), kEmit2Threads, 0, stream>>>(
         N, w.perm, means2d, radii, radii_is_float, p, w.offsets, lo_bits, w.tkeys, w.ids, w.hist + 4 * kRadix);
     BSPLAT_LAUNCH_CHECK();
     int rc = BSPLAT_OK;

@@ -77,12 +77,19 @@ class FramePipeline:
     # -- driver -----------------------------------------------------------------------------
     @torch.no_grad()
     def render(self, means3d, scales, quats, opacities, features, cameras: Sequence[Camera], background,
-               out: torch.Tensor | None = None) -> torch.Tensor:
+               out: torch.Tensor | None = None, scene_of=None) -> torch.Tensor:
         """Render all cameras; returns images [n, H, W, C] (valid on the current stream on return).
-        If ``out`` has fewer than n slots it is used as a ring (frame k -> out[k % len(out)])."""
-        g = [_lib.as_f32(means3d, "means3d"), _lib.as_f32(scales, "scales"), _lib.as_f32(quats, "quats"),
-             _lib.as_f32(opacities, "opacities").reshape(-1), _lib.as_f32(features, "features")]
-        assert g[0].shape[0] == self.N and g[4].shape == (self.N, self.C)
+        If ``out`` has fewer than n slots it is used as a ring (frame k -> out[k % len(out)]).
+        ``scene_of`` (optional): callable k -> (means3d, scales, quats, opacities, features) giving frame k
+        its own Gaussian set of the same N (dynamic scenes; bench.py rotates copies so that the inputs
+        touched between two uses of one copy exceed the L2)."""
+        def prep(t):
+            q = [_lib.as_f32(t[0], "means3d"), _lib.as_f32(t[1], "scales"), _lib.as_f32(t[2], "quats"),
+                 _lib.as_f32(t[3], "opacities").reshape(-1), _lib.as_f32(t[4], "features")]
+            assert q[0].shape[0] == self.N and q[4].shape == (self.N, self.C)
+            return q
+        g0 = prep((means3d, scales, quats, opacities, features))
+        gs = [g0] * len(cameras) if scene_of is None else [prep(scene_of(k)) for k in range(len(cameras))]
         bg = _lib.as_f32(background, "background").to(self.dev)
         n = len(cameras)
         if out is None:
@@ -93,14 +100,14 @@ class FramePipeline:
             for s in self.streams:
                 s.wait_stream(cur)  # inputs were produced on the caller's stream
             if n > 0:
-                self._begin(0, g, cams[0])
+                self._begin(0, gs[0], cams[0])
             for k in range(n):
                 slot = k % self.depth
-                self._end(slot, g, cams[k], bg, out[k % out.shape[0]])
+                self._end(slot, gs[k], cams[k], bg, out[k % out.shape[0]])
                 # enqueue the next frame's first half right behind: it overlaps end(k) on the GPU.
                 # With depth 2 the slot of frame k+1 finished end(k-1) long ago in stream order.
                 if k + 1 < n:
-                    self._begin((k + 1) % self.depth, g, cams[k + 1])
+                    self._begin((k + 1) % self.depth, gs[k + 1], cams[k + 1])
             for s in self.streams:
                 cur.wait_stream(s)
         return out
