@@ -47,7 +47,11 @@ def parse_args():
     ap.add_argument("--n-gaussians", type=int, default=None, help="override N (debug only; marks the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--semantics", default="torch", choices=["torch", "gsplat"])
-    ap.add_argument("--pipeline-depth", type=int, default=2, help="frames in flight per GPU")
+    ap.add_argument("--pipeline-depth", type=int, default=2, help="frames in flight per GPU (sync pipeline)")
+    ap.add_argument("--pipeline", default="overlapped", choices=["overlapped", "sync"],
+                    help="overlapped: sync-free frames, binning(k+1) inside rasterization(k); sync: FramePipeline")
+    ap.add_argument("--slots", type=int, default=3, help="workspaces cycled by the overlapped pipeline")
+    ap.add_argument("--bin-streams", type=int, default=2, help="high-priority binning streams (overlapped pipeline)")
     return ap.parse_args()
 
 
@@ -216,8 +220,11 @@ def run_b200(args, rank, world, local_rank):
     def frame(k, **kw):
         return ms.render_fused(*g, view_of(k), bg, 16, semantics=sem, **kw)
 
-    from mojosplat_b200.pipeline import FramePipeline
-    pipe = FramePipeline(dev, N, W, H, semantics=sem, depth=args.pipeline_depth)
+    from mojosplat_b200.pipeline import FramePipeline, OverlappedPipeline
+    if args.pipeline == "overlapped":
+        pipe = OverlappedPipeline(dev, N, W, H, semantics=sem, slots=args.slots, bin_streams=args.bin_streams)
+    else:
+        pipe = FramePipeline(dev, N, W, H, semantics=sem, depth=args.pipeline_depth)
     ring = torch.empty((4, H, W, 3), dtype=torch.float32, device=dev)
 
     # clocks are sampled from the first warm-up frame to the end of the e2e loop (the GPU is under this
@@ -246,6 +253,8 @@ def run_b200(args, rank, world, local_rank):
     e_end.record()
     torch.cuda.synchronize(dev)
     wall = time.perf_counter() - wall0
+    if args.pipeline == "overlapped":
+        assert pipe.check() == 0, "a timed frame overflowed its pair capacity"
     if world > 1:
         dist.barrier()
     total_ms = float(e_beg.elapsed_time(e_end))
@@ -374,7 +383,10 @@ def run_b200(args, rank, world, local_rank):
                          f"({RING} x 56 MB = {RING * 56} MB > 126 MB L2) and stream ~230 MB of intermediates each; "
                          "single_frame_latency_ms and the per-stage times use a 512 MiB flush between frames",
                    "parallelism": f"views split across {world} rank(s); Gaussians NCCL-broadcast once at load; "
-                                  f"{args.pipeline_depth} frames in flight per GPU (begin(k+1) overlaps end(k), FramePipeline)",
+                                  + ("sync-free frames (device-side M); projection+binning on a high-priority stream, "
+                                     f"rasterizer on a second stream, {args.slots} workspaces / {args.bin_streams} binning streams: binning(k+1) runs inside "
+                                     "rasterization(k) (OverlappedPipeline)" if args.pipeline == "overlapped" else
+                                     f"{args.pipeline_depth} frames in flight per GPU (begin(k+1) overlaps end(k), FramePipeline)"),
                    "timing": "one CUDA-event pair around the K steps, max over ranks",
                    "wall_ms_per_step": 1e3 * wall / K, "single_frame_latency_ms": latency_ms},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

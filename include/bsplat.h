@@ -25,6 +25,7 @@
  *                              kernels/rasterization.mojo:169-240, call at rasterization.py:167-183)
  *   bsplat_render_fwd         mojosplat/render.py:12-103 render_gaussians (the three stages chained
  *                              on one stream with a single 16-byte read-back)
+ *   bsplat_render_enqueue     same without the read-back (device-side M, two-stream overlap, graph capture)
  *   bsplat_render_fwd_host    same, host buffers in / host image out (end-to-end path)
  *
  * Array layouts are the reference's: row-major AoS, fp32 / int32, single camera per launch.
@@ -58,6 +59,10 @@ extern "C" {
 
 /* bsplat_render_fwd `flags`: low byte = rasterizer mode, plus */
 #define BSPLAT_FLAG_BIN_SINGLE_LEVEL 0x100  /* one sort of packed 64-bit keys instead of the two-level sort */
+#define BSPLAT_FLAG_CAMERA_INDIRECT 0x200   /* bsplat_render_enqueue: the camera pose / intrinsics are read
+                                               from `cam` (pinned host memory) when the stream gets there, so a
+                                               captured CUDA graph can be replayed with a new pose; width and
+                                               height are still read on the host at enqueue time */
 
 /* Pinhole camera, world->camera. Mirrors mojosplat/utils.py:5-31 (Camera.view_matrix, Ks, H, W,
  * near, far) as a POD. viewmat is row-major 4x4. */
@@ -73,7 +78,7 @@ typedef struct bsplat_bin_info {
     uint64_t n_isect;        /* M: number of (gaussian, tile) intersections */
     uint32_t min_depth_key;  /* min / max monotone depth key over Gaussians with >= 1 tile */
     uint32_t max_depth_key;
-    uint32_t reserved[4];
+    uint32_t reserved[4];    /* [0]: scratch; [1]: 1 = M exceeded the capacity of a sync-free frame (bsplat_render_enqueue) */
 } bsplat_bin_info;
 
 /* Key layout chosen on the host from a bsplat_bin_info. */
@@ -215,6 +220,20 @@ int bsplat_render_end(int64_t N, int64_t M, const float* colors, const float* op
                       const bsplat_camera* cam_host, const float* background, int32_t tile_size,
                       int32_t semantics, int32_t flags, float* image, void* workspace,
                       size_t workspace_bytes, size_t* needed_bytes, void* stream);
+/* Sync-free frame (render.py:63-101 without the M read-back): nothing in this call waits for the GPU.
+ * The workspace is sized for M_capacity pairs; the real M stays on the device. If a frame produces more
+ * pairs than that, info.reserved[1] is set and the image is invalid: the caller inspects
+ * *info_host_pinned (copied asynchronously on stream_bin; nullable) after synchronising and re-renders
+ * with a larger capacity. stream_raster may be NULL / equal to stream_bin (single stream) or a second,
+ * lower-priority stream: event_bin_done (a cudaEvent_t) then orders rasterization behind binning, and
+ * binning of the next frame overlaps rasterization of this one. Safe to capture into a CUDA graph. */
+int bsplat_render_enqueue(int64_t N, const float* means3d, const float* log_scales, const float* quats,
+                          const float* opacities, const float* colors, int32_t channels,
+                          const bsplat_camera* cam, const float* background, int32_t tile_size,
+                          int32_t semantics, int32_t flags, float* image, void* workspace,
+                          size_t workspace_bytes, int64_t M_capacity, size_t* needed_bytes,
+                          bsplat_bin_info* info_host_pinned, void* stream_bin, void* stream_raster,
+                          void* event_bin_done);
 /* Same with HOST buffers (pinned or pageable): copies the Gaussians in, renders, copies the
  * image out and synchronises the stream. device_scratch must hold
  * bsplat_render_host_scratch_bytes() in addition to the render workspace. */

@@ -24,6 +24,7 @@ E_ARG, E_WORKSPACE, E_OVERFLOW, E_NODEVICE = -1, -2, -3, -4
 SEM_TORCH, SEM_GSPLAT = 0, 1
 RASTER_FAST, RASTER_FAITHFUL, RASTER_FAST_NOCULL = 0, 1, 2
 FLAG_BIN_SINGLE_LEVEL = 0x100
+FLAG_CAMERA_INDIRECT = 0x200
 
 # every symbol include/bsplat.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
@@ -34,6 +35,7 @@ SYMBOLS = [
     "bsplat_render_workspace_bytes", "bsplat_render_fwd", "bsplat_render_host_scratch_bytes",
     "bsplat_render_fwd_host", "bsplat_microbench", "bsplat_bin2_workspace_bytes", "bsplat_bin2_prepare",
     "bsplat_bin2_finish", "bsplat_tile_order", "bsplat_render_begin", "bsplat_render_end",
+    "bsplat_render_enqueue",
 ]
 
 
@@ -125,6 +127,10 @@ def load() -> ctypes.CDLL:
         L.bsplat_render_end.argtypes = [c_int64, c_int64, c_void_p, c_void_p, c_int32, POINTER(BsplatCamera),
                                         c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
                                         POINTER(c_size_t), c_void_p]
+        L.bsplat_render_enqueue.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                            POINTER(BsplatCamera), c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                            c_void_p, c_size_t, c_int64, POINTER(c_size_t), c_void_p, c_void_p,
+                                            c_void_p, c_void_p]
         L.bsplat_rasterize_stats.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                              c_int32, c_void_p, c_void_p, c_void_p]

@@ -63,7 +63,14 @@ __global__ void __launch_bounds__(kEmit2Threads)
 bin_emit2_kernel(const int64_t N, const int32_t* __restrict__ perm, const float* __restrict__ means2d,
                  const void* __restrict__ radii, const int radii_is_float, const BinParams p,
                  const uint32_t* __restrict__ offsets, const int lo_bits, uint32_t* __restrict__ tile_keys,
-                 int32_t* __restrict__ ids, uint32_t* __restrict__ hist /* [2][256] */) {
+                 int32_t* __restrict__ ids, uint32_t* __restrict__ hist /* [2][256] */,
+                 bsplat_bin_info* __restrict__ info_dev, const int64_t m_cap) {
+    // sync-free frames: the pair buffers hold m_cap entries; if this frame produced more, emit nothing,
+    // raise the overflow flag (reserved[1]) and let the later passes see it (they skip too)
+    if (info_dev != nullptr && (int64_t)info_dev->n_isect > m_cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) info_dev->reserved[1] = 1u;
+        return;
+    }
     __shared__ uint32_t s_hist[2][kRadix];
     __shared__ int s_queue[kEmit2Threads];
     __shared__ int s_nqueue;
@@ -334,12 +341,16 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
                                  w.scan_ws, /*finalize_key_range=*/false, stream);
 }
 
-int bin2_finish(int64_t N, int64_t M, const float* means2d, const void* radii, int radii_is_float,
+// device_m: M is a capacity; the real count is read on the device from the bin info (n_isect) written by
+// prepare -- no host read-back between prepare and finish (sync-free / graph-capturable frames).
+int bin2_finish(int64_t N, int64_t M, bool device_m, const float* means2d, const void* radii, int radii_is_float,
                 const BinParams& p, void* workspace, size_t workspace_bytes, int32_t* sorted_ids,
                 int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream) {
     const int n_tiles = p.tiles_w * p.tiles_h;
     Bin2Ws w = carve_bin2(workspace, N, M, n_tiles);
     if (!workspace || workspace_bytes < w.total) return BSPLAT_E_WORKSPACE;
+    bsplat_bin_info* info_dev = device_m ? w.info : nullptr;
+    const uint64_t* m_dev = device_m ? reinterpret_cast<const uint64_t*>(w.info) : nullptr;
     if (M == 0) {
         BSPLAT_CUDA_TRY(cudaMemsetAsync(tile_ranges, 0, (size_t)n_tiles * 2 * sizeof(int32_t), stream));
         if (tile_order)
@@ -354,20 +365,21 @@ int bin2_finish(int64_t N, int64_t M, const float* means2d, const void* radii, i
     const int hi_bits = tb - lo_bits;
     const int64_t emit_chunks = ceil_div(N, kEmit2Threads);
     bin_emit2_kernel<<<(unsigned)(emit_chunks < 148 * 6 ? emit_chunks : 148 * 6), kEmit2Threads, 0, stream>>>(
-        N, w.perm, means2d, radii, radii_is_float, p, w.offsets, lo_bits, w.tkeys, w.ids, w.hist + 4 * kRadix);
+        N, w.perm, means2d, radii, radii_is_float, p, w.offsets, lo_bits, w.tkeys, w.ids, w.hist + 4 * kRadix,
+        info_dev, M);
     BSPLAT_LAUNCH_CHECK();
     int rc = BSPLAT_OK;
     const int64_t tm = sort_tiles_u32(M);
     if (hi_bits > 0) {
-        rc = onesweep_pass_u32(M, nullptr, w.tkeys, w.tkeys_alt, w.ids, w.ids_alt, 0, lo_bits, w.hist + 4 * kRadix,
+        rc = onesweep_pass_u32(M, m_dev, w.tkeys, w.tkeys_alt, w.ids, w.ids_alt, 0, lo_bits, w.hist + 4 * kRadix,
                                0, w.tickets + 4, w.status_m, nullptr, stream);
         if (rc != BSPLAT_OK) return rc;
         // last pass: sorted tile ids are not written; per-tile counts come out of the pass instead
-        rc = onesweep_pass_u32(M, nullptr, w.tkeys_alt, nullptr, w.ids_alt, sorted_ids, lo_bits, hi_bits,
+        rc = onesweep_pass_u32(M, m_dev, w.tkeys_alt, nullptr, w.ids_alt, sorted_ids, lo_bits, hi_bits,
                                w.hist + 5 * kRadix, 0, w.tickets + 5, w.status_m + (size_t)tm * kRadix,
                                w.tile_counts, stream);
     } else {
-        rc = onesweep_pass_u32(M, nullptr, w.tkeys, nullptr, w.ids, sorted_ids, 0, lo_bits, w.hist + 4 * kRadix,
+        rc = onesweep_pass_u32(M, m_dev, w.tkeys, nullptr, w.ids, sorted_ids, 0, lo_bits, w.hist + 4 * kRadix,
                                0, w.tickets + 4, w.status_m, w.tile_counts, stream);
     }
     if (rc != BSPLAT_OK) return rc;
@@ -422,6 +434,6 @@ extern "C" int bsplat_bin2_finish(int64_t N, int64_t M, const float* means2d, co
     if (N < 0 || M < 0 || !tile_ranges) return BSPLAT_E_ARG;
     if (M >= (int64_t)kStatMask) return BSPLAT_E_OVERFLOW;
     if (M > 0 && (!means2d || !radii || !sorted_ids)) return BSPLAT_E_ARG;
-    return bin2_finish(N, M, means2d, radii, radii_is_float, p, workspace, workspace_bytes, sorted_ids,
+    return bin2_finish(N, M, false, means2d, radii, radii_is_float, p, workspace, workspace_bytes, sorted_ids,
                        tile_ranges, tile_order, stream);
 }

@@ -3,17 +3,23 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "binning.cuh"
 
 namespace bsplat {
+int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_is_float, const float* depths,
+                 const BinParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int bin2_finish(int64_t N, int64_t M, bool device_m, const float* means2d, const void* radii, int radii_is_float,
+                const BinParams& p, void* workspace, size_t workspace_bytes, int32_t* sorted_ids,
+                int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream);
 int project_fwd_launch(int64_t N, const float* means3d, const float* log_scales, const float* quats,
                        const float* opacities, const bsplat_camera& cam, float eps2d, int semantics,
-                       float* means2d, float* conics, float* depths, int32_t* radii, cudaStream_t stream);
+                       float* means2d, float* conics, float* depths, int32_t* radii, cudaStream_t stream,
+                       const bsplat_camera* cam_dev = nullptr);
 int rasterize_launch(int64_t N, int channels, const float* means2d, const float* conics, const float* colors,
                      const float* opacities, const float* background_dev, const int32_t* tile_ranges,
                      const int32_t* tile_order, const int32_t* sorted_ids, int W, int H, int tile_size,
                      int row_begin, int row_end, int mode, float* image, unsigned long long* stats,
-                     cudaStream_t stream);
+                     const unsigned long long* m_dev, cudaStream_t stream);
 int tile_order_launch(int first_tile, int n_tiles, const int32_t* tile_ranges, int32_t* order,
                       cudaStream_t stream);
 }  // namespace bsplat
@@ -55,7 +61,7 @@ extern "C" int bsplat_rasterize_fwd(int64_t N, int32_t channels, const float* me
     if (M > 0 && (!sorted_ids || !means2d || !conics || !colors || !opacities)) return BSPLAT_E_ARG;
     return rasterize_launch(N, channels, means2d, conics, colors, opacities, background, tile_ranges, tile_order,
                             sorted_ids, width, height, tile_size, tile_row_begin, tile_row_end, mode, image,
-                            nullptr, (cudaStream_t)stream);
+                            nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int bsplat_tile_order(int32_t first_tile, int32_t n_tiles, const int32_t* tile_ranges,
@@ -75,7 +81,7 @@ extern "C" int bsplat_rasterize_stats(int64_t N, int32_t channels, const float* 
     if (N < 0 || M < 0 || !tile_ranges || !image || !background || !stats) return BSPLAT_E_ARG;
     return rasterize_launch(N, channels, means2d, conics, colors, opacities, background, tile_ranges, nullptr,
                             sorted_ids, width, height, tile_size, 0, 1 << 30, BSPLAT_RASTER_FAITHFUL, image,
-                            reinterpret_cast<unsigned long long*>(stats), (cudaStream_t)stream);
+                            reinterpret_cast<unsigned long long*>(stats), nullptr, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -122,6 +128,7 @@ Bin1Ws carve_bin1(void* base, int64_t N, int64_t M) {
 struct RenderWs {
     float* means2d; float* conics; float* depths; int32_t* radii;
     int32_t* tile_ranges; int32_t* tile_order; int32_t* sorted_ids;
+    bsplat_camera* cam_dev;  // indirect camera of captured frames
     void* bin_ws; size_t bin_bytes;
     size_t total;
 };
@@ -139,6 +146,7 @@ RenderWs carve_render(void* base, int64_t N, int64_t M, int W, int H, int tile_s
     w.radii = (int32_t*)take(n * 2 * sizeof(int32_t));
     w.tile_ranges = (int32_t*)take((size_t)tiles_w * tiles_h * 2 * sizeof(int32_t));
     w.tile_order = (int32_t*)take((size_t)tiles_w * tiles_h * sizeof(int32_t));
+    w.cam_dev = (bsplat_camera*)take(sizeof(bsplat_camera));
     // the N-dependent part of the binning scratch comes first so that it survives the re-carve with M
     w.bin_bytes = single_level ? carve_bin1(nullptr, N, M).total : bin2_workspace_bytes(N, M, (int64_t)tiles_w * tiles_h);
     w.bin_ws = take(w.bin_bytes);
@@ -281,7 +289,7 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[3], stream));
     rc = rasterize_launch(N, channels, d_means2d, d_conics, colors, opacities, background, d_ranges,
                           fast_raster ? w.tile_order : nullptr, sorted_ids, W, H, tile_size, 0, tiles_h, raster_mode,
-                          image, nullptr, stream);
+                          image, nullptr, nullptr, stream);
     if (rc != BSPLAT_OK) { drop_events(); return rc; }
     if (aux && aux->sorted_ids && aux->sorted_ids_capacity >= M)
         BSPLAT_CUDA_TRY(cudaMemcpyAsync(aux->sorted_ids, sorted_ids, (size_t)M * sizeof(int32_t),
@@ -349,7 +357,71 @@ extern "C" int bsplat_render_end(int64_t N, int64_t M, const float* colors, cons
     const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
     return rasterize_launch(N, channels, w.means2d, w.conics, colors, opacities, background, w.tile_ranges,
                             fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, 0, tiles_h,
-                            raster_mode, image, nullptr, stream);
+                            raster_mode, image, nullptr, nullptr, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// sync-free frame: nothing in here waits for the GPU.  The pair buffers are sized by M_capacity, the
+// real M stays on the device (bin info written by the count+scan kernel) and every M-scale kernel
+// reads it there; a frame that produces more than M_capacity pairs raises info.reserved[1] and renders
+// nothing useful -- the caller looks at the (asynchronously copied) info once the frame is done and
+// re-renders with a larger workspace.  Binning and rasterization may go to different streams
+// (priorities): with the binning stream at high priority, binning(k+1) fills the slots that
+// rasterization(k) frees, which hides the latency-bound binning kernels behind the issue-bound rasterizer.
+// Capturable into a CUDA graph (single stream or fork/join through event_bin_done).
+// ------------------------------------------------------------------------------------------
+extern "C" int bsplat_render_enqueue(int64_t N, const float* means3d, const float* log_scales, const float* quats,
+                                     const float* opacities, const float* colors, int32_t channels,
+                                     const bsplat_camera* cam, const float* background, int32_t tile_size,
+                                     int32_t semantics, int32_t flags, float* image, void* workspace,
+                                     size_t workspace_bytes, int64_t M_capacity, size_t* needed_bytes,
+                                     bsplat_bin_info* info_host_pinned, void* stream_bin_, void* stream_raster_,
+                                     void* event_bin_done) {
+    cudaStream_t sb = (cudaStream_t)stream_bin_;
+    cudaStream_t sr = stream_raster_ ? (cudaStream_t)stream_raster_ : sb;
+    if (!cam || !image || !background || N <= 0 || M_capacity <= 0 || channels <= 0 || tile_size <= 0 ||
+        tile_size > 32)
+        return BSPLAT_E_ARG;
+    if (!means3d || !log_scales || !quats || !opacities || !colors) return BSPLAT_E_ARG;
+    if (M_capacity >= (1ll << 30)) return BSPLAT_E_OVERFLOW;
+    if (sr != sb && !event_bin_done) return BSPLAT_E_ARG;
+    const int W = cam->width, H = cam->height;
+    if (W <= 0 || H <= 0) return BSPLAT_E_ARG;
+    const int raster_mode = flags & 0xff;
+    RenderWs w = carve_render(workspace, N, M_capacity, W, H, tile_size, false);
+    if (!workspace || workspace_bytes < w.total) {
+        if (needed_bytes) *needed_bytes = w.total;
+        return BSPLAT_E_WORKSPACE;
+    }
+    const bsplat_camera* cam_dev = nullptr;
+    if (flags & BSPLAT_FLAG_CAMERA_INDIRECT) {
+        // `cam` is pinned host (or managed) memory: copied when the stream gets here, i.e. at every replay
+        BSPLAT_CUDA_TRY(cudaMemcpyAsync(w.cam_dev, cam, sizeof(bsplat_camera), cudaMemcpyDefault, sb));
+        cam_dev = w.cam_dev;
+    }
+    int rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, *cam, 0.3f, semantics, w.means2d, w.conics,
+                                w.depths, w.radii, sb, cam_dev);
+    if (rc != BSPLAT_OK) return rc;
+    const int tiles_h = (H + tile_size - 1) / tile_size;
+    BinParams p;
+    rc = make_bin_params(W, H, tile_size, 0, tiles_h, semantics, &p);
+    if (rc != BSPLAT_OK) return rc;
+    rc = bin2_prepare(N, w.means2d, w.radii, 0, w.depths, p, w.bin_ws, w.bin_bytes, sb);
+    if (rc != BSPLAT_OK) return rc;
+    rc = bin2_finish(N, M_capacity, /*device_m=*/true, w.means2d, w.radii, 0, p, w.bin_ws, w.bin_bytes, w.sorted_ids,
+                     w.tile_ranges, w.tile_order, sb);
+    if (rc != BSPLAT_OK) return rc;
+    bsplat_bin_info* d_info = bin2_info_ptr(w.bin_ws, N);
+    if (info_host_pinned)
+        BSPLAT_CUDA_TRY(cudaMemcpyAsync(info_host_pinned, d_info, sizeof(bsplat_bin_info), cudaMemcpyDeviceToHost, sb));
+    if (sr != sb) {
+        BSPLAT_CUDA_TRY(cudaEventRecord((cudaEvent_t)event_bin_done, sb));
+        BSPLAT_CUDA_TRY(cudaStreamWaitEvent(sr, (cudaEvent_t)event_bin_done, 0));
+    }
+    const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
+    return rasterize_launch(N, channels, w.means2d, w.conics, colors, opacities, background, w.tile_ranges,
+                            fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, 0, tiles_h,
+                            raster_mode, image, nullptr, reinterpret_cast<const unsigned long long*>(d_info), sr);
 }
 
 extern "C" size_t bsplat_render_host_scratch_bytes(int64_t N, int32_t channels, int32_t width, int32_t height) {

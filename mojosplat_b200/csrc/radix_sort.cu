@@ -87,7 +87,13 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
     __shared__ uint32_t s_warp_tot[kSortWarps];
     __shared__ uint32_t s_tile;
 
-    const int64_t M = m_dev ? (int64_t)(*m_dev) : M_host;
+    // device-side count (sync-free frames): M_host is then the capacity the launch and the buffers were
+    // sized for; a count beyond it disables the pass (the emitter has flagged the overflow)
+    int64_t M = M_host;
+    if (m_dev) {
+        const int64_t md = (int64_t)(*m_dev);
+        M = md <= M_host ? md : 0;
+    }
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const int warp = tid >> 5;

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(1024) raster_faithful_kernel(const int64_t N, 
                                        const int32_t* __restrict__ tile_ranges,
                                        const int32_t* __restrict__ sorted_ids, const int W, const int H,
                                        const int ts, const int tiles_w, const int row_begin,
-                                       float* __restrict__ image, unsigned long long* __restrict__ stats) {
+                                       float* __restrict__ image, unsigned long long* __restrict__ stats,
+                                       const unsigned long long* __restrict__ m_dev) {
     extern __shared__ float s_buf[];
     const int nthreads = ts * ts;
     float* s_mx = s_buf;
@@ -113,11 +114,13 @@ __global__ void __launch_bounds__(1024) raster_faithful_kernel(const int64_t N, 
         }
     }
     if (inside) {
+        // sync-free frames: no intersections at all => all-zero image (render.py:73-76), decided on the device
+        const bool empty = (m_dev != nullptr) && (*m_dev == 0ull);
 #pragma unroll
         for (int ch = 0; ch < CH; ++ch)
             if (c0 + ch < cdim)
                 image[((int64_t)i * W + j) * cdim + c0 + ch] =
-                    __fadd_rn(acc[ch], __fmul_rn(T, background[c0 + ch]));
+                    empty ? 0.0f : __fadd_rn(acc[ch], __fmul_rn(T, background[c0 + ch]));
     }
     if (stats != nullptr) {
         // blocks may end in a partial warp (tile sizes like 10): plain per-thread atomics
@@ -150,7 +153,8 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                    const float* __restrict__ background, const int32_t* __restrict__ tile_ranges,
                    const int32_t* __restrict__ tile_order, const int first_tile,
                    const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
-                   float* __restrict__ image, const int vec_store) {
+                   float* __restrict__ image, const int vec_store,
+                   const unsigned long long* __restrict__ m_dev) {
     __shared__ float4 s_g[kFastBatch * 3];
 
     const int tid = threadIdx.x;
@@ -286,8 +290,10 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
     }
 
     // ---- write the tile: through shared memory as 128-bit rows when the layout allows ----
-    const float outr = fmaf(T, __ldg(background), accr), outg = fmaf(T, __ldg(background + 1), accg),
-                outb = fmaf(T, __ldg(background + 2), accb);
+    // sync-free frames: no intersections at all => all-zero image (render.py:73-76), decided on the device
+    const float bgs = (m_dev != nullptr && *m_dev == 0ull) ? 0.0f : 1.0f;
+    const float outr = fmaf(T, bgs * __ldg(background), accr), outg = fmaf(T, bgs * __ldg(background + 1), accg),
+                outb = fmaf(T, bgs * __ldg(background + 2), accb);
     const bool full_tile = (tile_x * kFastTile + kFastTile <= W) && (tile_y * kFastTile + kFastTile <= H);
     if (vec_store && full_tile) {
         __syncthreads();  // staging buffers are dead from here on
@@ -347,13 +353,13 @@ static int launch_faithful(int64_t N, int cdim, int c0, const float* means2d, co
                            const float* colors, const float* opacities, const float* background,
                            const int32_t* tile_ranges, const int32_t* sorted_ids, int W, int H, int ts,
                            int row_begin, int row_end, float* image, unsigned long long* stats,
-                           cudaStream_t stream) {
+                           const unsigned long long* m_dev, cudaStream_t stream) {
     const int tiles_w = (W + ts - 1) / ts;
     const dim3 grid(tiles_w, row_end - row_begin), block(ts, ts);
     const size_t smem = (size_t)ts * ts * (6 + CH) * sizeof(float);
     raster_faithful_kernel<CH><<<grid, block, smem, stream>>>(N, cdim, c0, means2d, conics, colors, opacities,
                                                               background, tile_ranges, sorted_ids, W, H, ts,
-                                                              tiles_w, row_begin, image, stats);
+                                                              tiles_w, row_begin, image, stats, m_dev);
     BSPLAT_LAUNCH_CHECK();
     return BSPLAT_OK;
 }
@@ -364,7 +370,7 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
                      const float* opacities, const float* background_dev,
                      const int32_t* tile_ranges, const int32_t* tile_order, const int32_t* sorted_ids, int W,
                      int H, int tile_size, int row_begin, int row_end, int mode, float* image,
-                     unsigned long long* stats, cudaStream_t stream) {
+                     unsigned long long* stats, const unsigned long long* m_dev, cudaStream_t stream) {
     if (W <= 0 || H <= 0 || tile_size <= 0 || tile_size > 32 || channels <= 0 || !background_dev)
         return BSPLAT_E_ARG;
     const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
@@ -383,11 +389,11 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         if (mode == 2)
             raster_fast_kernel<false><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
                                                                          tile_ranges, tile_order, first_tile, sorted_ids,
-                                                                         W, H, tiles_w, image, vec);
+                                                                         W, H, tiles_w, image, vec, m_dev);
         else
             raster_fast_kernel<true><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
                                                                         tile_ranges, tile_order, first_tile, sorted_ids,
-                                                                        W, H, tiles_w, image, vec);
+                                                                        W, H, tiles_w, image, vec, m_dev);
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
     }
@@ -397,10 +403,10 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         int rc;
         unsigned long long* st = (c0 == 0) ? stats : nullptr;
         switch (ch) {
-            case 1: rc = launch_faithful<1>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, stream); break;
-            case 2: rc = launch_faithful<2>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, stream); break;
-            case 3: rc = launch_faithful<3>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, stream); break;
-            default: rc = launch_faithful<4>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, stream); break;
+            case 1: rc = launch_faithful<1>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, m_dev, stream); break;
+            case 2: rc = launch_faithful<2>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, m_dev, stream); break;
+            case 3: rc = launch_faithful<3>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, m_dev, stream); break;
+            default: rc = launch_faithful<4>(N, channels, c0, means2d, conics, colors, opacities, background_dev, tile_ranges, sorted_ids, W, H, tile_size, row_begin, row_end, image, st, m_dev, stream); break;
         }
         if (rc != BSPLAT_OK) return rc;
     }

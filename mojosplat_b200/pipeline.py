@@ -111,3 +111,115 @@ class FramePipeline:
             for s in self.streams:
                 cur.wait_stream(s)
         return out
+
+
+class OverlappedPipeline:
+    """Sync-free multi-view rendering with binning/rasterization overlap (bsplat_render_enqueue).
+
+    Two CUDA streams: a HIGH-priority one for projection + binning (about ten latency-bound kernels that
+    leave most of the chip idle) and a LOW-priority one for the rasterizer (fills every SM, bound by
+    instruction issue).  Nothing on the host waits for the GPU: M stays on the device, the pair buffers are
+    sized by a capacity.  The block scheduler serves the high-priority stream first whenever rasterizer
+    CTAs retire, so binning(k+1) runs inside rasterization(k) and the frame rate approaches the
+    rasterizer's alone.  ``slots`` workspaces are cycled; binning of frame k waits (on the device) for the
+    rasterizer of frame k - slots.  After the batch the per-frame bin infos are checked; a frame whose M
+    exceeded the capacity is re-rendered synchronously with a larger workspace (rare: capacity adapts).
+    Results are identical to frame-by-frame rendering.
+    """
+
+    def __init__(self, device, N: int, W: int, H: int, channels: int = 3, tile_size: int = 16,
+                 semantics: int = _lib.SEM_TORCH, slots: int = 3, m_capacity: int | None = None,
+                 raster_mode: str = "fast", bin_streams: int = 2):
+        self.dev = torch.device(device)
+        self.L = _lib.require_device(self.dev)
+        self.N, self.W, self.H, self.C, self.ts = int(N), int(W), int(H), int(channels), int(tile_size)
+        self.semantics, self.flags = semantics, RASTER_MODES[raster_mode]
+        self.slots = slots
+        self.n_bin = max(1, min(bin_streams, slots))
+        self.m_cap = int(m_capacity) if m_capacity else 8 * self.N + 4096
+        with torch.cuda.device(self.dev):
+            # binning chains of consecutive frames alternate between high-priority streams: two chains in
+            # flight keep the rasterizer stream fed (one chain under contention is slower than a rasterization)
+            self.s_bins = [torch.cuda.Stream(self.dev, priority=-1) for _ in range(self.n_bin)]
+            self.s_bin = self.s_bins[0]
+            self.s_ras = torch.cuda.Stream(self.dev, priority=0)
+            self.ev_bin = [torch.cuda.Event() for _ in range(slots)]
+            self.ev_ras = [torch.cuda.Event() for _ in range(slots)]
+            self._alloc_all()
+        self.last_M = 0
+
+    def _alloc_all(self):
+        nbytes = self.L.bsplat_render_workspace_bytes(self.N, self.m_cap, self.W, self.H, self.ts)
+        self.ws = [torch.empty(nbytes, dtype=torch.uint8, device=self.dev) for _ in range(self.slots)]
+
+    def _enqueue(self, slot, g, cam_struct, bg, image, info_host, s_bin=None):
+        s_bin = s_bin or self.s_bin
+        needed = c_size_t(0)
+        rc = self.L.bsplat_render_enqueue(
+            self.N, _lib.ptr(g[0]), _lib.ptr(g[1]), _lib.ptr(g[2]), _lib.ptr(g[3]), _lib.ptr(g[4]), self.C,
+            byref(cam_struct), _lib.ptr(bg), self.ts, self.semantics, self.flags, _lib.ptr(image),
+            _lib.ptr(self.ws[slot]), self.ws[slot].numel(), self.m_cap, byref(needed), info_host.data_ptr(),
+            s_bin.cuda_stream, self.s_ras.cuda_stream, self.ev_bin[slot].cuda_event)
+        _lib.check(rc, "bsplat_render_enqueue")
+
+    @torch.no_grad()
+    def render(self, means3d, scales, quats, opacities, features, cameras: Sequence[Camera], background,
+               out: torch.Tensor | None = None, scene_of=None) -> torch.Tensor:
+        """Render all cameras; images [n, H, W, C] (or a ring, see FramePipeline.render)."""
+        def prep(t):
+            q = [_lib.as_f32(t[0], "means3d"), _lib.as_f32(t[1], "scales"), _lib.as_f32(t[2], "quats"),
+                 _lib.as_f32(t[3], "opacities").reshape(-1), _lib.as_f32(t[4], "features")]
+            assert q[0].shape[0] == self.N and q[4].shape == (self.N, self.C)
+            return q
+        g0 = prep((means3d, scales, quats, opacities, features))
+        n = len(cameras)
+        gs = [g0] * n if scene_of is None else [prep(scene_of(k)) for k in range(n)]
+        bg = _lib.as_f32(background, "background").to(self.dev)
+        if out is None:
+            out = torch.empty((n, self.H, self.W, self.C), dtype=torch.float32, device=self.dev)
+        cams = [_lib.camera_struct(c) for c in cameras]
+        infos = torch.zeros((max(n, 1), 32), dtype=torch.uint8).pin_memory()
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.device(self.dev):
+            for sb in self.s_bins:
+                sb.wait_stream(cur)
+            self.s_ras.wait_stream(cur)
+            for k in range(n):
+                slot = k % self.slots
+                sb = self.s_bins[k % self.n_bin]
+                if k >= self.slots:
+                    sb.wait_event(self.ev_ras[slot])  # workspace of frame k - slots is free again
+                # (ring output: frame k - len(out) was rasterized earlier on the same in-order stream)
+                self.ev_bin[slot].record(sb)  # materialise the handle; re-recorded inside the call
+                self._enqueue(slot, gs[k], cams[k], bg, out[k % out.shape[0]], infos[k], sb)
+                self.ev_ras[slot].record(self.s_ras)
+            cur.wait_stream(self.s_ras)
+            for sb in self.s_bins:
+                cur.wait_stream(sb)
+        self._pending = (infos, gs, cams, bg, out, n)
+        return out
+
+    def check(self) -> int:
+        """Synchronise and verify the last batch: re-render frames whose M exceeded the capacity.
+        Returns the number of frames that had to be redone."""
+        infos, gs, cams, bg, out, n = self._pending
+        torch.cuda.synchronize(self.dev)
+        redone = 0
+        max_m = 0
+        for k in range(n):
+            info = _lib.BsplatBinInfo.from_buffer_copy(infos[k].numpy().tobytes())
+            max_m = max(max_m, int(info.n_isect))
+            if info.reserved[1]:
+                redone += 1
+        self.last_M = max_m
+        if redone:
+            self.m_cap = int(max_m * 1.25) + 4096
+            self._alloc_all()
+            for k in range(n):
+                info = _lib.BsplatBinInfo.from_buffer_copy(infos[k].numpy().tobytes())
+                if info.reserved[1]:
+                    with torch.cuda.device(self.dev):
+                        self.ev_bin[0].record(self.s_bin)
+                        self._enqueue(0, gs[k], cams[k], bg, out[k % out.shape[0]], infos[k])
+                    torch.cuda.synchronize(self.dev)
+        return redone

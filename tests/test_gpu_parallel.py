@@ -64,3 +64,48 @@ def test_pipelined_views_equal_sequential(cuda_device):
     pipe.render(m, s, q, o, c, cams, bg, out=ring)
     torch.cuda.synchronize()
     assert torch.equal(ring[0], imgs[6]) and torch.equal(ring[1], imgs[5])
+
+
+def test_overlapped_pipeline_equals_sequential(cuda_device):
+    """Sync-free frames (device-side M, binning on a high-priority stream, rasterizer on a second one)
+    give exactly the frame-by-frame images; a too-small capacity is detected and redone."""
+    from mojosplat_b200.pipeline import OverlappedPipeline
+    sc = synthetic.make_scene("config3_1m_1080p", N=200_000)
+    (m, s, q, o, c), _ = scene_on(sc, cuda_device)
+    cams = synthetic.orbit_cameras(9, 960, 540, 500.0)
+    bg = sc.background.to(cuda_device)
+    pipe = OverlappedPipeline(cuda_device, sc.N, 960, 540)
+    imgs = pipe.render(m, s, q, o, c, cams, bg)
+    assert pipe.check() == 0
+    ref = [ms.render_gaussians(m, s, q, o, c, cam, background_color=bg) for cam in cams]
+    for k in range(len(cams)):
+        assert torch.equal(imgs[k], ref[k]), k
+    assert pipe.last_M > 0
+    # capacity far too small: every frame overflows, is flagged on the device and re-rendered
+    small = OverlappedPipeline(cuda_device, sc.N, 960, 540, m_capacity=5000)
+    imgs2 = small.render(m, s, q, o, c, cams[:3], bg)
+    assert small.check() == 3
+    for k in range(3):
+        assert torch.equal(imgs2[k], ref[k]), k
+    # second batch runs with the adapted capacity, nothing to redo
+    imgs3 = small.render(m, s, q, o, c, cams[3:6], bg)
+    assert small.check() == 0
+    for k in range(3):
+        assert torch.equal(imgs3[k], ref[3 + k]), k
+
+
+def test_enqueue_empty_scene_gives_zero_image(cuda_device):
+    """gsplat rules + everything behind the camera: M == 0 is only known on the device; the image must
+    be all zeros (render.py:73-76), not the background."""
+    from mojosplat_b200 import _lib
+    from mojosplat_b200.pipeline import OverlappedPipeline
+    sc = synthetic.make_scene("config1_1k_256")
+    (m, s, q, o, c), cam = scene_on(sc, cuda_device)
+    m = m.clone(); m[:, 2] += 1000.0  # far beyond the far plane for this pose
+    pipe = OverlappedPipeline(cuda_device, sc.N, cam.W, cam.H, semantics=_lib.SEM_GSPLAT)
+    img = pipe.render(m, s, q, o, c, [cam], sc.background.to(cuda_device))
+    assert pipe.check() == 0
+    if pipe.last_M == 0:
+        assert float(img.abs().max()) == 0.0
+    else:
+        pytest.skip("scene still produced intersections")
