@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--pipeline-depth", type=int, default=2, help="frames in flight per GPU (sync pipeline)")
     ap.add_argument("--pipeline", default="overlapped", choices=["overlapped", "sync"],
                     help="overlapped: sync-free frames, binning(k+1) inside rasterization(k); sync: FramePipeline")
+    ap.add_argument("--raster-mode", default="fast", choices=["fast", "warp", "single"], help="rasterizer kernel (A/B)")
     ap.add_argument("--slots", type=int, default=3, help="workspaces cycled by the overlapped pipeline")
     ap.add_argument("--bin-streams", type=int, default=2, help="high-priority binning streams (overlapped pipeline)")
     return ap.parse_args()
@@ -64,7 +65,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-RASTER_KERNEL = "raster_fast_kernel"
+RASTER_KERNEL = "raster_pair_kernel"
 
 
 def ncu_traffic(key):
@@ -222,9 +223,10 @@ def run_b200(args, rank, world, local_rank):
 
     from mojosplat_b200.pipeline import FramePipeline, OverlappedPipeline
     if args.pipeline == "overlapped":
-        pipe = OverlappedPipeline(dev, N, W, H, semantics=sem, slots=args.slots, bin_streams=args.bin_streams)
+        pipe = OverlappedPipeline(dev, N, W, H, semantics=sem, slots=args.slots, bin_streams=args.bin_streams,
+                                  raster_mode=args.raster_mode)
     else:
-        pipe = FramePipeline(dev, N, W, H, semantics=sem, depth=args.pipeline_depth)
+        pipe = FramePipeline(dev, N, W, H, semantics=sem, depth=args.pipeline_depth, raster_mode=args.raster_mode)
     ring = torch.empty((4, H, W, 3), dtype=torch.float32, device=dev)
 
     # clocks are sampled from the first warm-up frame to the end of the e2e loop (the GPU is under this

@@ -54,8 +54,11 @@ extern "C" {
 #define BSPLAT_SEM_GSPLAT 1  /* gsplat / Mojo rules: projection.mojo:59-87,213-244; isect_tiles */
 
 /* rasterizer arithmetic */
-#define BSPLAT_RASTER_FAST 0      /* folded exp2 form, sub-tile culling (default) */
+#define BSPLAT_RASTER_FAST 0      /* folded exp2 form, packed FP32 pairs, sub-tile culling (default) */
 #define BSPLAT_RASTER_FAITHFUL 1  /* operation order of kernels/rasterization.mojo:138-157 */
+#define BSPLAT_RASTER_FAST_NOCULL 2  /* fast arithmetic without sub-tile culling (exactness A/B) */
+#define BSPLAT_RASTER_WARP 3      /* independent-warp kernel on per-Gaussian raster records (needs the workspace; A/B) */
+#define BSPLAT_RASTER_SINGLE 4    /* one pixel per lane (first fast kernel, A/B) */
 
 /* bsplat_render_fwd `flags`: low byte = rasterizer mode, plus */
 #define BSPLAT_FLAG_BIN_SINGLE_LEVEL 0x100  /* one sort of packed 64-bit keys instead of the two-level sort */
@@ -162,13 +165,16 @@ int bsplat_tile_order(int32_t first_tile, int32_t n_tiles, const int32_t* tile_r
 /* image[height, width, channels]. opacities are used raw (no sigmoid), like the reference.
  * tile_order may be NULL (row-major tile order). Only tile rows [tile_row_begin, tile_row_end) are
  * rasterized and written (pass 0 and tiles_h for the whole frame; a row band for the multi-GPU split --
- * tile_order, if given, must then list exactly the band's tiles). */
+ * tile_order, if given, must then list exactly the band's tiles).
+ * workspace (optional, bsplat_rasterize_workspace_bytes(N) = 48 B per Gaussian, 16-byte aligned): holds the
+ * per-Gaussian raster records of BSPLAT_RASTER_WARP; the other modes do not need it. */
+size_t bsplat_rasterize_workspace_bytes(int64_t N);
 int bsplat_rasterize_fwd(int64_t N, int32_t channels, const float* means2d, const float* conics,
                          const float* colors, const float* opacities, const float* background,
                          const int32_t* tile_ranges, const int32_t* tile_order,
                          const int32_t* sorted_ids, int64_t M, int32_t width, int32_t height,
                          int32_t tile_size, int32_t tile_row_begin, int32_t tile_row_end, int32_t mode,
-                         float* image, void* stream);
+                         float* image, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Faithful kernel + counters: stats[0] += evaluated (pixel, Gaussian) pairs, stats[1] += contributing
  * pairs (device uint64[2], caller-zeroed) -- the algorithmic work E_all / E_pass of SURVEY.md 8d. */

@@ -22,7 +22,7 @@ LIB_PATH = CSRC / "libbsplat.so"
 OK = 0
 E_ARG, E_WORKSPACE, E_OVERFLOW, E_NODEVICE = -1, -2, -3, -4
 SEM_TORCH, SEM_GSPLAT = 0, 1
-RASTER_FAST, RASTER_FAITHFUL, RASTER_FAST_NOCULL = 0, 1, 2
+RASTER_FAST, RASTER_FAITHFUL, RASTER_FAST_NOCULL, RASTER_WARP, RASTER_SINGLE = 0, 1, 2, 3, 4
 FLAG_BIN_SINGLE_LEVEL = 0x100
 FLAG_CAMERA_INDIRECT = 0x200
 
@@ -35,7 +35,7 @@ SYMBOLS = [
     "bsplat_render_workspace_bytes", "bsplat_render_fwd", "bsplat_render_host_scratch_bytes",
     "bsplat_render_fwd_host", "bsplat_microbench", "bsplat_bin2_workspace_bytes", "bsplat_bin2_prepare",
     "bsplat_bin2_finish", "bsplat_tile_order", "bsplat_render_begin", "bsplat_render_end",
-    "bsplat_render_enqueue",
+    "bsplat_render_enqueue", "bsplat_rasterize_workspace_bytes",
 ]
 
 
@@ -120,7 +120,10 @@ def load() -> ctypes.CDLL:
         L.bsplat_tile_ranges.argtypes = [c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
         L.bsplat_rasterize_fwd.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
-                                           c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+                                           c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
+                                           c_void_p]
+        L.bsplat_rasterize_workspace_bytes.restype = c_size_t
+        L.bsplat_rasterize_workspace_bytes.argtypes = [c_int64]
         L.bsplat_tile_order.argtypes = [c_int32, c_int32, c_void_p, c_void_p, c_void_p]
         L.bsplat_render_begin.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(BsplatCamera),
                                           c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_void_p]

@@ -19,7 +19,8 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
                      const float* opacities, const float* background_dev, const int32_t* tile_ranges,
                      const int32_t* tile_order, const int32_t* sorted_ids, int W, int H, int tile_size,
                      int row_begin, int row_end, int mode, float* image, unsigned long long* stats,
-                     const unsigned long long* m_dev, cudaStream_t stream);
+                     const unsigned long long* m_dev, void* rec_ws, cudaStream_t stream);
+size_t raster_workspace_bytes(int64_t N);
 int tile_order_launch(int first_tile, int n_tiles, const int32_t* tile_ranges, int32_t* order,
                       cudaStream_t stream);
 }  // namespace bsplat
@@ -56,13 +57,18 @@ extern "C" int bsplat_rasterize_fwd(int64_t N, int32_t channels, const float* me
                                     const int32_t* tile_ranges, const int32_t* tile_order,
                                     const int32_t* sorted_ids, int64_t M, int32_t width, int32_t height,
                                     int32_t tile_size, int32_t tile_row_begin, int32_t tile_row_end,
-                                    int32_t mode, float* image, void* stream) {
+                                    int32_t mode, float* image, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
     if (N < 0 || M < 0 || !tile_ranges || !image || !background) return BSPLAT_E_ARG;
     if (M > 0 && (!sorted_ids || !means2d || !conics || !colors || !opacities)) return BSPLAT_E_ARG;
+    // the record workspace is optional: without it the fast mode runs the (slower) workspace-free kernel
+    void* rec_ws = (workspace && workspace_bytes >= raster_workspace_bytes(N)) ? workspace : nullptr;
     return rasterize_launch(N, channels, means2d, conics, colors, opacities, background, tile_ranges, tile_order,
                             sorted_ids, width, height, tile_size, tile_row_begin, tile_row_end, mode, image,
-                            nullptr, nullptr, (cudaStream_t)stream);
+                            nullptr, nullptr, rec_ws, (cudaStream_t)stream);
 }
+
+extern "C" size_t bsplat_rasterize_workspace_bytes(int64_t N) { return N < 0 ? 0 : raster_workspace_bytes(N); }
 
 extern "C" int bsplat_tile_order(int32_t first_tile, int32_t n_tiles, const int32_t* tile_ranges,
                                  int32_t* tile_order, void* stream) {
@@ -81,7 +87,7 @@ extern "C" int bsplat_rasterize_stats(int64_t N, int32_t channels, const float* 
     if (N < 0 || M < 0 || !tile_ranges || !image || !background || !stats) return BSPLAT_E_ARG;
     return rasterize_launch(N, channels, means2d, conics, colors, opacities, background, tile_ranges, nullptr,
                             sorted_ids, width, height, tile_size, 0, 1 << 30, BSPLAT_RASTER_FAITHFUL, image,
-                            reinterpret_cast<unsigned long long*>(stats), nullptr, (cudaStream_t)stream);
+                            reinterpret_cast<unsigned long long*>(stats), nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -129,6 +135,7 @@ struct RenderWs {
     float* means2d; float* conics; float* depths; int32_t* radii;
     int32_t* tile_ranges; int32_t* tile_order; int32_t* sorted_ids;
     bsplat_camera* cam_dev;  // indirect camera of captured frames
+    void* raster_rec;        // 48 B per Gaussian: raster records (raster_prep_kernel)
     void* bin_ws; size_t bin_bytes;
     size_t total;
 };
@@ -147,6 +154,7 @@ RenderWs carve_render(void* base, int64_t N, int64_t M, int W, int H, int tile_s
     w.tile_ranges = (int32_t*)take((size_t)tiles_w * tiles_h * 2 * sizeof(int32_t));
     w.tile_order = (int32_t*)take((size_t)tiles_w * tiles_h * sizeof(int32_t));
     w.cam_dev = (bsplat_camera*)take(sizeof(bsplat_camera));
+    w.raster_rec = take(raster_workspace_bytes(N));
     // the N-dependent part of the binning scratch comes first so that it survives the re-carve with M
     w.bin_bytes = single_level ? carve_bin1(nullptr, N, M).total : bin2_workspace_bytes(N, M, (int64_t)tiles_w * tiles_h);
     w.bin_ws = take(w.bin_bytes);
@@ -289,7 +297,7 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[3], stream));
     rc = rasterize_launch(N, channels, d_means2d, d_conics, colors, opacities, background, d_ranges,
                           fast_raster ? w.tile_order : nullptr, sorted_ids, W, H, tile_size, 0, tiles_h, raster_mode,
-                          image, nullptr, nullptr, stream);
+                          image, nullptr, nullptr, w.raster_rec, stream);
     if (rc != BSPLAT_OK) { drop_events(); return rc; }
     if (aux && aux->sorted_ids && aux->sorted_ids_capacity >= M)
         BSPLAT_CUDA_TRY(cudaMemcpyAsync(aux->sorted_ids, sorted_ids, (size_t)M * sizeof(int32_t),
@@ -357,7 +365,7 @@ extern "C" int bsplat_render_end(int64_t N, int64_t M, const float* colors, cons
     const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
     return rasterize_launch(N, channels, w.means2d, w.conics, colors, opacities, background, w.tile_ranges,
                             fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, 0, tiles_h,
-                            raster_mode, image, nullptr, nullptr, stream);
+                            raster_mode, image, nullptr, nullptr, w.raster_rec, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -421,7 +429,8 @@ extern "C" int bsplat_render_enqueue(int64_t N, const float* means3d, const floa
     const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
     return rasterize_launch(N, channels, w.means2d, w.conics, colors, opacities, background, w.tile_ranges,
                             fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, 0, tiles_h,
-                            raster_mode, image, nullptr, reinterpret_cast<const unsigned long long*>(d_info), sr);
+                            raster_mode, image, nullptr, reinterpret_cast<const unsigned long long*>(d_info),
+                            w.raster_rec, sr);
 }
 
 extern "C" size_t bsplat_render_host_scratch_bytes(int64_t N, int32_t channels, int32_t width, int32_t height) {

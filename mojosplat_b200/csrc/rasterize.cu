@@ -315,6 +315,447 @@ raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const flo
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// pair kernel (tile 16, RGB): the default fast path.
+// sm_100 executes packed FP32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot, two lanes of work), and the
+// rasterizer is bound by instruction issue, not by the FP32 pipe.  So each lane owns TWO pixels -- (x, y) and
+// (x, y + 4) of the warp's 8x8 block -- and the whole quadratic runs as f32x2 instructions on
+// register pairs.  Staged records keep every per-Gaussian operand duplicated {v, v}, so the pairs come
+// straight out of LDS.128 with no packing moves.  4 warps (128 threads) per 16x16 tile.
+//   record t (80 B): s[5t] = {mx, mx, my, my}  s[5t+1] = {-A, -A, -B, -B}  s[5t+2] = {-C, -C, L, L}
+//                    s[5t+3] = {r, g, b, tau}  s[5t+4] = {hy, hx, -, -}
+//   power = L - (A dx^2 + B dx dy + C dy^2) as  fma2(fma2(-A, dx, -B dy), dx, fma2(-C dy, dy, L))
+// A finished pixel carries -x = -inf (every later power is -inf or NaN and fails the alpha test).
+// Same culling as above on the 8x8 block; a skipped Gaussian has alpha < 1/255 on all 64 pixels.
+// ------------------------------------------------------------------------------------------
+constexpr int kPairThreads = 128;
+constexpr int kPairBatch = 256;
+constexpr int kPairRec = 5;  // float4 per staged Gaussian
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+template <bool kCull>
+__global__ void __launch_bounds__(kPairThreads)
+raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
+                   const float* __restrict__ colors, const float* __restrict__ opacities,
+                   const float* __restrict__ background, const int32_t* __restrict__ tile_ranges,
+                   const int32_t* __restrict__ tile_order, const int first_tile,
+                   const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
+                   float* __restrict__ image, const int vec_store,
+                   const unsigned long long* __restrict__ m_dev) {
+    __shared__ float4 s_g[kPairBatch * kPairRec];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int tile = tile_order ? __ldg(tile_order + blockIdx.x) : first_tile + (int)blockIdx.x;
+    const int tile_y = tile / tiles_w, tile_x = tile - tile_y * tiles_w;
+    // warp -> 8x8 pixel block; lane -> column (lane & 7), rows (lane >> 3) and (lane >> 3) + 4
+    const int bx = tile_x * kFastTile + (warp & 1) * 8;
+    const int by = tile_y * kFastTile + (warp >> 1) * 8;
+    const int j = bx + (lane & 7);
+    const int i0 = by + (lane >> 3), i1 = i0 + 4;
+    const bool in0 = (i0 < H) && (j < W), in1 = (i1 < H) && (j < W);
+    float npx0 = in0 ? -((float)j + 0.5f) : -INFINITY;  // negated x per pixel; -inf = finished
+    float npx1 = in1 ? -((float)j + 0.5f) : -INFINITY;
+    const f32x2 npy = pk2(-((float)i0 + 0.5f), -((float)i1 + 0.5f));
+    const float X0 = (float)bx + 0.5f, X1 = (float)bx + 7.5f;
+    const float Y0 = (float)by + 0.5f, Y1 = (float)by + 7.5f;
+
+    const int32_t r0 = tile_ranges[2 * tile], r1 = tile_ranges[2 * tile + 1];
+    float T0 = 1.0f, T1 = 1.0f;
+    float ar0 = 0.f, ag0 = 0.f, ab0 = 0.f, ar1 = 0.f, ag1 = 0.f, ab1 = 0.f;
+    const f32x2 one2 = pk2(1.0f, 1.0f), mone2 = pk2(-1.0f, -1.0f);
+
+    for (int32_t b0 = r0; b0 < r1; b0 += kPairBatch) {
+        const bool fin = !(npx0 > -INFINITY) && !(npx1 > -INFINITY);
+        if (__syncthreads_count(fin) >= kPairThreads) break;
+#pragma unroll
+        for (int h = 0; h < kPairBatch / kPairThreads; ++h) {
+            const int t = tid + h * kPairThreads;
+            const int32_t idx = b0 + t;
+            if (idx < r1) {
+                const int32_t g = __ldg(sorted_ids + idx);
+                float4 q0, q1, q2, q3, q4;
+                if (g >= 0 && (int64_t)g < N) {
+                    const float2 m = __ldg(reinterpret_cast<const float2*>(means2d) + g);
+                    const float ca = __ldg(conics + 3 * (int64_t)g), cb = __ldg(conics + 3 * (int64_t)g + 1),
+                                cc = __ldg(conics + 3 * (int64_t)g + 2);
+                    const float op = __ldg(opacities + g);
+                    const float A = 0.5f * kLog2e * ca, B = kLog2e * cb, C = 0.5f * kLog2e * cc;
+                    const float L = (op > 0.0f) ? log2f(op) : -INFINITY;
+                    const bool pd = (A > 0.0f) && (C > 0.0f) && (4.0f * A * C - B * B > 0.0f);
+                    float tau = pd ? (L - kLog2AlphaThreshold) : INFINITY;
+                    if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
+                    q0 = make_float4(m.x, m.x, m.y, m.y);
+                    q1 = make_float4(-A, -A, -B, -B);
+                    q2 = make_float4(-C, -C, L, L);
+                    q3 = make_float4(__ldg(colors + 3 * (int64_t)g), __ldg(colors + 3 * (int64_t)g + 1),
+                                     __ldg(colors + 3 * (int64_t)g + 2), tau);
+                    q4 = make_float4(pd ? -B / (2.0f * C) : 0.0f, pd ? -B / (2.0f * A) : 0.0f, 0.f, 0.f);
+                } else {
+                    q0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    q1 = q0;
+                    q2 = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
+                    q3 = make_float4(0.f, 0.f, 0.f, -INFINITY);
+                    q4 = q0;
+                }
+                float4* dst = s_g + kPairRec * t;
+                dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3; dst[4] = q4;
+            }
+        }
+        __syncthreads();
+
+        const int bs = min(kPairBatch, (int)(r1 - b0));
+        for (int c0 = 0; c0 < bs; c0 += 32) {
+            if (__all_sync(0xffffffffu, !(npx0 > -INFINITY) && !(npx1 > -INFINITY))) break;
+            unsigned int mask;
+            if (kCull) {
+                bool hit = false;
+                const int gi = c0 + 31 - lane;  // earliest Gaussian = highest ballot bit
+                if (gi < bs) {
+                    const float4* r = s_g + kPairRec * gi;
+                    const float4 p0 = r[0], p1 = r[1], p2 = r[2];
+                    const float tau = r[3].w;
+                    const float2 hh = *reinterpret_cast<const float2*>(r + 4);
+                    const float A = -p1.x, B = -p1.z, C = -p2.x;
+                    const float u0 = p0.x - X1, u1 = p0.x - X0;
+                    const float v0 = p0.z - Y1, v1 = p0.z - Y0;
+                    const bool zu = (u0 <= 0.0f) && (u1 >= 0.0f);
+                    const bool zv = (v0 <= 0.0f) && (v1 >= 0.0f);
+                    float qmin = 0.0f;
+                    if (!(zu && zv)) {
+                        float q1 = INFINITY, q2 = INFINITY;
+                        if (!zu) {
+                            const float ue = (u0 > 0.0f) ? u0 : u1;
+                            const float vstar = hh.x * ue;
+                            const float dv = vstar - fminf(fmaxf(vstar, v0), v1);
+                            q1 = fmaf(fmaf(0.5f * B, hh.x, A) * ue, ue, C * dv * dv);
+                        }
+                        if (!zv) {
+                            const float ve = (v0 > 0.0f) ? v0 : v1;
+                            const float ustar = hh.y * ve;
+                            const float du = ustar - fminf(fmaxf(ustar, u0), u1);
+                            q2 = fmaf(fmaf(0.5f * B, hh.y, C) * ve, ve, A * du * du);
+                        }
+                        qmin = fminf(q1, q2);
+                    }
+                    const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
+                    const float slack = 4e-6f * (A * um * um + C * vm * vm) + 1e-3f;
+                    hit = !(qmin > tau + slack);  // NaN-safe: anything odd counts as a hit
+                }
+                mask = __ballot_sync(0xffffffffu, hit);
+            } else {
+                const int rem = bs - c0;
+                mask = rem >= 32 ? 0xffffffffu : ~(0xffffffffu >> rem);
+            }
+            const float4* rec_hi = s_g + kPairRec * (c0 + 31);
+            while (mask) {
+                unsigned int b_hi;
+                asm("bfind.u32 %0, %1;" : "=r"(b_hi) : "r"(mask));
+                mask ^= 1u << b_hi;
+                const float4* r = rec_hi - kPairRec * (int)b_hi;
+                const float4 p0 = r[0], p1 = r[1], p2 = r[2];
+                const f32x2 dx = add2(pk2(p0.x, p0.y), pk2(npx0, npx1));
+                const f32x2 dy = add2(pk2(p0.z, p0.w), npy);
+                const f32x2 nbdy = mul2(pk2(p1.z, p1.w), dy);
+                const f32x2 ncdy = mul2(pk2(p2.x, p2.y), dy);
+                const f32x2 L2 = pk2(p2.z, p2.w);
+                const f32x2 lmc = fma2(ncdy, dy, L2);
+                const f32x2 t = fma2(pk2(p1.x, p1.y), dx, nbdy);
+                const f32x2 pw = fma2(t, dx, lmc);
+                float pw0, pw1;
+                upk2(pw, pw0, pw1);
+                const float L = p2.z;
+                const bool pass0 = (pw0 <= L) && (pw0 >= kLog2AlphaThreshold);
+                const bool pass1 = (pw1 <= L) && (pw1 >= kLog2AlphaThreshold);
+                const float a0 = fminf(0.999f, ex2_approx(pw0)), a1 = fminf(0.999f, ex2_approx(pw1));
+                const f32x2 a2 = pk2(a0, a1), T2 = pk2(T0, T1);
+                const f32x2 nT2 = mul2(T2, fma2(a2, mone2, one2));
+                const f32x2 vis2 = mul2(a2, T2);
+                float nT0, nT1, vis0, vis1;
+                upk2(nT2, nT0, nT1);
+                upk2(vis2, vis0, vis1);
+                const bool live0 = nT0 > 1e-4f, live1 = nT1 > 1e-4f;
+                const float4 c = r[3];
+                vis0 = (pass0 && live0) ? vis0 : 0.0f;
+                vis1 = (pass1 && live1) ? vis1 : 0.0f;
+                T0 = (pass0 && live0) ? nT0 : T0;
+                T1 = (pass1 && live1) ? nT1 : T1;
+                npx0 = (pass0 && !live0) ? -INFINITY : npx0;
+                npx1 = (pass1 && !live1) ? -INFINITY : npx1;
+                ar0 = fmaf(c.x, vis0, ar0); ag0 = fmaf(c.y, vis0, ag0); ab0 = fmaf(c.z, vis0, ab0);
+                ar1 = fmaf(c.x, vis1, ar1); ag1 = fmaf(c.y, vis1, ag1); ab1 = fmaf(c.z, vis1, ab1);
+            }
+        }
+    }
+
+    const float bgs = (m_dev != nullptr && *m_dev == 0ull) ? 0.0f : 1.0f;
+    const float bgr = bgs * __ldg(background), bgg = bgs * __ldg(background + 1), bgb = bgs * __ldg(background + 2);
+    const float o0r = fmaf(T0, bgr, ar0), o0g = fmaf(T0, bgg, ag0), o0b = fmaf(T0, bgb, ab0);
+    const float o1r = fmaf(T1, bgr, ar1), o1g = fmaf(T1, bgg, ag1), o1b = fmaf(T1, bgb, ab1);
+    const bool full_tile = (tile_x * kFastTile + kFastTile <= W) && (tile_y * kFastTile + kFastTile <= H);
+    if (vec_store && full_tile) {
+        __syncthreads();  // staging buffers are dead from here on
+        float* s_out = reinterpret_cast<float*>(s_g);  // 16 rows x 48 floats = 3 KB
+        const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 8 + (lane >> 3);
+        float* d0 = s_out + (ly * kFastTile + lx) * 3;
+        float* d1 = d0 + 4 * kFastTile * 3;
+        d0[0] = o0r; d0[1] = o0g; d0[2] = o0b;
+        d1[0] = o1r; d1[1] = o1g; d1[2] = o1b;
+        __syncthreads();
+        for (int v = tid; v < 16 * 12; v += kPairThreads) {
+            const int row = v / 12, c4 = v % 12;
+            const float4 val = reinterpret_cast<const float4*>(s_out)[row * 12 + c4];
+            float* dst = image + ((int64_t)(tile_y * kFastTile + row) * W + tile_x * kFastTile) * 3;
+            reinterpret_cast<float4*>(dst)[c4] = val;
+        }
+    } else {
+        if (in0) { float* dst = image + ((int64_t)i0 * W + j) * 3; dst[0] = o0r; dst[1] = o0g; dst[2] = o0b; }
+        if (in1) { float* dst = image + ((int64_t)i1 * W + j) * 3; dst[0] = o1r; dst[1] = o1g; dst[2] = o1b; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// warp kernel (tile 16, RGB, needs a 48 B/Gaussian record workspace): the default fast path.
+// Same packed-pair arithmetic as raster_pair_kernel, but the four warps of a tile never meet:
+//   * raster_prep_kernel turns every Gaussian ONCE per frame into a 48-byte raster record
+//     {mx, my, -A, -B | -C, L, hy, hx | r, g, b, tau} (log2-folded conic, culling constants),
+//     instead of once per (tile, Gaussian) inside the rasterizer;
+//   * each warp walks the tile's list by itself in chunks of 32: the records of chunk k+1 are gathered
+//     by sorted id with cp.async (16 B x 3 per lane) into the warp's own staging slot while chunk k is
+//     composited; lane l tests Gaussian l of the chunk against the warp's 8x8 block, the survivors are
+//     compacted (ballot prefix) into the warp's survivor slot in the duplicated {v, v} layout and walked
+//     front to back.  No __syncthreads in the loop: a warp whose 64 pixels are saturated just leaves.
+// ------------------------------------------------------------------------------------------
+constexpr int kWarpKStages = 3;  // chunk k is consumed while k+1 and k+2 are in flight
+
+__global__ void __launch_bounds__(256)
+raster_prep_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
+                   const float* __restrict__ colors, const float* __restrict__ opacities,
+                   float4* __restrict__ rec) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const float mx = __ldg(means2d + 2 * g), my = __ldg(means2d + 2 * g + 1);
+    const float ca = __ldg(conics + 3 * g), cb = __ldg(conics + 3 * g + 1), cc = __ldg(conics + 3 * g + 2);
+    const float op = __ldg(opacities + g);
+    const float A = 0.5f * kLog2e * ca, B = kLog2e * cb, C = 0.5f * kLog2e * cc;
+    // accurate log2 keeps alpha = 2^(L - q) within a few ulp of o*exp(-sigma)
+    const float L = (op > 0.0f) ? log2f(op) : -INFINITY;
+    const bool pd = (A > 0.0f) && (C > 0.0f) && (4.0f * A * C - B * B > 0.0f);
+    float tau = pd ? (L - kLog2AlphaThreshold) : INFINITY;
+    if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
+    rec[3 * g] = make_float4(mx, my, -A, -B);
+    rec[3 * g + 1] = make_float4(-C, L, pd ? -B / (2.0f * C) : 0.0f, pd ? -B / (2.0f * A) : 0.0f);
+    rec[3 * g + 2] = make_float4(__ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), tau);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <bool kCull>
+__global__ void __launch_bounds__(32, 32)
+raster_warp_kernel(const int64_t N, const float4* __restrict__ rec, const float* __restrict__ background,
+                   const int32_t* __restrict__ tile_ranges, const int32_t* __restrict__ tile_order,
+                   const int first_tile, const int32_t* __restrict__ sorted_ids, const int W, const int H,
+                   const int tiles_w, float* __restrict__ image, const int vec_store,
+                   const unsigned long long* __restrict__ m_dev) {
+    __shared__ float4 s_stage1[kWarpKStages][32 * 3];  // gathered records, a ring
+    __shared__ float4 s_surv1[32 * kPairRec];          // compacted survivors, {v, v} layout
+    float4 (*const s_stage)[32 * 3] = s_stage1;
+
+    // one warp per CTA: the four 8x8 blocks of a tile are scheduled (and retire) independently
+    const int lane = threadIdx.x;
+    const int warp = (int)blockIdx.x & 3;
+    const int tile_slot = (int)blockIdx.x >> 2;
+    const int tile = tile_order ? __ldg(tile_order + tile_slot) : first_tile + tile_slot;
+    const int tile_y = tile / tiles_w, tile_x = tile - tile_y * tiles_w;
+    const int bx = tile_x * kFastTile + (warp & 1) * 8;
+    const int by = tile_y * kFastTile + (warp >> 1) * 8;
+    const int j = bx + (lane & 7);
+    const int i0 = by + (lane >> 3), i1 = i0 + 4;
+    const bool in0 = (i0 < H) && (j < W), in1 = (i1 < H) && (j < W);
+    float npx0 = in0 ? -((float)j + 0.5f) : -INFINITY;  // negated x per pixel; -inf = finished
+    float npx1 = in1 ? -((float)j + 0.5f) : -INFINITY;
+    const f32x2 npy = pk2(-((float)i0 + 0.5f), -((float)i1 + 0.5f));
+    const float X0 = (float)bx + 0.5f, X1 = (float)bx + 7.5f;
+    const float Y0 = (float)by + 0.5f, Y1 = (float)by + 7.5f;
+
+    const int32_t r0 = tile_ranges[2 * tile], r1 = tile_ranges[2 * tile + 1];
+    float T0 = 1.0f, T1 = 1.0f;
+    float ar0 = 0.f, ag0 = 0.f, ab0 = 0.f, ar1 = 0.f, ag1 = 0.f, ab1 = 0.f;
+    const f32x2 one2 = pk2(1.0f, 1.0f), mone2 = pk2(-1.0f, -1.0f);
+    const unsigned int lt = (1u << lane) - 1u;
+    float4* const surv = s_surv1;
+
+    // gather of one chunk: lane l fetches the record of list entry (chunk base + l) into stage[buf]
+    auto gather = [&](int buf, int32_t id) {
+        float4* dst = &s_stage[buf][lane * 3];
+        if (id >= 0 && (int64_t)id < N) {
+            const float4* src = rec + 3 * (int64_t)id;
+            cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
+        } else {
+            // past the end of the list / invalid id (rasterization.mojo:109 guard): can never hit
+            dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[1] = make_float4(0.f, -INFINITY, 0.f, 0.f);
+            dst[2] = make_float4(0.f, 0.f, 0.f, -INFINITY);
+        }
+        cp_async_commit();
+    };
+
+    // Software pipeline: list ids are fetched 3 chunks ahead of their gather, records 2 chunks ahead of their
+    // use, so that a run of chunks without survivors (the culled Gaussians that the torch binning rules pile
+    // up in the corner tiles: ~10 k entries, 300 chunks per warp) advances at the speed of the test, not of
+    // an L2 round trip per chunk.
+    auto load_id = [&](int32_t at) { return (at < r1) ? __ldg(sorted_ids + at) : -1; };
+    int32_t id_a = -1, id_b = -1, id_c = -1;  // ids of this lane's entries in chunks k+2, k+3, k+4
+    if (r0 < r1) {
+        const int32_t id0 = load_id(r0 + lane), id1 = load_id(r0 + 32 + lane);
+        id_a = load_id(r0 + 64 + lane); id_b = load_id(r0 + 96 + lane); id_c = load_id(r0 + 128 + lane);
+        gather(0, id0);
+        gather(1, id1);
+    }
+    int buf = 0;
+    for (int32_t base = r0; base < r1; base += 32, buf = (buf + 1 == kWarpKStages) ? 0 : buf + 1) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // chunk k has landed (k+1 may still fly)
+        __syncwarp();
+        const float4* st = &s_stage[buf][lane * 3];
+        const float4 p0 = st[0], p1 = st[1], p2 = st[2];
+        // chunk k+2 goes into the slot chunk k-1 was read from (all lanes passed the vote that ended k-1)
+        gather((buf + 2 >= kWarpKStages) ? buf + 2 - kWarpKStages : buf + 2, id_a);
+        id_a = id_b; id_b = id_c;
+        id_c = load_id(base + 160 + lane);
+
+        bool hit;
+        if (kCull) {
+            const float A = -p0.z, B = -p0.w, C = -p1.x, tau = p2.w;
+            const float u0 = p0.x - X1, u1 = p0.x - X0;
+            const float v0 = p0.y - Y1, v1 = p0.y - Y0;
+            const bool zu = (u0 <= 0.0f) && (u1 >= 0.0f);
+            const bool zv = (v0 <= 0.0f) && (v1 >= 0.0f);
+            // min of q over the block = min over the (<= 2) edges facing the mean (see raster_fast_kernel)
+            float qmin = 0.0f;
+            if (!(zu && zv)) {
+                float q1 = INFINITY, q2 = INFINITY;
+                if (!zu) {
+                    const float ue = (u0 > 0.0f) ? u0 : u1;
+                    const float vstar = p1.z * ue;
+                    const float dv = vstar - fminf(fmaxf(vstar, v0), v1);
+                    q1 = fmaf(fmaf(0.5f * B, p1.z, A) * ue, ue, C * dv * dv);
+                }
+                if (!zv) {
+                    const float ve = (v0 > 0.0f) ? v0 : v1;
+                    const float ustar = p1.w * ve;
+                    const float du = ustar - fminf(fmaxf(ustar, u0), u1);
+                    q2 = fmaf(fmaf(0.5f * B, p1.w, C) * ve, ve, A * du * du);
+                }
+                qmin = fminf(q1, q2);
+            }
+            const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
+            const float slack = 4e-6f * (A * um * um + C * vm * vm) + 1e-3f;
+            hit = !(qmin > tau + slack);  // NaN-safe: anything odd counts as a hit
+        } else {
+            hit = !(p2.w == -INFINITY);  // every real Gaussian
+        }
+        const unsigned int mask = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            float4* d = surv + kPairRec * __popc(mask & lt);
+            d[0] = make_float4(p0.x, p0.x, p0.y, p0.y);
+            d[1] = make_float4(p0.z, p0.z, p0.w, p0.w);
+            d[2] = make_float4(p1.x, p1.x, p1.y, p1.y);
+            d[3] = p2;
+        }
+        __syncwarp();
+        const float4* r = surv;
+        const float4* const r_end = surv + kPairRec * __popc(mask);
+        for (; r != r_end; r += kPairRec) {
+            const float4 q0 = r[0], q1 = r[1], q2 = r[2];
+            const f32x2 dx = add2(pk2(q0.x, q0.y), pk2(npx0, npx1));
+            const f32x2 dy = add2(pk2(q0.z, q0.w), npy);
+            const f32x2 nbdy = mul2(pk2(q1.z, q1.w), dy);
+            const f32x2 ncdy = mul2(pk2(q2.x, q2.y), dy);
+            const f32x2 lmc = fma2(ncdy, dy, pk2(q2.z, q2.w));
+            const f32x2 t = fma2(pk2(q1.x, q1.y), dx, nbdy);
+            const f32x2 pw = fma2(t, dx, lmc);
+            float pw0, pw1;
+            upk2(pw, pw0, pw1);
+            const float L = q2.z;
+            const bool pass0 = (pw0 <= L) && (pw0 >= kLog2AlphaThreshold);
+            const bool pass1 = (pw1 <= L) && (pw1 >= kLog2AlphaThreshold);
+            const float a0 = fminf(0.999f, ex2_approx(pw0)), a1 = fminf(0.999f, ex2_approx(pw1));
+            const f32x2 a2 = pk2(a0, a1), T2 = pk2(T0, T1);
+            const f32x2 nT2 = mul2(T2, fma2(a2, mone2, one2));
+            const f32x2 vis2 = mul2(a2, T2);
+            float nT0, nT1, vis0, vis1;
+            upk2(nT2, nT0, nT1);
+            upk2(vis2, vis0, vis1);
+            const bool live0 = nT0 > 1e-4f, live1 = nT1 > 1e-4f;
+            const float4 c = r[3];
+            vis0 = (pass0 && live0) ? vis0 : 0.0f;
+            vis1 = (pass1 && live1) ? vis1 : 0.0f;
+            T0 = (pass0 && live0) ? nT0 : T0;
+            T1 = (pass1 && live1) ? nT1 : T1;
+            // saturated: this Gaussian is not added (rasterization.mojo:146-150) and the pixel retires
+            npx0 = (pass0 && !live0) ? -INFINITY : npx0;
+            npx1 = (pass1 && !live1) ? -INFINITY : npx1;
+            ar0 = fmaf(c.x, vis0, ar0); ag0 = fmaf(c.y, vis0, ag0); ab0 = fmaf(c.z, vis0, ab0);
+            ar1 = fmaf(c.x, vis1, ar1); ag1 = fmaf(c.y, vis1, ag1); ab1 = fmaf(c.z, vis1, ab1);
+        }
+        if (__all_sync(0xffffffffu, !(npx0 > -INFINITY) && !(npx1 > -INFINITY))) break;  // also orders surv reuse
+    }
+    cp_async_wait_all();  // nothing may still be landing in shared memory when it is reused below
+
+    const float bgs = (m_dev != nullptr && *m_dev == 0ull) ? 0.0f : 1.0f;
+    const float bgr = bgs * __ldg(background), bgg = bgs * __ldg(background + 1), bgb = bgs * __ldg(background + 2);
+    const float o0r = fmaf(T0, bgr, ar0), o0g = fmaf(T0, bgg, ag0), o0b = fmaf(T0, bgb, ab0);
+    const float o1r = fmaf(T1, bgr, ar1), o1g = fmaf(T1, bgg, ag1), o1b = fmaf(T1, bgb, ab1);
+    const bool full_block = (bx + 8 <= W) && (by + 8 <= H);
+    if (vec_store && full_block) {
+        __syncwarp();  // the survivor slot is dead from here on
+        float* s_out = reinterpret_cast<float*>(surv);  // 8 rows x 24 floats
+        float* d0 = s_out + ((lane >> 3) * 8 + (lane & 7)) * 3;
+        float* d1 = d0 + 4 * 8 * 3;
+        d0[0] = o0r; d0[1] = o0g; d0[2] = o0b;
+        d1[0] = o1r; d1[1] = o1g; d1[2] = o1b;
+        __syncwarp();
+        for (int v = lane; v < 8 * 6; v += 32) {  // 8 rows of 96 contiguous bytes
+            const int row = v / 6, c4 = v % 6;
+            const float4 val = reinterpret_cast<const float4*>(s_out)[row * 6 + c4];
+            float* dst = image + ((int64_t)(by + row) * W + bx) * 3;
+            reinterpret_cast<float4*>(dst)[c4] = val;
+        }
+    } else {
+        if (in0) { float* dst = image + ((int64_t)i0 * W + j) * 3; dst[0] = o0r; dst[1] = o0g; dst[2] = o0b; }
+        if (in1) { float* dst = image + ((int64_t)i1 * W + j) * 3; dst[0] = o1r; dst[1] = o1g; dst[2] = o1b; }
+    }
+}
+
 // Tiles sorted by list length, longest first (counting sort on len/32 capped to 255 buckets; order
 // inside a bucket is arbitrary and does not affect results).  One CTA, n_tiles is small.
 __global__ void __launch_bounds__(1024)
@@ -365,12 +806,19 @@ static int launch_faithful(int64_t N, int cdim, int c0, const float* means2d, co
 }
 
 namespace bsplat {
-// shared with capi.cu; mode 2 = fast arithmetic without sub-tile culling (A/B testing)
+// shared with capi.cu.  mode 0 = fast (pair kernel), 2 = the same without sub-tile culling (exactness A/B),
+// 3 = warp kernel (independent warps, needs the record workspace; pair kernel without it), 4 = one pixel
+// per lane (first fast kernel), 1 = faithful.  On config 3 the three fast kernels are within 3 % of each other
+// (0.29-0.30 ms): 264 M / 211 M / 187 M warp instructions, but the lighter ones issue less densely
+// (profiles/r01_raster_*): the pair kernel is the default.
+size_t raster_workspace_bytes(int64_t N) { return (size_t)(N > 0 ? N : 1) * 3 * sizeof(float4); }
+
 int rasterize_launch(int64_t N, int channels, const float* means2d, const float* conics, const float* colors,
                      const float* opacities, const float* background_dev,
                      const int32_t* tile_ranges, const int32_t* tile_order, const int32_t* sorted_ids, int W,
                      int H, int tile_size, int row_begin, int row_end, int mode, float* image,
-                     unsigned long long* stats, const unsigned long long* m_dev, cudaStream_t stream) {
+                     unsigned long long* stats, const unsigned long long* m_dev, void* rec_ws,
+                     cudaStream_t stream) {
     if (W <= 0 || H <= 0 || tile_size <= 0 || tile_size > 32 || channels <= 0 || !background_dev)
         return BSPLAT_E_ARG;
     const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
@@ -378,7 +826,7 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
     if (row_begin < 0) row_begin = 0;
     if (row_end > tiles_h) row_end = tiles_h;
     if (row_end <= row_begin) return BSPLAT_OK;  // empty band
-    const bool fast_ok = (mode == BSPLAT_RASTER_FAST || mode == 2) && tile_size == kFastTile &&
+    const bool fast_ok = (mode == BSPLAT_RASTER_FAST || (mode >= 2 && mode <= 4)) && tile_size == kFastTile &&
                          channels == 3 && stats == nullptr &&
                          (reinterpret_cast<uintptr_t>(means2d) & 7u) == 0;
     if (fast_ok) {
@@ -386,14 +834,28 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         const int vec = ((reinterpret_cast<uintptr_t>(image) & 15u) == 0 && (W % 4) == 0) ? 1 : 0;
         const unsigned grid = (unsigned)(tiles_w * (row_end - row_begin));
         const int first_tile = row_begin * tiles_w;
-        if (mode == 2)
-            raster_fast_kernel<false><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
+        const bool warp_path = mode == 3 && rec_ws != nullptr && N > 0 &&
+                               (reinterpret_cast<uintptr_t>(rec_ws) & 15u) == 0;
+        if (warp_path) {
+            float4* rec = static_cast<float4*>(rec_ws);
+            raster_prep_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(N, means2d, conics, colors, opacities, rec);
+            BSPLAT_LAUNCH_CHECK();
+            raster_warp_kernel<true><<<grid * 4, 32, 0, stream>>>(N, rec, bg, tile_ranges, tile_order,
+                                                                             first_tile, sorted_ids, W, H, tiles_w,
+                                                                             image, vec, m_dev);
+        } else if (mode == 2) {
+            raster_pair_kernel<false><<<grid, kPairThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
                                                                          tile_ranges, tile_order, first_tile, sorted_ids,
                                                                          W, H, tiles_w, image, vec, m_dev);
-        else
+        } else if (mode == 4) {
             raster_fast_kernel<true><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
                                                                         tile_ranges, tile_order, first_tile, sorted_ids,
                                                                         W, H, tiles_w, image, vec, m_dev);
+        } else {
+            raster_pair_kernel<true><<<grid, kPairThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
+                                                                        tile_ranges, tile_order, first_tile, sorted_ids,
+                                                                        W, H, tiles_w, image, vec, m_dev);
+        }
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
     }
