@@ -23,6 +23,9 @@
  *   bsplat_rasterize_fwd      mojosplat/rasterization.py:13-57 rasterize_gaussians
  *                             (= MAX op `rasterize_to_pixels_3dgs_fwd`,
  *                              kernels/rasterization.mojo:169-240, call at rasterization.py:167-183)
+ *   bsplat_rasterize_fwd_train / bsplat_rasterize_bwd   no reference counterpart (the reference is
+ *                             forward-only: render.py:11 @torch.no_grad, README.md:145); derivative of
+ *                             kernels/rasterization.mojo:138-162, checked against torch autograd
  *   bsplat_render_fwd         mojosplat/render.py:12-103 render_gaussians (the three stages chained
  *                              on one stream with a single 16-byte read-back)
  *   bsplat_render_enqueue     same without the read-back (device-side M, two-stream overlap, graph capture)
@@ -183,6 +186,28 @@ int bsplat_rasterize_stats(int64_t N, int32_t channels, const float* means2d, co
                            const int32_t* tile_ranges, const int32_t* sorted_ids, int64_t M,
                            int32_t width, int32_t height, int32_t tile_size, float* image,
                            uint64_t* stats, void* stream);
+
+/* ---- stage 3, training side (the reference is forward-only, render.py:11) --------- */
+/* Forward with the faithful arithmetic (kernels/rasterization.mojo:138-162) that also stores what the
+ * backward pass needs: final_T[height, width] (transmittance left at each pixel) and
+ * last_idx[height, width] (index INTO sorted_ids of the last Gaussian composited there, -1 if none).
+ * channels in 1..4; any tile size <= 32. */
+int bsplat_rasterize_fwd_train(int64_t N, int32_t channels, const float* means2d, const float* conics,
+                               const float* colors, const float* opacities, const float* background,
+                               const int32_t* tile_ranges, const int32_t* sorted_ids, int64_t M,
+                               int32_t width, int32_t height, int32_t tile_size, float* image,
+                               float* final_T, int32_t* last_idx, void* stream);
+/* Backward of the compositing: ACCUMULATES d loss / d (means2d[N,2], conics[N,3], colors[N,C],
+ * opacities[N]) into the caller-zeroed gradient arrays, given grad_image[height, width, C] and the
+ * final_T / last_idx of bsplat_rasterize_fwd_train on the same inputs. Threshold tests are piecewise
+ * constant; no gradient flows through the 0.999 alpha clamp. (d loss / d background =
+ * sum_pixels final_T * grad_image is left to the caller.) */
+int bsplat_rasterize_bwd(int64_t N, int32_t channels, const float* means2d, const float* conics,
+                         const float* colors, const float* opacities, const float* background,
+                         const int32_t* tile_ranges, const int32_t* sorted_ids, int64_t M,
+                         int32_t width, int32_t height, int32_t tile_size, const float* final_T,
+                         const int32_t* last_idx, const float* grad_image, float* grad_means2d,
+                         float* grad_conics, float* grad_colors, float* grad_opacities, void* stream);
 
 /* ---- fused forward ------------------------------------------------------------------------- */
 /* Optional outputs of the fused path (any pointer may be NULL). */

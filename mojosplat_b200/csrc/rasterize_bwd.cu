@@ -1,0 +1,324 @@
+// Stage 3, training side -- rasterization forward that keeps what the backward pass needs, and the
+// backward pass itself (BASELINE.json config 5 asks for it).
+//
+// The reference is forward-only (`@torch.no_grad`, mojosplat/render.py:11; README.md:145 lists the
+// backward pass as future work), so there is no reference implementation to restate: the gradient is
+// the derivative of the forward algorithm of mojosplat/kernels/rasterization.mojo:138-162,
+//   out = sum_k c_k alpha_k T_k + T_end bg,  T_k = prod_{j<k} (1 - alpha_j),  alpha = min(0.999, o exp(-sigma)),
+//   sigma = 0.5 (a dx^2 + c dy^2) + b dx dy,  d = mean - pixel,
+// with the skip / stop tests treated as piecewise constant, and it is checked against torch autograd
+// (fp64) through a pure-torch restatement of that forward (tests/test_gpu_raster_bwd.py).
+//
+//   raster_train_fwd_kernel  the faithful forward (same operation order as raster_faithful_kernel) that also
+//                            stores, per pixel, the final transmittance and the list index of the last
+//                            Gaussian that was composited.
+//   raster_bwd_kernel        one CTA per tile, one pixel per thread, the tile's list walked BACK to front
+//                            from the furthest "last index" of the tile, 1 Gaussian staged per thread per
+//                            batch; per Gaussian the 6 + C partial gradients are reduced over the warp
+//                            (butterfly shuffles, skipped when no lane of the warp contributes) and added
+//                            to the per-Gaussian gradient arrays with one atomic per value and warp.
+//   d out / d alpha_k = c_k T_k - (sum_{m>k} c_m alpha_m T_m + T_end bg) / (1 - alpha_k)
+//   d alpha / d sigma = -alpha, d alpha / d o = exp(-sigma)        (zero through the 0.999 clamp)
+//   d sigma / d(a, b, c) = (0.5 dx^2, dx dy, 0.5 dy^2),  d sigma / d mean = (a dx + b dy, b dx + c dy)
+#include "common.cuh"
+
+namespace bsplat {
+
+constexpr float kAlphaMin = 1.0f / 255.0f;
+
+template <int CH>
+__global__ void __launch_bounds__(1024)
+raster_train_fwd_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
+                        const float* __restrict__ colors, const float* __restrict__ opacities,
+                        const float* __restrict__ background, const int32_t* __restrict__ tile_ranges,
+                        const int32_t* __restrict__ sorted_ids, const int W, const int H, const int ts,
+                        const int tiles_w, float* __restrict__ image, float* __restrict__ final_T,
+                        int32_t* __restrict__ last_idx) {
+    extern __shared__ float s_buf[];
+    const int nthreads = blockDim.x;  // ts*ts rounded up to a multiple of 32
+    float* s_mx = s_buf;
+    float* s_my = s_mx + nthreads;
+    float* s_a = s_my + nthreads;
+    float* s_b = s_a + nthreads;
+    float* s_c = s_b + nthreads;
+    float* s_o = s_c + nthreads;
+    float* s_col = s_o + nthreads;  // [nthreads][CH]
+
+    const int tid = threadIdx.x;
+    const int ly = tid / ts, lx = tid - ly * ts;
+    const int tile = blockIdx.y * tiles_w + blockIdx.x;
+    const int i = blockIdx.y * ts + ly;
+    const int j = blockIdx.x * ts + lx;
+    const bool inside = (ly < ts) && (i < H) && (j < W);
+    bool done = !inside;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+
+    const int32_t r0 = tile_ranges[2 * tile], r1 = tile_ranges[2 * tile + 1];
+    float T = 1.0f;
+    float acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = 0.0f;
+    int32_t last = -1;
+
+    for (int32_t b0 = r0; b0 < r1; b0 += nthreads) {
+        if (__syncthreads_count(done) >= nthreads) break;
+        const int32_t idx = b0 + tid;
+        if (idx < r1) {
+            const int32_t g = sorted_ids[idx];
+            if (g >= 0 && (int64_t)g < N) {
+                s_mx[tid] = means2d[2 * (int64_t)g];
+                s_my[tid] = means2d[2 * (int64_t)g + 1];
+                s_a[tid] = conics[3 * (int64_t)g];
+                s_b[tid] = conics[3 * (int64_t)g + 1];
+                s_c[tid] = conics[3 * (int64_t)g + 2];
+                s_o[tid] = opacities[g];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) s_col[tid * CH + c] = colors[(int64_t)g * CH + c];
+            } else {
+                s_mx[tid] = s_my[tid] = s_a[tid] = s_b[tid] = s_c[tid] = 0.0f;
+                s_o[tid] = __int_as_float(0x7fc00000);  // NaN marks "not a Gaussian"
+            }
+        }
+        __syncthreads();
+        if (!done) {
+            const int bs = min(nthreads, (int)(r1 - b0));
+            for (int t = 0; t < bs; ++t) {
+                const float op = s_o[t];
+                if (op != op) continue;
+                const float dx = __fsub_rn(s_mx[t], px), dy = __fsub_rn(s_my[t], py);
+                const float a = s_a[t], b = s_b[t], c = s_c[t];
+                const float q = __fadd_rn(__fmul_rn(__fmul_rn(a, dx), dx), __fmul_rn(__fmul_rn(c, dy), dy));
+                const float sigma = __fadd_rn(__fmul_rn(0.5f, q), __fmul_rn(__fmul_rn(b, dx), dy));
+                float alpha = __fmul_rn(op, expf(-sigma));
+                alpha = fminf(alpha, 0.999f);
+                if (sigma < 0.0f || alpha < kAlphaMin) continue;
+                const float next_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                if (next_T <= 1e-4f) { done = true; break; }
+                const float vis = __fmul_rn(alpha, T);
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) acc[ch] = __fadd_rn(acc[ch], __fmul_rn(s_col[t * CH + ch], vis));
+                T = next_T;
+                last = b0 + t;
+            }
+        }
+    }
+    if (inside) {
+        const int64_t pix = (int64_t)i * W + j;
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) image[pix * CH + ch] = __fadd_rn(acc[ch], __fmul_rn(T, background[ch]));
+        final_T[pix] = T;
+        last_idx[pix] = last;
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(1024)
+raster_bwd_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
+                  const float* __restrict__ colors, const float* __restrict__ opacities,
+                  const float* __restrict__ background, const int32_t* __restrict__ tile_ranges,
+                  const int32_t* __restrict__ sorted_ids, const int W, const int H, const int ts,
+                  const int tiles_w, const float* __restrict__ final_T, const int32_t* __restrict__ last_idx,
+                  const float* __restrict__ grad_image, float* __restrict__ g_means2d,
+                  float* __restrict__ g_conics, float* __restrict__ g_colors, float* __restrict__ g_opac) {
+    extern __shared__ float s_buf[];
+    const int nthreads = blockDim.x;
+    float* s_mx = s_buf;
+    float* s_my = s_mx + nthreads;
+    float* s_a = s_my + nthreads;
+    float* s_b = s_a + nthreads;
+    float* s_c = s_b + nthreads;
+    float* s_o = s_c + nthreads;
+    float* s_col = s_o + nthreads;                                  // [nthreads][CH]
+    int32_t* s_id = reinterpret_cast<int32_t*>(s_col + nthreads * CH);  // [nthreads]
+    __shared__ int s_max_last;
+
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u;
+    const int ly = tid / ts, lx = tid - ly * ts;
+    const int tile = blockIdx.y * tiles_w + blockIdx.x;
+    const int i = blockIdx.y * ts + ly;
+    const int j = blockIdx.x * ts + lx;
+    const bool inside = (ly < ts) && (i < H) && (j < W);
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const int32_t r0 = tile_ranges[2 * tile];
+
+    const int64_t pix = (int64_t)i * W + j;
+    const float T_final = inside ? final_T[pix] : 0.0f;
+    const int32_t last = inside ? last_idx[pix] : -1;
+    float gout[CH], buffer[CH];
+    float bg_dot = 0.0f;  // sum_ch bg_ch * dL/dout_ch
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch) {
+        gout[ch] = inside ? grad_image[pix * CH + ch] : 0.0f;
+        buffer[ch] = 0.0f;
+        bg_dot += background[ch] * gout[ch];
+    }
+    float T = T_final;
+
+    if (tid == 0) s_max_last = -1;
+    __syncthreads();
+    if (last >= 0) atomicMax(&s_max_last, last);
+    __syncthreads();
+    const int32_t hi_all = s_max_last;  // furthest composited entry of the tile
+    if (hi_all < r0) return;
+
+    for (int32_t hi = hi_all; hi >= r0; hi -= nthreads) {
+        __syncthreads();  // previous batch fully consumed
+        const int32_t idx = hi - tid;  // staged back to front: slot t holds entry hi - t
+        if (idx >= r0) {
+            const int32_t g = sorted_ids[idx];
+            s_id[tid] = g;
+            if (g >= 0 && (int64_t)g < N) {
+                s_mx[tid] = means2d[2 * (int64_t)g];
+                s_my[tid] = means2d[2 * (int64_t)g + 1];
+                s_a[tid] = conics[3 * (int64_t)g];
+                s_b[tid] = conics[3 * (int64_t)g + 1];
+                s_c[tid] = conics[3 * (int64_t)g + 2];
+                s_o[tid] = opacities[g];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) s_col[tid * CH + c] = colors[(int64_t)g * CH + c];
+            } else {
+                s_mx[tid] = s_my[tid] = s_a[tid] = s_b[tid] = s_c[tid] = 0.0f;
+                s_o[tid] = __int_as_float(0x7fc00000);
+            }
+        }
+        __syncthreads();
+        const int bs = min(nthreads, (int)(hi - r0 + 1));
+        for (int t = 0; t < bs; ++t) {
+            const float op = s_o[t];
+            if (op != op) continue;  // uniform across the block
+            bool valid = inside && (hi - t <= last);
+            float dx = 0.f, dy = 0.f, alpha = 0.f, vis = 0.f;
+            const float a = s_a[t], b = s_b[t], c = s_c[t];
+            if (valid) {
+                dx = __fsub_rn(s_mx[t], px); dy = __fsub_rn(s_my[t], py);
+                const float q = __fadd_rn(__fmul_rn(__fmul_rn(a, dx), dx), __fmul_rn(__fmul_rn(c, dy), dy));
+                const float sigma = __fadd_rn(__fmul_rn(0.5f, q), __fmul_rn(__fmul_rn(b, dx), dy));
+                vis = expf(-sigma);
+                alpha = fminf(__fmul_rn(op, vis), 0.999f);
+                if (sigma < 0.0f || alpha < kAlphaMin) valid = false;
+            }
+            if (!__any_sync(0xffffffffu, valid)) continue;  // nothing to reduce for this warp
+            float v_rgb[CH];
+            float v_ca = 0.f, v_cb = 0.f, v_cc = 0.f, v_mx = 0.f, v_my = 0.f, v_op = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) v_rgb[ch] = 0.f;
+            if (valid) {
+                const float ra = 1.0f / (1.0f - alpha);
+                T *= ra;  // transmittance in front of this Gaussian
+                const float fac = alpha * T;
+                float v_alpha = 0.0f;
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) {
+                    const float col = s_col[t * CH + ch];
+                    v_rgb[ch] = fac * gout[ch];
+                    v_alpha += (col * T - buffer[ch] * ra) * gout[ch];
+                    buffer[ch] += col * fac;
+                }
+                v_alpha += -T_final * ra * bg_dot;
+                if (op * vis <= 0.999f) {  // no gradient through the clamp
+                    const float v_sigma = -op * vis * v_alpha;
+                    v_ca = 0.5f * v_sigma * dx * dx;
+                    v_cb = v_sigma * dx * dy;
+                    v_cc = 0.5f * v_sigma * dy * dy;
+                    v_mx = v_sigma * (a * dx + b * dy);
+                    v_my = v_sigma * (b * dx + c * dy);
+                    v_op = vis * v_alpha;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) v_rgb[ch] += __shfl_xor_sync(0xffffffffu, v_rgb[ch], d);
+                v_ca += __shfl_xor_sync(0xffffffffu, v_ca, d);
+                v_cb += __shfl_xor_sync(0xffffffffu, v_cb, d);
+                v_cc += __shfl_xor_sync(0xffffffffu, v_cc, d);
+                v_mx += __shfl_xor_sync(0xffffffffu, v_mx, d);
+                v_my += __shfl_xor_sync(0xffffffffu, v_my, d);
+                v_op += __shfl_xor_sync(0xffffffffu, v_op, d);
+            }
+            if (lane == 0) {
+                const int64_t g = s_id[t];
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) atomicAdd(g_colors + g * CH + ch, v_rgb[ch]);
+                atomicAdd(g_conics + 3 * g, v_ca);
+                atomicAdd(g_conics + 3 * g + 1, v_cb);
+                atomicAdd(g_conics + 3 * g + 2, v_cc);
+                atomicAdd(g_means2d + 2 * g, v_mx);
+                atomicAdd(g_means2d + 2 * g + 1, v_my);
+                atomicAdd(g_opac + g, v_op);
+            }
+        }
+    }
+}
+
+}  // namespace bsplat
+
+using namespace bsplat;
+
+namespace {
+inline int round_up32(int v) { return (v + 31) / 32 * 32; }
+}
+
+extern "C" int bsplat_rasterize_fwd_train(int64_t N, int32_t channels, const float* means2d, const float* conics,
+                                          const float* colors, const float* opacities, const float* background,
+                                          const int32_t* tile_ranges, const int32_t* sorted_ids, int64_t M,
+                                          int32_t width, int32_t height, int32_t tile_size, float* image,
+                                          float* final_T, int32_t* last_idx, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (N < 0 || M < 0 || !tile_ranges || !image || !background || !final_T || !last_idx) return BSPLAT_E_ARG;
+    if (M > 0 && (!sorted_ids || !means2d || !conics || !colors || !opacities)) return BSPLAT_E_ARG;
+    if (width <= 0 || height <= 0 || tile_size <= 0 || tile_size > 32) return BSPLAT_E_ARG;
+    if (channels < 1 || channels > 4) return BSPLAT_E_ARG;
+    const int tiles_w = (width + tile_size - 1) / tile_size, tiles_h = (height + tile_size - 1) / tile_size;
+    if (tiles_h > 65535) return BSPLAT_E_ARG;
+    const int nthreads = round_up32(tile_size * tile_size);
+    const dim3 grid(tiles_w, tiles_h);
+    const size_t smem = (size_t)nthreads * (6 + channels) * sizeof(float);
+#define BSPLAT_TRAIN_FWD(CH)                                                                                    \
+    raster_train_fwd_kernel<CH><<<grid, nthreads, smem, stream>>>(N, means2d, conics, colors, opacities,       \
+        background, tile_ranges, sorted_ids, width, height, tile_size, tiles_w, image, final_T, last_idx)
+    switch (channels) {
+        case 1: BSPLAT_TRAIN_FWD(1); break;
+        case 2: BSPLAT_TRAIN_FWD(2); break;
+        case 3: BSPLAT_TRAIN_FWD(3); break;
+        default: BSPLAT_TRAIN_FWD(4); break;
+    }
+#undef BSPLAT_TRAIN_FWD
+    BSPLAT_LAUNCH_CHECK();
+    return BSPLAT_OK;
+}
+
+extern "C" int bsplat_rasterize_bwd(int64_t N, int32_t channels, const float* means2d, const float* conics,
+                                    const float* colors, const float* opacities, const float* background,
+                                    const int32_t* tile_ranges, const int32_t* sorted_ids, int64_t M,
+                                    int32_t width, int32_t height, int32_t tile_size, const float* final_T,
+                                    const int32_t* last_idx, const float* grad_image, float* grad_means2d,
+                                    float* grad_conics, float* grad_colors, float* grad_opacities,
+                                    void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (N < 0 || M < 0 || !tile_ranges || !background || !final_T || !last_idx || !grad_image) return BSPLAT_E_ARG;
+    if (N > 0 && (!grad_means2d || !grad_conics || !grad_colors || !grad_opacities)) return BSPLAT_E_ARG;
+    if (M > 0 && (!sorted_ids || !means2d || !conics || !colors || !opacities)) return BSPLAT_E_ARG;
+    if (width <= 0 || height <= 0 || tile_size <= 0 || tile_size > 32) return BSPLAT_E_ARG;
+    if (channels < 1 || channels > 4) return BSPLAT_E_ARG;
+    if (N == 0 || M == 0) return BSPLAT_OK;  // gradients stay as the caller initialised them (zeros)
+    const int tiles_w = (width + tile_size - 1) / tile_size, tiles_h = (height + tile_size - 1) / tile_size;
+    if (tiles_h > 65535) return BSPLAT_E_ARG;
+    const int nthreads = round_up32(tile_size * tile_size);
+    const dim3 grid(tiles_w, tiles_h);
+    const size_t smem = (size_t)nthreads * (7 + channels) * sizeof(float);
+#define BSPLAT_BWD(CH)                                                                                          \
+    raster_bwd_kernel<CH><<<grid, nthreads, smem, stream>>>(N, means2d, conics, colors, opacities, background,  \
+        tile_ranges, sorted_ids, width, height, tile_size, tiles_w, final_T, last_idx, grad_image, grad_means2d, \
+        grad_conics, grad_colors, grad_opacities)
+    switch (channels) {
+        case 1: BSPLAT_BWD(1); break;
+        case 2: BSPLAT_BWD(2); break;
+        case 3: BSPLAT_BWD(3); break;
+        default: BSPLAT_BWD(4); break;
+    }
+#undef BSPLAT_BWD
+    BSPLAT_LAUNCH_CHECK();
+    return BSPLAT_OK;
+}

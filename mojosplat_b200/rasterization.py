@@ -107,3 +107,59 @@ def rasterize_gaussians_stats(means2d, conics, colors, opacities, background_col
     _lib.check(rc, "bsplat_rasterize_stats")
     e_all, e_pass = stats.tolist()
     return image, int(e_all), int(e_pass)
+
+
+class _RasterizeFn(torch.autograd.Function):
+    """Differentiable compositing (bsplat_rasterize_fwd_train / bsplat_rasterize_bwd)."""
+
+    @staticmethod
+    def forward(ctx, means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, H, W, tile_size):
+        L = _lib.require_device(means2d.device)
+        dev, means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, N, C = _prep(
+            means2d, conics, colors, opacities, background, tile_ranges, sorted_ids)
+        if not 1 <= C <= 4:
+            raise ValueError("the differentiable rasterizer supports 1..4 colour channels")
+        image = torch.empty((H, W, C), dtype=torch.float32, device=dev)
+        final_T = torch.empty((H, W), dtype=torch.float32, device=dev)
+        last_idx = torch.empty((H, W), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.bsplat_rasterize_fwd_train(N, C, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
+                                              _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
+                                              _lib.ptr(sorted_ids), sorted_ids.numel(), W, H, int(tile_size),
+                                              _lib.ptr(image), _lib.ptr(final_T), _lib.ptr(last_idx),
+                                              _lib.stream_ptr(dev))
+        _lib.check(rc, "bsplat_rasterize_fwd_train")
+        ctx.save_for_backward(means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, final_T,
+                              last_idx)
+        ctx.dims = (H, W, int(tile_size))
+        return image
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, final_T, last_idx = ctx.saved_tensors
+        H, W, ts = ctx.dims
+        dev = means2d.device
+        L = _lib.require_device(dev)
+        N, C = colors.shape
+        grad_image = grad_image.to(torch.float32).contiguous()
+        g_m = torch.zeros_like(means2d); g_k = torch.zeros_like(conics)
+        g_c = torch.zeros_like(colors); g_o = torch.zeros_like(opacities)
+        with torch.cuda.device(dev):
+            rc = L.bsplat_rasterize_bwd(N, C, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
+                                        _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
+                                        _lib.ptr(sorted_ids), sorted_ids.numel(), W, H, ts, _lib.ptr(final_T),
+                                        _lib.ptr(last_idx), _lib.ptr(grad_image), _lib.ptr(g_m), _lib.ptr(g_k),
+                                        _lib.ptr(g_c), _lib.ptr(g_o), _lib.stream_ptr(dev))
+        _lib.check(rc, "bsplat_rasterize_bwd")
+        g_bg = (final_T.unsqueeze(-1) * grad_image).sum(dim=(0, 1))
+        return g_m, g_k, g_c, g_o, g_bg, None, None, None, None, None
+
+
+def rasterize_gaussians_diff(means2d, conics, colors, opacities, background_color, tile_ranges,
+                             sorted_gaussian_indices, camera, tile_size=16):
+    """Differentiable ``rasterize_gaussians`` (additive: the reference is forward-only, render.py:11).
+    Gradients flow to means2d, conics, colors, opacities and background_color; the tile lists are
+    treated as constants. Forward values are those of the faithful kernel."""
+    opac = opacities.reshape(-1)
+    return _RasterizeFn.apply(means2d, conics, colors, opac, background_color, tile_ranges,
+                              sorted_gaussian_indices, int(camera.H), int(camera.W), int(tile_size))
