@@ -278,6 +278,21 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     latency_ms = float(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))) / Kl
 
+    # ---- the same single frame as ONE CUDA-graph launch (captured sync-free frame, indirect camera) ----
+    from mojosplat_b200.pipeline import GraphRenderer
+    gr = GraphRenderer(*g, view_of(0), bg, semantics=sem)
+    for k in range(3):
+        gr.render(view_of(k))
+    for k in range(Kl):
+        flush.zero_()
+        ev_s[k].record()
+        gr.render(view_of(k))
+        ev_e[k].record()
+    torch.cuda.synchronize(dev)
+    gr.check()
+    graph_latency_ms = float(sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))) / Kl
+    del gr
+
     # ---- end-to-end through the public host-buffer API (pinned host in, host image out) ----
     host_all = host if host is not None else [x.cpu().pin_memory() for x in g]
     out_img = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
@@ -390,7 +405,8 @@ def run_b200(args, rank, world, local_rank):
                                      "rasterization(k) (OverlappedPipeline)" if args.pipeline == "overlapped" else
                                      f"{args.pipeline_depth} frames in flight per GPU (begin(k+1) overlaps end(k), FramePipeline)"),
                    "timing": "one CUDA-event pair around the K steps, max over ranks",
-                   "wall_ms_per_step": 1e3 * wall / K, "single_frame_latency_ms": latency_ms},
+                   "wall_ms_per_step": 1e3 * wall / K, "single_frame_latency_ms": latency_ms,
+                   "graph_frame_latency_ms": graph_latency_ms},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "api": "mojosplat_b200.render_gaussians_host (pinned host tensors in, host image out)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "stages": stages,

@@ -138,7 +138,7 @@ def load() -> ctypes.CDLL:
                                         c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
                                         POINTER(c_size_t), c_void_p]
         L.bsplat_render_enqueue.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
-                                            POINTER(BsplatCamera), c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                            c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
                                             c_void_p, c_size_t, c_int64, POINTER(c_size_t), c_void_p, c_void_p,
                                             c_void_p, c_void_p]
         L.bsplat_rasterize_stats.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -10,6 +10,7 @@ frame-by-frame rendering (same kernels, same order inside a frame).
 """
 from __future__ import annotations
 
+import ctypes
 from ctypes import byref, c_size_t
 from typing import Sequence
 
@@ -157,7 +158,7 @@ class OverlappedPipeline:
         needed = c_size_t(0)
         rc = self.L.bsplat_render_enqueue(
             self.N, _lib.ptr(g[0]), _lib.ptr(g[1]), _lib.ptr(g[2]), _lib.ptr(g[3]), _lib.ptr(g[4]), self.C,
-            byref(cam_struct), _lib.ptr(bg), self.ts, self.semantics, self.flags, _lib.ptr(image),
+            ctypes.addressof(cam_struct), _lib.ptr(bg), self.ts, self.semantics, self.flags, _lib.ptr(image),
             _lib.ptr(self.ws[slot]), self.ws[slot].numel(), self.m_cap, byref(needed), info_host.data_ptr(),
             s_bin.cuda_stream, self.s_ras.cuda_stream, self.ev_bin[slot].cuda_event)
         _lib.check(rc, "bsplat_render_enqueue")
@@ -223,3 +224,96 @@ class OverlappedPipeline:
                         self._enqueue(0, gs[k], cams[k], bg, out[k % out.shape[0]], infos[k])
                     torch.cuda.synchronize(self.dev)
         return redone
+
+
+class GraphRenderer:
+    """One frame captured into a CUDA graph and replayed per view.
+
+    The sync-free frame (bsplat_render_enqueue) is captured once with BSPLAT_FLAG_CAMERA_INDIRECT: the
+    graph starts by copying the camera POD from a pinned host struct, so ``render(camera)`` only rewrites
+    that struct and launches the graph -- one driver call instead of ~15 kernel/memset launches, no host
+    read-back.  Gaussians, background and the output image are fixed device buffers owned by the renderer
+    (``update_gaussians`` copies new values in place; N, image size and channel count are fixed).
+    The pair capacity is fixed at capture time; ``check()`` reports an overflow of the last frame (the
+    caller then rebuilds the renderer with a larger ``m_capacity``).
+    """
+
+    def __init__(self, means3d, scales, quats, opacities, features, camera: Camera, background,
+                 tile_size: int = 16, semantics: int = _lib.SEM_TORCH, m_capacity: int | None = None,
+                 raster_mode: str = "fast"):
+        self.dev = means3d.device
+        self.L = _lib.require_device(self.dev)
+        self.g = [_lib.as_f32(means3d, "means3d").clone(), _lib.as_f32(scales, "scales").clone(),
+                  _lib.as_f32(quats, "quats").clone(), _lib.as_f32(opacities, "opacities").reshape(-1).clone(),
+                  _lib.as_f32(features, "features").clone()]
+        self.N, self.C = self.g[4].shape
+        self.W, self.H, self.ts = int(camera.W), int(camera.H), int(tile_size)
+        self.bg = _lib.as_f32(background, "background").to(self.dev).clone()
+        self.image = torch.empty((self.H, self.W, self.C), dtype=torch.float32, device=self.dev)
+        self.m_cap = int(m_capacity) if m_capacity else 8 * self.N + 4096
+        nbytes = self.L.bsplat_render_workspace_bytes(self.N, self.m_cap, self.W, self.H, self.ts)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+        # pinned host blocks the graph reads / writes at replay time
+        self.cam_host = torch.zeros(ctypes_sizeof_camera(), dtype=torch.uint8).pin_memory()
+        self.info_host = torch.zeros(32, dtype=torch.uint8).pin_memory()
+        self._write_camera(camera)
+        flags = RASTER_MODES[raster_mode] | _lib.FLAG_CAMERA_INDIRECT
+        self.stream = torch.cuda.Stream(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+
+        def enqueue():
+            needed = c_size_t(0)
+            rc = self.L.bsplat_render_enqueue(
+                self.N, _lib.ptr(self.g[0]), _lib.ptr(self.g[1]), _lib.ptr(self.g[2]), _lib.ptr(self.g[3]),
+                _lib.ptr(self.g[4]), self.C, self.cam_host.data_ptr(), _lib.ptr(self.bg), self.ts, semantics, flags,
+                _lib.ptr(self.image), _lib.ptr(self.ws), self.ws.numel(), self.m_cap, byref(needed),
+                self.info_host.data_ptr(), torch.cuda.current_stream(self.dev).cuda_stream, None, None)
+            _lib.check(rc, "bsplat_render_enqueue")
+
+        with torch.cuda.device(self.dev):
+            self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(self.stream):
+                enqueue()  # warm-up outside the capture (module loading, lazy allocations)
+            self.stream.synchronize()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                enqueue()
+
+    def _write_camera(self, camera: Camera) -> None:
+        if int(camera.W) != self.W or int(camera.H) != self.H:
+            raise ValueError("GraphRenderer: the image size is fixed at capture time")
+        cs = _lib.camera_struct(camera)
+        import ctypes
+        ctypes.memmove(self.cam_host.data_ptr(), ctypes.addressof(cs), ctypes.sizeof(cs))
+
+    def update_gaussians(self, means3d=None, scales=None, quats=None, opacities=None, features=None) -> None:
+        for dst, src in zip(self.g, (means3d, scales, quats, opacities, features)):
+            if src is not None:
+                dst.copy_(src.reshape(dst.shape))
+
+    @torch.no_grad()
+    def render(self, camera: Camera) -> torch.Tensor:
+        """Replays the frame for ``camera``; returns the renderer's image buffer (valid on the current
+        stream; overwritten by the next call)."""
+        # the previous replay must have consumed the pinned camera before it is rewritten
+        self.stream.synchronize()
+        self._write_camera(camera)
+        cur = torch.cuda.current_stream(self.dev)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+        cur.wait_stream(self.stream)
+        return self.image
+
+    def check(self) -> int:
+        """Synchronise; returns M of the last frame, raises if it exceeded the captured capacity."""
+        self.stream.synchronize()
+        info = _lib.BsplatBinInfo.from_buffer_copy(self.info_host.numpy().tobytes())
+        if info.reserved[1]:
+            raise RuntimeError(f"GraphRenderer: {int(info.n_isect)} intersections exceed the captured capacity "
+                               f"{self.m_cap}; rebuild with a larger m_capacity")
+        return int(info.n_isect)
+
+
+def ctypes_sizeof_camera() -> int:
+    import ctypes
+    return ctypes.sizeof(_lib.BsplatCamera)

@@ -36,7 +36,7 @@ for k in range(n):
     b1[k].record(sb)
     needed = c_size_t(0)
     rc = pipe.L.bsplat_render_enqueue(pipe.N, _lib.ptr(g[0]), _lib.ptr(g[1]), _lib.ptr(g[2]), _lib.ptr(g[3]), _lib.ptr(g[4]), 3,
-        byref(cs[k]), _lib.ptr(bg), 16, pipe.semantics, pipe.flags, _lib.ptr(out[k % 4]), _lib.ptr(pipe.ws[slot]), pipe.ws[slot].numel(),
+        __import__('ctypes').addressof(cs[k]), _lib.ptr(bg), 16, pipe.semantics, pipe.flags, _lib.ptr(out[k % 4]), _lib.ptr(pipe.ws[slot]), pipe.ws[slot].numel(),
         pipe.m_cap, byref(needed), infos[k].data_ptr(), sb.cuda_stream, pipe.s_ras.cuda_stream, b1[k].cuda_event)
     assert rc == 0
     r1[k].record(pipe.s_ras)

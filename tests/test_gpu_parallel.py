@@ -109,3 +109,27 @@ def test_enqueue_empty_scene_gives_zero_image(cuda_device):
         assert float(img.abs().max()) == 0.0
     else:
         pytest.skip("scene still produced intersections")
+
+
+def test_graph_renderer_replays_equal_direct_renders(cuda_device):
+    """One captured frame (CUDA graph, indirect camera) replayed for several poses == direct renders."""
+    from mojosplat_b200.pipeline import GraphRenderer
+    sc = synthetic.make_scene("config3_1m_1080p", N=150_000)
+    (m, s, q, o, c), _ = scene_on(sc, cuda_device)
+    cams = synthetic.orbit_cameras(5, 640, 360, 330.0)
+    bg = sc.background.to(cuda_device)
+    gr = GraphRenderer(m, s, q, o, c, cams[0], bg)
+    for cam in cams:
+        img = gr.render(cam).clone()
+        assert gr.check() > 0
+        assert torch.equal(img, ms.render_gaussians(m, s, q, o, c, cam, background_color=bg))
+    # new Gaussian values in the same buffers
+    c2 = c.flip(0).contiguous()
+    gr.update_gaussians(features=c2)
+    assert torch.equal(gr.render(cams[1]), ms.render_gaussians(m, s, q, o, c2, cams[1], background_color=bg))
+    with pytest.raises(ValueError):
+        gr.render(synthetic.orbit_cameras(1, 320, 200, 100.0)[0])
+    small = GraphRenderer(m, s, q, o, c, cams[0], bg, m_capacity=1000)
+    small.render(cams[0])
+    with pytest.raises(RuntimeError):
+        small.check()
