@@ -317,3 +317,75 @@ class GraphRenderer:
 def ctypes_sizeof_camera() -> int:
     import ctypes
     return ctypes.sizeof(_lib.BsplatCamera)
+
+
+class HostFramePipeline:
+    """End-to-end frames from HOST buffers: every frame uploads its Gaussians (pinned host -> device),
+    renders (sync-free frame, binning / rasterizer streams as in OverlappedPipeline) and downloads its image
+    (device -> pinned host), with the three phases of consecutive frames overlapped on separate streams:
+    H2D(k+1) | render(k) | D2H(k-1).  PCIe is full duplex, so the frame period approaches the larger of the
+    upload time and the render time instead of their sum.  This is the path bench.py's `e2e` figure times.
+    """
+
+    def __init__(self, device, N: int, W: int, H: int, channels: int = 3, tile_size: int = 16,
+                 semantics: int = _lib.SEM_TORCH, m_capacity: int | None = None, raster_mode: str = "fast",
+                 in_slots: int = 2, out_slots: int = 3):
+        self.dev = torch.device(device)
+        self.N, self.W, self.H, self.C = int(N), int(W), int(H), int(channels)
+        self.in_slots, self.out_slots = in_slots, out_slots
+        self.core = OverlappedPipeline(device, N, W, H, channels, tile_size, semantics, slots=out_slots,
+                                       m_capacity=m_capacity, raster_mode=raster_mode, bin_streams=2)
+        with torch.cuda.device(self.dev):
+            self.s_in = torch.cuda.Stream(self.dev)
+            self.s_out = torch.cuda.Stream(self.dev)
+            shapes = [(N, 3), (N, 3), (N, 4), (N,), (N, channels)]
+            self.g_dev = [[torch.empty(sh, dtype=torch.float32, device=self.dev) for sh in shapes]
+                          for _ in range(in_slots)]
+            self.img_dev = torch.empty((out_slots, H, W, channels), dtype=torch.float32, device=self.dev)
+            self.bg_dev = torch.empty((channels,), dtype=torch.float32, device=self.dev)
+
+    @torch.no_grad()
+    def render(self, host_scenes, cameras: Sequence[Camera], background_host: torch.Tensor,
+               out_host: torch.Tensor) -> torch.Tensor:
+        """host_scenes: callable k -> 5 contiguous float32 CPU tensors (pinned for full speed);
+        out_host: pinned [n or ring, H, W, C].  Returns out_host after a final synchronisation."""
+        core = self.core
+        n = len(cameras)
+        cams = [_lib.camera_struct(c) for c in cameras]
+        infos = torch.zeros((max(n, 1), 32), dtype=torch.uint8).pin_memory()
+        ev_in = [torch.cuda.Event() for _ in range(n)]
+        ev_used = [torch.cuda.Event() for _ in range(n)]   # frame k no longer reads its input slot
+        ev_ras = [torch.cuda.Event() for _ in range(n)]
+        ev_out = [torch.cuda.Event() for _ in range(n)]
+        with torch.cuda.device(self.dev):
+            with torch.cuda.stream(self.s_in):
+                self.bg_dev.copy_(background_host.reshape(-1), non_blocking=True)
+            for k in range(n):
+                islot, oslot = k % self.in_slots, k % self.out_slots
+                src = host_scenes(k)
+                with torch.cuda.stream(self.s_in):
+                    if k >= self.in_slots:
+                        self.s_in.wait_event(ev_used[k - self.in_slots])
+                    for d, h in zip(self.g_dev[islot], src):
+                        d.copy_(h.reshape(d.shape), non_blocking=True)
+                    ev_in[k].record(self.s_in)
+                sb = core.s_bins[k % core.n_bin]
+                sb.wait_event(ev_in[k])
+                if k >= self.out_slots:
+                    sb.wait_event(ev_ras[k - self.out_slots])    # workspace slot free
+                    core.s_ras.wait_event(ev_out[k - self.out_slots])  # image slot downloaded
+                core.ev_bin[oslot].record(sb)
+                core._enqueue(oslot, self.g_dev[islot], cams[k], self.bg_dev, self.img_dev[oslot], infos[k], sb)
+                ev_ras[k].record(core.s_ras)   # rasterizer read colours/opacities: inputs are free after it
+                ev_used[k] = ev_ras[k]
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(ev_ras[k])
+                    out_host[k % out_host.shape[0]].copy_(self.img_dev[oslot], non_blocking=True)
+                    ev_out[k].record(self.s_out)
+        torch.cuda.synchronize(self.dev)
+        for k in range(n):
+            info = _lib.BsplatBinInfo.from_buffer_copy(infos[k].numpy().tobytes())
+            if info.reserved[1]:
+                raise RuntimeError(f"frame {k}: {int(info.n_isect)} intersections exceed the pair capacity "
+                                   f"{core.m_cap}; construct HostFramePipeline with a larger m_capacity")
+        return out_host

@@ -133,3 +133,19 @@ def test_graph_renderer_replays_equal_direct_renders(cuda_device):
     small.render(cams[0])
     with pytest.raises(RuntimeError):
         small.check()
+
+
+def test_host_frame_pipeline_equals_host_api(cuda_device):
+    """Pipelined end-to-end path (H2D | render | D2H overlapped) == render_gaussians_host frame by frame."""
+    from mojosplat_b200.pipeline import HostFramePipeline
+    sc = synthetic.make_scene("config3_1m_1080p", N=120_000)
+    host = [t.pin_memory() for t in sc.gaussians()]
+    host2 = [host[0], host[1], host[2], host[3], host[4].flip(0).contiguous().pin_memory()]
+    cams = synthetic.orbit_cameras(7, 640, 360, 330.0)
+    pipe = HostFramePipeline(cuda_device, sc.N, 640, 360)
+    out = torch.empty((7, 360, 640, 3), dtype=torch.float32).pin_memory()
+    scenes = lambda k: host2 if k % 3 == 2 else host
+    pipe.render(scenes, cams, sc.background, out)
+    for k, cam in enumerate(cams):
+        ref = ms.render_gaussians_host(*scenes(k), cam, background_color=sc.background, device=cuda_device)
+        assert torch.equal(out[k], ref), k
