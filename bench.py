@@ -27,6 +27,7 @@ import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
+_emit = print
 sys.path.insert(0, str(ROOT))
 
 import numpy as np  # noqa: E402
@@ -166,7 +167,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def workload_name(args, sc):
@@ -423,10 +424,18 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "stages": stages,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line, default=float), flush=True)
+    _emit(json.dumps(line, default=float))
 
 
 def main():
+    # The contract is ONE JSON line on stdout: NCCL and friends print banners there ("NCCL version ..."), so
+    # everything written to fd 1 during the run goes to stderr and the line is written to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(text):
+        os.write(real_stdout, (text + "\n").encode())
     args = parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -437,6 +446,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL_DEBUG=VERSION/INFO makes NCCL print a banner on stdout; the contract is one JSON line there
+        os.environ["NCCL_DEBUG"] = os.environ.get("BSPLAT_NCCL_DEBUG", "WARN")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:

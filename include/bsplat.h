@@ -265,6 +265,15 @@ int bsplat_render_enqueue(int64_t N, const float* means3d, const float* log_scal
                           size_t workspace_bytes, int64_t M_capacity, size_t* needed_bytes,
                           bsplat_bin_info* info_host_pinned, void* stream_bin, void* stream_raster,
                           void* event_bin_done);
+/* The sync-free frame restricted to tile rows [tile_row_begin, tile_row_end) (row-band multi-GPU split):
+ * all N Gaussians are projected, only the band is binned / rasterized / written into `image`. */
+int bsplat_render_enqueue_band(int64_t N, const float* means3d, const float* log_scales, const float* quats,
+                               const float* opacities, const float* colors, int32_t channels,
+                               const bsplat_camera* cam, const float* background, int32_t tile_size,
+                               int32_t semantics, int32_t flags, int32_t tile_row_begin, int32_t tile_row_end,
+                               float* image, void* workspace, size_t workspace_bytes, int64_t M_capacity,
+                               size_t* needed_bytes, bsplat_bin_info* info_host_pinned, void* stream_bin,
+                               void* stream_raster, void* event_bin_done);
 /* Same with HOST buffers (pinned or pageable): copies the Gaussians in, renders, copies the
  * image out and synchronises the stream. device_scratch must hold
  * bsplat_render_host_scratch_bytes() in addition to the render workspace. */

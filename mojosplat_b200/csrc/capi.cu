@@ -385,6 +385,22 @@ extern "C" int bsplat_render_enqueue(int64_t N, const float* means3d, const floa
                                      size_t workspace_bytes, int64_t M_capacity, size_t* needed_bytes,
                                      bsplat_bin_info* info_host_pinned, void* stream_bin_, void* stream_raster_,
                                      void* event_bin_done) {
+    return bsplat_render_enqueue_band(N, means3d, log_scales, quats, opacities, colors, channels, cam, background,
+                                      tile_size, semantics, flags, 0, 1 << 30, image, workspace, workspace_bytes,
+                                      M_capacity, needed_bytes, info_host_pinned, stream_bin_, stream_raster_,
+                                      event_bin_done);
+}
+
+// The same frame restricted to tile rows [tile_row_begin, tile_row_end): every Gaussian is projected, only the
+// band is binned and rasterized, only the band's rows of `image` are written (row-band multi-GPU split).
+extern "C" int bsplat_render_enqueue_band(int64_t N, const float* means3d, const float* log_scales,
+                                          const float* quats, const float* opacities, const float* colors,
+                                          int32_t channels, const bsplat_camera* cam, const float* background,
+                                          int32_t tile_size, int32_t semantics, int32_t flags,
+                                          int32_t tile_row_begin, int32_t tile_row_end, float* image,
+                                          void* workspace, size_t workspace_bytes, int64_t M_capacity,
+                                          size_t* needed_bytes, bsplat_bin_info* info_host_pinned,
+                                          void* stream_bin_, void* stream_raster_, void* event_bin_done) {
     cudaStream_t sb = (cudaStream_t)stream_bin_;
     cudaStream_t sr = stream_raster_ ? (cudaStream_t)stream_raster_ : sb;
     if (!cam || !image || !background || N <= 0 || M_capacity <= 0 || channels <= 0 || tile_size <= 0 ||
@@ -411,8 +427,11 @@ extern "C" int bsplat_render_enqueue(int64_t N, const float* means3d, const floa
                                 w.depths, w.radii, sb, cam_dev);
     if (rc != BSPLAT_OK) return rc;
     const int tiles_h = (H + tile_size - 1) / tile_size;
+    const int row0 = tile_row_begin < 0 ? 0 : tile_row_begin;
+    const int row1 = tile_row_end > tiles_h ? tiles_h : tile_row_end;
+    if (row1 <= row0) return BSPLAT_OK;  // empty band: nothing to write
     BinParams p;
-    rc = make_bin_params(W, H, tile_size, 0, tiles_h, semantics, &p);
+    rc = make_bin_params(W, H, tile_size, row0, row1, semantics, &p);
     if (rc != BSPLAT_OK) return rc;
     rc = bin2_prepare(N, w.means2d, w.radii, 0, w.depths, p, w.bin_ws, w.bin_bytes, sb);
     if (rc != BSPLAT_OK) return rc;
@@ -428,7 +447,7 @@ extern "C" int bsplat_render_enqueue(int64_t N, const float* means3d, const floa
     }
     const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
     return rasterize_launch(N, channels, w.means2d, w.conics, colors, opacities, background, w.tile_ranges,
-                            fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, 0, tiles_h,
+                            fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, row0, row1,
                             raster_mode, image, nullptr, reinterpret_cast<const unsigned long long*>(d_info),
                             w.raster_rec, sr);
 }

@@ -195,3 +195,95 @@ def assemble_bands(image: torch.Tensor, bands, tile_size: int, rank: int, world:
     for r, (s, e) in enumerate(rows):
         full[s:e] = parts[r][: e - s]
     return full
+
+
+class RowBandRenderer:
+    """One huge frame per step, split into tile-row bands across the ranks (BASELINE.json config 5).
+
+    Per frame and rank: ONE sync-free C call (bsplat_render_enqueue_band: project all N, bin + rasterize the
+    band only, write the band rows) followed by the exchange of the bands.  Bands are balanced by
+    intersection count; they are computed once (``rebalance``) and reused -- consecutive frames of a
+    sequence have near-identical row costs -- instead of per frame.  The assembled image equals the
+    single-GPU image bit for bit (per-tile lists do not depend on the split).
+
+    exchange="nccl": bands padded to equal height, one all_gather_into_tensor, rows copied into place.
+    exchange="p2p" : the rasterizer itself stores every finished tile into the image buffer of EVERY rank
+                     (symmetric memory over NVLink / NVSwitch peer mappings) -- compute and gather are one
+                     kernel, followed only by a device-side barrier.
+    """
+
+    def __init__(self, N: int, camera: Camera, channels: int = 3, tile_size: int = TILE_SIZE,
+                 semantics=_lib.SEM_TORCH, group=None, m_capacity: int | None = None, exchange: str = "nccl"):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.L = _lib.require_device(self.dev)
+        self.N, self.C, self.ts, self.semantics = int(N), int(channels), int(tile_size), semantics
+        self.H, self.W = int(camera.H), int(camera.W)
+        self.th = math.ceil(self.H / self.ts)
+        self.m_cap = int(m_capacity) if m_capacity else 4 * self.N + 4096
+        nbytes = self.L.bsplat_render_workspace_bytes(self.N, self.m_cap, self.W, self.H, self.ts)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+        self.info = torch.zeros(32, dtype=torch.uint8).pin_memory()
+        self.exchange = exchange if self.world > 1 else "none"
+        self.bands = [(r * self.th // self.world, (r + 1) * self.th // self.world) for r in range(self.world)]
+        self.image = torch.zeros((self.H, self.W, self.C), dtype=torch.float32, device=self.dev)
+        self._pad = None
+
+    def rebalance(self, means3d, scales, quats, opacities, camera: Camera) -> list:
+        """Bands with equal intersection counts for this pose (projection + a row histogram; one host sync)."""
+        proj = project_gaussians_cuda(means3d, scales, quats, opacities, camera, semantics=self.semantics)
+        cost = tile_row_cost(proj[0], proj[3], self.H, self.W, self.ts)
+        if self.world > 1:
+            dist.broadcast(cost, src=0, group=self.group)
+        cost_list = cost.tolist()
+        self.bands = balanced_row_bands(cost_list, self.world)
+        self._pad = None
+        # size the pair buffers for this rank's band (the cost is the torch-rule intersection count per row)
+        b0, b1 = self.bands[self.rank]
+        self._resize(int(1.25 * sum(cost_list[b0:b1])) + 65536)
+        return self.bands
+
+    def _resize(self, m_cap: int) -> None:
+        self.m_cap = int(m_cap)
+        nbytes = self.L.bsplat_render_workspace_bytes(self.N, self.m_cap, self.W, self.H, self.ts)
+        if nbytes > self.ws.numel():
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+
+    @torch.no_grad()
+    def render(self, means3d, scales, quats, opacities, features, camera: Camera, background) -> torch.Tensor:
+        from ctypes import byref, c_size_t
+        b0, b1 = self.bands[self.rank]
+        cam = _lib.camera_struct(camera)
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        needed = c_size_t(0)
+        import ctypes
+        rc = self.L.bsplat_render_enqueue_band(
+            self.N, _lib.ptr(means3d), _lib.ptr(scales), _lib.ptr(quats), _lib.ptr(opacities), _lib.ptr(features),
+            self.C, ctypes.addressof(cam), _lib.ptr(background), self.ts, self.semantics, _lib.RASTER_FAST, b0, b1,
+            _lib.ptr(self.image), _lib.ptr(self.ws), self.ws.numel(), self.m_cap, byref(needed),
+            self.info.data_ptr(), stream, None, None)
+        _lib.check(rc, "bsplat_render_enqueue_band")
+        if self.exchange == "nccl":
+            rows = [(min(a * self.ts, self.H), min(b * self.ts, self.H)) for a, b in self.bands]
+            n_max = max(e - s for s, e in rows)
+            if self._pad is None or self._pad.shape[1] != n_max:
+                self._pad = torch.empty((self.world, n_max, self.W, self.C), dtype=torch.float32, device=self.dev)
+            s, e = rows[self.rank]
+            mine = self._pad[self.rank]
+            mine[: e - s].copy_(self.image[s:e])
+            dist.all_gather_into_tensor(self._pad.view(-1), mine.reshape(-1), group=self.group)
+            for r, (s, e) in enumerate(rows):
+                if r != self.rank:
+                    self.image[s:e].copy_(self._pad[r, : e - s])
+        return self.image
+
+    def check(self) -> int:
+        torch.cuda.synchronize(self.dev)
+        info = _lib.BsplatBinInfo.from_buffer_copy(self.info.numpy().tobytes())
+        if info.reserved[1]:
+            need = int(info.n_isect)
+            self._resize(int(1.25 * need) + 65536)  # the next render() fits; this frame must be redone
+            raise RuntimeError(f"band produced {need} intersections > capacity; workspace grown, render again")
+        return int(info.n_isect)
