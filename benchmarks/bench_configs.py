@@ -42,7 +42,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL_DEBUG=VERSION/INFO makes NCCL print a banner on stdout; the contract is one JSON line there
-        os.environ["NCCL_DEBUG"] = os.environ.get("BSPLAT_NCCL_DEBUG", "WARN")
+        # (the version banner is printed at every level but NONE: send NCCL's log to stderr instead)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     import mojosplat_b200 as ms
     from mojosplat_b200 import parallel, synthetic

@@ -274,6 +274,18 @@ int bsplat_render_enqueue_band(int64_t N, const float* means3d, const float* log
                                float* image, void* workspace, size_t workspace_bytes, int64_t M_capacity,
                                size_t* needed_bytes, bsplat_bin_info* info_host_pinned, void* stream_bin,
                                void* stream_raster, void* event_bin_done);
+/* ... with the band exchange fused into the rasterizer: every finished tile is also stored (128-bit stores)
+ * into the image buffers of the n_peers (<= 7) other ranks -- peer-mapped device pointers of the same layout,
+ * e.g. torch symmetric memory over NVLink / NVSwitch. Follow with a cross-device barrier on the stream; no
+ * all-gather is needed. 16x16 tiles, RGB, BSPLAT_RASTER_FAST only. */
+int bsplat_render_enqueue_band_p2p(int64_t N, const float* means3d, const float* log_scales, const float* quats,
+                                   const float* opacities, const float* colors, int32_t channels,
+                                   const bsplat_camera* cam, const float* background, int32_t tile_size,
+                                   int32_t semantics, int32_t flags, int32_t tile_row_begin,
+                                   int32_t tile_row_end, float* image, float* const* peer_images,
+                                   int32_t n_peers, void* workspace, size_t workspace_bytes,
+                                   int64_t M_capacity, size_t* needed_bytes, bsplat_bin_info* info_host_pinned,
+                                   void* stream_bin, void* stream_raster, void* event_bin_done);
 /* Same with HOST buffers (pinned or pageable): copies the Gaussians in, renders, copies the
  * image out and synchronises the stream. device_scratch must hold
  * bsplat_render_host_scratch_bytes() in addition to the render workspace. */

@@ -19,7 +19,8 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
                      const float* opacities, const float* background_dev, const int32_t* tile_ranges,
                      const int32_t* tile_order, const int32_t* sorted_ids, int W, int H, int tile_size,
                      int row_begin, int row_end, int mode, float* image, unsigned long long* stats,
-                     const unsigned long long* m_dev, void* rec_ws, cudaStream_t stream);
+                     const unsigned long long* m_dev, void* rec_ws, cudaStream_t stream,
+                     const PeerImages* peers = nullptr);
 size_t raster_workspace_bytes(int64_t N);
 int tile_order_launch(int first_tile, int n_tiles, const int32_t* tile_ranges, int32_t* order,
                       cudaStream_t stream);
@@ -401,6 +402,31 @@ extern "C" int bsplat_render_enqueue_band(int64_t N, const float* means3d, const
                                           void* workspace, size_t workspace_bytes, int64_t M_capacity,
                                           size_t* needed_bytes, bsplat_bin_info* info_host_pinned,
                                           void* stream_bin_, void* stream_raster_, void* event_bin_done) {
+    return bsplat_render_enqueue_band_p2p(N, means3d, log_scales, quats, opacities, colors, channels, cam, background,
+                                          tile_size, semantics, flags, tile_row_begin, tile_row_end, image, nullptr, 0,
+                                          workspace, workspace_bytes, M_capacity, needed_bytes, info_host_pinned,
+                                          stream_bin_, stream_raster_, event_bin_done);
+}
+
+// ... and with the band exchange fused into the rasterizer: every finished tile is also stored into the image
+// buffers of the n_peers other ranks (peer-mapped pointers, e.g. torch symmetric memory over NVLink/NVSwitch).
+// The caller follows the call with a cross-device barrier on the stream; no all-gather is needed.
+extern "C" int bsplat_render_enqueue_band_p2p(int64_t N, const float* means3d, const float* log_scales,
+                                              const float* quats, const float* opacities, const float* colors,
+                                              int32_t channels, const bsplat_camera* cam, const float* background,
+                                              int32_t tile_size, int32_t semantics, int32_t flags,
+                                              int32_t tile_row_begin, int32_t tile_row_end, float* image,
+                                              float* const* peer_images, int32_t n_peers, void* workspace,
+                                              size_t workspace_bytes, int64_t M_capacity, size_t* needed_bytes,
+                                              bsplat_bin_info* info_host_pinned, void* stream_bin_,
+                                              void* stream_raster_, void* event_bin_done) {
+    if (n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !peer_images)) return BSPLAT_E_ARG;
+    PeerImages peers;
+    peers.n = n_peers;
+    for (int q = 0; q < n_peers; ++q) {
+        if (!peer_images[q]) return BSPLAT_E_ARG;
+        peers.p[q] = peer_images[q];
+    }
     cudaStream_t sb = (cudaStream_t)stream_bin_;
     cudaStream_t sr = stream_raster_ ? (cudaStream_t)stream_raster_ : sb;
     if (!cam || !image || !background || N <= 0 || M_capacity <= 0 || channels <= 0 || tile_size <= 0 ||
@@ -449,7 +475,7 @@ extern "C" int bsplat_render_enqueue_band(int64_t N, const float* means3d, const
     return rasterize_launch(N, channels, w.means2d, w.conics, colors, opacities, background, w.tile_ranges,
                             fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, row0, row1,
                             raster_mode, image, nullptr, reinterpret_cast<const unsigned long long*>(d_info),
-                            w.raster_rec, sr);
+                            w.raster_rec, sr, &peers);
 }
 
 extern "C" size_t bsplat_render_host_scratch_bytes(int64_t N, int32_t channels, int32_t width, int32_t height) {

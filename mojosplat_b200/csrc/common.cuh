@@ -22,6 +22,14 @@ namespace bsplat {
 
 constexpr int kWarp = 32;
 
+// Image buffers of the OTHER ranks (peer-mapped device pointers, same layout as the local image): the
+// rasterizer stores every finished tile there as well, so the row-band exchange needs no separate collective.
+constexpr int kMaxPeers = 7;
+struct PeerImages {
+    float* p[kMaxPeers];
+    int n;
+};
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Monotone float -> uint32 map: ascending float order, -0.0 == +0.0, NaN last.

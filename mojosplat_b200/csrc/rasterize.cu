@@ -365,7 +365,7 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                    const int32_t* __restrict__ tile_order, const int first_tile,
                    const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
                    float* __restrict__ image, const int vec_store,
-                   const unsigned long long* __restrict__ m_dev) {
+                   const unsigned long long* __restrict__ m_dev, const PeerImages peers) {
     __shared__ float4 s_g[kPairBatch * kPairRec];
 
     const int tid = threadIdx.x;
@@ -529,12 +529,17 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
         for (int v = tid; v < 16 * 12; v += kPairThreads) {
             const int row = v / 12, c4 = v % 12;
             const float4 val = reinterpret_cast<const float4*>(s_out)[row * 12 + c4];
-            float* dst = image + ((int64_t)(tile_y * kFastTile + row) * W + tile_x * kFastTile) * 3;
-            reinterpret_cast<float4*>(dst)[c4] = val;
+            const int64_t off = ((int64_t)(tile_y * kFastTile + row) * W + tile_x * kFastTile) * 3;
+            reinterpret_cast<float4*>(image + off)[c4] = val;
+            // fused band exchange: the same 128-bit store into every peer's image (NVLink posted writes)
+            for (int q = 0; q < peers.n; ++q) reinterpret_cast<float4*>(peers.p[q] + off)[c4] = val;
         }
     } else {
-        if (in0) { float* dst = image + ((int64_t)i0 * W + j) * 3; dst[0] = o0r; dst[1] = o0g; dst[2] = o0b; }
-        if (in1) { float* dst = image + ((int64_t)i1 * W + j) * 3; dst[0] = o1r; dst[1] = o1g; dst[2] = o1b; }
+        for (int q = -1; q < peers.n; ++q) {
+            float* img = q < 0 ? image : peers.p[q];
+            if (in0) { float* dst = img + ((int64_t)i0 * W + j) * 3; dst[0] = o0r; dst[1] = o0g; dst[2] = o0b; }
+            if (in1) { float* dst = img + ((int64_t)i1 * W + j) * 3; dst[0] = o1r; dst[1] = o1g; dst[2] = o1b; }
+        }
     }
 }
 
@@ -818,7 +823,10 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
                      const int32_t* tile_ranges, const int32_t* tile_order, const int32_t* sorted_ids, int W,
                      int H, int tile_size, int row_begin, int row_end, int mode, float* image,
                      unsigned long long* stats, const unsigned long long* m_dev, void* rec_ws,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const PeerImages* peers_in) {
+    PeerImages peers;
+    peers.n = 0;
+    if (peers_in) peers = *peers_in;
     if (W <= 0 || H <= 0 || tile_size <= 0 || tile_size > 32 || channels <= 0 || !background_dev)
         return BSPLAT_E_ARG;
     const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
@@ -826,6 +834,9 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
     if (row_begin < 0) row_begin = 0;
     if (row_end > tiles_h) row_end = tiles_h;
     if (row_end <= row_begin) return BSPLAT_OK;  // empty band
+    if (peers.n > 0 && !(mode == BSPLAT_RASTER_FAST && tile_size == kFastTile && channels == 3 && stats == nullptr &&
+                         (reinterpret_cast<uintptr_t>(means2d) & 7u) == 0))
+        return BSPLAT_E_ARG;  // the fused exchange exists in the default 16x16 RGB kernel only
     const bool fast_ok = (mode == BSPLAT_RASTER_FAST || (mode >= 2 && mode <= 4)) && tile_size == kFastTile &&
                          channels == 3 && stats == nullptr &&
                          (reinterpret_cast<uintptr_t>(means2d) & 7u) == 0;
@@ -846,7 +857,7 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         } else if (mode == 2) {
             raster_pair_kernel<false><<<grid, kPairThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
                                                                          tile_ranges, tile_order, first_tile, sorted_ids,
-                                                                         W, H, tiles_w, image, vec, m_dev);
+                                                                         W, H, tiles_w, image, vec, m_dev, peers);
         } else if (mode == 4) {
             raster_fast_kernel<true><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
                                                                         tile_ranges, tile_order, first_tile, sorted_ids,
@@ -854,7 +865,7 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         } else {
             raster_pair_kernel<true><<<grid, kPairThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
                                                                         tile_ranges, tile_order, first_tile, sorted_ids,
-                                                                        W, H, tiles_w, image, vec, m_dev);
+                                                                        W, H, tiles_w, image, vec, m_dev, peers);
         }
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;

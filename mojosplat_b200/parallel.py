@@ -228,8 +228,22 @@ class RowBandRenderer:
         self.info = torch.zeros(32, dtype=torch.uint8).pin_memory()
         self.exchange = exchange if self.world > 1 else "none"
         self.bands = [(r * self.th // self.world, (r + 1) * self.th // self.world) for r in range(self.world)]
-        self.image = torch.zeros((self.H, self.W, self.C), dtype=torch.float32, device=self.dev)
         self._pad = None
+        self._hdl, self._peer_arr = None, None
+        if self.exchange == "p2p":
+            # symmetric memory: every rank maps every rank's image buffer (NVLink / NVSwitch peer access)
+            import ctypes
+            import torch.distributed._symmetric_memory as symm_mem
+            pg = group if group is not None else dist.group.WORLD
+            self.image = symm_mem.empty((self.H, self.W, self.C), dtype=torch.float32, device=self.dev)
+            self.image.zero_()
+            self._hdl = symm_mem.rendezvous(self.image, pg)
+            ptrs = [int(p) for r, p in enumerate(self._hdl.buffer_ptrs) if r != self.rank]
+            if len(ptrs) > 7:
+                raise ValueError("fused band exchange supports up to 8 ranks")
+            self._peer_arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        else:
+            self.image = torch.zeros((self.H, self.W, self.C), dtype=torch.float32, device=self.dev)
 
     def rebalance(self, means3d, scales, quats, opacities, camera: Camera) -> list:
         """Bands with equal intersection counts for this pose (projection + a row histogram; one host sync)."""
@@ -259,6 +273,18 @@ class RowBandRenderer:
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         needed = c_size_t(0)
         import ctypes
+        if self.exchange == "p2p":
+            # nobody may still be reading the previous frame out of a buffer this frame writes into
+            self._hdl.barrier(channel=0)
+            rc = self.L.bsplat_render_enqueue_band_p2p(
+                self.N, _lib.ptr(means3d), _lib.ptr(scales), _lib.ptr(quats), _lib.ptr(opacities),
+                _lib.ptr(features), self.C, ctypes.addressof(cam), _lib.ptr(background), self.ts, self.semantics,
+                _lib.RASTER_FAST, b0, b1, _lib.ptr(self.image), self._peer_arr, len(self._peer_arr),
+                _lib.ptr(self.ws), self.ws.numel(), self.m_cap, byref(needed), self.info.data_ptr(), stream,
+                None, None)
+            _lib.check(rc, "bsplat_render_enqueue_band_p2p")
+            self._hdl.barrier(channel=1)  # every rank's tiles have landed everywhere
+            return self.image
         rc = self.L.bsplat_render_enqueue_band(
             self.N, _lib.ptr(means3d), _lib.ptr(scales), _lib.ptr(quats), _lib.ptr(opacities), _lib.ptr(features),
             self.C, ctypes.addressof(cam), _lib.ptr(background), self.ts, self.semantics, _lib.RASTER_FAST, b0, b1,
