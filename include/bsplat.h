@@ -187,6 +187,13 @@ int bsplat_rasterize_stats(int64_t N, int32_t channels, const float* means2d, co
                            int32_t width, int32_t height, int32_t tile_size, float* image,
                            uint64_t* stats, void* stream);
 
+/* ---- colours: spherical harmonics (placeholder in the reference, render.py:82-87) -- */
+/* colors[N,3] = max(sum_k Y_k(dir) coeffs[n,k,:] + 0.5, 0), dir = normalize(means3d[n] - campos), real SH of
+ * `degree` (0..3), coeffs [N, K_stored, 3] with K_stored >= (degree+1)^2 (extra bands ignored).
+ * campos_host: camera position in world space, 3 floats on the host. */
+int bsplat_sh_eval(int64_t N, int32_t degree, int32_t K_stored, const float* coeffs, const float* means3d,
+                   const float* campos_host, float* colors, void* stream);
+
 /* ---- stage 3, training side (the reference is forward-only, render.py:11) --------- */
 /* Forward with the faithful arithmetic (kernels/rasterization.mojo:138-162) that also stores what the
  * backward pass needs: final_T[height, width] (transmittance left at each pixel) and

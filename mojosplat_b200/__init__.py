@@ -10,6 +10,7 @@ from .projection import project_gaussians  # noqa: F401
 from .binning import bin_gaussians_to_tiles  # noqa: F401
 from .rasterization import rasterize_gaussians  # noqa: F401
 from .render import TILE_SIZE, render_gaussians, render_gaussians_host, render_fused  # noqa: F401
+from .sh import eval_sh  # noqa: F401
 
 __all__ = ["Camera", "project_gaussians", "bin_gaussians_to_tiles", "rasterize_gaussians",
-           "render_gaussians", "render_gaussians_host", "render_fused", "TILE_SIZE"]
+           "render_gaussians", "render_gaussians_host", "render_fused", "eval_sh", "TILE_SIZE"]

@@ -36,7 +36,7 @@ SYMBOLS = [
     "bsplat_render_fwd_host", "bsplat_microbench", "bsplat_bin2_workspace_bytes", "bsplat_bin2_prepare",
     "bsplat_bin2_finish", "bsplat_tile_order", "bsplat_render_begin", "bsplat_render_end",
     "bsplat_render_enqueue", "bsplat_rasterize_workspace_bytes", "bsplat_rasterize_fwd_train",
-    "bsplat_rasterize_bwd", "bsplat_render_enqueue_band", "bsplat_render_enqueue_band_p2p",
+    "bsplat_rasterize_bwd", "bsplat_render_enqueue_band", "bsplat_render_enqueue_band_p2p", "bsplat_sh_eval",
 ]
 
 
@@ -149,6 +149,8 @@ def load() -> ctypes.CDLL:
                                                      c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                                      c_void_p, c_void_p, c_int32, c_void_p, c_size_t, c_int64,
                                                      POINTER(c_size_t), c_void_p, c_void_p, c_void_p, c_void_p]
+        L.bsplat_sh_eval.argtypes = [c_int64, c_int32, c_int32, c_void_p, c_void_p, POINTER(c_float * 3), c_void_p,
+                                     c_void_p]
         L.bsplat_rasterize_stats.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                              c_int32, c_void_p, c_void_p, c_void_p]

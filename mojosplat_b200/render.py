@@ -47,6 +47,12 @@ def render_gaussians(
     required = [means3d, scales, quats, opacities, features]
     if not all(isinstance(t, torch.Tensor) and t.is_cuda for t in required):
         raise ValueError("All input gaussian tensors must be CUDA tensors.")
+    if sh_degree is not None and features.dim() == 3:
+        # real SH coefficients (N, K, 3): evaluate them along the view direction (additive; the reference
+        # only has the placeholder below, render.py:82-87)
+        from .sh import eval_sh
+        features = eval_sh(int(sh_degree), features, means3d, camera).to(features.dtype)
+        sh_degree = None
     num_channels = features.shape[-1]
     bg = _background_tensor(background_color, num_channels, means3d.device, features.dtype)
     if bg.shape[0] != num_channels:

@@ -45,3 +45,29 @@ def rasterize_np(means2d, conics, colors, opacities, background, tile_ranges, so
                 T = np.where(live, next_T, T)
             img[i0:i1, j0:j1] = out + T[..., None] * background
     return img
+
+
+def sh_eval_np(degree, coeffs, means3d, campos):
+    """float64 restatement of the standard 3DGS spherical-harmonics colour (real SH, degree <= 3):
+    colour = max(sum_k Y_k(dir) c_k + 0.5, 0), dir = normalize(mean - campos).  The reference only has a
+    placeholder (render.py:82-87); this follows the published basis (constants of the 3DGS paper's code).
+    TEST INFRASTRUCTURE ONLY."""
+    c = np.asarray(coeffs, np.float64)
+    d = np.asarray(means3d, np.float64) - np.asarray(campos, np.float64)[None, :]
+    d = d / np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-15)
+    x, y, z = d[:, 0:1], d[:, 1:2], d[:, 2:3]
+    out = 0.28209479177387814 * c[:, 0]
+    if degree >= 1:
+        out = out + 0.4886025119029199 * (-y * c[:, 1] + z * c[:, 2] - x * c[:, 3])
+    if degree >= 2:
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        out = out + (1.0925484305920792 * xy * c[:, 4] - 1.0925484305920792 * yz * c[:, 5]
+                     + 0.31539156525252005 * (2 * zz - xx - yy) * c[:, 6] - 1.0925484305920792 * xz * c[:, 7]
+                     + 0.5462742152960396 * (xx - yy) * c[:, 8])
+    if degree >= 3:
+        out = out + (-0.5900435899266435 * y * (3 * xx - yy) * c[:, 9] + 2.890611442640554 * xy * z * c[:, 10]
+                     - 0.4570457994644658 * y * (4 * zz - xx - yy) * c[:, 11]
+                     + 0.3731763325901154 * z * (2 * zz - 3 * xx - 3 * yy) * c[:, 12]
+                     - 0.4570457994644658 * x * (4 * zz - xx - yy) * c[:, 13]
+                     + 1.445305721320277 * z * (xx - yy) * c[:, 14] - 0.5900435899266435 * x * (xx - 3 * yy) * c[:, 15])
+    return np.maximum(out + 0.5, 0.0)
