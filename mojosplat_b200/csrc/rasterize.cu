@@ -532,11 +532,15 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
             const int64_t off = ((int64_t)(tile_y * kFastTile + row) * W + tile_x * kFastTile) * 3;
             reinterpret_cast<float4*>(image + off)[c4] = val;
             // fused band exchange: the same 128-bit store into every peer's image (NVLink posted writes)
-            for (int q = 0; q < peers.n; ++q) reinterpret_cast<float4*>(peers.p[q] + off)[c4] = val;
+#pragma unroll
+            for (int q = 0; q < kMaxPeers; ++q)  // constant indices: the pointer array stays in the parameter bank
+                if (q < peers.n) reinterpret_cast<float4*>(peers.p[q] + off)[c4] = val;
         }
     } else {
-        for (int q = -1; q < peers.n; ++q) {
-            float* img = q < 0 ? image : peers.p[q];
+#pragma unroll
+        for (int q = -1; q < kMaxPeers; ++q) {
+            if (q >= peers.n) break;
+            float* img = q < 0 ? image : peers.p[q < 0 ? 0 : q];
             if (in0) { float* dst = img + ((int64_t)i0 * W + j) * 3; dst[0] = o0r; dst[1] = o0g; dst[2] = o0b; }
             if (in1) { float* dst = img + ((int64_t)i1 * W + j) * 3; dst[0] = o1r; dst[1] = o1g; dst[2] = o1b; }
         }
