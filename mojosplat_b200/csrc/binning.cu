@@ -20,7 +20,7 @@ bin_count_scan_kernel(const int64_t N, const int32_t* __restrict__ perm, const f
                       const void* __restrict__ radii, const int radii_is_float,
                       const float* __restrict__ depths, const BinParams p,
                       uint32_t* __restrict__ offsets, bsplat_bin_info* __restrict__ info,
-                      unsigned long long* __restrict__ ws) {
+                      unsigned long long* __restrict__ ws, uint2* __restrict__ rects) {
     __shared__ unsigned int s_chunk;
     __shared__ unsigned long long s_warp_sum[kScanThreads / 32];
     __shared__ unsigned long long s_prefix;
@@ -49,7 +49,11 @@ bin_count_scan_kernel(const int64_t N, const int32_t* __restrict__ perm, const f
             const TileRect r = tile_rect(mx, my, rx, ry, p.W, p.H, p.tile_size_f, p.tiles_w, p.tiles_h,
                                          p.semantics, p.row_begin, p.row_end);
             c = (uint32_t)((r.x1 - r.x0) * (r.y1 - r.y0));
-            if (c > 0) {
+            // two-level path: keep the rectangle for the emitter (x0 | y0 << 16, w | h << 16), in depth order
+            if (rects != nullptr)
+                rects[jj] = make_uint2((uint32_t)r.x0 | ((uint32_t)r.y0 << 16),
+                                       (uint32_t)(r.x1 - r.x0) | ((uint32_t)(r.y1 - r.y0) << 16));
+            if (c > 0 && depths != nullptr) {  // depth-key range: only the single-level key layout needs it
                 const uint32_t dk = depth_key(__ldg(depths + i));
                 kmax = max(kmax, dk);
                 kmin_inv = max(kmin_inv, ~dk);
@@ -212,11 +216,12 @@ __global__ void tile_ranges_kernel(const int64_t M, const KeyT* __restrict__ key
 // workspace and info must be zeroed by the caller (stream-ordered memset)
 int bin_count_scan_launch(int64_t N, const int32_t* perm, const float* means2d, const void* radii,
                           int radii_is_float, const float* depths, const BinParams& p, uint32_t* offsets,
-                          bsplat_bin_info* info, void* workspace, bool finalize_key_range, cudaStream_t stream) {
+                          bsplat_bin_info* info, void* workspace, bool finalize_key_range, cudaStream_t stream,
+                          uint2* rects) {
     const unsigned grid = (unsigned)ceil_div(N, kScanChunk);
-    bin_count_scan_kernel<<<grid, kScanThreads, 0, stream>>>(N, perm, means2d, radii, radii_is_float, depths, p,
-                                                             offsets, info,
-                                                             static_cast<unsigned long long*>(workspace));
+    bin_count_scan_kernel<<<grid, kScanThreads, 0, stream>>>(N, perm, means2d, radii, radii_is_float,
+                                                             finalize_key_range ? depths : nullptr, p, offsets, info,
+                                                             static_cast<unsigned long long*>(workspace), rects);
     BSPLAT_LAUNCH_CHECK();
     if (finalize_key_range) {  // only the single-level path needs min/max depth keys
         bin_finalize_info_kernel<<<1, 1, 0, stream>>>(info);
@@ -281,7 +286,7 @@ extern "C" int bsplat_bin_count_scan(int64_t N, const float* means2d, const void
     }
     const unsigned grid = (unsigned)ceil_div(N, kScanChunk);
     return bin_count_scan_launch(N, nullptr, means2d, radii, radii_is_float, depths, p, offsets, info, workspace,
-                                 true, stream);
+                                 true, stream, nullptr);
 }
 
 extern "C" bsplat_key_layout bsplat_make_key_layout(const bsplat_bin_info* info_host, int32_t width,

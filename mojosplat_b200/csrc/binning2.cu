@@ -50,20 +50,20 @@ depth_key_hist_kernel(const int64_t N, const float* __restrict__ depths, uint32_
 }
 
 // ---- 3. emission in depth order ------------------------------------------------------------
-// CTA = 256 consecutive Gaussians of the depth-sorted order.  Small rectangles (<= kEmitSmall tiles,
-// the common case: ~4 tiles per Gaussian in garden-sized scenes) are written by their own thread
-// with a running (row, column) counter -- no search, no division; large rectangles are queued in shared
-// memory and written by whole warps with coalesced stores.  The digit histograms of the two tile-sort
-// passes are accumulated on the fly (shared-memory atomics, run-length aggregated for the high digit).
+// Work is balanced over OUTPUT PAIRS, not over Gaussians: a warp takes 32 consecutive Gaussians of the
+// depth-sorted order (rectangles and offsets come from the count + scan kernel, all coalesced), and its lanes
+// then walk the warp's contiguous output range 32 pairs at a time.  The owner of pair j is found with a 5-step
+// binary search over the lanes' exclusive offsets (register shuffles), its rectangle fetched with shuffles, the
+// tile id computed and both words stored -- every store instruction writes 128 contiguous bytes, no lane idles
+// on a short rectangle, a rectangle of thousands of tiles just takes more rounds.  The digit histograms of the
+// two tile-sort passes are accumulated on the fly (shared-memory atomics; the high digit is run-length
+// aggregated with match.any: neighbouring pairs share it).
 constexpr int kEmit2Threads = 256;
-constexpr int kEmitSmall = 16;
-constexpr int kEmitStage = 2048;  // pairs staged in shared memory per CTA (coalesced copy-out)
 
 __global__ void __launch_bounds__(kEmit2Threads)
-bin_emit2_kernel(const int64_t N, const int32_t* __restrict__ perm, const float* __restrict__ means2d,
-                 const void* __restrict__ radii, const int radii_is_float, const BinParams p,
-                 const uint32_t* __restrict__ offsets, const int lo_bits, uint32_t* __restrict__ tile_keys,
-                 int32_t* __restrict__ ids, uint32_t* __restrict__ hist /* [2][256] */,
+bin_emit2_kernel(const int64_t N, const int32_t* __restrict__ perm, const uint2* __restrict__ rects,
+                 const int tiles_w, const uint32_t* __restrict__ offsets, const int lo_bits,
+                 uint32_t* __restrict__ tile_keys, int32_t* __restrict__ ids, uint32_t* __restrict__ hist /* [2][256] */,
                  bsplat_bin_info* __restrict__ info_dev, const int64_t m_cap) {
     // sync-free frames: the pair buffers hold m_cap entries; if this frame produced more, emit nothing,
     // raise the overflow flag (reserved[1]) and let the later passes see it (they skip too)
@@ -72,106 +72,70 @@ bin_emit2_kernel(const int64_t N, const int32_t* __restrict__ perm, const float*
         return;
     }
     __shared__ uint32_t s_hist[2][kRadix];
-    __shared__ int s_queue[kEmit2Threads];
-    __shared__ int s_nqueue;
-    __shared__ uint32_t s_off[kEmit2Threads];
-    __shared__ uint32_t s_xy[kEmit2Threads];   // x0 | y0 << 16
-    __shared__ uint32_t s_wh[kEmit2Threads];   // w | h << 16
-    __shared__ int32_t s_id[kEmit2Threads];
-    __shared__ uint32_t s_keys[kEmitStage];
-    __shared__ int32_t s_ids[kEmitStage];
-
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
-    const int warp = tid >> 5;
     for (int i = tid; i < 2 * kRadix; i += kEmit2Threads) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
     const uint32_t lo_mask = (1u << lo_bits) - 1u;
-    const uint32_t tw = (uint32_t)p.tiles_w;
-    // persistent CTAs: each walks several 256-Gaussian chunks and flushes its histograms ONCE -- the
-    // flush is ~190 same-address global atomics per CTA, which dominated the kernel with one CTA per chunk
-    const int64_t n_chunks = ceil_div(N, kEmit2Threads);
-    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int64_t base = chunk * kEmit2Threads;
-    const int n_here = (int)min((int64_t)kEmit2Threads, N - base);
-    __syncthreads();  // previous chunk's staging buffers and queue are fully consumed
-    if (tid == 0) s_nqueue = 0;
-    __syncthreads();
-    // the CTA's pairs are one contiguous output range; when it fits, build it in shared memory and copy it
-    // out with coalesced stores (per-thread runs of ~4 pairs would otherwise cost ~4 partial-sector writes each)
-    const uint32_t cta_begin = __ldg(offsets + base), cta_end = __ldg(offsets + base + n_here);
-    const bool staged = (cta_end - cta_begin) <= (uint32_t)kEmitStage;
-    uint32_t* const okeys = staged ? s_keys : tile_keys + cta_begin;
-    int32_t* const oids = staged ? s_ids : ids + cta_begin;
-
-    if (tid < n_here) {
-        const int32_t g = __ldg(perm + base + tid);
-        float mx, my, rx, ry;
-        load_mean_radii(means2d, radii, radii_is_float, g, mx, my, rx, ry);
-        const TileRect r = tile_rect(mx, my, rx, ry, p.W, p.H, p.tile_size_f, p.tiles_w, p.tiles_h,
-                                     p.semantics, p.row_begin, p.row_end);
-        const uint32_t w = (uint32_t)(r.x1 - r.x0), h = (uint32_t)(r.y1 - r.y0);
-        const uint32_t off = __ldg(offsets + base + tid);
-        const uint32_t count = w * h;
-        if (count > (uint32_t)kEmitSmall) {
-            const int q = atomicAdd(&s_nqueue, 1);
-            s_queue[q] = tid;
-            s_off[tid] = off; s_xy[tid] = (uint32_t)r.x0 | ((uint32_t)r.y0 << 16);
-            s_wh[tid] = w | (h << 16); s_id[tid] = g;
-        } else if (count > 0) {
-            uint32_t pos = off - cta_begin;
-            uint32_t run_top = 0xffffffffu, run_len = 0;
-            for (uint32_t dy = 0; dy < h; ++dy) {
-                uint32_t tile = ((uint32_t)r.y0 + dy) * tw + (uint32_t)r.x0;
-                for (uint32_t dx = 0; dx < w; ++dx, ++tile, ++pos) {
-                    okeys[pos] = tile;
-                    oids[pos] = g;
-                    atomicAdd(&s_hist[0][tile & lo_mask], 1u);
-                    const uint32_t top = tile >> lo_bits;
-                    if (top != run_top) {
-                        if (run_len) atomicAdd(&s_hist[1][run_top], run_len);
-                        run_top = top; run_len = 0;
-                    }
-                    ++run_len;
-                }
-            }
-            if (run_len) atomicAdd(&s_hist[1][run_top], run_len);
+    const uint32_t tw = (uint32_t)tiles_w;
+    // persistent warps: each walks several 32-Gaussian chunks; the CTA flushes its histograms once
+    const int64_t n_chunks = ceil_div(N, 32);
+    const int64_t warp_global = (int64_t)blockIdx.x * (kEmit2Threads / 32) + (tid >> 5);
+    const int64_t warp_stride = (int64_t)gridDim.x * (kEmit2Threads / 32);
+    for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warp_stride) {
+        const int64_t jg = chunk * 32 + lane;
+        const bool have = jg < N;
+        int32_t g = 0;
+        uint2 rc = make_uint2(0u, 0u);
+        uint32_t off = 0;
+        if (have) {
+            g = __ldg(perm + jg);
+            rc = __ldg(rects + jg);
+            off = __ldg(offsets + jg);
         }
-    }
-    __syncthreads();
-
-    // large rectangles: one warp per queued Gaussian, lanes stride over its tiles (coalesced stores)
-    const int nq = s_nqueue;
-    for (int q = warp; q < nq; q += kEmit2Threads / 32) {
-        const int j = s_queue[q];
-        const uint32_t off = s_off[j], xy = s_xy[j], wh = s_wh[j];
-        const uint32_t w = wh & 0xffffu, count = w * (wh >> 16);
-        const int32_t g = s_id[j];
-        for (uint32_t k0 = 0; k0 < count; k0 += 32) {  // warp-uniform trip count
-            const uint32_t k = k0 + lane;
-            const bool valid = k < count;
+        const uint32_t w = rc.y & 0xffffu, cnt = w * (rc.y >> 16);
+        const uint32_t begin = __shfl_sync(0xffffffffu, off, 0);
+        // exclusive offset inside the warp's range; lanes past N get the total (they own nothing)
+        const uint32_t last_end = off + cnt;
+        const int n_live = (int)min((int64_t)32, N - chunk * 32);
+        const uint32_t total = __shfl_sync(0xffffffffu, last_end, n_live - 1) - begin;
+        const uint32_t e = have ? off - begin : total;
+        const float inv_w = 1.0f / (float)(w ? w : 1u);
+        for (uint32_t j0 = 0; j0 < total; j0 += 32) {  // warp-uniform trip count
+            const uint32_t j = j0 + lane;
+            const bool valid = j < total;
+            // owner = largest lane l with e_l <= j  (e is non-decreasing; e_{l+1} = e_l + cnt_l)
+            uint32_t lo = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t cand = lo + step;
+                const uint32_t ec = __shfl_sync(0xffffffffu, e, cand & 31u);
+                if (ec <= j) lo = cand;  // cand <= 31 always: lo + step never exceeds 31
+            }
+            const uint32_t eo = __shfl_sync(0xffffffffu, e, lo);
+            const uint32_t xy = __shfl_sync(0xffffffffu, rc.x, lo);
+            const uint32_t wo = __shfl_sync(0xffffffffu, w, lo);
+            const float iw = __shfl_sync(0xffffffffu, inv_w, lo);
+            const int32_t go = __shfl_sync(0xffffffffu, g, lo);
             uint32_t tile = 0;
             if (valid) {
-                const uint32_t dy = k / w, dx = k - dy * w;
+                const uint32_t k = j - eo;
+                // k / w through the reciprocal, corrected to be exact (k < 2^24: a rectangle has < 2^24 tiles
+                // whenever the image has, which tile ids as 32-bit keys already require)
+                uint32_t dy = (uint32_t)__float2int_rz(__fmul_rn((float)k, iw));
+                if (dy * wo > k) --dy;
+                else if ((dy + 1u) * wo <= k) ++dy;
+                const uint32_t dx = k - dy * wo;
                 tile = ((xy >> 16) + dy) * tw + (xy & 0xffffu) + dx;
-                okeys[off - cta_begin + k] = tile;
-                oids[off - cta_begin + k] = g;
+                tile_keys[begin + j] = tile;
+                ids[begin + j] = go;
                 atomicAdd(&s_hist[0][tile & lo_mask], 1u);
             }
-            // high digit: the lanes of a row share it -> aggregate (few distinct values: match.any is cheap)
             const uint32_t top = valid ? (tile >> lo_bits) : 0x100u;
             const uint32_t peers = __match_any_sync(0xffffffffu, top);
             if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[1][top], (uint32_t)__popc(peers));
         }
     }
-    __syncthreads();
-    if (staged) {
-        const uint32_t total = cta_end - cta_begin;
-        for (uint32_t i = tid; i < total; i += kEmit2Threads) {
-            tile_keys[cta_begin + i] = s_keys[i];
-            ids[cta_begin + i] = s_ids[i];
-        }
-    }
-    }  // chunk loop
     __syncthreads();
     for (int i = tid; i < 2 * kRadix; i += kEmit2Threads) {
         const uint32_t v = (&s_hist[0][0])[i];
@@ -260,7 +224,7 @@ static inline size_t bin_align(size_t v) { return (v + kBinAlign - 1) / kBinAlig
 struct Bin2Ws {
     // N part (lives from prepare to finish)
     uint32_t* dkeys; uint32_t* dkeys_alt; int32_t* perm; int32_t* perm_alt;
-    uint32_t* offsets; bsplat_bin_info* info; void* scan_ws; size_t scan_bytes;
+    uint32_t* offsets; uint2* rects; bsplat_bin_info* info; void* scan_ws; size_t scan_bytes;
     uint32_t* hist;      // [6][256]: 4 depth passes + 2 tile passes
     uint32_t* tickets;   // [8]
     uint32_t* status_n;  // [4][tilesN][256]
@@ -283,6 +247,7 @@ static Bin2Ws carve_bin2(void* base, int64_t N, int64_t M, int64_t n_tiles) {
     w.dkeys = (uint32_t*)take(n * 4); w.dkeys_alt = (uint32_t*)take(n * 4);
     w.perm = (int32_t*)take(n * 4); w.perm_alt = (int32_t*)take(n * 4);
     w.offsets = (uint32_t*)take((n + 1) * 4);
+    w.rects = (uint2*)take(n * sizeof(uint2));
     w.zero_begin = off;
     w.info = (bsplat_bin_info*)take(sizeof(bsplat_bin_info));
     w.scan_bytes = bsplat_bin_scan_workspace_bytes(N);
@@ -338,7 +303,7 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
     }
     // after 4 passes the sorted permutation is in w.perm (passes 1 and 3 write w.perm)
     return bin_count_scan_launch(N, w.perm, means2d, radii, radii_is_float, depths, p, w.offsets, w.info,
-                                 w.scan_ws, /*finalize_key_range=*/false, stream);
+                                 w.scan_ws, /*finalize_key_range=*/false, stream, w.rects);
 }
 
 // device_m: M is a capacity; the real count is read on the device from the bin info (n_isect) written by
@@ -363,10 +328,9 @@ int bin2_finish(int64_t N, int64_t M, bool device_m, const float* means2d, const
     const int tb = tile_bits_of(p);
     const int lo_bits = tb > 8 ? (tb + 1) / 2 : tb;  // split the tile id evenly over <= 2 passes
     const int hi_bits = tb - lo_bits;
-    const int64_t emit_chunks = ceil_div(N, kEmit2Threads);
-    bin_emit2_kernel<<<(unsigned)(emit_chunks < 148 * 6 ? emit_chunks : 148 * 6), kEmit2Threads, 0, stream>>>(
-        N, w.perm, means2d, radii, radii_is_float, p, w.offsets, lo_bits, w.tkeys, w.ids, w.hist + 4 * kRadix,
-        info_dev, M);
+    const int64_t emit_ctas = ceil_div(N, kEmit2Threads);
+    bin_emit2_kernel<<<(unsigned)(emit_ctas < 148 * 8 ? emit_ctas : 148 * 8), kEmit2Threads, 0, stream>>>(
+        N, w.perm, w.rects, p.tiles_w, w.offsets, lo_bits, w.tkeys, w.ids, w.hist + 4 * kRadix, info_dev, M);
     BSPLAT_LAUNCH_CHECK();
     int rc = BSPLAT_OK;
     const int64_t tm = sort_tiles_u32(M);
