@@ -19,6 +19,8 @@
 //       the tile is written with 128-bit stores.  Skipping is exact: a skipped Gaussian has
 //       alpha < 1/255 on every pixel of the block, so the composited result is unchanged.
 // No tensor cores: no stage of this path is a dense contraction.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace bsplat {
@@ -414,7 +416,13 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                     q2 = make_float4(-C, -C, L, L);
                     q3 = make_float4(__ldg(colors + 3 * (int64_t)g), __ldg(colors + 3 * (int64_t)g + 1),
                                      __ldg(colors + 3 * (int64_t)g + 2), tau);
-                    q4 = make_float4(pd ? -B / (2.0f * C) : 0.0f, pd ? -B / (2.0f * A) : 0.0f, 0.f, 0.f);
+                    // "plain" Gaussians (positive-definite conic, opacity <= 0.999, no NaN) have q >= 0 and
+                    // alpha <= opacity <= 0.999 by construction: the walk may skip the sigma < 0 test and the clamp
+                    // (0.99, not 0.999: ex2.approx may overshoot by an ulp).  q4.w is the bound of the sigma >= 0 test
+                    // used by the full walk: +inf for plain Gaussians, so both walks treat them identically.
+                    const bool plain = pd && (op <= 0.99f);
+                    q4 = make_float4(pd ? -B / (2.0f * C) : 0.0f, pd ? -B / (2.0f * A) : 0.0f, plain ? 0.f : 1.f,
+                                     plain ? INFINITY : L);
                 } else {
                     q0 = make_float4(0.f, 0.f, 0.f, 0.f);
                     q1 = q0;
@@ -432,6 +440,7 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
         for (int c0 = 0; c0 < bs; c0 += 32) {
             if (__all_sync(0xffffffffu, !(npx0 > -INFINITY) && !(npx1 > -INFINITY))) break;
             unsigned int mask;
+            bool special = false;  // this lane's Gaussian needs the full alpha test (see staging)
             if (kCull) {
                 bool hit = false;
                 const int gi = c0 + 31 - lane;  // earliest Gaussian = highest ballot bit
@@ -439,7 +448,9 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                     const float4* r = s_g + kPairRec * gi;
                     const float4 p0 = r[0], p1 = r[1], p2 = r[2];
                     const float tau = r[3].w;
-                    const float2 hh = *reinterpret_cast<const float2*>(r + 4);
+                    const float4 hh4 = r[4];
+                    const float2 hh = make_float2(hh4.x, hh4.y);
+                    special = hh4.z != 0.0f;
                     const float A = -p1.x, B = -p1.z, C = -p2.x;
                     const float u0 = p0.x - X1, u1 = p0.x - X0;
                     const float v0 = p0.z - Y1, v1 = p0.z - Y0;
@@ -467,48 +478,63 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                     hit = !(qmin > tau + slack);  // NaN-safe: anything odd counts as a hit
                 }
                 mask = __ballot_sync(0xffffffffu, hit);
+                special = special && hit;
             } else {
                 const int rem = bs - c0;
                 mask = rem >= 32 ? 0xffffffffu : ~(0xffffffffu >> rem);
+                special = true;
             }
+            const bool any_special = __any_sync(0xffffffffu, special);
             const float4* rec_hi = s_g + kPairRec * (c0 + 31);
-            while (mask) {
-                unsigned int b_hi;
-                asm("bfind.u32 %0, %1;" : "=r"(b_hi) : "r"(mask));
-                mask ^= 1u << b_hi;
-                const float4* r = rec_hi - kPairRec * (int)b_hi;
-                const float4 p0 = r[0], p1 = r[1], p2 = r[2];
-                const f32x2 dx = add2(pk2(p0.x, p0.y), pk2(npx0, npx1));
-                const f32x2 dy = add2(pk2(p0.z, p0.w), npy);
-                const f32x2 nbdy = mul2(pk2(p1.z, p1.w), dy);
-                const f32x2 ncdy = mul2(pk2(p2.x, p2.y), dy);
-                const f32x2 L2 = pk2(p2.z, p2.w);
-                const f32x2 lmc = fma2(ncdy, dy, L2);
-                const f32x2 t = fma2(pk2(p1.x, p1.y), dx, nbdy);
-                const f32x2 pw = fma2(t, dx, lmc);
-                float pw0, pw1;
-                upk2(pw, pw0, pw1);
-                const float L = p2.z;
-                const bool pass0 = (pw0 <= L) && (pw0 >= kLog2AlphaThreshold);
-                const bool pass1 = (pw1 <= L) && (pw1 >= kLog2AlphaThreshold);
-                const float a0 = fminf(0.999f, ex2_approx(pw0)), a1 = fminf(0.999f, ex2_approx(pw1));
-                const f32x2 a2 = pk2(a0, a1), T2 = pk2(T0, T1);
-                const f32x2 nT2 = mul2(T2, fma2(a2, mone2, one2));
-                const f32x2 vis2 = mul2(a2, T2);
-                float nT0, nT1, vis0, vis1;
-                upk2(nT2, nT0, nT1);
-                upk2(vis2, vis0, vis1);
-                const bool live0 = nT0 > 1e-4f, live1 = nT1 > 1e-4f;
-                const float4 c = r[3];
-                vis0 = (pass0 && live0) ? vis0 : 0.0f;
-                vis1 = (pass1 && live1) ? vis1 : 0.0f;
-                T0 = (pass0 && live0) ? nT0 : T0;
-                T1 = (pass1 && live1) ? nT1 : T1;
-                npx0 = (pass0 && !live0) ? -INFINITY : npx0;
-                npx1 = (pass1 && !live1) ? -INFINITY : npx1;
-                ar0 = fmaf(c.x, vis0, ar0); ag0 = fmaf(c.y, vis0, ag0); ab0 = fmaf(c.z, vis0, ab0);
-                ar1 = fmaf(c.x, vis1, ar1); ag1 = fmaf(c.y, vis1, ag1); ab1 = fmaf(c.z, vis1, ab1);
-            }
+            // two copies of the walk: chunks whose survivors are all "plain" (the common case) run without the
+            // sigma < 0 test and without the 0.999 clamp (4 of 47 instructions)
+            auto walk = [&](auto plain_tag) {
+                constexpr bool kPlain = decltype(plain_tag)::value;
+                while (mask) {
+                    unsigned int b_hi;
+                    asm("bfind.u32 %0, %1;" : "=r"(b_hi) : "r"(mask));
+                    mask ^= 1u << b_hi;
+                    const float4* r = rec_hi - kPairRec * (int)b_hi;
+                    const float4 p0 = r[0], p1 = r[1], p2 = r[2];
+                    const f32x2 dx = add2(pk2(p0.x, p0.y), pk2(npx0, npx1));
+                    const f32x2 dy = add2(pk2(p0.z, p0.w), npy);
+                    const f32x2 nbdy = mul2(pk2(p1.z, p1.w), dy);
+                    const f32x2 ncdy = mul2(pk2(p2.x, p2.y), dy);
+                    const f32x2 L2 = pk2(p2.z, p2.w);
+                    const f32x2 lmc = fma2(ncdy, dy, L2);
+                    const f32x2 t = fma2(pk2(p1.x, p1.y), dx, nbdy);
+                    const f32x2 pw = fma2(t, dx, lmc);
+                    float pw0, pw1;
+                    upk2(pw, pw0, pw1);
+                    bool pass0 = pw0 >= kLog2AlphaThreshold, pass1 = pw1 >= kLog2AlphaThreshold;
+                    float a0 = ex2_approx(pw0), a1 = ex2_approx(pw1);
+                    if (!kPlain) {
+                        const float Lt = r[4].w;  // sigma >= 0  <=>  power <= L (never fails for plain Gaussians)
+                        pass0 = pass0 && (pw0 <= Lt);
+                        pass1 = pass1 && (pw1 <= Lt);
+                        a0 = fminf(0.999f, a0);
+                        a1 = fminf(0.999f, a1);
+                    }
+                    const f32x2 a2 = pk2(a0, a1), T2 = pk2(T0, T1);
+                    const f32x2 nT2 = mul2(T2, fma2(a2, mone2, one2));
+                    const f32x2 vis2 = mul2(a2, T2);
+                    float nT0, nT1, vis0, vis1;
+                    upk2(nT2, nT0, nT1);
+                    upk2(vis2, vis0, vis1);
+                    const bool live0 = nT0 > 1e-4f, live1 = nT1 > 1e-4f;
+                    const float4 c = r[3];
+                    vis0 = (pass0 && live0) ? vis0 : 0.0f;
+                    vis1 = (pass1 && live1) ? vis1 : 0.0f;
+                    T0 = (pass0 && live0) ? nT0 : T0;
+                    T1 = (pass1 && live1) ? nT1 : T1;
+                    npx0 = (pass0 && !live0) ? -INFINITY : npx0;
+                    npx1 = (pass1 && !live1) ? -INFINITY : npx1;
+                    ar0 = fmaf(c.x, vis0, ar0); ag0 = fmaf(c.y, vis0, ag0); ab0 = fmaf(c.z, vis0, ab0);
+                    ar1 = fmaf(c.x, vis1, ar1); ag1 = fmaf(c.y, vis1, ag1); ab1 = fmaf(c.z, vis1, ab1);
+                }
+            };
+            if (any_special) walk(std::false_type{});
+            else walk(std::true_type{});
         }
     }
 
