@@ -359,6 +359,11 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     return r;
 }
 
+struct LoopConsts {
+    unsigned int one_u;
+    float one_f, mone_f;
+};
+
 template <bool kCull>
 __global__ void __launch_bounds__(kPairThreads)
 raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
@@ -367,7 +372,7 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                    const int32_t* __restrict__ tile_order, const int first_tile,
                    const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
                    float* __restrict__ image, const int vec_store,
-                   const unsigned long long* __restrict__ m_dev, const PeerImages peers) {
+                   const unsigned long long* __restrict__ m_dev, const PeerImages peers, const LoopConsts consts) {
     __shared__ float4 s_g[kPairBatch * kPairRec];
 
     const int tid = threadIdx.x;
@@ -389,7 +394,10 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
     const int32_t r0 = tile_ranges[2 * tile], r1 = tile_ranges[2 * tile + 1];
     float T0 = 1.0f, T1 = 1.0f;
     float ar0 = 0.f, ag0 = 0.f, ab0 = 0.f, ar1 = 0.f, ag1 = 0.f, ab1 = 0.f;
-    const f32x2 one2 = pk2(1.0f, 1.0f), mone2 = pk2(-1.0f, -1.0f);
+    // loop constants come in as kernel parameters (constant bank operands): ptxas otherwise re-materialises
+    // literal constants with a MOV in every iteration of the walk, which is bound by issue slots
+    const unsigned int bit_one = consts.one_u;
+    const f32x2 one2 = pk2(consts.one_f, consts.one_f), mone2 = pk2(consts.mone_f, consts.mone_f);
 
     for (int32_t b0 = r0; b0 < r1; b0 += kPairBatch) {
         const bool fin = !(npx0 > -INFINITY) && !(npx1 > -INFINITY);
@@ -493,7 +501,7 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                 while (mask) {
                     unsigned int b_hi;
                     asm("bfind.u32 %0, %1;" : "=r"(b_hi) : "r"(mask));
-                    mask ^= 1u << b_hi;
+                    mask ^= bit_one << b_hi;
                     const float4* r = rec_hi - kPairRec * (int)b_hi;
                     const float4 p0 = r[0], p1 = r[1], p2 = r[2];
                     const f32x2 dx = add2(pk2(p0.x, p0.y), pk2(npx0, npx1));
@@ -875,6 +883,7 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         const int vec = ((reinterpret_cast<uintptr_t>(image) & 15u) == 0 && (W % 4) == 0) ? 1 : 0;
         const unsigned grid = (unsigned)(tiles_w * (row_end - row_begin));
         const int first_tile = row_begin * tiles_w;
+        const LoopConsts loop_consts = {1u, 1.0f, -1.0f};
         const bool warp_path = mode == 3 && rec_ws != nullptr && N > 0 &&
                                (reinterpret_cast<uintptr_t>(rec_ws) & 15u) == 0;
         if (warp_path) {
@@ -887,7 +896,7 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         } else if (mode == 2) {
             raster_pair_kernel<false><<<grid, kPairThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
                                                                          tile_ranges, tile_order, first_tile, sorted_ids,
-                                                                         W, H, tiles_w, image, vec, m_dev, peers);
+                                                                         W, H, tiles_w, image, vec, m_dev, peers, loop_consts);
         } else if (mode == 4) {
             raster_fast_kernel<true><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
                                                                         tile_ranges, tile_order, first_tile, sorted_ids,
@@ -895,7 +904,7 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         } else {
             raster_pair_kernel<true><<<grid, kPairThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
                                                                         tile_ranges, tile_order, first_tile, sorted_ids,
-                                                                        W, H, tiles_w, image, vec, m_dev, peers);
+                                                                        W, H, tiles_w, image, vec, m_dev, peers, loop_consts);
         }
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
