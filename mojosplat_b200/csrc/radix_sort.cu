@@ -162,9 +162,16 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
 #pragma unroll
             for (int b = 0; b < kRadixBits; ++b) {
                 if (b < bits) {
-                    const bool bit = (d & (1u << b)) != 0u;
-                    const uint32_t m = __ballot_sync(0xffffffffu, bit);
-                    p &= bit ? m : ~m;
+                    // lanes sharing bit b with this lane: m ^ (bit ? 0 : ~0).  Written in PTX so that it stays at
+                    // 4 instructions (LOP3 -> predicate, VOTE, SEL, LOP3); nvcc's own lowering took 6.
+                    uint32_t m, x;
+                    asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\t"
+                        "and.b32 t, %2, %3;\n\t"
+                        "setp.ne.b32 q, t, 0;\n\t"
+                        "vote.sync.ballot.b32 %0, q, 0xffffffff;\n\t"
+                        "selp.b32 %1, 0, 0xffffffff, q;\n\t}"
+                        : "=r"(m), "=r"(x) : "r"(d), "r"(1u << b));
+                    p &= (m ^ x);
                 }
             }
             peers[it] = p;
