@@ -415,7 +415,9 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                                 cc = __ldg(conics + 3 * (int64_t)g + 2);
                     const float op = __ldg(opacities + g);
                     const float A = 0.5f * kLog2e * ca, B = kLog2e * cb, C = 0.5f * kLog2e * cc;
-                    const float L = (op > 0.0f) ? log2f(op) : -INFINITY;
+                    // MUFU.LG2 (abs. error ~2^-22): alpha = 2^(L - q) stays within 1e-6 of o*exp(-sigma); the staging
+                    // runs once per (tile, Gaussian), so libdevice log2f / IEEE divisions would cost ~40 instructions
+                    const float L = (op > 0.0f) ? __log2f(op) : -INFINITY;
                     const bool pd = (A > 0.0f) && (C > 0.0f) && (4.0f * A * C - B * B > 0.0f);
                     float tau = pd ? (L - kLog2AlphaThreshold) : INFINITY;
                     if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
@@ -429,7 +431,9 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                     // (0.99, not 0.999: ex2.approx may overshoot by an ulp).  q4.w is the bound of the sigma >= 0 test
                     // used by the full walk: +inf for plain Gaussians, so both walks treat them identically.
                     const bool plain = pd && (op <= 0.99f);
-                    q4 = make_float4(pd ? -B / (2.0f * C) : 0.0f, pd ? -B / (2.0f * A) : 0.0f, plain ? 0.f : 1.f,
+                    // (edge minimisers feed the conservative culling bound only: approximate division is inside its slack)
+                    q4 = make_float4(pd ? __fdividef(-B, 2.0f * C) : 0.0f, pd ? __fdividef(-B, 2.0f * A) : 0.0f,
+                                     plain ? 0.f : 1.f,
                                      plain ? INFINITY : L);
                 } else {
                     q0 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -606,12 +610,12 @@ raster_prep_kernel(const int64_t N, const float* __restrict__ means2d, const flo
     const float op = __ldg(opacities + g);
     const float A = 0.5f * kLog2e * ca, B = kLog2e * cb, C = 0.5f * kLog2e * cc;
     // accurate log2 keeps alpha = 2^(L - q) within a few ulp of o*exp(-sigma)
-    const float L = (op > 0.0f) ? log2f(op) : -INFINITY;
+    const float L = (op > 0.0f) ? __log2f(op) : -INFINITY;  // same arithmetic as the pair kernel's staging
     const bool pd = (A > 0.0f) && (C > 0.0f) && (4.0f * A * C - B * B > 0.0f);
     float tau = pd ? (L - kLog2AlphaThreshold) : INFINITY;
     if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
     rec[3 * g] = make_float4(mx, my, -A, -B);
-    rec[3 * g + 1] = make_float4(-C, L, pd ? -B / (2.0f * C) : 0.0f, pd ? -B / (2.0f * A) : 0.0f);
+    rec[3 * g + 1] = make_float4(-C, L, pd ? __fdividef(-B, 2.0f * C) : 0.0f, pd ? __fdividef(-B, 2.0f * A) : 0.0f);
     rec[3 * g + 2] = make_float4(__ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), tau);
 }
 
