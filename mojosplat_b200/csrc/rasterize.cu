@@ -359,14 +359,102 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     return r;
 }
 
+// Conservative test "can this Gaussian reach alpha >= 1/255 anywhere in the pixel rectangle [X0, X1] x [Y0, Y1]
+// (pixel centres)?"  min of q over the rectangle = min over the (<= 2) edges facing the mean; along the edge
+// u = ue the quadratic is D ue^2 + C (v - hy ue)^2 with D = A + B hy / 2 (and symmetrically for v = ve), so each
+// edge costs a clamp and two FMAs.  NaN-safe: anything odd counts as a hit.
+__device__ __forceinline__ bool pair_cull_hit(const float mx, const float my, const float A, const float B,
+                                              const float C, const float tau, const float hy, const float hx,
+                                              const float X0, const float X1, const float Y0, const float Y1) {
+    const float u0 = mx - X1, u1 = mx - X0;
+    const float v0 = my - Y1, v1 = my - Y0;
+    const bool zu = (u0 <= 0.0f) && (u1 >= 0.0f);
+    const bool zv = (v0 <= 0.0f) && (v1 >= 0.0f);
+    float qmin = 0.0f;
+    if (!(zu && zv)) {
+        float q1 = INFINITY, q2 = INFINITY;
+        if (!zu) {
+            const float ue = (u0 > 0.0f) ? u0 : u1;
+            const float vstar = hy * ue;
+            const float dv = vstar - fminf(fmaxf(vstar, v0), v1);
+            q1 = fmaf(fmaf(0.5f * B, hy, A) * ue, ue, C * dv * dv);
+        }
+        if (!zv) {
+            const float ve = (v0 > 0.0f) ? v0 : v1;
+            const float ustar = hx * ve;
+            const float du = ustar - fminf(fmaxf(ustar, u0), u1);
+            q2 = fmaf(fmaf(0.5f * B, hx, C) * ve, ve, A * du * du);
+        }
+        qmin = fminf(q1, q2);
+    }
+    const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
+    const float slack = 4e-6f * (A * um * um + C * vm * vm) + 1e-3f;
+    return !(qmin > tau + slack);
+}
+
+constexpr int kLongTile = 2048;  // lists longer than this get a tile-level pre-test (see the kernel)
+
 struct LoopConsts {
     unsigned int one_u;
     float one_f, mone_f;
 };
 
-template <bool kCull>
+// The staged record of one Gaussian (5 x float4, layout above).  One definition for the in-kernel staging and for
+// raster_pair_prep_kernel, so both paths composite bit-identical values.
+__device__ __forceinline__ void pair_record(const int64_t g, const float* __restrict__ means2d,
+                                            const float* __restrict__ conics, const float* __restrict__ colors,
+                                            const float* __restrict__ opacities, float4& q0, float4& q1, float4& q2,
+                                            float4& q3, float4& q4) {
+    const float2 m = __ldg(reinterpret_cast<const float2*>(means2d) + g);
+    const float ca = __ldg(conics + 3 * g), cb = __ldg(conics + 3 * g + 1), cc = __ldg(conics + 3 * g + 2);
+    const float op = __ldg(opacities + g);
+    const float A = 0.5f * kLog2e * ca, B = kLog2e * cb, C = 0.5f * kLog2e * cc;
+    // MUFU.LG2 (abs. error ~2^-22): alpha = 2^(L - q) stays within 1e-6 of o*exp(-sigma)
+    const float L = (op > 0.0f) ? __log2f(op) : -INFINITY;
+    const bool pd = (A > 0.0f) && (C > 0.0f) && (4.0f * A * C - B * B > 0.0f);
+    float tau = pd ? (L - kLog2AlphaThreshold) : INFINITY;
+    if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
+    q0 = make_float4(m.x, m.x, m.y, m.y);
+    q1 = make_float4(-A, -A, -B, -B);
+    q2 = make_float4(-C, -C, L, L);
+    q3 = make_float4(__ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), tau);
+    // "plain" Gaussians (positive-definite conic, opacity <= 0.99, no NaN) have q >= 0 and alpha <= opacity by
+    // construction: the walk may skip the sigma < 0 test and the 0.999 clamp (0.99, not 0.999: ex2.approx may
+    // overshoot by an ulp).  q4.w is the bound of the sigma >= 0 test of the full walk: +inf for plain Gaussians,
+    // so both walks treat them identically.  The edge minimisers hy, hx feed the conservative culling bound only:
+    // approximate division is inside its slack.
+    const bool plain = pd && (op <= 0.99f);
+    q4 = make_float4(pd ? __fdividef(-B, 2.0f * C) : 0.0f, pd ? __fdividef(-B, 2.0f * A) : 0.0f, plain ? 0.f : 1.f,
+                     plain ? INFINITY : L);
+}
+
+// Records of ALL Gaussians, once per frame (80 B each): with them the rasterizer's staging is a pure gather that
+// cp.async can run one batch ahead, and the per-(tile, Gaussian) staging arithmetic disappears.
+__global__ void __launch_bounds__(256)
+raster_pair_prep_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
+                        const float* __restrict__ colors, const float* __restrict__ opacities,
+                        float4* __restrict__ rec) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    float4 q0, q1, q2, q3, q4;
+    pair_record(g, means2d, conics, colors, opacities, q0, q1, q2, q3, q4);
+    float4* d = rec + kPairRec * g;
+    d[0] = q0; d[1] = q1; d[2] = q2; d[3] = q3; d[4] = q4;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// kRec: the Gaussians come as prepared records (raster_pair_prep_kernel); batches of 128 are gathered by sorted id
+// with cp.async into the two halves of the staging buffer, one batch ahead of the walk (ids two batches ahead),
+// one barrier per batch.  !kRec: workspace-free staging of 256 per batch from the raw arrays.
+template <bool kCull, bool kRec>
 __global__ void __launch_bounds__(kPairThreads)
-raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
+raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float* __restrict__ means2d, const float* __restrict__ conics,
                    const float* __restrict__ colors, const float* __restrict__ opacities,
                    const float* __restrict__ background, const int32_t* __restrict__ tile_ranges,
                    const int32_t* __restrict__ tile_order, const int first_tile,
@@ -374,6 +462,7 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                    float* __restrict__ image, const int vec_store,
                    const unsigned long long* __restrict__ m_dev, const PeerImages peers, const LoopConsts consts) {
     __shared__ float4 s_g[kPairBatch * kPairRec];
+    __shared__ unsigned int s_tmask[kPairBatch / 32];  // long tiles: survivors of the tile-level test
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -392,6 +481,14 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
     const float Y0 = (float)by + 0.5f, Y1 = (float)by + 7.5f;
 
     const int32_t r0 = tile_ranges[2 * tile], r1 = tile_ranges[2 * tile + 1];
+    // Very long lists are mostly Gaussians that cannot touch the tile at all (under the torch binning rules every
+    // culled Gaussian is clamped into a border tile: ~10 k entries in each corner tile at config 3, ~350 k at
+    // config 5).  For those tiles the four warps first share ONE test of every staged Gaussian against the whole
+    // 16x16 tile (64 entries per warp instead of 256), and a warp only runs its own 8x8 test on the survivors:
+    // the serial walk of such a list, which bounds the kernel once a frame is split across GPUs, gets ~4x shorter.
+    const bool long_tile = kCull && (r1 - r0 > kLongTile);
+    const float TX0 = (float)(tile_x * kFastTile) + 0.5f, TX1 = TX0 + 15.0f;
+    const float TY0 = (float)(tile_y * kFastTile) + 0.5f, TY1 = TY0 + 15.0f;
     float T0 = 1.0f, T1 = 1.0f;
     float ar0 = 0.f, ag0 = 0.f, ab0 = 0.f, ar1 = 0.f, ag1 = 0.f, ab1 = 0.f;
     // loop constants come in as kernel parameters (constant bank operands): ptxas otherwise re-materialises
@@ -399,95 +496,101 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
     const unsigned int bit_one = consts.one_u;
     const f32x2 one2 = pk2(consts.one_f, consts.one_f), mone2 = pk2(consts.mone_f, consts.mone_f);
 
-    for (int32_t b0 = r0; b0 < r1; b0 += kPairBatch) {
-        const bool fin = !(npx0 > -INFINITY) && !(npx1 > -INFINITY);
-        if (__syncthreads_count(fin) >= kPairThreads) break;
+    constexpr int kBatch = kRec ? kPairThreads : kPairBatch;
+    constexpr int kPer = kBatch / kPairThreads;  // staged entries per thread and batch
+    auto load_id = [&](int32_t at) { return (at < r1) ? __ldg(sorted_ids + at) : -1; };
+    auto gather = [&](int half, int32_t id) {  // kRec: this thread's entry of a batch -> record buffer `half`
+        float4* dst = s_g + (half * kPairThreads + tid) * kPairRec;
+        if (id >= 0 && (int64_t)id < N) {
+            const float4* src = rec + kPairRec * (int64_t)id;
 #pragma unroll
-        for (int h = 0; h < kPairBatch / kPairThreads; ++h) {
-            const int t = tid + h * kPairThreads;
-            const int32_t idx = b0 + t;
-            if (idx < r1) {
-                const int32_t g = __ldg(sorted_ids + idx);
-                float4 q0, q1, q2, q3, q4;
-                if (g >= 0 && (int64_t)g < N) {
-                    const float2 m = __ldg(reinterpret_cast<const float2*>(means2d) + g);
-                    const float ca = __ldg(conics + 3 * (int64_t)g), cb = __ldg(conics + 3 * (int64_t)g + 1),
-                                cc = __ldg(conics + 3 * (int64_t)g + 2);
-                    const float op = __ldg(opacities + g);
-                    const float A = 0.5f * kLog2e * ca, B = kLog2e * cb, C = 0.5f * kLog2e * cc;
-                    // MUFU.LG2 (abs. error ~2^-22): alpha = 2^(L - q) stays within 1e-6 of o*exp(-sigma); the staging
-                    // runs once per (tile, Gaussian), so libdevice log2f / IEEE divisions would cost ~40 instructions
-                    const float L = (op > 0.0f) ? __log2f(op) : -INFINITY;
-                    const bool pd = (A > 0.0f) && (C > 0.0f) && (4.0f * A * C - B * B > 0.0f);
-                    float tau = pd ? (L - kLog2AlphaThreshold) : INFINITY;
-                    if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
-                    q0 = make_float4(m.x, m.x, m.y, m.y);
-                    q1 = make_float4(-A, -A, -B, -B);
-                    q2 = make_float4(-C, -C, L, L);
-                    q3 = make_float4(__ldg(colors + 3 * (int64_t)g), __ldg(colors + 3 * (int64_t)g + 1),
-                                     __ldg(colors + 3 * (int64_t)g + 2), tau);
-                    // "plain" Gaussians (positive-definite conic, opacity <= 0.999, no NaN) have q >= 0 and
-                    // alpha <= opacity <= 0.999 by construction: the walk may skip the sigma < 0 test and the clamp
-                    // (0.99, not 0.999: ex2.approx may overshoot by an ulp).  q4.w is the bound of the sigma >= 0 test
-                    // used by the full walk: +inf for plain Gaussians, so both walks treat them identically.
-                    const bool plain = pd && (op <= 0.99f);
-                    // (edge minimisers feed the conservative culling bound only: approximate division is inside its slack)
-                    q4 = make_float4(pd ? __fdividef(-B, 2.0f * C) : 0.0f, pd ? __fdividef(-B, 2.0f * A) : 0.0f,
-                                     plain ? 0.f : 1.f,
-                                     plain ? INFINITY : L);
-                } else {
-                    q0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    q1 = q0;
-                    q2 = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
-                    q3 = make_float4(0.f, 0.f, 0.f, -INFINITY);
-                    q4 = q0;
-                }
-                float4* dst = s_g + kPairRec * t;
-                dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3; dst[4] = q4;
-            }
+            for (int q = 0; q < kPairRec; ++q) cp_async16(dst + q, src + q);
+        } else {  // past the end of the list / invalid id (rasterization.mojo:109 guard): can never hit
+            dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[1] = dst[0];
+            dst[2] = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
+            dst[3] = make_float4(0.f, 0.f, 0.f, -INFINITY);
+            dst[4] = dst[0];
         }
-        __syncthreads();
+        cp_async_commit();
+    };
+    int32_t id_next = -1;
+    if (kRec && r0 < r1) {
+        gather(0, load_id(r0 + tid));
+        id_next = load_id(r0 + kBatch + tid);
+    }
+    int batch = 0;
+    for (int32_t b0 = r0; b0 < r1; b0 += kBatch, ++batch) {
+        const bool fin = !(npx0 > -INFINITY) && !(npx1 > -INFINITY);
+        const float4* s_rec = s_g;
+        if (kRec) {
+            cp_async_wait_all();  // this thread's part of batch `batch` has landed ...
+            if (__syncthreads_count(fin) >= kPairThreads) break;  // ... everyone's has; batch - 1 is fully consumed
+            if (b0 + kBatch < r1) gather((batch + 1) & 1, id_next);  // next batch flies during this walk
+            id_next = load_id(b0 + 2 * kBatch + tid);
+            s_rec = s_g + (batch & 1) * kPairThreads * kPairRec;
+        } else {
+            if (__syncthreads_count(fin) >= kPairThreads) break;
+#pragma unroll
+            for (int h = 0; h < kPer; ++h) {
+                const int t = tid + h * kPairThreads;
+                const int32_t idx = b0 + t;
+                if (idx < r1) {
+                    const int32_t g = __ldg(sorted_ids + idx);
+                    float4 q0, q1, q2, q3, q4;
+                    if (g >= 0 && (int64_t)g < N) {
+                        pair_record(g, means2d, conics, colors, opacities, q0, q1, q2, q3, q4);
+                    } else {
+                        q0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        q1 = q0;
+                        q2 = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
+                        q3 = make_float4(0.f, 0.f, 0.f, -INFINITY);
+                        q4 = q0;
+                    }
+                    float4* dst = s_g + kPairRec * t;
+                    dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3; dst[4] = q4;
+                }
+            }
+            __syncthreads();
+        }
 
-        const int bs = min(kPairBatch, (int)(r1 - b0));
+        const int bs = min(kBatch, (int)(r1 - b0));
+        if (long_tile) {
+#pragma unroll
+            for (int h = 0; h < kPer; ++h) {
+                const int e = warp * (32 * kPer) + h * 32 + lane;
+                bool hit = false;
+                if (e < bs) {
+                    const float4* r = s_rec + kPairRec * e;
+                    const float4 p0 = r[0], p1 = r[1], p2 = r[2];
+                    const float4 hh4 = r[4];
+                    hit = pair_cull_hit(p0.x, p0.z, -p1.x, -p1.z, -p2.x, r[3].w, hh4.x, hh4.y, TX0, TX1, TY0, TY1);
+                }
+                const unsigned int word = __ballot_sync(0xffffffffu, hit);  // bit l <-> entry chunk base + l
+                if (lane == 0) s_tmask[warp * kPer + h] = word;
+            }
+            __syncthreads();
+        }
         for (int c0 = 0; c0 < bs; c0 += 32) {
             if (__all_sync(0xffffffffu, !(npx0 > -INFINITY) && !(npx1 > -INFINITY))) break;
+            unsigned int tword = 0xffffffffu;
+            if (long_tile) {
+                tword = s_tmask[c0 >> 5];
+                if (tword == 0u) continue;  // nothing of this chunk reaches the tile
+            }
             unsigned int mask;
             bool special = false;  // this lane's Gaussian needs the full alpha test (see staging)
             if (kCull) {
                 bool hit = false;
                 const int gi = c0 + 31 - lane;  // earliest Gaussian = highest ballot bit
-                if (gi < bs) {
-                    const float4* r = s_g + kPairRec * gi;
+                if (gi < bs && ((tword >> (31 - lane)) & 1u)) {
+                    const float4* r = s_rec + kPairRec * gi;
                     const float4 p0 = r[0], p1 = r[1], p2 = r[2];
                     const float tau = r[3].w;
                     const float4 hh4 = r[4];
                     const float2 hh = make_float2(hh4.x, hh4.y);
                     special = hh4.z != 0.0f;
-                    const float A = -p1.x, B = -p1.z, C = -p2.x;
-                    const float u0 = p0.x - X1, u1 = p0.x - X0;
-                    const float v0 = p0.z - Y1, v1 = p0.z - Y0;
-                    const bool zu = (u0 <= 0.0f) && (u1 >= 0.0f);
-                    const bool zv = (v0 <= 0.0f) && (v1 >= 0.0f);
-                    float qmin = 0.0f;
-                    if (!(zu && zv)) {
-                        float q1 = INFINITY, q2 = INFINITY;
-                        if (!zu) {
-                            const float ue = (u0 > 0.0f) ? u0 : u1;
-                            const float vstar = hh.x * ue;
-                            const float dv = vstar - fminf(fmaxf(vstar, v0), v1);
-                            q1 = fmaf(fmaf(0.5f * B, hh.x, A) * ue, ue, C * dv * dv);
-                        }
-                        if (!zv) {
-                            const float ve = (v0 > 0.0f) ? v0 : v1;
-                            const float ustar = hh.y * ve;
-                            const float du = ustar - fminf(fmaxf(ustar, u0), u1);
-                            q2 = fmaf(fmaf(0.5f * B, hh.y, C) * ve, ve, A * du * du);
-                        }
-                        qmin = fminf(q1, q2);
-                    }
-                    const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
-                    const float slack = 4e-6f * (A * um * um + C * vm * vm) + 1e-3f;
-                    hit = !(qmin > tau + slack);  // NaN-safe: anything odd counts as a hit
+                    hit = pair_cull_hit(p0.x, p0.z, -p1.x, -p1.z, -p2.x, tau, hh.x, hh.y, X0, X1, Y0, Y1);
                 }
                 mask = __ballot_sync(0xffffffffu, hit);
                 special = special && hit;
@@ -497,7 +600,7 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
                 special = true;
             }
             const bool any_special = __any_sync(0xffffffffu, special);
-            const float4* rec_hi = s_g + kPairRec * (c0 + 31);
+            const float4* rec_hi = s_rec + kPairRec * (c0 + 31);
             // two copies of the walk: chunks whose survivors are all "plain" (the common case) run without the
             // sigma < 0 test and without the 0.999 clamp (4 of 47 instructions)
             auto walk = [&](auto plain_tag) {
@@ -550,6 +653,7 @@ raster_pair_kernel(const int64_t N, const float* __restrict__ means2d, const flo
         }
     }
 
+    if (kRec) cp_async_wait_all();  // nothing may still be landing in shared memory when it is reused below
     const float bgs = (m_dev != nullptr && *m_dev == 0ull) ? 0.0f : 1.0f;
     const float bgr = bgs * __ldg(background), bgg = bgs * __ldg(background + 1), bgb = bgs * __ldg(background + 2);
     const float o0r = fmaf(T0, bgr, ar0), o0g = fmaf(T0, bgg, ag0), o0b = fmaf(T0, bgb, ab0);
@@ -618,13 +722,6 @@ raster_prep_kernel(const int64_t N, const float* __restrict__ means2d, const flo
     rec[3 * g + 1] = make_float4(-C, L, pd ? __fdividef(-B, 2.0f * C) : 0.0f, pd ? __fdividef(-B, 2.0f * A) : 0.0f);
     rec[3 * g + 2] = make_float4(__ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), tau);
 }
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <bool kCull>
 __global__ void __launch_bounds__(32, 32)
@@ -853,12 +950,12 @@ static int launch_faithful(int64_t N, int cdim, int c0, const float* means2d, co
 }
 
 namespace bsplat {
-// shared with capi.cu.  mode 0 = fast (pair kernel), 2 = the same without sub-tile culling (exactness A/B),
-// 3 = warp kernel (independent warps, needs the record workspace; pair kernel without it), 4 = one pixel
-// per lane (first fast kernel), 1 = faithful.  On config 3 the three fast kernels are within 3 % of each other
+// shared with capi.cu.  mode 0 = fast (pair kernel; with a record workspace: records + cp.async staging),
+// 2 = the same without sub-tile culling (exactness A/B), 3 = warp kernel (independent warps, needs the record
+// workspace; pair kernel without it), 4 = one pixel per lane (first fast kernel), 1 = faithful.  On config 3 the three fast kernels are within 3 % of each other
 // (0.29-0.30 ms): 264 M / 211 M / 187 M warp instructions, but the lighter ones issue less densely
 // (profiles/r01_raster_*): the pair kernel is the default.
-size_t raster_workspace_bytes(int64_t N) { return (size_t)(N > 0 ? N : 1) * 3 * sizeof(float4); }
+size_t raster_workspace_bytes(int64_t N) { return (size_t)(N > 0 ? N : 1) * kPairRec * sizeof(float4); }
 
 int rasterize_launch(int64_t N, int channels, const float* means2d, const float* conics, const float* colors,
                      const float* opacities, const float* background_dev,
@@ -888,27 +985,39 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         const unsigned grid = (unsigned)(tiles_w * (row_end - row_begin));
         const int first_tile = row_begin * tiles_w;
         const LoopConsts loop_consts = {1u, 1.0f, -1.0f};
-        const bool warp_path = mode == 3 && rec_ws != nullptr && N > 0 &&
-                               (reinterpret_cast<uintptr_t>(rec_ws) & 15u) == 0;
-        if (warp_path) {
-            float4* rec = static_cast<float4*>(rec_ws);
-            raster_prep_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(N, means2d, conics, colors, opacities, rec);
+        const bool have_rec = rec_ws != nullptr && N > 0 && (reinterpret_cast<uintptr_t>(rec_ws) & 15u) == 0;
+        float4* recp = static_cast<float4*>(rec_ws);
+        if (mode == 3 && have_rec) {
+            raster_prep_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(N, means2d, conics, colors, opacities, recp);
             BSPLAT_LAUNCH_CHECK();
-            raster_warp_kernel<true><<<grid * 4, 32, 0, stream>>>(N, rec, bg, tile_ranges, tile_order,
-                                                                             first_tile, sorted_ids, W, H, tiles_w,
-                                                                             image, vec, m_dev);
-        } else if (mode == 2) {
-            raster_pair_kernel<false><<<grid, kPairThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
-                                                                         tile_ranges, tile_order, first_tile, sorted_ids,
-                                                                         W, H, tiles_w, image, vec, m_dev, peers, loop_consts);
+            raster_warp_kernel<true><<<grid * 4, 32, 0, stream>>>(N, recp, bg, tile_ranges, tile_order,
+                                                                  first_tile, sorted_ids, W, H, tiles_w,
+                                                                  image, vec, m_dev);
         } else if (mode == 4) {
             raster_fast_kernel<true><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
                                                                         tile_ranges, tile_order, first_tile, sorted_ids,
                                                                         W, H, tiles_w, image, vec, m_dev);
+        } else if (have_rec) {
+            // default: records once per frame, then the cp.async-staged pair kernel
+            raster_pair_prep_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(N, means2d, conics, colors,
+                                                                                    opacities, recp);
+            BSPLAT_LAUNCH_CHECK();
+            if (mode == 2)
+                raster_pair_kernel<false, true><<<grid, kPairThreads, 0, stream>>>(
+                    N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
+                    tiles_w, image, vec, m_dev, peers, loop_consts);
+            else
+                raster_pair_kernel<true, true><<<grid, kPairThreads, 0, stream>>>(
+                    N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
+                    tiles_w, image, vec, m_dev, peers, loop_consts);
+        } else if (mode == 2) {
+            raster_pair_kernel<false, false><<<grid, kPairThreads, 0, stream>>>(
+                N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
+                tiles_w, image, vec, m_dev, peers, loop_consts);
         } else {
-            raster_pair_kernel<true><<<grid, kPairThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
-                                                                        tile_ranges, tile_order, first_tile, sorted_ids,
-                                                                        W, H, tiles_w, image, vec, m_dev, peers, loop_consts);
+            raster_pair_kernel<true, false><<<grid, kPairThreads, 0, stream>>>(
+                N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
+                tiles_w, image, vec, m_dev, peers, loop_consts);
         }
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
