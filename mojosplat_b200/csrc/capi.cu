@@ -290,6 +290,7 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
         }
     }
     const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
+    if (aux && fast_raster && raster_mode != BSPLAT_RASTER_SINGLE) aux->n_launches += 1;  // raster record prep kernel
     if (fast_raster && !have_order) {
         rc = tile_order_launch(0, tiles_w * tiles_h, d_ranges, w.tile_order, stream);
         if (rc != BSPLAT_OK) { drop_events(); return rc; }
