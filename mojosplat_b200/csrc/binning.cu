@@ -16,7 +16,8 @@
 namespace bsplat {
 
 __global__ void __launch_bounds__(kScanThreads)
-bin_count_scan_kernel(const int64_t N, const int32_t* __restrict__ perm, const float* __restrict__ means2d,
+bin_count_scan_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_dev,
+                      const int32_t* __restrict__ perm, const float* __restrict__ means2d,
                       const void* __restrict__ radii, const int radii_is_float,
                       const float* __restrict__ depths, const BinParams p,
                       uint32_t* __restrict__ offsets, bsplat_bin_info* __restrict__ info,
@@ -27,11 +28,17 @@ bin_count_scan_kernel(const int64_t N, const int32_t* __restrict__ perm, const f
     __shared__ unsigned int s_red[2][kScanThreads / 32];
 
     const int tid = threadIdx.x;
+    // n_dev: the number of items lives on the device (band-compacted depth order); the grid is sized by N_host
+    const int64_t N = n_dev ? (int64_t)(*n_dev) : N_host;
     if (tid == 0) s_chunk = atomicAdd(reinterpret_cast<unsigned int*>(ws), 1u);
     __syncthreads();
     const unsigned int chunk = s_chunk;
     unsigned long long* status = ws + 1;
     const int64_t base = (int64_t)chunk * kScanChunk;
+    if (base >= N) {  // surplus chunk (tickets are handed out in order: no lower chunk ever waits for this one)
+        if (N == 0 && chunk == 0 && tid == 0) { offsets[0] = 0u; info->n_isect = 0ull; }
+        return;
+    }
 
     // blocked arrangement: thread t owns items base + t*kScanItems + k (keeps the scan trivial)
     uint32_t cnt[kScanItems];
@@ -217,9 +224,9 @@ __global__ void tile_ranges_kernel(const int64_t M, const KeyT* __restrict__ key
 int bin_count_scan_launch(int64_t N, const int32_t* perm, const float* means2d, const void* radii,
                           int radii_is_float, const float* depths, const BinParams& p, uint32_t* offsets,
                           bsplat_bin_info* info, void* workspace, bool finalize_key_range, cudaStream_t stream,
-                          uint2* rects) {
+                          uint2* rects, const unsigned long long* n_dev) {
     const unsigned grid = (unsigned)ceil_div(N, kScanChunk);
-    bin_count_scan_kernel<<<grid, kScanThreads, 0, stream>>>(N, perm, means2d, radii, radii_is_float,
+    bin_count_scan_kernel<<<grid, kScanThreads, 0, stream>>>(N, n_dev, perm, means2d, radii, radii_is_float,
                                                              finalize_key_range ? depths : nullptr, p, offsets, info,
                                                              static_cast<unsigned long long*>(workspace), rects);
     BSPLAT_LAUNCH_CHECK();
@@ -286,7 +293,7 @@ extern "C" int bsplat_bin_count_scan(int64_t N, const float* means2d, const void
     }
     const unsigned grid = (unsigned)ceil_div(N, kScanChunk);
     return bin_count_scan_launch(N, nullptr, means2d, radii, radii_is_float, depths, p, offsets, info, workspace,
-                                 true, stream, nullptr);
+                                 true, stream, nullptr, nullptr);
 }
 
 extern "C" bsplat_key_layout bsplat_make_key_layout(const bsplat_bin_info* info_host, int32_t width,

@@ -38,7 +38,7 @@ __device__ inline void load_mean_radii(const float* __restrict__ means2d, const 
 int bin_count_scan_launch(int64_t N, const int32_t* perm, const float* means2d, const void* radii,
                           int radii_is_float, const float* depths, const BinParams& p, uint32_t* offsets,
                           bsplat_bin_info* info, void* workspace, bool finalize_key_range, cudaStream_t stream,
-                          uint2* rects);
+                          uint2* rects, const unsigned long long* n_dev);
 int tile_ranges_u32_launch(int64_t M, const uint32_t* sorted_tile_ids, int n_tiles, int32_t* tile_ranges,
                            cudaStream_t stream);
 int make_bin_params(int32_t width, int32_t height, int32_t tile_size, int32_t row_begin, int32_t row_end,

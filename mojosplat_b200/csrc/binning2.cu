@@ -49,6 +49,80 @@ depth_key_hist_kernel(const int64_t N, const float* __restrict__ depths, uint32_
     }
 }
 
+// ---- 1b. row-band frames: only the Gaussians that reach the band are depth-sorted -----------------------
+// flag = 0 for a Gaussian whose tile rectangle intersects the band, 1 otherwise; a 1-bit onesweep pass on the
+// flags is a stable partition of the indices (in-band first, ascending index), band_gather_hist_kernel then
+// collects the depth keys of the in-band prefix.  Every rank of a row-band split used to sort all N Gaussians.
+__global__ void __launch_bounds__(256)
+band_flag_kernel(const int64_t N, const float* __restrict__ means2d, const void* __restrict__ radii,
+                 const int radii_is_float, const float* __restrict__ depths, const BinParams p,
+                 uint32_t* __restrict__ flags, uint32_t* __restrict__ keys_full, uint32_t* __restrict__ hist2,
+                 unsigned long long* __restrict__ n_band) {
+    __shared__ unsigned int s_in;
+    if (threadIdx.x == 0) s_in = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int mine = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        float mx, my, rx, ry;
+        load_mean_radii(means2d, radii, radii_is_float, i, mx, my, rx, ry);
+        const TileRect r = tile_rect(mx, my, rx, ry, p.W, p.H, p.tile_size_f, p.tiles_w, p.tiles_h, p.semantics,
+                                     p.row_begin, p.row_end);
+        const bool in = (r.x1 > r.x0) && (r.y1 > r.y0);
+        flags[i] = in ? 0u : 1u;
+        keys_full[i] = depth_key(__ldg(depths + i));
+        mine += in ? 1u : 0u;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_in, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_in) {
+            atomicAdd(hist2 + 0, s_in);
+            atomicAdd(n_band, (unsigned long long)s_in);
+        }
+    }
+}
+
+// hist2[1] = N - hist2[0]; one thread, stream-ordered behind band_flag_kernel.
+__global__ void band_fix_hist_kernel(const int64_t N, uint32_t* __restrict__ hist2) {
+    hist2[1] = (uint32_t)N - hist2[0];
+}
+
+__global__ void __launch_bounds__(256)
+band_gather_hist_kernel(const unsigned long long* __restrict__ n_band, const int32_t* __restrict__ perm0,
+                        const uint32_t* __restrict__ keys_full, uint32_t* __restrict__ keys,
+                        uint32_t* __restrict__ hist /* [4][256] */) {
+    __shared__ uint32_t s_hist[4][kRadix];
+    for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t n = (int64_t)(*n_band);
+    const uint32_t lane = lane_id();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t warp_start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane;
+    for (int64_t wi = warp_start; wi < n; wi += stride) {  // warp-uniform trip count
+        const int64_t j = wi + lane;
+        const bool valid = j < n;
+        uint32_t k = 0;
+        if (valid) {
+            k = __ldg(keys_full + __ldg(perm0 + j));
+            keys[j] = k;
+            atomicAdd(&s_hist[0][k & 0xffu], 1u);
+            atomicAdd(&s_hist[1][(k >> 8) & 0xffu], 1u);
+            atomicAdd(&s_hist[2][(k >> 16) & 0xffu], 1u);
+        }
+        const uint32_t top = valid ? (k >> 24) : 0x100u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, top);
+        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[3][top], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) {
+        const uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(hist + i, v);
+    }
+}
+
 // ---- 3. emission in depth order ------------------------------------------------------------
 // Work is balanced over OUTPUT PAIRS, not over Gaussians: a warp takes 32 consecutive Gaussians of the
 // depth-sorted order (rectangles and offsets come from the count + scan kernel, all coalesced), and its lanes
@@ -61,7 +135,8 @@ depth_key_hist_kernel(const int64_t N, const float* __restrict__ depths, uint32_
 constexpr int kEmit2Threads = 256;
 
 __global__ void __launch_bounds__(kEmit2Threads)
-bin_emit2_kernel(const int64_t N, const int32_t* __restrict__ perm, const uint2* __restrict__ rects,
+bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_dev,
+                 const int32_t* __restrict__ perm, const uint2* __restrict__ rects,
                  const int tiles_w, const uint32_t* __restrict__ offsets, const int lo_bits,
                  uint32_t* __restrict__ tile_keys, int32_t* __restrict__ ids, uint32_t* __restrict__ hist /* [2][256] */,
                  bsplat_bin_info* __restrict__ info_dev, const int64_t m_cap) {
@@ -72,6 +147,7 @@ bin_emit2_kernel(const int64_t N, const int32_t* __restrict__ perm, const uint2*
         return;
     }
     __shared__ uint32_t s_hist[2][kRadix];
+    const int64_t N = n_dev ? (int64_t)(*n_dev) : N_host;  // band-compacted order: the count is on the device
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     for (int i = tid; i < 2 * kRadix; i += kEmit2Threads) (&s_hist[0][0])[i] = 0;
@@ -225,9 +301,10 @@ struct Bin2Ws {
     // N part (lives from prepare to finish)
     uint32_t* dkeys; uint32_t* dkeys_alt; int32_t* perm; int32_t* perm_alt;
     uint32_t* offsets; uint2* rects; bsplat_bin_info* info; void* scan_ws; size_t scan_bytes;
-    uint32_t* hist;      // [6][256]: 4 depth passes + 2 tile passes
+    uint32_t* hist;      // [7][256]: 4 depth passes + 2 tile passes + band partition
     uint32_t* tickets;   // [8]
-    uint32_t* status_n;  // [4][tilesN][256]
+    unsigned long long* n_band;  // in-band Gaussians (row-band frames)
+    uint32_t* status_n;  // [5][tilesN][256]: 4 depth passes + band partition
     size_t zero_begin, zero_end_n;  // byte range zeroed by prepare
     size_t n_bytes;
     // M part
@@ -252,9 +329,10 @@ static Bin2Ws carve_bin2(void* base, int64_t N, int64_t M, int64_t n_tiles) {
     w.info = (bsplat_bin_info*)take(sizeof(bsplat_bin_info));
     w.scan_bytes = bsplat_bin_scan_workspace_bytes(N);
     w.scan_ws = take(w.scan_bytes);
-    w.hist = (uint32_t*)take(6 * kRadix * 4);
+    w.hist = (uint32_t*)take(7 * kRadix * 4);
     w.tickets = (uint32_t*)take(8 * 4);
-    w.status_n = (uint32_t*)take(sort_status_words(sort_tiles_u32(N), 4) * 4);
+    w.n_band = (unsigned long long*)take(16);
+    w.status_n = (uint32_t*)take(sort_status_words(sort_tiles_u32(N), 5) * 4);
     w.zero_end_n = off;
     w.n_bytes = off;
     w.tkeys = (uint32_t*)take(m * 4); w.tkeys_alt = (uint32_t*)take(m * 4);
@@ -285,15 +363,38 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
         BSPLAT_CUDA_TRY(cudaMemsetAsync(w.offsets, 0, sizeof(uint32_t), stream));
         return BSPLAT_OK;
     }
-    int64_t hb = ceil_div(N, 256 * 8);
-    depth_key_hist_kernel<<<(unsigned)(hb < 148 * 2 ? hb : 148 * 2), 256, 0, stream>>>(N, depths, w.dkeys, w.hist);
-    BSPLAT_LAUNCH_CHECK();
     int rc = BSPLAT_OK;
     const int64_t tn = sort_tiles_u32(N);
+    const int64_t hb = ceil_div(N, 256 * 8);
+    const unsigned hist_grid = (unsigned)(hb < 148 * 2 ? hb : 148 * 2);
+    // A band that is not the whole image: partition the indices first, sort only the in-band prefix (device count)
+    const bool band = p.row_begin > 0 || p.row_end < p.tiles_h;
+    const uint64_t* n_dev = nullptr;
+    const int32_t* vsrc = nullptr;
+    if (band) {
+        uint32_t* flags = w.offsets;                               // dead until the count + scan kernel
+        uint32_t* keys_full = reinterpret_cast<uint32_t*>(w.rects);  // dead until the count + scan kernel
+        uint32_t* hist2 = w.hist + 6 * kRadix;
+        band_flag_kernel<<<hist_grid * 2, 256, 0, stream>>>(N, means2d, radii, radii_is_float, depths, p, flags,
+                                                            keys_full, hist2, w.n_band);
+        BSPLAT_LAUNCH_CHECK();
+        band_fix_hist_kernel<<<1, 1, 0, stream>>>(N, hist2);
+        BSPLAT_LAUNCH_CHECK();
+        rc = onesweep_pass_u32(N, nullptr, flags, nullptr, nullptr, w.perm, 0, 1, hist2, 0, w.tickets + 6,
+                               w.status_n + (size_t)4 * tn * kRadix, nullptr, stream);
+        if (rc != BSPLAT_OK) return rc;
+        band_gather_hist_kernel<<<hist_grid, 256, 0, stream>>>(w.n_band, w.perm, keys_full, w.dkeys, w.hist);
+        BSPLAT_LAUNCH_CHECK();
+        n_dev = reinterpret_cast<const uint64_t*>(w.n_band);
+        vsrc = w.perm;
+    } else {
+        depth_key_hist_kernel<<<hist_grid, 256, 0, stream>>>(N, depths, w.dkeys, w.hist);
+        BSPLAT_LAUNCH_CHECK();
+    }
     const uint32_t* ksrc = w.dkeys; uint32_t* kdst = w.dkeys_alt;
-    const int32_t* vsrc = nullptr; int32_t* vdst = w.perm_alt;
+    int32_t* vdst = w.perm_alt;
     for (int pass = 0; pass < 4; ++pass) {
-        rc = onesweep_pass_u32(N, nullptr, ksrc, pass == 3 ? nullptr : kdst, vsrc, vdst, 8 * pass, 8,
+        rc = onesweep_pass_u32(N, n_dev, ksrc, pass == 3 ? nullptr : kdst, vsrc, vdst, 8 * pass, 8,
                                w.hist + (size_t)pass * kRadix, 0, w.tickets + pass,
                                w.status_n + (size_t)pass * tn * kRadix, nullptr, stream);
         if (rc != BSPLAT_OK) return rc;
@@ -303,7 +404,8 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
     }
     // after 4 passes the sorted permutation is in w.perm (passes 1 and 3 write w.perm)
     return bin_count_scan_launch(N, w.perm, means2d, radii, radii_is_float, depths, p, w.offsets, w.info,
-                                 w.scan_ws, /*finalize_key_range=*/false, stream, w.rects);
+                                 w.scan_ws, /*finalize_key_range=*/false, stream, w.rects,
+                                 reinterpret_cast<const unsigned long long*>(n_dev));
 }
 
 // device_m: M is a capacity; the real count is read on the device from the bin info (n_isect) written by
@@ -329,8 +431,10 @@ int bin2_finish(int64_t N, int64_t M, bool device_m, const float* means2d, const
     const int lo_bits = tb > 8 ? (tb + 1) / 2 : tb;  // split the tile id evenly over <= 2 passes
     const int hi_bits = tb - lo_bits;
     const int64_t emit_ctas = ceil_div(N, kEmit2Threads);
+    const bool band = p.row_begin > 0 || p.row_end < p.tiles_h;  // prepare compacted the depth order to the band
     bin_emit2_kernel<<<(unsigned)(emit_ctas < 148 * 8 ? emit_ctas : 148 * 8), kEmit2Threads, 0, stream>>>(
-        N, w.perm, w.rects, p.tiles_w, w.offsets, lo_bits, w.tkeys, w.ids, w.hist + 4 * kRadix, info_dev, M);
+        N, band ? w.n_band : nullptr, w.perm, w.rects, p.tiles_w, w.offsets, lo_bits, w.tkeys, w.ids,
+        w.hist + 4 * kRadix, info_dev, M);
     BSPLAT_LAUNCH_CHECK();
     int rc = BSPLAT_OK;
     const int64_t tm = sort_tiles_u32(M);
@@ -352,6 +456,11 @@ int bin2_finish(int64_t N, int64_t M, bool device_m, const float* means2d, const
 }
 
 size_t bin2_workspace_bytes(int64_t N, int64_t M, int64_t n_tiles) { return carve_bin2(nullptr, N, M, n_tiles).total; }
+void bin2_band_list(void* workspace, int64_t N, const int32_t** perm, const unsigned long long** n_band) {
+    const Bin2Ws w = carve_bin2(workspace, N, 0, 0);
+    *perm = w.perm;
+    *n_band = w.n_band;
+}
 bsplat_bin_info* bin2_info_ptr(void* workspace, int64_t N) { return carve_bin2(workspace, N, 0, 0).info; }
 
 }  // namespace bsplat

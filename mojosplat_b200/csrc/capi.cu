@@ -20,7 +20,9 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
                      const int32_t* tile_order, const int32_t* sorted_ids, int W, int H, int tile_size,
                      int row_begin, int row_end, int mode, float* image, unsigned long long* stats,
                      const unsigned long long* m_dev, void* rec_ws, cudaStream_t stream,
-                     const PeerImages* peers = nullptr);
+                     const PeerImages* peers = nullptr, const int32_t* rec_list = nullptr,
+                     const unsigned long long* rec_list_n = nullptr);
+void bin2_band_list(void* workspace, int64_t N, const int32_t** perm, const unsigned long long** n_band);
 size_t raster_workspace_bytes(int64_t N);
 int tile_order_launch(int first_tile, int n_tiles, const int32_t* tile_ranges, int32_t* order,
                       cudaStream_t stream);
@@ -473,10 +475,19 @@ extern "C" int bsplat_render_enqueue_band_p2p(int64_t N, const float* means3d, c
         BSPLAT_CUDA_TRY(cudaStreamWaitEvent(sr, (cudaEvent_t)event_bin_done, 0));
     }
     const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
+    // a band that is not the whole image: raster records only for the band's Gaussians (the depth-sorted list of
+    // the band-compacted binning)
+    const bool band_partial = row0 > 0 || row1 < tiles_h;
+    const int32_t* band_list = nullptr;
+    const unsigned long long* band_n = nullptr;
+    // (gathering by the depth-ordered list is scattered: it only pays when the band is a small part of the frame)
+    if (band_partial && 3 * (row1 - row0) <= tiles_h) bin2_band_list(w.bin_ws, N, &band_list, &band_n);
     return rasterize_launch(N, channels, w.means2d, w.conics, colors, opacities, background, w.tile_ranges,
                             fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, row0, row1,
-                            raster_mode, image, nullptr, reinterpret_cast<const unsigned long long*>(d_info),
-                            w.raster_rec, sr, &peers);
+                            raster_mode, image, nullptr,
+                            // "no intersections at all => zero image" is a whole-frame rule: a band cannot decide it
+                            band_partial ? nullptr : reinterpret_cast<const unsigned long long*>(d_info),
+                            w.raster_rec, sr, &peers, band_list, band_n);
 }
 
 extern "C" size_t bsplat_render_host_scratch_bytes(int64_t N, int32_t channels, int32_t width, int32_t height) {

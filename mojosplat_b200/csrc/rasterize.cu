@@ -430,12 +430,18 @@ __device__ __forceinline__ void pair_record(const int64_t g, const float* __rest
 
 // Records of ALL Gaussians, once per frame (80 B each): with them the rasterizer's staging is a pure gather that
 // cp.async can run one batch ahead, and the per-(tile, Gaussian) staging arithmetic disappears.
+// With a list (row-band frames: the band's Gaussians in depth order, count on the device) only those get a record.
 __global__ void __launch_bounds__(256)
 raster_pair_prep_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
                         const float* __restrict__ colors, const float* __restrict__ opacities,
-                        float4* __restrict__ rec) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= N) return;
+                        float4* __restrict__ rec, const int32_t* __restrict__ list,
+                        const unsigned long long* __restrict__ list_n) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (list != nullptr) {
+        if (g >= (int64_t)(*list_n)) return;
+        g = __ldg(list + g);
+    }
+    if (g < 0 || g >= N) return;
     float4 q0, q1, q2, q3, q4;
     pair_record(g, means2d, conics, colors, opacities, q0, q1, q2, q3, q4);
     float4* d = rec + kPairRec * g;
@@ -962,7 +968,8 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
                      const int32_t* tile_ranges, const int32_t* tile_order, const int32_t* sorted_ids, int W,
                      int H, int tile_size, int row_begin, int row_end, int mode, float* image,
                      unsigned long long* stats, const unsigned long long* m_dev, void* rec_ws,
-                     cudaStream_t stream, const PeerImages* peers_in) {
+                     cudaStream_t stream, const PeerImages* peers_in, const int32_t* rec_list,
+                     const unsigned long long* rec_list_n) {
     PeerImages peers;
     peers.n = 0;
     if (peers_in) peers = *peers_in;
@@ -1000,7 +1007,8 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         } else if (have_rec) {
             // default: records once per frame, then the cp.async-staged pair kernel
             raster_pair_prep_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(N, means2d, conics, colors,
-                                                                                    opacities, recp);
+                                                                                    opacities, recp, rec_list,
+                                                                                    rec_list_n);
             BSPLAT_LAUNCH_CHECK();
             if (mode == 2)
                 raster_pair_kernel<false, true><<<grid, kPairThreads, 0, stream>>>(
