@@ -6,7 +6,7 @@
 // the standard 3D-Gaussian-splatting convention: dir = normalize(mean - camera position),
 // colour = max(sum_k Y_k(dir) c_k + 0.5, 0), Y_k the real SH basis with the usual constants, coefficients
 // laid out [N, K, 3] with K = (degree_used + 1)^2 <= coefficients stored per Gaussian.  Checked against a float64
-// numpy restatement (oracle/oracle_np.py::sh_eval_np).
+// numpy restatement kept with the tests (sh_eval_np).
 //
 // HBM-bound: 12 B (mean) + 12 K B (coefficients) read + 12 B written per Gaussian.  The [N, K, 3] rows of a
 // CTA are one contiguous block: they are copied into shared memory with fully coalesced 128-bit loads and each
