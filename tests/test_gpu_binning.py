@@ -129,3 +129,25 @@ def test_radix_sort_pairs(cuda_device, M, bits):
     rk, rv = (ka, va) if in_alt.value else (k, v)
     assert np.array_equal(rv.cpu().numpy(), order.astype(np.int32))
     assert np.array_equal(rk.cpu().numpy(), keys.numpy()[order])
+
+
+@pytest.mark.parametrize("sem", [0, 1])
+@pytest.mark.parametrize("W,H,ts", [(1920, 1080, 16), (1000, 700, 10), (3840, 2160, 16)])
+def test_binning_mixed_huge_and_tiny_rectangles(cuda_device, W, H, ts, sem):
+    """Rectangles from a single tile up to the whole image (thousands of tiles per Gaussian) in one warp of the
+    pair-balanced emitter, odd widths (exact division by the rectangle width), zero radii, means far outside."""
+    rng = np.random.default_rng(W + ts + sem)
+    N = 3000
+    means = np.stack([rng.uniform(-0.2 * W, 1.2 * W, N), rng.uniform(-0.2 * H, 1.2 * H, N)], 1).astype(np.float32)
+    radii = rng.integers(0, 40, (N, 2)).astype(np.int32)
+    huge = rng.choice(N, 60, replace=False)
+    radii[huge] = rng.integers(200, 3 * max(W, H), (60, 2))
+    radii[rng.choice(N, 300, replace=False)] = 0
+    depths = rng.uniform(0.2, 50.0, N).astype(np.float32)
+    depths[rng.choice(N, 200, replace=False)] = 7.0  # ties
+    o_ids, o_ranges = oracle.bin_tiles(means, radii, depths, H, W, ts, semantics=sem)
+    ids, ranges = binning.bin_gaussians_to_tiles_cuda(dev(means, cuda_device), dev(radii, cuda_device),
+                                                      dev(depths, cuda_device), H, W, ts, semantics=sem)
+    assert np.array_equal(ranges.cpu().numpy(), o_ranges)
+    assert np.array_equal(ids.cpu().numpy(), o_ids)
+    assert ids.numel() > 20 * N  # the huge ones dominate
