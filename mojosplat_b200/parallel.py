@@ -92,21 +92,39 @@ def broadcast_gaussians(tensors: Sequence[torch.Tensor], src: int = 0, group=Non
 def render_gaussians_batched(means3d, scales, quats, opacities, features, cameras: Sequence[Camera],
                              background_color=None, tile_size: int = TILE_SIZE, backend: str = "cuda",
                              out: torch.Tensor | None = None) -> torch.Tensor:
-    """All cameras on this GPU: images [C, H, W, 3].  Views are independent; each is one fused C call
-    on the current stream, workspace reused."""
+    """All cameras on this GPU: images [C, H, W, 3].  Views are independent.  Batches of equal-size views
+    go through the sync-free overlapped pipeline (pipeline.OverlappedPipeline: no host read-back, binning
+    of view k+1 inside the rasterization of view k); a frame whose pair count outgrows the workspace is redone
+    after the batch.  Results are identical to one render_gaussians call per view."""
     from .projection import CUDA_BACKENDS
     from .render import _background_tensor
     if backend not in CUDA_BACKENDS:
         raise ValueError(f"Invalid backend: {backend}")
     C = features.shape[-1]
-    bg = _background_tensor(background_color, C, means3d.device, torch.float32)
+    dev = means3d.device
+    bg = _background_tensor(background_color, C, dev, torch.float32)
     cam0 = cameras[0]
     if out is None:
-        out = torch.empty((len(cameras), cam0.H, cam0.W, C), dtype=torch.float32, device=means3d.device)
+        out = torch.empty((len(cameras), cam0.H, cam0.W, C), dtype=torch.float32, device=dev)
+    same_size = all(c.H == cam0.H and c.W == cam0.W for c in cameras)
+    N = means3d.shape[0]
+    if len(cameras) >= 3 and same_size and N > 0 and out.shape[0] == len(cameras):
+        from .pipeline import OverlappedPipeline
+        key = (dev.index, N, int(cam0.W), int(cam0.H), C, int(tile_size), CUDA_BACKENDS[backend])
+        pipe = _pipelines.get(key)
+        if pipe is None:
+            _pipelines.clear()  # one cached pipeline (three workspaces) at a time
+            pipe = _pipelines[key] = OverlappedPipeline(dev, N, cam0.W, cam0.H, C, tile_size, CUDA_BACKENDS[backend])
+        pipe.render(means3d, scales, quats, opacities, features, cameras, bg, out=out)
+        pipe.check()
+        return out
     for k, cam in enumerate(cameras):
         out[k] = render_fused(means3d, scales, quats, opacities, features, cam, bg, tile_size,
                               semantics=CUDA_BACKENDS[backend])
     return out
+
+
+_pipelines: dict = {}
 
 
 def render_views(means3d, scales, quats, opacities, features, cameras: Sequence[Camera], background_color=None,
