@@ -124,15 +124,18 @@ band_gather_hist_kernel(const unsigned long long* __restrict__ n_band, const int
 }
 
 // ---- 3. emission in depth order ------------------------------------------------------------
-// Work is balanced over OUTPUT PAIRS, not over Gaussians: a warp takes 32 consecutive Gaussians of the
-// depth-sorted order (rectangles and offsets come from the count + scan kernel, all coalesced), and its lanes
-// then walk the warp's contiguous output range 32 pairs at a time.  The owner of pair j is found with a 5-step
-// binary search over the lanes' exclusive offsets (register shuffles), its rectangle fetched with shuffles, the
-// tile id computed and both words stored -- every store instruction writes 128 contiguous bytes, no lane idles
-// on a short rectangle, a rectangle of thousands of tiles just takes more rounds.  The digit histograms of the
-// two tile-sort passes are accumulated on the fly (shared-memory atomics; the high digit is run-length
-// aggregated with match.any: neighbouring pairs share it).
+// Work is balanced over OUTPUT PAIRS, not over Gaussians: the M pairs are cut into tasks of kEmitTask
+// consecutive pairs, a warp takes a task, finds the Gaussian that owns its first pair with a 32-ary search over the
+// exclusive offsets (4 probes for 1 M Gaussians) and then walks the task 32 pairs at a time: it keeps a window of
+// 32 depth-consecutive Gaussians (rectangles and offsets come from the count + scan kernel, coalesced), the owner
+// of pair p is found with a 5-step shuffle binary search over the window's offsets, its rectangle fetched with
+// shuffles, the tile id computed and both words stored -- every store instruction writes 128 contiguous bytes,
+// no lane idles on a short rectangle, and a Gaussian that covers thousands of tiles (the nearest ones, which the
+// depth order puts side by side) is shared by as many warps as it has tasks.  The digit histograms of the two
+// tile-sort passes are accumulated on the fly (shared-memory atomics; the high digit is run-length aggregated with
+// match.any: neighbouring pairs share it).
 constexpr int kEmit2Threads = 256;
+constexpr uint32_t kEmitTask = 1024;
 
 __global__ void __launch_bounds__(kEmit2Threads)
 bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_dev,
@@ -154,62 +157,82 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
     __syncthreads();
     const uint32_t lo_mask = (1u << lo_bits) - 1u;
     const uint32_t tw = (uint32_t)tiles_w;
-    // persistent warps: each walks several 32-Gaussian chunks; the CTA flushes its histograms once
-    const int64_t n_chunks = ceil_div(N, 32);
+    const uint32_t M = N > 0 ? __ldg(offsets + N) : 0u;  // total number of pairs (written by the count + scan kernel)
+    // persistent warps: each takes several tasks; the CTA flushes its histograms once
     const int64_t warp_global = (int64_t)blockIdx.x * (kEmit2Threads / 32) + (tid >> 5);
     const int64_t warp_stride = (int64_t)gridDim.x * (kEmit2Threads / 32);
-    for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warp_stride) {
-        const int64_t jg = chunk * 32 + lane;
-        const bool have = jg < N;
-        int32_t g = 0;
-        uint2 rc = make_uint2(0u, 0u);
-        uint32_t off = 0;
-        if (have) {
-            g = __ldg(perm + jg);
-            rc = __ldg(rects + jg);
-            off = __ldg(offsets + jg);
+    for (int64_t task = warp_global; task * kEmitTask < (int64_t)M; task += warp_stride) {
+        const uint32_t S = (uint32_t)(task * kEmitTask);
+        const uint32_t E = min(M, S + kEmitTask);
+        // owner of pair S: the largest j in [0, N) with offsets[j] <= S -- 32-ary search, all lanes probe
+        int64_t lo = 0, hi = N;  // invariant: offsets[lo] <= S, answer in [lo, hi)
+        while (hi - lo > 1) {
+            const int64_t span = hi - lo;
+            const int64_t step = (span + 31) / 32;
+            const int64_t probe = lo + (int64_t)(lane + 1) * step;  // lane l probes lo + (l+1) step
+            const bool le = probe < hi && __ldg(offsets + probe) <= S;
+            const uint32_t m = __ballot_sync(0xffffffffu, le);  // offsets are non-decreasing: a prefix of lanes
+            const int k = __popc(m);
+            const int64_t new_lo = lo + (int64_t)k * step;
+            const int64_t new_hi = min(hi, lo + (int64_t)(k + 1) * step);
+            lo = new_lo; hi = new_hi;
         }
-        const uint32_t w = rc.y & 0xffffu, cnt = w * (rc.y >> 16);
-        const uint32_t begin = __shfl_sync(0xffffffffu, off, 0);
-        // exclusive offset inside the warp's range; lanes past N get the total (they own nothing)
-        const uint32_t last_end = off + cnt;
-        const int n_live = (int)min((int64_t)32, N - chunk * 32);
-        const uint32_t total = __shfl_sync(0xffffffffu, last_end, n_live - 1) - begin;
-        const uint32_t e = have ? off - begin : total;
-        const float inv_w = 1.0f / (float)(w ? w : 1u);
-        for (uint32_t j0 = 0; j0 < total; j0 += 32) {  // warp-uniform trip count
-            const uint32_t j = j0 + lane;
-            const bool valid = j < total;
-            // owner = largest lane l with e_l <= j  (e is non-decreasing; e_{l+1} = e_l + cnt_l)
-            uint32_t lo = 0;
+        int64_t jg0 = lo;       // first Gaussian of the current window
+        uint32_t cur = S;       // next pair to write
+        while (cur < E) {
+            const int64_t jg = jg0 + lane;
+            const bool have = jg < N;
+            int32_t g = 0;
+            uint2 rc = make_uint2(0u, 0u);
+            uint32_t off = M;   // lanes past N own nothing
+            if (have) {
+                g = __ldg(perm + jg);
+                rc = __ldg(rects + jg);
+                off = __ldg(offsets + jg);
+            }
+            const uint32_t w = rc.y & 0xffffu, cnt = w * (rc.y >> 16);
+            const float inv_w = 1.0f / (float)(w ? w : 1u);
+            // pairs covered by this window: [off of lane 0, end of the last live lane)
+            const int n_live = (int)min((int64_t)32, N - jg0);
+            const uint32_t win_end = __shfl_sync(0xffffffffu, off + cnt, n_live - 1);
+            const uint32_t stop = min(E, win_end);
+            for (uint32_t p0 = cur; p0 < stop; p0 += 32) {  // warp-uniform trip count
+                const uint32_t pidx = p0 + lane;
+                const bool valid = pidx < stop;
+                // owner = largest lane l with off_l <= pidx (offsets are non-decreasing; off_{l+1} = off_l + cnt_l)
+                uint32_t ol = 0;
 #pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                const uint32_t cand = lo + step;
-                const uint32_t ec = __shfl_sync(0xffffffffu, e, cand & 31u);
-                if (ec <= j) lo = cand;  // cand <= 31 always: lo + step never exceeds 31
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const uint32_t cand = ol + step;
+                    const uint32_t oc = __shfl_sync(0xffffffffu, off, cand & 31u);
+                    if (oc <= pidx) ol = cand;
+                }
+                const uint32_t eo = __shfl_sync(0xffffffffu, off, ol);
+                const uint32_t xy = __shfl_sync(0xffffffffu, rc.x, ol);
+                const uint32_t wo = __shfl_sync(0xffffffffu, w, ol);
+                const float iw = __shfl_sync(0xffffffffu, inv_w, ol);
+                const int32_t go = __shfl_sync(0xffffffffu, g, ol);
+                uint32_t tile = 0;
+                if (valid) {
+                    const uint32_t k = pidx - eo;
+                    // k / w through the reciprocal, corrected to be exact (k < 2^24: a rectangle has < 2^24 tiles
+                    // whenever the image has, which tile ids as 32-bit keys already require)
+                    uint32_t dy = (uint32_t)__float2int_rz(__fmul_rn((float)k, iw));
+                    if (dy * wo > k) --dy;
+                    else if ((dy + 1u) * wo <= k) ++dy;
+                    const uint32_t dx = k - dy * wo;
+                    tile = ((xy >> 16) + dy) * tw + (xy & 0xffffu) + dx;
+                    tile_keys[pidx] = tile;
+                    ids[pidx] = go;
+                    atomicAdd(&s_hist[0][tile & lo_mask], 1u);
+                }
+                const uint32_t top = valid ? (tile >> lo_bits) : 0x100u;
+                const uint32_t peers = __match_any_sync(0xffffffffu, top);
+                if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[1][top], (uint32_t)__popc(peers));
             }
-            const uint32_t eo = __shfl_sync(0xffffffffu, e, lo);
-            const uint32_t xy = __shfl_sync(0xffffffffu, rc.x, lo);
-            const uint32_t wo = __shfl_sync(0xffffffffu, w, lo);
-            const float iw = __shfl_sync(0xffffffffu, inv_w, lo);
-            const int32_t go = __shfl_sync(0xffffffffu, g, lo);
-            uint32_t tile = 0;
-            if (valid) {
-                const uint32_t k = j - eo;
-                // k / w through the reciprocal, corrected to be exact (k < 2^24: a rectangle has < 2^24 tiles
-                // whenever the image has, which tile ids as 32-bit keys already require)
-                uint32_t dy = (uint32_t)__float2int_rz(__fmul_rn((float)k, iw));
-                if (dy * wo > k) --dy;
-                else if ((dy + 1u) * wo <= k) ++dy;
-                const uint32_t dx = k - dy * wo;
-                tile = ((xy >> 16) + dy) * tw + (xy & 0xffffu) + dx;
-                tile_keys[begin + j] = tile;
-                ids[begin + j] = go;
-                atomicAdd(&s_hist[0][tile & lo_mask], 1u);
-            }
-            const uint32_t top = valid ? (tile >> lo_bits) : 0x100u;
-            const uint32_t peers = __match_any_sync(0xffffffffu, top);
-            if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[1][top], (uint32_t)__popc(peers));
+            cur = stop;
+            jg0 += 32;
+            // (a window whose last Gaussian reaches beyond E ends the task; one that ends before E continues)
         }
     }
     __syncthreads();
@@ -430,7 +453,8 @@ int bin2_finish(int64_t N, int64_t M, bool device_m, const float* means2d, const
     const int tb = tile_bits_of(p);
     const int lo_bits = tb > 8 ? (tb + 1) / 2 : tb;  // split the tile id evenly over <= 2 passes
     const int hi_bits = tb - lo_bits;
-    const int64_t emit_ctas = ceil_div(N, kEmit2Threads);
+    // one warp per task of kEmitTask pairs; M is the capacity in sync-free frames
+    const int64_t emit_ctas = ceil_div(ceil_div(M, (int64_t)kEmitTask), kEmit2Threads / 32);
     const bool band = p.row_begin > 0 || p.row_end < p.tiles_h;  // prepare compacted the depth order to the band
     bin_emit2_kernel<<<(unsigned)(emit_ctas < 148 * 8 ? emit_ctas : 148 * 8), kEmit2Threads, 0, stream>>>(
         N, band ? w.n_band : nullptr, w.perm, w.rects, p.tiles_w, w.offsets, lo_bits, w.tkeys, w.ids,
