@@ -21,13 +21,11 @@
 // No tensor cores: no stage of this path is a dense contraction.
 #include <type_traits>
 
-#include "common.cuh"
+#include "raster_common.cuh"
 
 namespace bsplat {
 
 constexpr float kAlphaThreshold = 1.0f / 255.0f;
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLog2AlphaThreshold = -7.994353436858858f;  // log2(1/255)
 
 // ------------------------------------------------------------------------------------------
 // faithful kernel
@@ -357,39 +355,6 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     f32x2 r;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
-}
-
-// Conservative test "can this Gaussian reach alpha >= 1/255 anywhere in the pixel rectangle [X0, X1] x [Y0, Y1]
-// (pixel centres)?"  min of q over the rectangle = min over the (<= 2) edges facing the mean; along the edge
-// u = ue the quadratic is D ue^2 + C (v - hy ue)^2 with D = A + B hy / 2 (and symmetrically for v = ve), so each
-// edge costs a clamp and two FMAs.  NaN-safe: anything odd counts as a hit.
-__device__ __forceinline__ bool pair_cull_hit(const float mx, const float my, const float A, const float B,
-                                              const float C, const float tau, const float hy, const float hx,
-                                              const float X0, const float X1, const float Y0, const float Y1) {
-    const float u0 = mx - X1, u1 = mx - X0;
-    const float v0 = my - Y1, v1 = my - Y0;
-    const bool zu = (u0 <= 0.0f) && (u1 >= 0.0f);
-    const bool zv = (v0 <= 0.0f) && (v1 >= 0.0f);
-    float qmin = 0.0f;
-    if (!(zu && zv)) {
-        float q1 = INFINITY, q2 = INFINITY;
-        if (!zu) {
-            const float ue = (u0 > 0.0f) ? u0 : u1;
-            const float vstar = hy * ue;
-            const float dv = vstar - fminf(fmaxf(vstar, v0), v1);
-            q1 = fmaf(fmaf(0.5f * B, hy, A) * ue, ue, C * dv * dv);
-        }
-        if (!zv) {
-            const float ve = (v0 > 0.0f) ? v0 : v1;
-            const float ustar = hx * ve;
-            const float du = ustar - fminf(fmaxf(ustar, u0), u1);
-            q2 = fmaf(fmaf(0.5f * B, hx, C) * ve, ve, A * du * du);
-        }
-        qmin = fminf(q1, q2);
-    }
-    const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
-    const float slack = 4e-6f * (A * um * um + C * vm * vm) + 1e-3f;
-    return !(qmin > tau + slack);
 }
 
 constexpr int kLongTile = 2048;  // lists longer than this get a tile-level pre-test (see the kernel)

@@ -12,6 +12,10 @@
 //   raster_train_fwd_kernel  the faithful forward (same operation order as raster_faithful_kernel) that also
 //                            stores, per pixel, the final transmittance and the list index of the last
 //                            Gaussian that was composited.
+//   Both kernels cull per warp like the fast forward kernel: the 32 lanes test 32 staged Gaussians at once against
+//   the bounding box of the warp's pixels with the exact conservative bound (raster_common.cuh) and only the
+//   survivors are walked.  A skipped Gaussian has alpha < 1/255 on every pixel of the warp, i.e. it is skipped by
+//   the reference arithmetic as well: values and gradients are unchanged.
 //   raster_bwd_kernel        one CTA per tile, one pixel per thread, the tile's list walked BACK to front
 //                            from the furthest "last index" of the tile, 1 Gaussian staged per thread per
 //                            batch; per Gaussian the 6 + C partial gradients are reduced over the warp
@@ -20,7 +24,7 @@
 //   d out / d alpha_k = c_k T_k - (sum_{m>k} c_m alpha_m T_m + T_end bg) / (1 - alpha_k)
 //   d alpha / d sigma = -alpha, d alpha / d o = exp(-sigma)        (zero through the 0.999 clamp)
 //   d sigma / d(a, b, c) = (0.5 dx^2, dx dy, 0.5 dy^2),  d sigma / d mean = (a dx + b dy, b dx + c dy)
-#include "common.cuh"
+#include "raster_common.cuh"
 
 namespace bsplat {
 
@@ -42,9 +46,13 @@ raster_train_fwd_kernel(const int64_t N, const float* __restrict__ means2d, cons
     float* s_b = s_a + nthreads;
     float* s_c = s_b + nthreads;
     float* s_o = s_c + nthreads;
-    float* s_col = s_o + nthreads;  // [nthreads][CH]
+    float* s_tau = s_o + nthreads;
+    float* s_hy = s_tau + nthreads;
+    float* s_hx = s_hy + nthreads;
+    float* s_col = s_hx + nthreads;  // [nthreads][CH]
 
     const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u;
     const int ly = tid / ts, lx = tid - ly * ts;
     const int tile = blockIdx.y * tiles_w + blockIdx.x;
     const int i = blockIdx.y * ts + ly;
@@ -52,6 +60,14 @@ raster_train_fwd_kernel(const int64_t N, const float* __restrict__ means2d, cons
     const bool inside = (ly < ts) && (i < H) && (j < W);
     bool done = !inside;
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    // bounding box of this warp's pixels (any tile size: a warp is not always a rectangle of the tile)
+    float X0 = inside ? px : INFINITY, X1 = inside ? px : -INFINITY;
+    float Y0 = inside ? py : INFINITY, Y1 = inside ? py : -INFINITY;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        X0 = fminf(X0, __shfl_xor_sync(0xffffffffu, X0, d)); X1 = fmaxf(X1, __shfl_xor_sync(0xffffffffu, X1, d));
+        Y0 = fminf(Y0, __shfl_xor_sync(0xffffffffu, Y0, d)); Y1 = fmaxf(Y1, __shfl_xor_sync(0xffffffffu, Y1, d));
+    }
 
     const int32_t r0 = tile_ranges[2 * tile], r1 = tile_ranges[2 * tile + 1];
     float T = 1.0f;
@@ -72,17 +88,28 @@ raster_train_fwd_kernel(const int64_t N, const float* __restrict__ means2d, cons
                 s_b[tid] = conics[3 * (int64_t)g + 1];
                 s_c[tid] = conics[3 * (int64_t)g + 2];
                 s_o[tid] = opacities[g];
+                cull_constants(s_a[tid], s_b[tid], s_c[tid], s_o[tid], s_tau[tid], s_hy[tid], s_hx[tid]);
 #pragma unroll
                 for (int c = 0; c < CH; ++c) s_col[tid * CH + c] = colors[(int64_t)g * CH + c];
             } else {
                 s_mx[tid] = s_my[tid] = s_a[tid] = s_b[tid] = s_c[tid] = 0.0f;
                 s_o[tid] = __int_as_float(0x7fc00000);  // NaN marks "not a Gaussian"
+                s_tau[tid] = -INFINITY; s_hy[tid] = s_hx[tid] = 0.0f;
             }
         }
         __syncthreads();
-        if (!done) {
-            const int bs = min(nthreads, (int)(r1 - b0));
-            for (int t = 0; t < bs; ++t) {
+        const int bs = min(nthreads, (int)(r1 - b0));
+        for (int c0 = 0; c0 < bs; c0 += 32) {  // warp-uniform
+            if (__all_sync(0xffffffffu, done)) break;
+            const int e = c0 + (int)lane;
+            bool hit = false;
+            if (e < bs && X0 <= X1)
+                hit = pair_cull_hit(s_mx[e], s_my[e], 0.5f * kLog2e * s_a[e], kLog2e * s_b[e], 0.5f * kLog2e * s_c[e],
+                                    s_tau[e], s_hy[e], s_hx[e], X0, X1, Y0, Y1);
+            unsigned mask = __ballot_sync(0xffffffffu, hit);
+            while (mask && !done) {
+                const int t = c0 + __ffs(mask) - 1;
+                mask &= mask - 1;
                 const float op = s_o[t];
                 if (op != op) continue;
                 const float dx = __fsub_rn(s_mx[t], px), dy = __fsub_rn(s_my[t], py);
@@ -128,7 +155,10 @@ raster_bwd_kernel(const int64_t N, const float* __restrict__ means2d, const floa
     float* s_b = s_a + nthreads;
     float* s_c = s_b + nthreads;
     float* s_o = s_c + nthreads;
-    float* s_col = s_o + nthreads;                                  // [nthreads][CH]
+    float* s_tau = s_o + nthreads;
+    float* s_hy = s_tau + nthreads;
+    float* s_hx = s_hy + nthreads;
+    float* s_col = s_hx + nthreads;                                 // [nthreads][CH]
     int32_t* s_id = reinterpret_cast<int32_t*>(s_col + nthreads * CH);  // [nthreads]
     __shared__ int s_max_last;
 
@@ -141,6 +171,14 @@ raster_bwd_kernel(const int64_t N, const float* __restrict__ means2d, const floa
     const bool inside = (ly < ts) && (i < H) && (j < W);
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
     const int32_t r0 = tile_ranges[2 * tile];
+    // bounding box of this warp's pixels
+    float X0 = inside ? px : INFINITY, X1 = inside ? px : -INFINITY;
+    float Y0 = inside ? py : INFINITY, Y1 = inside ? py : -INFINITY;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        X0 = fminf(X0, __shfl_xor_sync(0xffffffffu, X0, d)); X1 = fmaxf(X1, __shfl_xor_sync(0xffffffffu, X1, d));
+        Y0 = fminf(Y0, __shfl_xor_sync(0xffffffffu, Y0, d)); Y1 = fmaxf(Y1, __shfl_xor_sync(0xffffffffu, Y1, d));
+    }
 
     const int64_t pix = (int64_t)i * W + j;
     const float T_final = inside ? final_T[pix] : 0.0f;
@@ -175,18 +213,33 @@ raster_bwd_kernel(const int64_t N, const float* __restrict__ means2d, const floa
                 s_b[tid] = conics[3 * (int64_t)g + 1];
                 s_c[tid] = conics[3 * (int64_t)g + 2];
                 s_o[tid] = opacities[g];
+                cull_constants(s_a[tid], s_b[tid], s_c[tid], s_o[tid], s_tau[tid], s_hy[tid], s_hx[tid]);
 #pragma unroll
                 for (int c = 0; c < CH; ++c) s_col[tid * CH + c] = colors[(int64_t)g * CH + c];
             } else {
                 s_mx[tid] = s_my[tid] = s_a[tid] = s_b[tid] = s_c[tid] = 0.0f;
                 s_o[tid] = __int_as_float(0x7fc00000);
+                s_tau[tid] = -INFINITY; s_hy[tid] = s_hx[tid] = 0.0f;
             }
         }
         __syncthreads();
         const int bs = min(nthreads, (int)(hi - r0 + 1));
-        for (int t = 0; t < bs; ++t) {
+        // the furthest composited entry of THIS warp: slots in front of it are skipped without a test
+        int warp_last = last;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, d));
+        for (int c0 = 0; c0 < bs; c0 += 32) {  // warp-uniform; slot t holds entry hi - t (back to front)
+          const int e = c0 + (int)lane;
+          bool hit = false;
+          if (e < bs && hi - e <= warp_last)
+              hit = pair_cull_hit(s_mx[e], s_my[e], 0.5f * kLog2e * s_a[e], kLog2e * s_b[e], 0.5f * kLog2e * s_c[e],
+                                  s_tau[e], s_hy[e], s_hx[e], X0, X1, Y0, Y1);
+          unsigned mask = __ballot_sync(0xffffffffu, hit);
+          while (mask) {  // warp-uniform: every lane walks the same survivors (shuffles below need all lanes)
+            const int t = c0 + __ffs(mask) - 1;
+            mask &= mask - 1;
             const float op = s_o[t];
-            if (op != op) continue;  // uniform across the block
+            if (op != op) continue;  // uniform across the warp
             bool valid = inside && (hi - t <= last);
             float dx = 0.f, dy = 0.f, alpha = 0.f, vis = 0.f;
             const float a = s_a[t], b = s_b[t], c = s_c[t];
@@ -248,6 +301,7 @@ raster_bwd_kernel(const int64_t N, const float* __restrict__ means2d, const floa
                 atomicAdd(g_means2d + 2 * g + 1, v_my);
                 atomicAdd(g_opac + g, v_op);
             }
+          }
         }
     }
 }
@@ -274,7 +328,7 @@ extern "C" int bsplat_rasterize_fwd_train(int64_t N, int32_t channels, const flo
     if (tiles_h > 65535) return BSPLAT_E_ARG;
     const int nthreads = round_up32(tile_size * tile_size);
     const dim3 grid(tiles_w, tiles_h);
-    const size_t smem = (size_t)nthreads * (6 + channels) * sizeof(float);
+    const size_t smem = (size_t)nthreads * (9 + channels) * sizeof(float);
 #define BSPLAT_TRAIN_FWD(CH)                                                                                    \
     raster_train_fwd_kernel<CH><<<grid, nthreads, smem, stream>>>(N, means2d, conics, colors, opacities,       \
         background, tile_ranges, sorted_ids, width, height, tile_size, tiles_w, image, final_T, last_idx)
@@ -307,7 +361,7 @@ extern "C" int bsplat_rasterize_bwd(int64_t N, int32_t channels, const float* me
     if (tiles_h > 65535) return BSPLAT_E_ARG;
     const int nthreads = round_up32(tile_size * tile_size);
     const dim3 grid(tiles_w, tiles_h);
-    const size_t smem = (size_t)nthreads * (7 + channels) * sizeof(float);
+    const size_t smem = (size_t)nthreads * (10 + channels) * sizeof(float);
 #define BSPLAT_BWD(CH)                                                                                          \
     raster_bwd_kernel<CH><<<grid, nthreads, smem, stream>>>(N, means2d, conics, colors, opacities, background,  \
         tile_ranges, sorted_ids, width, height, tile_size, tiles_w, final_T, last_idx, grad_image, grad_means2d, \
