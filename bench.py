@@ -389,6 +389,13 @@ def run_b200(args, rank, world, local_rank):
                 "peak_source": "measured in this run (FFMA chain micro-benchmark, bsplat_microbench)",
                 "work": "14*E_all + 10*E_pass flop per launch (SURVEY.md 8d)", "share_of_step": stage[3] / stage.sum()}
 
+    # the HBM-bound kernel of the path, for reference next to the (FP32-bound) dominant one
+    ptraffic, ptraffic_src = ncu_traffic("projection")
+    roofline_hbm = {"kernel": "project_kernel", "bound": "hbm", "achieved": proj_bytes / (stage[0] * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": proj_bytes / (stage[0] * 1e-3) / 1e9 / hbm_peak,
+                    "traffic": ptraffic, "traffic_source": ptraffic_src, "peak_source": hbm_src,
+                    "work": "72 B per Gaussian (SURVEY.md 8d): 40 B read + 32 B written"}
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle
@@ -423,7 +430,8 @@ def run_b200(args, rank, world, local_rank):
                                      "out EVERY frame; H2D(k+1) | render(k) | D2H(k-1) overlapped)",
                 "single_call_ms": e2e_single_call_ms,
                 "single_call_api": "mojosplat_b200.render_gaussians_host (copy in -> render -> copy out -> sync)"},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "stages": stages,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
+        "stages": stages,
         "cpu_baseline": cpu_baseline,
     }
     _emit(json.dumps(line, default=float))
