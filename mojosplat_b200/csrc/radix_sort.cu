@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kRadix) radix_scan_kernel(uint32_t* __restrict
 // free from here on) -> decoupled look-back, kLookback predecessors in flight per round trip ->
 // contiguous per-digit runs to global.
 template <typename KeyT, int ITEMS, int BITS>
-__global__ void __launch_bounds__(kSortThreads, 4)
+__global__ void __launch_bounds__(kSortThreads, 3)
 onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const KeyT* __restrict__ keys_in,
                 KeyT* __restrict__ keys_out, const int32_t* __restrict__ vals_in,
                 int32_t* __restrict__ vals_out, const int shift, const int bits_rt,

@@ -7,7 +7,7 @@ namespace bsplat {
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortItems64 = 10;  // 2560 (uint64 key, int32) pairs per CTA
-constexpr int kSortItems32 = 8;   // 2048 (uint32 key, int32) pairs per CTA
+constexpr int kSortItems32 = 16;  // 4096 (uint32 key, int32) pairs per CTA (80 registers, 3 CTAs per SM)
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
