@@ -350,6 +350,18 @@ def run_b200(args, rank, world, local_rank):
     _, e_all, e_pass = rasterization.rasterize_gaussians_stats(
         info["means2d"], info["conics"], g[4], g[3], bg, info["tile_ranges"], info["sorted_ids"], cams[0], 16)
 
+    # stand-in for "the reference's rasterizer on this GPU" (gsplat / MAX are not installable here): the faithful
+    # kernel has the structure and operation order of kernels/rasterization.mojo -- never reported as gsplat
+    fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rasterization.rasterize_gaussians_cuda(info["means2d"], info["conics"], g[4], g[3], bg, info["tile_ranges"],
+                                           info["sorted_ids"], cams[0], 16, mode="faithful")
+    fa.record()
+    rasterization.rasterize_gaussians_cuda(info["means2d"], info["conics"], g[4], g[3], bg, info["tile_ranges"],
+                                           info["sorted_ids"], cams[0], 16, mode="faithful")
+    fb.record()
+    torch.cuda.synchronize(dev)
+    faithful_ms = float(fa.elapsed_time(fb))
+
     # measured FP32 / SFU issue peaks (roofline denominators of the rasterizer)
     def micro(kind):
         out = torch.empty(1, dtype=torch.float32, device=dev)
@@ -382,7 +394,10 @@ def run_b200(args, rank, world, local_rank):
                     "bytes": bin_bytes, "M": M, "sort_passes": P, "key_bits": info["key_bits"]},
         "raster": {"ms": stage[3], "E_all": e_all, "E_pass": e_pass, "nominal_256M": 256 * M,
                    "G_splat_px_per_s": e_all / raster_s / 1e9,
-                   "sfu_frac": (e_all / raster_s) / ex2_per_s},
+                   "sfu_frac": (e_all / raster_s) / ex2_per_s,
+                   "reference_structure_kernel_ms": faithful_ms,
+                   "reference_structure_kernel": "raster_faithful_kernel (1 thread/pixel, 256-batch staging, operation "
+                                                 "order of kernels/rasterization.mojo; stand-in, NOT gsplat)"},
         "hbm_peak_GB/s": hbm_peak, "hbm_peak_source": hbm_src,
         "ffma_peak_T/s": ffma_per_s / 1e12, "ex2_peak_T/s": ex2_per_s / 1e12,
     }
