@@ -346,9 +346,11 @@ class HostFramePipeline:
 
     @torch.no_grad()
     def render(self, host_scenes, cameras: Sequence[Camera], background_host: torch.Tensor,
-               out_host: torch.Tensor) -> torch.Tensor:
+               out_host: torch.Tensor, upload: str = "every_frame") -> torch.Tensor:
         """host_scenes: callable k -> 5 contiguous float32 CPU tensors (pinned for full speed);
-        out_host: pinned [n or ring, H, W, C].  Returns out_host after a final synchronisation."""
+        out_host: pinned [n or ring, H, W, C].  Returns out_host after a final synchronisation.
+        upload="once": the scene of frame 0 is uploaded once and stays resident (a static scene seen from many
+        poses); every frame still sends its camera and downloads its image."""
         core = self.core
         n = len(cameras)
         cams = [_lib.camera_struct(c) for c in cameras]
@@ -362,13 +364,18 @@ class HostFramePipeline:
                 self.bg_dev.copy_(background_host.reshape(-1), non_blocking=True)
             for k in range(n):
                 islot, oslot = k % self.in_slots, k % self.out_slots
-                src = host_scenes(k)
-                with torch.cuda.stream(self.s_in):
-                    if k >= self.in_slots:
-                        self.s_in.wait_event(ev_used[k - self.in_slots])
-                    for d, h in zip(self.g_dev[islot], src):
-                        d.copy_(h.reshape(d.shape), non_blocking=True)
-                    ev_in[k].record(self.s_in)
+                if upload == "once":
+                    islot = 0
+                if upload != "once" or k == 0:
+                    src = host_scenes(k)
+                    with torch.cuda.stream(self.s_in):
+                        if k >= self.in_slots:
+                            self.s_in.wait_event(ev_used[k - self.in_slots])
+                        for d, h in zip(self.g_dev[islot], src):
+                            d.copy_(h.reshape(d.shape), non_blocking=True)
+                        ev_in[k].record(self.s_in)
+                else:
+                    ev_in[k] = ev_in[0]
                 sb = core.s_bins[k % core.n_bin]
                 sb.wait_event(ev_in[k])
                 if k >= self.out_slots:

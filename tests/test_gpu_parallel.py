@@ -149,6 +149,12 @@ def test_host_frame_pipeline_equals_host_api(cuda_device):
     for k, cam in enumerate(cams):
         ref = ms.render_gaussians_host(*scenes(k), cam, background_color=sc.background, device=cuda_device)
         assert torch.equal(out[k], ref), k
+    # static scene: uploaded once, every frame still gets its own camera and download
+    out2 = torch.empty_like(out)
+    pipe.render(lambda k: host, cams, sc.background, out2, upload="once")
+    for k, cam in enumerate(cams):
+        ref = ms.render_gaussians_host(*host, cam, background_color=sc.background, device=cuda_device)
+        assert torch.equal(out2[k], ref), k
 
 
 @pytest.mark.parametrize("cfg,N,world", [("config3_1m_1080p", 300_000, 8), ("config5_6m_4k", 200_000, 3),
