@@ -62,6 +62,8 @@ extern "C" {
 #define BSPLAT_RASTER_FAST_NOCULL 2  /* fast arithmetic without sub-tile culling (exactness A/B) */
 #define BSPLAT_RASTER_WARP 3      /* independent-warp kernel on per-Gaussian raster records (needs the workspace; A/B) */
 #define BSPLAT_RASTER_SINGLE 4    /* one pixel per lane (first fast kernel, A/B) */
+#define BSPLAT_RASTER_MBAR 5      /* fast kernel with an mbarrier producer/consumer pipeline instead of the per-batch
+                                     CTA barrier (needs the workspace; measured slower, kept as A/B) */
 
 /* bsplat_render_fwd `flags`: low byte = rasterizer mode, plus */
 #define BSPLAT_FLAG_BIN_SINGLE_LEVEL 0x100  /* one sort of packed 64-bit keys instead of the two-level sort */

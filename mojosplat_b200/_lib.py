@@ -22,7 +22,7 @@ LIB_PATH = CSRC / "libbsplat.so"
 OK = 0
 E_ARG, E_WORKSPACE, E_OVERFLOW, E_NODEVICE = -1, -2, -3, -4
 SEM_TORCH, SEM_GSPLAT = 0, 1
-RASTER_FAST, RASTER_FAITHFUL, RASTER_FAST_NOCULL, RASTER_WARP, RASTER_SINGLE = 0, 1, 2, 3, 4
+RASTER_FAST, RASTER_FAITHFUL, RASTER_FAST_NOCULL, RASTER_WARP, RASTER_SINGLE, RASTER_MBAR = 0, 1, 2, 3, 4, 5
 FLAG_BIN_SINGLE_LEVEL = 0x100
 FLAG_CAMERA_INDIRECT = 0x200
 

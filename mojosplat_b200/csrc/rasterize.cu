@@ -418,12 +418,39 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // kRec: the Gaussians come as prepared records (raster_pair_prep_kernel); batches of 128 are gathered by sorted id
 // with cp.async into the two halves of the staging buffer, one batch ahead of the walk (ids two batches ahead),
 // one barrier per batch.  !kRec: workspace-free staging of 256 per batch from the raw arrays.
-template <bool kCull, bool kRec>
+// kMbar (with kRec): no CTA barrier in the loop at all.  Three stages; the cp.async copies of a batch arrive on an
+// mbarrier by themselves ("full": the batch has landed, whatever the issuing threads are doing meanwhile), each
+// warp arrives on a second mbarrier when it has consumed a stage ("empty"), and a thread waits for "empty" of
+// batch b-1 before it gathers batch b+2 into the same stage -- so a warp with little to walk runs up to two batches
+// ahead of the slowest one instead of waiting for it at every batch.
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_cp_async_arrive(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    unsigned int ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+constexpr int kMbarStages = 3;
+
+template <bool kCull, bool kRec, bool kMbar = false>
 __global__ void __launch_bounds__(kPairThreads)
 raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float* __restrict__ means2d, const float* __restrict__ conics,
                    const float* __restrict__ colors, const float* __restrict__ opacities,
@@ -432,8 +459,10 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                    const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
                    float* __restrict__ image, const int vec_store,
                    const unsigned long long* __restrict__ m_dev, const PeerImages peers, const LoopConsts consts) {
-    __shared__ float4 s_g[kPairBatch * kPairRec];
+    __shared__ float4 s_g[(kMbar ? kMbarStages * kPairThreads : kPairBatch) * kPairRec];
     __shared__ unsigned int s_tmask[kPairBatch / 32];  // long tiles: survivors of the tile-level test
+    __shared__ unsigned long long s_full[kMbarStages], s_empty[kMbarStages];
+    __shared__ int s_done_warps;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -457,7 +486,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     // config 5).  For those tiles the four warps first share ONE test of every staged Gaussian against the whole
     // 16x16 tile (64 entries per warp instead of 256), and a warp only runs its own 8x8 test on the survivors:
     // the serial walk of such a list, which bounds the kernel once a frame is split across GPUs, gets ~4x shorter.
-    const bool long_tile = kCull && (r1 - r0 > kLongTile);
+    const bool long_tile = kCull && !kMbar && (r1 - r0 > kLongTile);  // (needs a CTA barrier per batch)
     const float TX0 = (float)(tile_x * kFastTile) + 0.5f, TX1 = TX0 + 15.0f;
     const float TY0 = (float)(tile_y * kFastTile) + 0.5f, TY1 = TY0 + 15.0f;
     float T0 = 1.0f, T1 = 1.0f;
@@ -486,7 +515,39 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
         cp_async_commit();
     };
     int32_t id_next = -1;
-    if (kRec && r0 < r1) {
+    bool warp_done = false;  // kMbar: this warp's 64 pixels are saturated (it keeps gathering and arriving)
+    if (kMbar) {
+        if (tid == 0) {
+#pragma unroll
+            for (int st = 0; st < kMbarStages; ++st) { mbar_init(&s_full[st], kPairThreads); mbar_init(&s_empty[st], kPairThreads / 32); }
+            s_done_warps = 0;
+        }
+        __syncthreads();
+    }
+    // kMbar: this thread's entry of batch b -> stage b % 3; the copies (or the sentinel store) arrive on "full"
+    auto gather_mbar = [&](int b, int32_t id) {
+        const int st = b % kMbarStages;
+        float4* dst = s_g + (st * kPairThreads + tid) * kPairRec;
+        if (id >= 0 && (int64_t)id < N) {
+            const float4* src = rec + kPairRec * (int64_t)id;
+#pragma unroll
+            for (int q = 0; q < kPairRec; ++q) cp_async16(dst + q, src + q);
+            mbar_cp_async_arrive(&s_full[st]);
+        } else {
+            dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[1] = dst[0];
+            dst[2] = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
+            dst[3] = make_float4(0.f, 0.f, 0.f, -INFINITY);
+            dst[4] = dst[0];
+            mbar_arrive(&s_full[st]);
+        }
+    };
+    const int n_batches = (int)((r1 - r0 + kBatch - 1) / kBatch);
+    if (kMbar) {
+        if (n_batches > 0) gather_mbar(0, load_id(r0 + tid));
+        if (n_batches > 1) gather_mbar(1, load_id(r0 + kBatch + tid));
+        id_next = load_id(r0 + 2 * kBatch + tid);
+    } else if (kRec && r0 < r1) {
         gather(0, load_id(r0 + tid));
         id_next = load_id(r0 + kBatch + tid);
     }
@@ -494,7 +555,17 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     for (int32_t b0 = r0; b0 < r1; b0 += kBatch, ++batch) {
         const bool fin = !(npx0 > -INFINITY) && !(npx1 > -INFINITY);
         const float4* s_rec = s_g;
-        if (kRec) {
+        if (kMbar) {
+            if (*reinterpret_cast<volatile int*>(&s_done_warps) >= kPairThreads / 32) break;  // every warp is done
+            if (batch + 2 < n_batches) {
+                // stage (batch + 2) % 3 was last read for batch - 1: wait until all four warps have consumed it
+                if (batch >= 1) mbar_wait(&s_empty[(batch - 1) % kMbarStages], ((batch - 1) / kMbarStages) & 1);
+                gather_mbar(batch + 2, id_next);
+                id_next = load_id(b0 + 3 * kBatch + tid);
+            }
+            mbar_wait(&s_full[batch % kMbarStages], (batch / kMbarStages) & 1);  // batch has landed
+            s_rec = s_g + (batch % kMbarStages) * kPairThreads * kPairRec;
+        } else if (kRec) {
             cp_async_wait_all();  // this thread's part of batch `batch` has landed ...
             if (__syncthreads_count(fin) >= kPairThreads) break;  // ... everyone's has; batch - 1 is fully consumed
             if (b0 + kBatch < r1) gather((batch + 1) & 1, id_next);  // next batch flies during this walk
@@ -621,6 +692,18 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             };
             if (any_special) walk(std::false_type{});
             else walk(std::true_type{});
+        }
+        if (kMbar) {
+            // a warp that is done says so BEFORE it releases the stage: whoever sees the release also sees the count
+            if (!warp_done && __all_sync(0xffffffffu, !(npx0 > -INFINITY) && !(npx1 > -INFINITY))) {
+                warp_done = true;
+                if (lane == 0) atomicAdd(&s_done_warps, 1);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                mbar_arrive(&s_empty[batch % kMbarStages]);  // this warp has consumed the stage
+            }
         }
     }
 
@@ -948,7 +1031,7 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
     if (peers.n > 0 && !(mode == BSPLAT_RASTER_FAST && tile_size == kFastTile && channels == 3 && stats == nullptr &&
                          (reinterpret_cast<uintptr_t>(means2d) & 7u) == 0))
         return BSPLAT_E_ARG;  // the fused exchange exists in the default 16x16 RGB kernel only
-    const bool fast_ok = (mode == BSPLAT_RASTER_FAST || (mode >= 2 && mode <= 4)) && tile_size == kFastTile &&
+    const bool fast_ok = (mode == BSPLAT_RASTER_FAST || (mode >= 2 && mode <= 5)) && tile_size == kFastTile &&
                          channels == 3 && stats == nullptr &&
                          (reinterpret_cast<uintptr_t>(means2d) & 7u) == 0;
     if (fast_ok) {
@@ -975,7 +1058,11 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
                                                                                     opacities, recp, rec_list,
                                                                                     rec_list_n);
             BSPLAT_LAUNCH_CHECK();
-            if (mode == 2)
+            if (mode == 5)
+                raster_pair_kernel<true, true, true><<<grid, kPairThreads, 0, stream>>>(
+                    N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
+                    tiles_w, image, vec, m_dev, peers, loop_consts);
+            else if (mode == 2)
                 raster_pair_kernel<false, true><<<grid, kPairThreads, 0, stream>>>(
                     N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
                     tiles_w, image, vec, m_dev, peers, loop_consts);

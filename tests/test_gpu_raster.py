@@ -23,7 +23,7 @@ def raster_inputs_from_golden(g, device):
 
 @pytest.mark.parametrize("name", ["config1_1k_256", "teststyle_500_offset", "teststyle_500_identity",
                                   "garden_6k_1080p", "dense_300_1080p"])
-@pytest.mark.parametrize("mode", ["faithful", "fast", "fast_nocull", "warp", "single"])
+@pytest.mark.parametrize("mode", ["faithful", "fast", "fast_nocull", "warp", "single", "mbar"])
 def test_raster_vs_oracle_golden_scenes(cuda_device, name, mode):
     g = load_golden(name)
     cam = camera_from_golden(g)
@@ -131,6 +131,8 @@ def test_raster_full_size(cuda_device, cfg, N):
     assert torch.equal(fast, nocull)
     # the independent-warp kernel (cp.async record gather) runs the same packed-pair arithmetic
     assert torch.equal(rasterization.rasterize_gaussians_cuda(*a, mode="warp"), fast)
+    # ... and so does the barrier-free (mbarrier producer/consumer) variant of the pair kernel
+    assert torch.equal(rasterization.rasterize_gaussians_cuda(*a, mode="mbar"), fast)
     r = image_gate(fast.cpu().numpy(), ref)
     assert r["ok"], r
     img_f, g_all, g_pass = rasterization.rasterize_gaussians_stats(*a)
