@@ -180,3 +180,26 @@ def test_row_band_renderer_bands_reassemble(cuda_device, cfg, N, world):
     assert torch.equal(rb.image, full)
     _, aux = ms.render_fused(m, s, q, o, c, cam, bg, return_aux=True)
     assert total == aux["n_isect"]  # every (Gaussian, tile) pair lands in exactly one band
+
+
+@pytest.mark.parametrize("cfg,N,W,H,f", [("config3_1m_1080p", 150_000, 800, 450, 420.0), ("config2_100k_1080p", 3_000, 640, 360, 170.0),
+                                         ("config1_1k_256", 1_000, 256, 256, 66.7)])
+def test_sync_free_paths_gsplat_rules(cuda_device, cfg, N, W, H, f):
+    """The sync-free frame (pipeline, graph) under the gsplat rule set equals render_gaussians(backend="cuda_gsplat")."""
+    from mojosplat_b200 import _lib
+    from mojosplat_b200.pipeline import GraphRenderer, OverlappedPipeline
+    sc = synthetic.make_scene(cfg, N=N)
+    (m, s, q, o, c), _ = scene_on(sc, cuda_device)
+    cams = synthetic.orbit_cameras(4, W, H, f)
+    bg = sc.background.to(cuda_device)
+    ref = [ms.render_gaussians(m, s, q, o, c, cam, background_color=bg, backend="cuda_gsplat") for cam in cams]
+    pipe = OverlappedPipeline(cuda_device, sc.N, W, H, semantics=_lib.SEM_GSPLAT, m_capacity=200 * sc.N)
+    imgs = pipe.render(m, s, q, o, c, cams, bg)
+    assert pipe.check() == 0
+    for k in range(len(cams)):
+        assert torch.equal(imgs[k], ref[k]), k
+    gr = GraphRenderer(m, s, q, o, c, cams[0], bg, semantics=_lib.SEM_GSPLAT, m_capacity=200 * sc.N)
+    for k, cam in enumerate(cams):
+        assert torch.equal(gr.render(cam), ref[k]), k
+        gr.check()
+    assert not torch.equal(ref[0], ms.render_gaussians(m, s, q, o, c, cams[0], background_color=bg, backend="cuda"))
