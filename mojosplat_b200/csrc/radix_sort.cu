@@ -135,15 +135,29 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
         KeyT key[ITEMS];
         int32_t val[ITEMS];
         const int warp_off = warp * (ITEMS * 32);
+        const bool has_vals = vals_in != nullptr;
+        const KeyT* kin = keys_in + tile_base + warp_off + lane;
+        const int32_t* vin = has_vals ? vals_in + tile_base + warp_off + lane : nullptr;
+        const int32_t idx0 = (int32_t)(tile_base + warp_off + lane);
+        if (n_valid == TILE) {  // every tile but the last: no bounds checks
 #pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-            const int local = warp_off + it * 32 + (int)lane;
-            if (local < n_valid) {
-                key[it] = keys_in[tile_base + local];
-                val[it] = vals_in ? vals_in[tile_base + local] : (int32_t)(tile_base + local);
-            } else {
-                key[it] = (KeyT)~(KeyT)0;
-                val[it] = 0;
+            for (int it = 0; it < ITEMS; ++it) {
+                key[it] = kin[it * 32];
+                val[it] = has_vals ? vin[it * 32] : idx0 + it * 32;
+            }
+        } else {
+            // slots past the end hold all-ones keys: they rank behind every real element of the last digit (same
+            // digit, later position), land at tile positions >= n_valid and are simply never written out
+#pragma unroll
+            for (int it = 0; it < ITEMS; ++it) {
+                const int local = warp_off + it * 32 + (int)lane;
+                if (local < n_valid) {
+                    key[it] = kin[it * 32];
+                    val[it] = has_vals ? vin[it * 32] : idx0 + it * 32;
+                } else {
+                    key[it] = (KeyT)~(KeyT)0;
+                    val[it] = 0;
+                }
             }
         }
 
@@ -156,9 +170,8 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
         const uint32_t lt = lanemask_lt();
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
-            const int local = warp_off + it * 32 + (int)lane;
             const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
-            uint32_t p = __ballot_sync(0xffffffffu, local < n_valid);
+            uint32_t p = 0xffffffffu;
 #pragma unroll
             for (int b = 0; b < kRadixBits; ++b) {
                 if (b < bits) {
@@ -178,12 +191,10 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
         }
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
-            const int local = warp_off + it * 32 + (int)lane;
-            const bool valid = local < n_valid;
             const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
             const int leader = __ffs(peers[it]) - 1;
             uint32_t pre = 0;
-            if (valid && (int)lane == leader) {
+            if ((int)lane == leader) {
                 pre = s_whist[warp][d];
                 s_whist[warp][d] = pre + __popc(peers[it]);
             }
@@ -201,7 +212,8 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
             s_whist[w][tid] = run;
             run += c;
         }
-        const uint32_t count = run;
+        // the padding slots of the last tile were counted under the last digit: take them out again
+        const uint32_t count = run - ((uint32_t)tid == digit_mask ? (uint32_t)(TILE - n_valid) : 0u);
         if (tid < n_digits) st_relaxed_u32(my_status, (tile == 0 ? kStatPrefix : kStatAgg) | count);
         uint32_t incl = count;
 #pragma unroll
@@ -221,13 +233,10 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
         // ---- scatter key / payload into shared memory in tile-sorted order ----
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
-            const int local = warp_off + it * 32 + (int)lane;
-            if (local < n_valid) {
-                const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
-                const uint32_t pos = s_local_off[d] + s_whist[warp][d] + rank[it];
-                s_keys[pos] = key[it];
-                s_vals[pos] = val[it];
-            }
+            const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
+            const uint32_t pos = s_local_off[d] + s_whist[warp][d] + rank[it];  // padding slots: pos >= n_valid
+            s_keys[pos] = key[it];
+            s_vals[pos] = val[it];
         }
     }
 
@@ -276,6 +285,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
     __syncthreads();
 
     // ---- contiguous per-digit runs to global ----
+    const bool write_keys = keys_out != nullptr, count_keys = key_counts != nullptr;
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const int j = tid + k * kSortThreads;
@@ -283,9 +293,9 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
             const KeyT kk = s_keys[j];
             const uint32_t d = (uint32_t)(kk >> shift) & digit_mask;
             const uint32_t dst = s_gbase[d] + (uint32_t)j;
-            if (keys_out) keys_out[dst] = kk;
+            if (write_keys) keys_out[dst] = kk;
             vals_out[dst] = s_vals[j];
-            if (key_counts) {
+            if (count_keys) {
                 // Final pass of the tile sort: the CTA's elements are now fully sorted by key (globally
                 // sorted by the low digit on input, stably re-sorted by the high digit here), so equal keys
                 // form runs.  Run start j adds -j, run end j adds j+1: two atomics per run give
