@@ -329,7 +329,7 @@ class HostFramePipeline:
 
     def __init__(self, device, N: int, W: int, H: int, channels: int = 3, tile_size: int = 16,
                  semantics: int = _lib.SEM_TORCH, m_capacity: int | None = None, raster_mode: str = "fast",
-                 in_slots: int = 2, out_slots: int = 3):
+                 in_slots: int = 3, out_slots: int = 3):
         self.dev = torch.device(device)
         self.N, self.W, self.H, self.C = int(N), int(W), int(H), int(channels)
         self.in_slots, self.out_slots = in_slots, out_slots
