@@ -445,10 +445,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int 
                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok) __nanosleep(40);  // polite: a waiting warp must not take issue slots from the walking ones
     } while (!ok);
 }
 
 constexpr int kMbarStages = 3;
+constexpr int kMbarBatch = 96;  // entries per stage (3 x 96 x 80 B = 23 KB: keeps 8-9 CTAs per SM)
 
 template <bool kCull, bool kRec, bool kMbar = false>
 __global__ void __launch_bounds__(kPairThreads)
@@ -459,7 +461,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                    const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
                    float* __restrict__ image, const int vec_store,
                    const unsigned long long* __restrict__ m_dev, const PeerImages peers, const LoopConsts consts) {
-    __shared__ float4 s_g[(kMbar ? kMbarStages * kPairThreads : kPairBatch) * kPairRec];
+    __shared__ float4 s_g[(kMbar ? kMbarStages * kMbarBatch : kPairBatch) * kPairRec];
     __shared__ unsigned int s_tmask[kPairBatch / 32];  // long tiles: survivors of the tile-level test
     __shared__ unsigned long long s_full[kMbarStages], s_empty[kMbarStages];
     __shared__ int s_done_warps;
@@ -496,7 +498,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     const unsigned int bit_one = consts.one_u;
     const f32x2 one2 = pk2(consts.one_f, consts.one_f), mone2 = pk2(consts.mone_f, consts.mone_f);
 
-    constexpr int kBatch = kRec ? kPairThreads : kPairBatch;
+    constexpr int kBatch = kMbar ? kMbarBatch : (kRec ? kPairThreads : kPairBatch);
     constexpr int kPer = kBatch / kPairThreads;  // staged entries per thread and batch
     auto load_id = [&](int32_t at) { return (at < r1) ? __ldg(sorted_ids + at) : -1; };
     auto gather = [&](int half, int32_t id) {  // kRec: this thread's entry of a batch -> record buffer `half`
@@ -519,7 +521,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     if (kMbar) {
         if (tid == 0) {
 #pragma unroll
-            for (int st = 0; st < kMbarStages; ++st) { mbar_init(&s_full[st], kPairThreads); mbar_init(&s_empty[st], kPairThreads / 32); }
+            for (int st = 0; st < kMbarStages; ++st) { mbar_init(&s_full[st], kMbarBatch); mbar_init(&s_empty[st], kPairThreads / 32); }
             s_done_warps = 0;
         }
         __syncthreads();
@@ -527,7 +529,8 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     // kMbar: this thread's entry of batch b -> stage b % 3; the copies (or the sentinel store) arrive on "full"
     auto gather_mbar = [&](int b, int32_t id) {
         const int st = b % kMbarStages;
-        float4* dst = s_g + (st * kPairThreads + tid) * kPairRec;
+        if (tid >= kMbarBatch) return;  // the last warp has no entry to fetch
+        float4* dst = s_g + (st * kMbarBatch + tid) * kPairRec;
         if (id >= 0 && (int64_t)id < N) {
             const float4* src = rec + kPairRec * (int64_t)id;
 #pragma unroll
@@ -564,7 +567,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                 id_next = load_id(b0 + 3 * kBatch + tid);
             }
             mbar_wait(&s_full[batch % kMbarStages], (batch / kMbarStages) & 1);  // batch has landed
-            s_rec = s_g + (batch % kMbarStages) * kPairThreads * kPairRec;
+            s_rec = s_g + (batch % kMbarStages) * kMbarBatch * kPairRec;
         } else if (kRec) {
             cp_async_wait_all();  // this thread's part of batch `batch` has landed ...
             if (__syncthreads_count(fin) >= kPairThreads) break;  // ... everyone's has; batch - 1 is fully consumed
