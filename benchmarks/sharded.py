@@ -1,0 +1,127 @@
+"""BASELINE.json configs 4 and 5, as functions: used by bench.py (key `sharded` of its JSON line, so the
+driver's 1/2/4/8-GPU scaling run carries them) and by benchmarks/bench_configs.py (stand-alone lines).
+
+config 4: 3 M Gaussians x 64 views @1080p.  Gaussians are drawn on rank 0 and NCCL-broadcast once, views are split
+          round-robin, no data-path collective; value = views/s (all ranks, max device time).
+config 5: 6 M Gaussians, one 3840x2160 frame split into tile-row bands balanced by intersection count; every rank
+          projects all N, bins + rasterizes its band; band exchange = one NCCL all-gather, or fused into the rasterizer
+          (peer stores over NVLink); value = frame latency (ms, max over ranks); the assembled image is compared bit for
+          bit with rank 0's single-GPU render.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+import torch.distributed as dist
+
+
+def _maxr(x, dev, world):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _scene(name, N, rank, world, dev):
+    from mojosplat_b200 import parallel, synthetic
+    sc = synthetic.make_scene(name, N=N if rank == 0 else 1)
+    shapes = [(N, 3), (N, 3), (N, 4), (N,), (N, 3)]
+    g = [t.to(dev) for t in sc.gaussians()] if rank == 0 else \
+        [torch.empty(s, dtype=torch.float32, device=dev) for s in shapes]
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    if world > 1:
+        parallel.broadcast_gaussians(g, src=0)
+    torch.cuda.synchronize(dev)
+    return sc, g, 1e3 * (time.perf_counter() - t0)
+
+
+def run_config4(dev, rank, world, n_gaussians=None, views=64, reps=2):
+    from mojosplat_b200 import parallel, synthetic
+    from mojosplat_b200.pipeline import OverlappedPipeline
+    name = "config4_3m_1080p"
+    N = synthetic.CONFIGS[name][0] if n_gaussians is None else n_gaussians
+    sc, g, bcast_ms = _scene(name, N, rank, world, dev)
+    cam0 = sc.camera
+    W, H = cam0.W, cam0.H
+    bg = sc.background.to(dev)
+    cams = synthetic.orbit_cameras(views, W, H, cam0.fx)
+    mine = parallel.split_views(len(cams), rank, world)
+    my_cams = [cams[v] for v in mine]
+    pipe = OverlappedPipeline(dev, N, W, H, slots=3, bin_streams=2, m_capacity=6 * N)
+    ring = torch.empty((4, H, W, 3), dtype=torch.float32, device=dev)
+    pipe.render(*g, my_cams[:4], bg, out=ring); pipe.check()
+    best = 1e30
+    for _ in range(max(1, reps)):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        pipe.render(*g, my_cams, bg, out=ring)
+        b.record()
+        torch.cuda.synchronize(dev)
+        assert pipe.check() == 0
+        best = min(best, _maxr(a.elapsed_time(b), dev, world))
+    out = {"workload": name, "N": N, "views": len(cams), "views_per_rank": len(mine), "n_gpus": world,
+           "views_per_s": len(cams) / (best * 1e-3), "ms_total": best, "M_max": pipe.last_M,
+           "broadcast_ms": bcast_ms, "broadcast_bytes": 56 * N, "scaling": "strong (64 views fixed)",
+           "timing": "CUDA events around this rank's views, max over ranks, best of repeats"}
+    del pipe, ring, g
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_config5(dev, rank, world, n_gaussians=None, steps=6, exchanges=("nccl", "p2p")):
+    import mojosplat_b200 as ms
+    from mojosplat_b200 import parallel, synthetic
+    name = "config5_6m_4k"
+    N = synthetic.CONFIGS[name][0] if n_gaussians is None else n_gaussians
+    sc, g, bcast_ms = _scene(name, N, rank, world, dev)
+    cam0 = sc.camera
+    bg = sc.background.to(dev)
+    ref = ms.render_fused(*g, cam0, bg, 16) if rank == 0 else None
+    out = {"workload": name, "N": N, "n_gpus": world, "broadcast_ms": bcast_ms,
+           "timing": "CUDA events around one sync-free band frame (project all, bin + rasterize the band) + the band "
+                     "exchange, max over ranks, best of repeats"}
+    t1 = None
+    if rank == 0:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms.render_fused(*g, cam0, bg, 16)
+        a.record()
+        for _ in range(3):
+            ms.render_fused(*g, cam0, bg, 16)
+        b.record(); torch.cuda.synchronize(dev)
+        t1 = a.elapsed_time(b) / 3
+    out["single_gpu_fused_ms"] = t1
+    all_same = True
+    for ex in (exchanges if world > 1 else ("none",)):
+        rb = parallel.RowBandRenderer(N, cam0, exchange=ex if world > 1 else "nccl")
+        bands = rb.rebalance(g[0], g[1], g[2], g[3], cam0)   # once per sequence, not per frame
+        img = rb.render(*g, cam0, bg); rb.check()            # warm-up
+        ts = []
+        for _ in range(steps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            img = rb.render(*g, cam0, bg)
+            b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(_maxr(a.elapsed_time(b), dev, world))
+        m_band = rb.check()
+        same = bool(torch.equal(img, ref)) if rank == 0 else True
+        all_same = all_same and same
+        key = "latency_ms" if world == 1 else f"latency_ms_{ex}"
+        out[key] = min(ts)
+        out[key + "_median"] = sorted(ts)[len(ts) // 2]
+        out["bands"] = bands
+        out["M_band_rank0"] = m_band
+        del rb
+        torch.cuda.empty_cache()
+    out["bit_identical"] = all_same
+    del g, ref
+    torch.cuda.empty_cache()
+    return out

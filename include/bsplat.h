@@ -56,14 +56,18 @@ extern "C" {
 #define BSPLAT_SEM_TORCH 0   /* reference torch backend: projection.py:199-283, binning.py:139-162 */
 #define BSPLAT_SEM_GSPLAT 1  /* gsplat / Mojo rules: projection.mojo:59-87,213-244; isect_tiles */
 
+/* or-ed into the `semantics` argument of the stage-level entry points */
+#define BSPLAT_PROJ_ALLOW_FMA 0x100  /* bsplat_project_fwd: let the compiler contract a*b+c into FMAs (A/B build of
+                                        the kernel; faster, radii may then differ from the reference by 1 for a few
+                                        Gaussians per million -- the default rounds like the eager torch ops) */
+#define BSPLAT_BIN_PACKED 0x100      /* bsplat_bin2_prepare / bsplat_bin2_finish (pass it to both): compact the
+                                        Gaussians that own no tile away before the depth sort (gsplat's packed
+                                        layout; identical lists) */
+
 /* rasterizer arithmetic */
 #define BSPLAT_RASTER_FAST 0      /* folded exp2 form, packed FP32 pairs, sub-tile culling (default) */
 #define BSPLAT_RASTER_FAITHFUL 1  /* operation order of kernels/rasterization.mojo:138-157 */
 #define BSPLAT_RASTER_FAST_NOCULL 2  /* fast arithmetic without sub-tile culling (exactness A/B) */
-#define BSPLAT_RASTER_WARP 3      /* independent-warp kernel on per-Gaussian raster records (needs the workspace; A/B) */
-#define BSPLAT_RASTER_SINGLE 4    /* one pixel per lane (first fast kernel, A/B) */
-#define BSPLAT_RASTER_MBAR 5      /* fast kernel with an mbarrier producer/consumer pipeline instead of the per-batch
-                                     CTA barrier (needs the workspace; measured slower, kept as A/B) */
 
 /* bsplat_render_fwd `flags`: low byte = rasterizer mode, plus */
 #define BSPLAT_FLAG_BIN_SINGLE_LEVEL 0x100  /* one sort of packed 64-bit keys instead of the two-level sort */
@@ -71,6 +75,12 @@ extern "C" {
                                                from `cam` (pinned host memory) when the stream gets there, so a
                                                captured CUDA graph can be replayed with a new pose; width and
                                                height are still read on the host at enqueue time */
+#define BSPLAT_FLAG_PACKED 0x400            /* packed (culled-compacted) layout: Gaussians without a tile leave the
+                                               frame right after projection (one stable compaction), so the depth
+                                               sort, count + scan and the raster records only see the visible ones
+                                               (projection.mojo:73-87,213-244; gsplat packed=True).  Same image and
+                                               lists.  A no-op under BSPLAT_SEM_TORCH, where every Gaussian owns a tile */
+#define BSPLAT_FLAG_PROJ_FMA 0x800          /* the BSPLAT_PROJ_ALLOW_FMA projection inside a fused frame */
 
 /* Pinhole camera, world->camera. Mirrors mojosplat/utils.py:5-31 (Camera.view_matrix, Ks, H, W,
  * near, far) as a POD. viewmat is row-major 4x4. */
@@ -145,8 +155,9 @@ int bsplat_tile_ranges(int64_t M, const uint64_t* sorted_keys, int32_t tile_shif
 
 /* Two-level binning (default path; same results, ~4x less sort traffic): depth-sort the N
  * Gaussians (4 onesweep passes over uint32 depth keys), count + scan and emit in depth order, then a
- * stable sort by tile id only (ceil(log2 n_tiles) bits, 2 passes over the M pairs) -- the structure
- * of the reference's argsort(depth) + stable argsort(tile) (binning.py:223-231).
+ * stable sort by tile id only (ceil(log2 n_tiles) bits in ceil(bits / 8) passes over the M pairs: 2 for up to
+ * 65 536 tiles, 3-4 beyond) -- the structure of the reference's argsort(depth) + stable argsort(tile)
+ * (binning.py:223-231).  means2d / radii / depths are read by prepare only (finish ignores them).
  * prepare: writes M to *info_out (device); the caller reads it back, sizes sorted_ids[M] and calls
  * finish with the same workspace (>= bsplat_bin2_workspace_bytes(N, M, n_tiles)). The last sort pass
  * also yields the per-tile counts, so tile_ranges (and the rasterizer's tile_order) cost one tiny kernel. */
@@ -173,7 +184,8 @@ int bsplat_tile_order(int32_t first_tile, int32_t n_tiles, const int32_t* tile_r
  * tile_order, if given, must then list exactly the band's tiles).
  * workspace (optional, bsplat_rasterize_workspace_bytes(N) = 80 B per Gaussian, 16-byte aligned): holds the
  * per-Gaussian raster records, written once per call; with it the fast kernel stages its batches with
- * cp.async one batch ahead (faster, identical results); without it it stages from the raw arrays. */
+ * cp.async one batch ahead (faster, identical results); without it it stages from the raw arrays.
+ * mode: BSPLAT_RASTER_FAST / _FAITHFUL / _FAST_NOCULL (anything else: BSPLAT_E_ARG). */
 size_t bsplat_rasterize_workspace_bytes(int64_t N);
 int bsplat_rasterize_fwd(int64_t N, int32_t channels, const float* means2d, const float* conics,
                          const float* colors, const float* opacities, const float* background,
@@ -298,7 +310,8 @@ int bsplat_render_enqueue_band_p2p(int64_t N, const float* means3d, const float*
                                    void* stream_bin, void* stream_raster, void* event_bin_done);
 /* Same with HOST buffers (pinned or pageable): copies the Gaussians in, renders, copies the
  * image out and synchronises the stream. device_scratch must hold
- * bsplat_render_host_scratch_bytes() in addition to the render workspace. */
+ * bsplat_render_host_scratch_bytes() in addition to the render workspace (a shorter one is BSPLAT_E_ARG;
+ * BSPLAT_E_WORKSPACE / *needed_bytes always refer to `workspace`). */
 size_t bsplat_render_host_scratch_bytes(int64_t N, int32_t channels, int32_t width, int32_t height);
 int bsplat_render_fwd_host(int64_t N, const float* means3d, const float* log_scales,
                            const float* quats, const float* opacities, const float* colors,

@@ -17,14 +17,19 @@ from pathlib import Path
 import torch
 
 CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = CSRC / "libbsplat.so"
+# (BSPLAT_LIB: another build of the same library, for A/B measurements of kernel variants)
+LIB_PATH = Path(os.environ["BSPLAT_LIB"]) if os.environ.get("BSPLAT_LIB") else CSRC / "libbsplat.so"
 
 OK = 0
 E_ARG, E_WORKSPACE, E_OVERFLOW, E_NODEVICE = -1, -2, -3, -4
 SEM_TORCH, SEM_GSPLAT = 0, 1
-RASTER_FAST, RASTER_FAITHFUL, RASTER_FAST_NOCULL, RASTER_WARP, RASTER_SINGLE, RASTER_MBAR = 0, 1, 2, 3, 4, 5
+RASTER_FAST, RASTER_FAITHFUL, RASTER_FAST_NOCULL = 0, 1, 2
 FLAG_BIN_SINGLE_LEVEL = 0x100
 FLAG_CAMERA_INDIRECT = 0x200
+FLAG_PACKED = 0x400
+FLAG_PROJ_FMA = 0x800
+PROJ_ALLOW_FMA = 0x100  # or-ed into `semantics` of bsplat_project_fwd
+BIN_PACKED = 0x100      # or-ed into `semantics` of bsplat_bin2_prepare / bsplat_bin2_finish
 
 # every symbol include/bsplat.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
@@ -213,11 +218,13 @@ def ptr(t: torch.Tensor | None) -> c_void_p:
 
 
 def camera_struct(camera) -> BsplatCamera:
-    """POD copy of a Camera (utils.py). Cached on the object; the view matrix is read back from
-    the device once per (tensor, version)."""
+    """POD copy of a Camera (utils.py). Cached on the object; the view matrix and the intrinsics matrix are read
+    back from the device once per (tensor, version).  Like the reference (projection.py:137-140, 156-159) the
+    intrinsics come from ``camera.Ks``, not from the scalar fields; a Ks that is not a plain pinhole matrix
+    (skew, or a last row other than [0, 0, 1]) has no counterpart in the C ABI and is rejected."""
     vm = camera.view_matrix
-    key = (vm.data_ptr(), vm._version, camera.H, camera.W, camera.fx, camera.fy, camera.cx, camera.cy,
-           camera.near, camera.far)
+    ks = camera.Ks
+    key = (vm.data_ptr(), vm._version, ks.data_ptr(), ks._version, camera.H, camera.W, camera.near, camera.far)
     cached = getattr(camera, "_bsplat_cam", None)
     if cached is not None and cached[0] == key:
         return cached[1]
@@ -225,7 +232,10 @@ def camera_struct(camera) -> BsplatCamera:
     flat = vm.detach().to(device="cpu", dtype=torch.float32).reshape(16).tolist()
     for k in range(16):
         c.viewmat[k] = flat[k]
-    c.fx, c.fy, c.cx, c.cy = float(camera.fx), float(camera.fy), float(camera.cx), float(camera.cy)
+    K = ks.detach().to(device="cpu", dtype=torch.float32).reshape(3, 3).tolist()
+    if K[0][1] != 0.0 or K[1][0] != 0.0 or K[2] != [0.0, 0.0, 1.0]:
+        raise ValueError("camera.Ks must be a pinhole matrix [[fx, 0, cx], [0, fy, cy], [0, 0, 1]] for the CUDA backend")
+    c.fx, c.fy, c.cx, c.cy = K[0][0], K[1][1], K[0][2], K[1][2]
     c.width, c.height = int(camera.W), int(camera.H)
     c.near_plane, c.far_plane = float(camera.near), float(camera.far)
     try:
@@ -236,18 +246,27 @@ def camera_struct(camera) -> BsplatCamera:
 
 
 class Workspace:
-    """Grow-only byte buffer per (device, tag), allocated from torch's caching allocator."""
+    """Grow-only byte buffer per (device, CUDA stream, tag), allocated from torch's caching allocator.  The stream is
+    part of the key: two renders issued on different streams of one device must not share scratch memory."""
 
     def __init__(self):
         self._bufs: dict = {}
 
+    @staticmethod
+    def key(device: torch.device, tag: str):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        return (idx, int(torch.cuda.current_stream(device).cuda_stream), tag)
+
     def get(self, device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
-        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        key = self.key(device, tag)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             grow = int(nbytes * 1.25) if buf is not None else int(nbytes)
             self._bufs[key] = buf = torch.empty(max(grow, 256), dtype=torch.uint8, device=device)
         return buf
+
+    def put(self, device: torch.device, tag: str, buf: torch.Tensor) -> None:
+        self._bufs[self.key(device, tag)] = buf
 
     def clear(self):
         self._bufs.clear()

@@ -44,7 +44,7 @@ def read_bin_info(info_dev: torch.Tensor) -> _lib.BsplatBinInfo:
 
 def bin_gaussians_to_tiles_cuda(means2d, radii, depths, img_height, img_width, tile_size,
                                 semantics=_lib.SEM_TORCH, tile_rows=None, return_keys=False,
-                                algo="two_level"):
+                                algo="two_level", packed=False):
     """Binning on the GPU, two algorithms with bit-identical results:
 
     ``algo="two_level"`` (default): depth-sort the N Gaussians, count+scan and emit in depth order,
@@ -54,9 +54,11 @@ def bin_gaussians_to_tiles_cuda(means2d, radii, depths, img_height, img_width, t
 
     ``tile_rows=(begin, end)`` restricts emission to a band of tile rows (row-band multi-GPU split);
     per-tile lists inside the band are identical to the full-frame ones.
+    ``packed`` (two-level only): Gaussians without a tile are compacted away before the depth sort (same lists).
     """
     if algo == "two_level" and not return_keys:
-        return _bin_two_level(means2d, radii, depths, img_height, img_width, tile_size, semantics, tile_rows)
+        return _bin_two_level(means2d, radii, depths, img_height, img_width, tile_size,
+                              semantics | (_lib.BIN_PACKED if packed else 0), tile_rows)
     dev = means2d.device
     L = _lib.require_device(dev)
     means2d = _lib.as_f32(means2d, "means2d")
@@ -143,7 +145,7 @@ def _bin_two_level(means2d, radii, depths, img_height, img_width, tile_size, sem
             ws = torch.empty(int(need * 1.25), dtype=torch.uint8, device=dev)
             n_part = L.bsplat_bin2_workspace_bytes(N, 0, 0)
             ws[:n_part].copy_(old[:n_part])
-            _lib.workspace._bufs[(dev.index if dev.index is not None else torch.cuda.current_device(), "bin2")] = ws
+            _lib.workspace.put(dev, "bin2", ws)
         sorted_ids = torch.empty((M,), dtype=torch.int32, device=dev)
         _lib.check(L.bsplat_bin2_finish(N, M, _lib.ptr(means2d), _lib.ptr(radii_c), radii_is_float, W, H, ts, r0, r1,
                                         semantics, _lib.ptr(ws), ws.numel(), _lib.ptr(sorted_ids),

@@ -3,11 +3,14 @@
 // The reference sorts the (gaussian, tile) pairs twice: argsort by depth, then a STABLE argsort by
 // tile id (mojosplat/binning.py:223-231).  This path keeps that structure but moves the depth sort to
 // where it is cheap:
-//   1. depth-sort the N Gaussians          4 onesweep passes over (uint32 depth key, index) -- N items
-//   2. count + scan in depth order         tile rects of Gaussian perm[j], exclusive prefix sum, M
-//   3. emit in depth order                 (tile id, gaussian id) pairs; tile-digit histograms on the fly
-//   4. stable sort by tile id only         ceil(log2(n_tiles)) bits -> 2 onesweep passes over M items
-//   5. tile ranges                         from the sorted tile ids
+//   0. per Gaussian: full-frame tile rectangle + monotone depth key + the 4 digit histograms of the keys
+//      (epilogue of the projection kernel in fused frames; bin_prep_kernel for the stage-level entry point)
+//   0b. row-band / packed frames only: one stable compaction of the Gaussians that own >= 1 tile
+//   1. depth-sort the (remaining) Gaussians  4 onesweep passes over (uint32 depth key, index) -- N items
+//   2. count + scan in depth order           gather the rectangle of Gaussian perm[j], exclusive prefix sum, M
+//   3. emit in depth order                   (tile id, gaussian id) pairs; tile-digit histograms on the fly
+//   4. stable sort by tile id only           ceil(log2(n_tiles)) bits in ceil(bits / 8) onesweep passes over M items
+//   5. tile ranges (+ heavy-first order)     from the per-tile counts the last pass yields
 // Result = ascending (tile, depth, gaussian index): bit-identical to the single-level sort of
 // (tile << depth_bits | depth_key) keys and to the reference's lists (canonical tie order),
 // with ~4x less sort traffic: M-scale data is moved by 2 passes of 8 B pairs instead of 6 passes of 12 B.
@@ -16,13 +19,18 @@
 
 namespace bsplat {
 
-// ---- 1. depth keys + digit histograms of the 4 depth passes ---------------------------------
+// ---- 0. stage-level entry point: rectangles + depth keys + digit histograms -----------------
 __global__ void __launch_bounds__(256)
-depth_key_hist_kernel(const int64_t N, const float* __restrict__ depths, uint32_t* __restrict__ keys,
-                      uint32_t* __restrict__ hist /* [4][256] */) {
+bin_prep_kernel(const int64_t N, const float* __restrict__ means2d, const void* __restrict__ radii,
+                const int radii_is_float, const float* __restrict__ depths, const BinParams p,
+                const float inv_tile_size, uint2* __restrict__ rects_in, uint32_t* __restrict__ keys,
+                uint32_t* __restrict__ hist /* [4][256], nullable */) {
     __shared__ uint32_t s_hist[4][kRadix];
-    for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) (&s_hist[0][0])[i] = 0;
-    __syncthreads();
+    const bool want_hist = hist != nullptr;
+    if (want_hist) {
+        for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+        __syncthreads();
+    }
     const uint32_t lane = lane_id();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t warp_start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane;
@@ -31,95 +39,262 @@ depth_key_hist_kernel(const int64_t N, const float* __restrict__ depths, uint32_
         const bool valid = i < N;
         uint32_t k = 0;
         if (valid) {
+            float mx, my, rx, ry;
+            load_mean_radii(means2d, radii, radii_is_float, i, mx, my, rx, ry);
+            const TileRect r = tile_rect_inv(mx, my, rx, ry, p.W, p.H, p.tile_size_f, inv_tile_size, p.tiles_w,
+                                             p.tiles_h, p.semantics);
+            rects_in[i] = make_uint2((uint32_t)r.x0 | ((uint32_t)r.y0 << 16),
+                                     (uint32_t)(r.x1 - r.x0) | ((uint32_t)(r.y1 - r.y0) << 16));
             k = depth_key(__ldg(depths + i));
             keys[i] = k;
-            atomicAdd(&s_hist[0][k & 0xffu], 1u);
-            atomicAdd(&s_hist[1][(k >> 8) & 0xffu], 1u);
-            atomicAdd(&s_hist[2][(k >> 16) & 0xffu], 1u);
+            if (want_hist) {
+                atomicAdd(&s_hist[0][k & 0xffu], 1u);
+                atomicAdd(&s_hist[1][(k >> 8) & 0xffu], 1u);
+                atomicAdd(&s_hist[2][(k >> 16) & 0xffu], 1u);
+            }
         }
-        // sign + exponent bits: a handful of distinct values per warp -> aggregate before the atomic
-        const uint32_t top = valid ? (k >> 24) : 0x100u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, top);
-        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[3][top], (uint32_t)__popc(peers));
+        if (want_hist) {
+            // sign + exponent bits: a handful of distinct values per warp -> aggregate before the atomic
+            const uint32_t top = valid ? (k >> 24) : 0x100u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, top);
+            if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[3][top], (uint32_t)__popc(peers));
+        }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) {
-        const uint32_t v = (&s_hist[0][0])[i];
-        if (v) atomicAdd(hist + i, v);
+    if (want_hist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) {
+            const uint32_t v = (&s_hist[0][0])[i];
+            if (v) atomicAdd(hist + i, v);
+        }
     }
 }
 
-// ---- 1b. row-band frames: only the Gaussians that reach the band are depth-sorted -----------------------
-// flag = 0 for a Gaussian whose tile rectangle intersects the band, 1 otherwise; a 1-bit onesweep pass on the
-// flags is a stable partition of the indices (in-band first, ascending index), band_gather_hist_kernel then
-// collects the depth keys of the in-band prefix.  Every rank of a row-band split used to sort all N Gaussians.
-__global__ void __launch_bounds__(256)
-band_flag_kernel(const int64_t N, const float* __restrict__ means2d, const void* __restrict__ radii,
-                 const int radii_is_float, const float* __restrict__ depths, const BinParams p,
-                 uint32_t* __restrict__ flags, uint32_t* __restrict__ keys_full, uint32_t* __restrict__ hist2,
-                 unsigned long long* __restrict__ n_band) {
-    __shared__ unsigned int s_in;
-    if (threadIdx.x == 0) s_in = 0;
+// ---- 0b. stable compaction of the Gaussians that own >= 1 tile of the band -------------------------------
+// Row-band frames (every rank of a band split would otherwise depth-sort all N Gaussians) and packed frames
+// (gsplat rules: culled Gaussians own no tile; projection.mojo:73-87, 213-244).  One pass: persistent CTAs take
+// chunks of 2 048 Gaussians in ticket order, flag = rectangle clipped to the band is non-empty, block scan +
+// decoupled look-back over the chunk totals, in-band (depth key, index) pairs written in index order, the digit
+// histograms of the surviving keys accumulated on the way.  n_out[0] = survivors, n_out[1] = Gaussians with a
+// non-empty FULL-FRAME rectangle (the "no intersections at all" rule of render.py:73-76 is a whole-frame rule).
+constexpr int kCompactThreads = 256;
+constexpr int kCompactItems = 8;
+constexpr int kCompactChunk = kCompactThreads * kCompactItems;
+
+__global__ void __launch_bounds__(kCompactThreads)
+bin_compact_kernel(const int64_t N, const uint2* __restrict__ rects_in, const uint32_t* __restrict__ keys_full,
+                   const int row_begin, const int row_end, uint32_t* __restrict__ keys, int32_t* __restrict__ perm,
+                   uint32_t* __restrict__ hist /* [4][256] */, unsigned long long* __restrict__ n_out,
+                   uint32_t* __restrict__ ticket, unsigned long long* __restrict__ status) {
+    __shared__ uint32_t s_hist[4][kRadix];
+    __shared__ unsigned int s_chunk;
+    __shared__ unsigned int s_warp_sum[kCompactThreads / 32];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_whole;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 4 * kRadix; i += kCompactThreads) (&s_hist[0][0])[i] = 0;
+    if (tid == 0) s_whole = 0;
+    const int64_t n_chunks = ceil_div(N, kCompactChunk);
+    while (true) {
+        __syncthreads();  // previous chunk is done with s_chunk / s_prefix / s_warp_sum (and the zeroing above)
+        if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const int64_t chunk = s_chunk;
+        if (chunk >= n_chunks) break;
+        const int64_t base = chunk * kCompactChunk + (int64_t)tid * kCompactItems;
+        uint32_t key[kCompactItems];
+        unsigned int flags = 0, whole = 0;
+#pragma unroll
+        for (int k = 0; k < kCompactItems; ++k) {
+            const int64_t i = base + k;
+            key[k] = 0;
+            if (i < N) {
+                const uint2 rc = __ldg(rects_in + i);
+                key[k] = __ldg(keys_full + i);
+                const uint2 cl = clip_rect_rows(rc, row_begin, row_end);
+                if ((cl.y & 0xffffu) != 0u && (cl.y >> 16) != 0u) flags |= 1u << k;
+                if ((rc.y & 0xffffu) != 0u && (rc.y >> 16) != 0u) ++whole;
+            }
+        }
+        const unsigned int cnt = __popc(flags);
+        unsigned int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) whole += __shfl_xor_sync(0xffffffffu, whole, d);
+        if (lane == 31) s_warp_sum[warp] = incl;
+        if (lane == 0 && whole) atomicAdd(&s_whole, whole);
+        __syncthreads();
+        unsigned int warp_excl = 0, block_total = 0;
+#pragma unroll
+        for (int w = 0; w < kCompactThreads / 32; ++w) {
+            const unsigned int v = s_warp_sum[w];
+            if (w < warp) warp_excl += v;
+            block_total += v;
+        }
+        // decoupled look-back over the previous chunks: warp 0 inspects 32 predecessors per round trip
+        if (warp == 0) {
+            unsigned long long prefix = 0;
+            if (chunk == 0) {
+                if (lane == 0) st_relaxed_u64(status + 0, kFlagPrefix | (unsigned long long)block_total);
+            } else {
+                if (lane == 0) st_relaxed_u64(status + chunk, kFlagAgg | (unsigned long long)block_total);
+                int64_t j = chunk - 1;
+                while (true) {
+                    const int64_t idx = j - lane;  // lane 0 = nearest predecessor
+                    const unsigned long long v = idx >= 0 ? ld_relaxed_u64(status + idx) : kFlagPrefix;
+                    const unsigned ready = __ballot_sync(0xffffffffu, (v & ~kValueMask) != 0);
+                    const unsigned pref = __ballot_sync(0xffffffffu, (v & kFlagPrefix) != 0);
+                    const unsigned first_pref = pref ? (unsigned)(__ffs(pref) - 1) : 32u;
+                    const unsigned need = first_pref == 32u ? 0xffffffffu : ((2u << first_pref) - 1u);
+                    if ((ready & need) != need) { __nanosleep(64); continue; }  // not published yet: polite re-poll
+                    unsigned long long contrib = ((unsigned)lane <= first_pref) ? (v & kValueMask) : 0ull;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                    prefix += contrib;
+                    if (first_pref != 32u) break;
+                    j -= 32;
+                }
+                if (lane == 0) st_relaxed_u64(status + chunk, kFlagPrefix | (prefix + block_total));
+            }
+            if (lane == 0) {
+                s_prefix = prefix;
+                if (chunk == n_chunks - 1) n_out[0] = prefix + block_total;  // the last chunk publishes the total
+            }
+        }
+        __syncthreads();
+        unsigned long long pos = s_prefix + warp_excl + incl - cnt;
+#pragma unroll
+        for (int k = 0; k < kCompactItems; ++k) {
+            if ((flags >> k) & 1u) {
+                const uint32_t kk = key[k];
+                keys[pos] = kk;
+                perm[pos] = (int32_t)(base + k);
+                ++pos;
+                atomicAdd(&s_hist[0][kk & 0xffu], 1u);
+                atomicAdd(&s_hist[1][(kk >> 8) & 0xffu], 1u);
+                atomicAdd(&s_hist[2][(kk >> 16) & 0xffu], 1u);
+                atomicAdd(&s_hist[3][kk >> 24], 1u);
+            }
+        }
+    }
+    // (every thread left the loop through the same break, after a barrier)
+    for (int i = tid; i < 4 * kRadix; i += kCompactThreads) {
+        const uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(hist + i, v);
+    }
+    if (tid == 0 && s_whole) atomicAdd(n_out + 1, (unsigned long long)s_whole);
+}
+
+// ---- 2. count + scan in depth order ----------------------------------------------------------
+// Slot j of the depth order holds Gaussian perm[j]: one 8-byte gather of its full-frame rectangle (the
+// rectangle arithmetic -- clamps, IEEE divisions -- happened once, in index order, in step 0), clip to the band,
+// count, single-pass decoupled-look-back exclusive scan (warp-parallel look-back, 2 048 Gaussians per CTA).
+// The clipped rectangles are kept in depth order for the emitter.
+// 1 024 threads x 8 slots per CTA: few chunks keep the look-back chain short (all chunks start together, so the last
+// one walks back through every predecessor, 32 per round trip), many threads keep all gathers of a chunk in flight.
+constexpr int kScan2Threads = 1024;
+constexpr int kScan2Chunk = kScan2Threads * kScanItems;
+
+__global__ void __launch_bounds__(kScan2Threads)
+bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_dev,
+                       const int32_t* __restrict__ perm, const uint2* __restrict__ rects_in, const int row_begin,
+                       const int row_end, uint32_t* __restrict__ offsets, bsplat_bin_info* __restrict__ info,
+                       unsigned long long* __restrict__ ws, uint2* __restrict__ rects) {
+    __shared__ unsigned int s_chunk;
+    __shared__ unsigned long long s_warp_sum[kScan2Threads / 32];
+    __shared__ unsigned long long s_prefix;
+
+    const int tid = threadIdx.x;
+    // n_dev: the number of items lives on the device (compacted depth order); the grid is sized by N_host
+    const int64_t N = n_dev ? (int64_t)(*n_dev) : N_host;
+    if (tid == 0) s_chunk = atomicAdd(reinterpret_cast<unsigned int*>(ws), 1u);
     __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    unsigned int mine = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        float mx, my, rx, ry;
-        load_mean_radii(means2d, radii, radii_is_float, i, mx, my, rx, ry);
-        const TileRect r = tile_rect(mx, my, rx, ry, p.W, p.H, p.tile_size_f, p.tiles_w, p.tiles_h, p.semantics,
-                                     p.row_begin, p.row_end);
-        const bool in = (r.x1 > r.x0) && (r.y1 > r.y0);
-        flags[i] = in ? 0u : 1u;
-        keys_full[i] = depth_key(__ldg(depths + i));
-        mine += in ? 1u : 0u;
+    const unsigned int chunk = s_chunk;
+    unsigned long long* status = ws + 1;
+    const int64_t base = (int64_t)chunk * kScan2Chunk;
+    if (base >= N) {  // surplus chunk (tickets are handed out in order: no lower chunk ever waits for this one)
+        if (N == 0 && chunk == 0 && tid == 0) { offsets[0] = 0u; info->n_isect = 0ull; }
+        return;
+    }
+    // blocked arrangement: thread t owns slots base + t*kScanItems + k (keeps the scan trivial); all gathers of a
+    // thread are issued before the first one is used
+    int32_t gi[kScanItems];
+    uint2 rc[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t jj = base + (int64_t)tid * kScanItems + k;
+        gi[k] = (jj < N) ? (perm ? __ldg(perm + jj) : (int32_t)jj) : -1;
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_in, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_in) {
-            atomicAdd(hist2 + 0, s_in);
-            atomicAdd(n_band, (unsigned long long)s_in);
-        }
+    for (int k = 0; k < kScanItems; ++k) rc[k] = gi[k] >= 0 ? __ldg(rects_in + gi[k]) : make_uint2(0u, 0u);
+    uint32_t cnt[kScanItems];
+    uint32_t thread_sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t jj = base + (int64_t)tid * kScanItems + k;
+        const uint2 cl = clip_rect_rows(rc[k], row_begin, row_end);
+        cnt[k] = (cl.y & 0xffffu) * (cl.y >> 16);
+        if (jj < N) rects[jj] = cl;
+        thread_sum += cnt[k];
     }
-}
-
-// hist2[1] = N - hist2[0]; one thread, stream-ordered behind band_flag_kernel.
-__global__ void band_fix_hist_kernel(const int64_t N, uint32_t* __restrict__ hist2) {
-    hist2[1] = (uint32_t)N - hist2[0];
-}
-
-__global__ void __launch_bounds__(256)
-band_gather_hist_kernel(const unsigned long long* __restrict__ n_band, const int32_t* __restrict__ perm0,
-                        const uint32_t* __restrict__ keys_full, uint32_t* __restrict__ keys,
-                        uint32_t* __restrict__ hist /* [4][256] */) {
-    __shared__ uint32_t s_hist[4][kRadix];
-    for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned long long incl = thread_sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp_sum[warp] = incl;
     __syncthreads();
-    const int64_t n = (int64_t)(*n_band);
-    const uint32_t lane = lane_id();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t warp_start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane;
-    for (int64_t wi = warp_start; wi < n; wi += stride) {  // warp-uniform trip count
-        const int64_t j = wi + lane;
-        const bool valid = j < n;
-        uint32_t k = 0;
-        if (valid) {
-            k = __ldg(keys_full + __ldg(perm0 + j));
-            keys[j] = k;
-            atomicAdd(&s_hist[0][k & 0xffu], 1u);
-            atomicAdd(&s_hist[1][(k >> 8) & 0xffu], 1u);
-            atomicAdd(&s_hist[2][(k >> 16) & 0xffu], 1u);
+    unsigned long long warp_excl = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kScan2Threads / 32; ++w) {
+        const unsigned long long s = s_warp_sum[w];
+        if (w < warp) warp_excl += s;
+        block_total += s;
+    }
+    const unsigned long long thread_excl = warp_excl + incl - thread_sum;
+    if (warp == 0) {
+        unsigned long long prefix = 0;
+        if (chunk == 0) {
+            if (lane == 0) st_relaxed_u64(status + 0, kFlagPrefix | block_total);
+        } else {
+            if (lane == 0) st_relaxed_u64(status + chunk, kFlagAgg | block_total);
+            int64_t j = (int64_t)chunk - 1;
+            while (true) {
+                const int64_t idx = j - lane;  // lane 0 = nearest predecessor
+                const unsigned long long v = idx >= 0 ? ld_relaxed_u64(status + idx) : kFlagPrefix;
+                const unsigned ready = __ballot_sync(0xffffffffu, (v & ~kValueMask) != 0);
+                const unsigned pref = __ballot_sync(0xffffffffu, (v & kFlagPrefix) != 0);
+                const unsigned first_pref = pref ? (unsigned)(__ffs(pref) - 1) : 32u;
+                const unsigned need = first_pref == 32u ? 0xffffffffu : ((2u << first_pref) - 1u);
+                if ((ready & need) != need) { __nanosleep(64); continue; }  // not published yet: polite re-poll
+                unsigned long long contrib = ((unsigned)lane <= first_pref) ? (v & kValueMask) : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                prefix += contrib;
+                if (first_pref != 32u) break;
+                j -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(status + chunk, kFlagPrefix | (prefix + block_total));
         }
-        const uint32_t top = valid ? (k >> 24) : 0x100u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, top);
-        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[3][top], (uint32_t)__popc(peers));
+        if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) {
-        const uint32_t v = (&s_hist[0][0])[i];
-        if (v) atomicAdd(hist + i, v);
+    unsigned long long run = s_prefix + thread_excl;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = base + (int64_t)tid * kScanItems + k;
+        if (i < N) offsets[i] = (uint32_t)run;
+        run += cnt[k];
+    }
+    // the chunk that owns the last slot publishes the total
+    if (tid == kScan2Threads - 1 && base + kScan2Chunk >= N) {
+        offsets[N] = (uint32_t)run;
+        info->n_isect = run;
     }
 }
 
@@ -131,17 +306,26 @@ band_gather_hist_kernel(const unsigned long long* __restrict__ n_band, const int
 // of pair p is found with a 5-step shuffle binary search over the window's offsets, its rectangle fetched with
 // shuffles, the tile id computed and both words stored -- every store instruction writes 128 contiguous bytes,
 // no lane idles on a short rectangle, and a Gaussian that covers thousands of tiles (the nearest ones, which the
-// depth order puts side by side) is shared by as many warps as it has tasks.  The digit histograms of the two
-// tile-sort passes are accumulated on the fly (shared-memory atomics; the high digit is run-length aggregated with
-// match.any: neighbouring pairs share it).
+// depth order puts side by side) is shared by as many warps as it has tasks.  The digit histograms of the
+// tile-sort passes are accumulated on the fly (shared-memory atomics; the highest digit is run-length aggregated
+// with match.any: neighbouring pairs share it).
 constexpr int kEmit2Threads = 256;
 constexpr uint32_t kEmitTask = 1024;
+constexpr int kMaxTilePasses = 4;
+
+// digit layout of the tile sort: pass q sorts bits [shift[q], shift[q] + bits[q]) of the tile id
+struct TilePasses {
+    int n;
+    int shift[kMaxTilePasses];
+    int bits[kMaxTilePasses];
+};
 
 __global__ void __launch_bounds__(kEmit2Threads)
 bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_dev,
                  const int32_t* __restrict__ perm, const uint2* __restrict__ rects,
-                 const int tiles_w, const uint32_t* __restrict__ offsets, const int lo_bits,
-                 uint32_t* __restrict__ tile_keys, int32_t* __restrict__ ids, uint32_t* __restrict__ hist /* [2][256] */,
+                 const int tiles_w, const uint32_t* __restrict__ offsets, const TilePasses tp,
+                 uint32_t* __restrict__ tile_keys, int32_t* __restrict__ ids,
+                 uint32_t* __restrict__ hist /* [kMaxTilePasses][256] */,
                  bsplat_bin_info* __restrict__ info_dev, const int64_t m_cap) {
     // sync-free frames: the pair buffers hold m_cap entries; if this frame produced more, emit nothing,
     // raise the overflow flag (reserved[1]) and let the later passes see it (they skip too)
@@ -149,13 +333,14 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
         if (blockIdx.x == 0 && threadIdx.x == 0) info_dev->reserved[1] = 1u;
         return;
     }
-    __shared__ uint32_t s_hist[2][kRadix];
-    const int64_t N = n_dev ? (int64_t)(*n_dev) : N_host;  // band-compacted order: the count is on the device
+    __shared__ uint32_t s_hist[kMaxTilePasses][kRadix];
+    const int64_t N = n_dev ? (int64_t)(*n_dev) : N_host;  // compacted depth order: the count is on the device
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
-    for (int i = tid; i < 2 * kRadix; i += kEmit2Threads) (&s_hist[0][0])[i] = 0;
+    for (int i = tid; i < kMaxTilePasses * kRadix; i += kEmit2Threads) (&s_hist[0][0])[i] = 0;
     __syncthreads();
-    const uint32_t lo_mask = (1u << lo_bits) - 1u;
+    const int top = tp.n - 1;
+    const int top_shift = tp.n == 1 ? tp.shift[0] : (tp.n == 2 ? tp.shift[1] : (tp.n == 3 ? tp.shift[2] : tp.shift[3]));
     const uint32_t tw = (uint32_t)tiles_w;
     const uint32_t M = N > 0 ? __ldg(offsets + N) : 0u;  // total number of pairs (written by the count + scan kernel)
     // persistent warps: each takes several tasks; the CTA flushes its histograms once
@@ -186,7 +371,7 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
             uint2 rc = make_uint2(0u, 0u);
             uint32_t off = M;   // lanes past N own nothing
             if (have) {
-                g = __ldg(perm + jg);
+                g = perm ? __ldg(perm + jg) : (int32_t)jg;
                 rc = __ldg(rects + jg);
                 off = __ldg(offsets + jg);
             }
@@ -224,11 +409,13 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
                     tile = ((xy >> 16) + dy) * tw + (xy & 0xffffu) + dx;
                     tile_keys[pidx] = tile;
                     ids[pidx] = go;
-                    atomicAdd(&s_hist[0][tile & lo_mask], 1u);
+#pragma unroll
+                    for (int q = 0; q < kMaxTilePasses - 1; ++q)  // (constant indices keep tp in the parameter bank)
+                        if (q < top) atomicAdd(&s_hist[q][(tile >> tp.shift[q]) & ((1u << tp.bits[q]) - 1u)], 1u);
                 }
-                const uint32_t top = valid ? (tile >> lo_bits) : 0x100u;
-                const uint32_t peers = __match_any_sync(0xffffffffu, top);
-                if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[1][top], (uint32_t)__popc(peers));
+                const uint32_t td = valid ? (tile >> top_shift) : 0x100u;
+                const uint32_t peers = __match_any_sync(0xffffffffu, td);
+                if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[top][td], (uint32_t)__popc(peers));
             }
             cur = stop;
             jg0 += 32;
@@ -236,139 +423,136 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
         }
     }
     __syncthreads();
-    for (int i = tid; i < 2 * kRadix; i += kEmit2Threads) {
+    for (int i = tid; i < tp.n * kRadix; i += kEmit2Threads) {
         const uint32_t v = (&s_hist[0][0])[i];
         if (v) atomicAdd(hist + i, v);
     }
 }
 
-// ---- 5. per-tile counts -> tile ranges (+ heavy-first tile order), one CTA ---------------------
+// ---- 5. per-tile counts -> tile ranges (+ heavy-first tile order) ------------------------------
 // ranges[t] = [exclusive prefix of counts, + count) -- searchsorted-left semantics for empty tiles
 // (binning.py:252-260).  order (optional) lists the tiles [first, first + n_order) by list length,
 // longest first (counting sort on len/32, 256 buckets; order inside a bucket is arbitrary).
-constexpr int kFinishThreads = 1024;
-constexpr int kFinishMaxPer = 32;  // tiles per thread held in registers (covers 32 768 tiles = 4K at 16 px)
+// Up to 128 CTAs, each owning a contiguous block of tiles, in two phases separated by a grid-wide flag (every
+// CTA publishes its block total and its bucket histogram, then waits until all have): the one-CTA version spent
+// 18 us issuing ~40 k warp instructions through a single SM.  The grid is small enough to be co-resident; if it
+// is not at once (other streams), waiting CTAs only delay the rest, which depend on nobody.
+constexpr int kFinThreads = 128;
+constexpr int kFinMaxCtas = 128;
+// scratch words (zeroed per frame): [0] arrivals, [1 .. 256] bucket sizes, [257 .. 512] bucket cursors,
+// [513 .. 640] block totals, [700] spare counter (bin2_spare_counter)
+constexpr int kFinScratchWords = 1024;
 
-// One CTA.  Warp w owns the consecutive tiles [w * 32 per, (w + 1) * 32 per) and walks them 32 at a time (lane =
-// consecutive tile): every load and store of the kernel is coalesced.  (The first version gave each THREAD
-// consecutive tiles: 32 sectors per warp instruction through the one SM's LSU -- 18 us for 8 160 tiles, all of it
-// lg-throttle stalls.)  Counts are read once into registers, scanned per row of 32 (shuffles) with a running
-// carry, warp totals are scanned across the block, ranges and bucket positions come from the registers.
-__global__ void __launch_bounds__(kFinishThreads)
-tile_finish_kernel(const int n_tiles, const int first, const int n_order, const uint32_t* __restrict__ counts,
-                   int32_t* __restrict__ ranges, int32_t* __restrict__ order) {
-    __shared__ uint32_t s_warp[kFinishThreads / 32];
+__device__ __forceinline__ int fin_bucket(const uint32_t cc) { return (int)(255u - min(255u, (cc + 31u) >> 5)); }
+
+__global__ void __launch_bounds__(kFinThreads)
+tile_finish2_kernel(const int n_tiles, const int first, const int n_order, const uint32_t* __restrict__ counts,
+                    int32_t* __restrict__ ranges, int32_t* __restrict__ order, uint32_t* __restrict__ scratch) {
     __shared__ int s_cnt[256];
-    __shared__ int s_base[256];
+    __shared__ int s_res[256];
+    __shared__ uint32_t s_w[kFinThreads / 32];
+    __shared__ uint32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 256) s_cnt[tid] = 0;
-    const int per = (n_tiles + kFinishThreads - 1) / kFinishThreads;  // rows of 32 tiles per warp
-    const int w0 = warp * per * 32;
-    const bool in_regs = per <= kFinishMaxPer;
-    auto count_at = [&](int t) { return (t < n_tiles && counts) ? __ldg(counts + t) : 0u; };
-    uint32_t c[kFinishMaxPer];   // this lane's count in row k
-    uint32_t ex[kFinishMaxPer];  // exclusive prefix inside the warp's tiles
-    uint32_t carry = 0;
-    auto row_scan = [&](uint32_t v, uint32_t& excl) {
-        uint32_t incl = v;
+    const int G = gridDim.x, b = blockIdx.x;
+    const int per = (n_tiles + G - 1) / G;
+    const int t0 = b * per, t1 = min(n_tiles, t0 + per);
+    uint32_t* arrivals = scratch;
+    uint32_t* g_bucket = scratch + 1;
+    uint32_t* g_cursor = scratch + 257;
+    uint32_t* g_total = scratch + 513;
+    auto count_at = [&](int t) { return (t < t1 && counts) ? __ldg(counts + t) : 0u; };
+    auto in_order = [&](int t) { return order && t < t1 && t >= first && t < first + n_order; };
+    auto block_sum = [&](uint32_t v) -> uint32_t {  // every thread gets the sum over the CTA
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        __syncthreads();
+        if (lane == 0) s_w[warp] = v;
+        __syncthreads();
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < kFinThreads / 32; ++w) s += s_w[w];
+        return s;
+    };
+    for (int i = tid; i < 256; i += kFinThreads) s_cnt[i] = 0;
+    __syncthreads();
+    // ---- phase 1: block total + bucket histogram of this CTA's tiles ----
+    uint32_t mine = 0;
+    for (int t = t0 + tid; t < t1; t += kFinThreads) {
+        const uint32_t cc = count_at(t);
+        mine += cc;
+        if (in_order(t)) atomicAdd(&s_cnt[fin_bucket(cc)], 1);
+    }
+    const uint32_t total = block_sum(mine);
+    if (tid == 0) st_relaxed_u32(g_total + b, total);
+    if (order)
+        for (int i = tid; i < 256; i += kFinThreads)
+            if (s_cnt[i]) atomicAdd(g_bucket + i, (uint32_t)s_cnt[i]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd(arrivals, 1u);
+        unsigned ns = 32;
+        while (ld_relaxed_u32(arrivals) < (uint32_t)G) {
+            __nanosleep(ns);
+            if (ns < 256) ns <<= 1;
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    // ---- phase 2: ranges from the block prefix, order from the bucket prefix ----
+    const uint32_t before = block_sum(tid < b ? ld_relaxed_u32(g_total + tid) : 0u);  // G <= 128 = kFinThreads
+    if (order) {
+        // exclusive prefix of the 256 global bucket sizes (two per thread), then this CTA's range in every bucket
+        const uint32_t a0 = ld_relaxed_u32(g_bucket + 2 * tid), a1 = ld_relaxed_u32(g_bucket + 2 * tid + 1);
+        uint32_t incl = a0 + a1;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += u;
         }
-        excl = carry + incl - v;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
-    };
-    if (in_regs) {
-#pragma unroll
-        for (int k = 0; k < kFinishMaxPer; ++k) c[k] = (k < per) ? count_at(w0 + k * 32 + lane) : 0u;
-#pragma unroll
-        for (int k = 0; k < kFinishMaxPer; ++k)
-            if (k < per) row_scan(c[k], ex[k]);
-    } else {
-        for (int k = 0; k < per; ++k) { uint32_t e; row_scan(count_at(w0 + k * 32 + lane), e); }
+        __syncthreads();
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        uint32_t excl = incl - (a0 + a1);
+        for (int w = 0; w < warp; ++w) excl += s_w[w];
+        const int c0 = s_cnt[2 * tid], c1 = s_cnt[2 * tid + 1];
+        s_res[2 * tid] = c0 ? (int)(excl + atomicAdd(g_cursor + 2 * tid, (uint32_t)c0)) : 0;
+        s_res[2 * tid + 1] = c1 ? (int)(excl + a0 + atomicAdd(g_cursor + 2 * tid + 1, (uint32_t)c1)) : 0;
     }
-    if (lane == 0) s_warp[warp] = carry;  // total of the warp's tiles
+    if (tid == 0) s_carry = before;
     __syncthreads();
-    if (warp == 0) {
-        const uint32_t w = s_warp[lane];
-        uint32_t wi = w;
+    for (int tb = t0; tb < t1; tb += kFinThreads) {  // CTA-uniform trip count
+        const int t = tb + tid;
+        const uint32_t cc = count_at(t);
+        uint32_t incl = cc;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= d) wi += v;
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += u;
         }
-        s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
-    }
-    __syncthreads();
-    const uint32_t warp_base = s_warp[warp];
-    // bucket counters are hit by thousands of tiles with a handful of distinct lengths: aggregate per warp
-    // (match.any on the bucket) so that one lane per distinct bucket issues the shared-memory atomic
-    auto bucket_add = [&](bool take, uint32_t cc, int* table) -> int {
-        const int bkt = take ? (int)(255u - min(255u, (cc + 31u) >> 5)) : 256;
-        const unsigned peers = __match_any_sync(0xffffffffu, bkt);
-        const int leader = __ffs(peers) - 1;
-        int base = 0;
-        if (take && lane == leader) base = atomicAdd(&table[bkt], __popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        return base + __popc(peers & ((1u << lane) - 1u));
-    };
-    auto in_order = [&](int t) { return order && t < n_tiles && t >= first && t < first + n_order; };
-    auto put_range = [&](int k, uint32_t cc, uint32_t e) {  // warp-uniform call sites (match.any inside)
-        const int t = w0 + k * 32 + lane;
-        if (t < n_tiles) {
-            ranges[2 * t] = (int32_t)(warp_base + e);
-            ranges[2 * t + 1] = (int32_t)(warp_base + e + cc);
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        uint32_t excl = s_carry + incl - cc;
+        for (int w = 0; w < warp; ++w) excl += s_w[w];
+        if (t < t1) {
+            ranges[2 * t] = (int32_t)excl;
+            ranges[2 * t + 1] = (int32_t)(excl + cc);
+            if (in_order(t)) {
+                const int bk = fin_bucket(cc);
+                order[s_res[bk] + atomicSub(&s_cnt[bk], 1) - 1] = t;
+            }
         }
-        if (order) bucket_add(in_order(t), cc, s_cnt);
-    };
-    if (in_regs) {
-#pragma unroll
-        for (int k = 0; k < kFinishMaxPer; ++k)
-            if (k < per) put_range(k, c[k], ex[k]);
-    } else {
-        carry = 0;
-        for (int k = 0; k < per; ++k) {
-            const uint32_t cc = count_at(w0 + k * 32 + lane);
-            uint32_t e;
-            row_scan(cc, e);
-            put_range(k, cc, e);
-        }
-    }
-    if (!order) return;
-    __syncthreads();
-    if (warp == 0) {  // exclusive scan of the 256 bucket sizes, 8 per lane
-        int local[8], tot = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { local[k] = tot; tot += s_cnt[lane * 8 + k]; }
-        int wi = tot;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= d) wi += v;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s_base[lane * 8 + k] = wi - tot + local[k];
-    }
-    __syncthreads();
-    auto put_order = [&](int k, uint32_t cc) {
-        const int t = w0 + k * 32 + lane;
-        const bool take = in_order(t);
-        const int pos = bucket_add(take, cc, s_base);
-        if (take) order[pos] = t;
-    };
-    if (in_regs) {
-#pragma unroll
-        for (int k = 0; k < kFinishMaxPer; ++k)
-            if (k < per) put_order(k, c[k]);
-    } else {
-        for (int k = 0; k < per; ++k) put_order(k, count_at(w0 + k * 32 + lane));
+        __syncthreads();
+        if (tid == kFinThreads - 1) s_carry = excl + cc;
+        __syncthreads();
     }
 }
 
 int tile_finish_launch(int n_tiles, int first, int n_order, const uint32_t* counts, int32_t* ranges,
-                       int32_t* order, cudaStream_t stream) {
-    tile_finish_kernel<<<1, kFinishThreads, 0, stream>>>(n_tiles, first, n_order, counts, ranges, order);
+                       int32_t* order, uint32_t* scratch, cudaStream_t stream) {
+    const int by_size = (n_tiles + 63) / 64;
+    const int G = by_size < 1 ? 1 : (by_size > kFinMaxCtas ? kFinMaxCtas : by_size);
+    tile_finish2_kernel<<<G, kFinThreads, 0, stream>>>(n_tiles, first, n_order, counts, ranges, order, scratch);
     BSPLAT_LAUNCH_CHECK();
     return BSPLAT_OK;
 }
@@ -377,21 +561,47 @@ int tile_finish_launch(int n_tiles, int first, int n_order, const uint32_t* coun
 constexpr size_t kBinAlign = 256;
 static inline size_t bin_align(size_t v) { return (v + kBinAlign - 1) / kBinAlign * kBinAlign; }
 
+static int tile_bits_of(int64_t n_tiles) {
+    int tb = 1;
+    while (((int64_t)1 << tb) < n_tiles) ++tb;
+    return tb;
+}
+
+// ceil(bits / 8) passes of (nearly) equal width: 13 bits -> 7 + 6, 17 bits -> 6 + 6 + 5, never more than 8 per pass
+static TilePasses tile_passes_of(int64_t n_tiles) {
+    TilePasses tp;
+    const int tb = tile_bits_of(n_tiles);
+    tp.n = (tb + kRadixBits - 1) / kRadixBits;
+    int shift = 0;
+    for (int q = 0; q < kMaxTilePasses; ++q) {
+        const int bits = q < tp.n ? tb / tp.n + (q < tb % tp.n ? 1 : 0) : 0;
+        tp.shift[q] = shift;
+        tp.bits[q] = bits;
+        shift += bits;
+    }
+    return tp;
+}
+
+constexpr int kHistRows = 4 + kMaxTilePasses;   // 4 depth passes + the tile passes
+constexpr int kTickets = 16;                    // [0..3] depth, [4..7] tile passes, [8] compaction
+
 struct Bin2Ws {
     // N part (lives from prepare to finish)
     uint32_t* dkeys; uint32_t* dkeys_alt; int32_t* perm; int32_t* perm_alt;
-    uint32_t* offsets; uint2* rects; bsplat_bin_info* info; void* scan_ws; size_t scan_bytes;
-    uint32_t* hist;      // [7][256]: 4 depth passes + 2 tile passes + band partition
-    uint32_t* tickets;   // [8]
-    unsigned long long* n_band;  // in-band Gaussians (row-band frames)
-    uint32_t* status_n;  // [5][tilesN][256]: 4 depth passes + band partition
-    size_t zero_begin, zero_end_n;  // byte range zeroed by prepare
+    uint32_t* offsets; uint2* rects; uint2* rects_in; bsplat_bin_info* info; void* scan_ws; size_t scan_bytes;
+    uint32_t* hist;      // [kHistRows][256]
+    uint32_t* tickets;   // [kTickets]
+    unsigned long long* n_band;  // [0] Gaussians with >= 1 tile in the band, [1] with >= 1 tile in the frame
+    unsigned long long* compact_status;
+    uint32_t* status_n;  // [4][tilesN][256]
+    size_t zero_begin, zero_end_n;  // byte range zeroed by begin
     size_t n_bytes;
     // M part
     uint32_t* tkeys; uint32_t* tkeys_alt; int32_t* ids; int32_t* ids_alt;
-    uint32_t* status_m;  // [2][tilesM][256]
+    uint32_t* status_m;     // [tile passes][tilesM][256]
     uint32_t* tile_counts;  // [n_tiles], directly behind status_m (zeroed together)
-    size_t status_m_off, status_m_bytes;
+    uint32_t* fin_scratch;  // [kFinScratchWords], directly behind tile_counts
+    size_t status_m_off, status_m_bytes, zero_m_bytes;
     size_t total;
 };
 
@@ -401,75 +611,99 @@ static Bin2Ws carve_bin2(void* base, int64_t N, int64_t M, int64_t n_tiles) {
     size_t off = 0;
     auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += bin_align(bytes); return r; };
     const size_t n = (size_t)(N > 0 ? N : 1), m = (size_t)(M > 0 ? M : 1);
+    const size_t nt = (size_t)(n_tiles > 0 ? n_tiles : 1);
     w.dkeys = (uint32_t*)take(n * 4); w.dkeys_alt = (uint32_t*)take(n * 4);
     w.perm = (int32_t*)take(n * 4); w.perm_alt = (int32_t*)take(n * 4);
     w.offsets = (uint32_t*)take((n + 1) * 4);
     w.rects = (uint2*)take(n * sizeof(uint2));
+    w.rects_in = (uint2*)take(n * sizeof(uint2));
     w.zero_begin = off;
     w.info = (bsplat_bin_info*)take(sizeof(bsplat_bin_info));
     w.scan_bytes = bsplat_bin_scan_workspace_bytes(N);
     w.scan_ws = take(w.scan_bytes);
-    w.hist = (uint32_t*)take(7 * kRadix * 4);
-    w.tickets = (uint32_t*)take(8 * 4);
+    w.hist = (uint32_t*)take((size_t)kHistRows * kRadix * 4);
+    w.tickets = (uint32_t*)take(kTickets * 4);
     w.n_band = (unsigned long long*)take(16);
-    w.status_n = (uint32_t*)take(sort_status_words(sort_tiles_u32(N), 5) * 4);
+    w.compact_status = (unsigned long long*)take((size_t)(ceil_div((int64_t)n, kCompactChunk) + 1) * 8);
+    w.status_n = (uint32_t*)take(sort_status_words(sort_tiles_u32(N), 4) * 4);
     w.zero_end_n = off;
     w.n_bytes = off;
     w.tkeys = (uint32_t*)take(m * 4); w.tkeys_alt = (uint32_t*)take(m * 4);
     w.ids = (int32_t*)take(m * 4); w.ids_alt = (int32_t*)take(m * 4);
     w.status_m_off = off;
-    w.status_m_bytes = sort_status_words(sort_tiles_u32(M), 2) * 4;
-    // status_m and tile_counts must be contiguous (single memset): take them as one block
-    w.status_m = (uint32_t*)take(w.status_m_bytes + (size_t)(n_tiles > 0 ? n_tiles : 1) * sizeof(uint32_t));
+    w.status_m_bytes = sort_status_words(sort_tiles_u32(M), tile_passes_of(n_tiles).n) * 4;
+    // status_m, tile_counts and the finish scratch must be contiguous (single memset): take them as one block
+    w.zero_m_bytes = w.status_m_bytes + (nt + kFinScratchWords) * sizeof(uint32_t);
+    w.status_m = (uint32_t*)take(w.zero_m_bytes);
     w.tile_counts = w.status_m ? w.status_m + w.status_m_bytes / sizeof(uint32_t) : nullptr;
+    w.fin_scratch = w.tile_counts ? w.tile_counts + nt : nullptr;
     w.total = off;
     return w;
 }
 
-static int tile_bits_of(const BinParams& p) {
-    const int64_t n_tiles = (int64_t)p.tiles_w * p.tiles_h;
-    int tb = 1;
-    while (((int64_t)1 << tb) < n_tiles) ++tb;
-    return tb;
+static inline float inv_tile_of(const BinParams& p) {
+    const int ts = (int)p.tile_size_f;
+    return ((ts & (ts - 1)) == 0) ? 1.0f / p.tile_size_f : 0.0f;  // exact only for powers of two
 }
 
-int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_is_float, const float* depths,
-                 const BinParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+static inline bool is_band(const BinParams& p) { return p.row_begin > 0 || p.row_end < p.tiles_h; }
+
+// Zeroes the per-frame control words; must precede whatever produces the histograms (the projection epilogue or
+// bin_prep_kernel).
+int bin2_begin(int64_t N, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     Bin2Ws w = carve_bin2(workspace, N, 0, 0);
     if (!workspace || workspace_bytes < w.n_bytes) return BSPLAT_E_WORKSPACE;
     char* base = static_cast<char*>(workspace);
     BSPLAT_CUDA_TRY(cudaMemsetAsync(base + w.zero_begin, 0, w.zero_end_n - w.zero_begin, stream));
+    return BSPLAT_OK;
+}
+
+// Where the producer of step 0 writes: rectangles in index order, depth keys (the compaction input when the
+// frame is compacted, the sort input otherwise) and -- only when nothing is compacted -- the digit histograms.
+void bin2_prep_targets(void* workspace, int64_t N, bool compact, uint2** rects_in, uint32_t** dkeys,
+                       uint32_t** hist) {
+    Bin2Ws w = carve_bin2(workspace, N, 0, 0);
+    *rects_in = w.rects_in;
+    *dkeys = compact ? w.dkeys_alt : w.dkeys;
+    *hist = compact ? nullptr : w.hist;
+}
+
+// have_prep: bin2_begin ran and step 0 is done (fused frames); otherwise both happen here from the stage inputs.
+// compact: sort only the Gaussians that own a tile of the band (always for partial bands).
+int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_is_float, const float* depths,
+                 const BinParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream, bool have_prep,
+                 bool compact) {
+    Bin2Ws w = carve_bin2(workspace, N, 0, 0);
+    if (!workspace || workspace_bytes < w.n_bytes) return BSPLAT_E_WORKSPACE;
+    compact = compact || is_band(p);
+    int rc = BSPLAT_OK;
+    if (!have_prep) {
+        rc = bin2_begin(N, workspace, workspace_bytes, stream);
+        if (rc != BSPLAT_OK) return rc;
+    }
     if (N == 0) {
         BSPLAT_CUDA_TRY(cudaMemsetAsync(w.offsets, 0, sizeof(uint32_t), stream));
         return BSPLAT_OK;
     }
-    int rc = BSPLAT_OK;
+    if (!have_prep) {
+        const int64_t hb = ceil_div(N, 256 * 8);
+        const unsigned grid = (unsigned)(hb < 148 * 4 ? hb : 148 * 4);
+        bin_prep_kernel<<<grid, 256, 0, stream>>>(N, means2d, radii, radii_is_float, depths, p, inv_tile_of(p),
+                                                  w.rects_in, compact ? w.dkeys_alt : w.dkeys,
+                                                  compact ? nullptr : w.hist);
+        BSPLAT_LAUNCH_CHECK();
+    }
     const int64_t tn = sort_tiles_u32(N);
-    const int64_t hb = ceil_div(N, 256 * 8);
-    const unsigned hist_grid = (unsigned)(hb < 148 * 2 ? hb : 148 * 2);
-    // A band that is not the whole image: partition the indices first, sort only the in-band prefix (device count)
-    const bool band = p.row_begin > 0 || p.row_end < p.tiles_h;
     const uint64_t* n_dev = nullptr;
     const int32_t* vsrc = nullptr;
-    if (band) {
-        uint32_t* flags = w.offsets;                               // dead until the count + scan kernel
-        uint32_t* keys_full = reinterpret_cast<uint32_t*>(w.rects);  // dead until the count + scan kernel
-        uint32_t* hist2 = w.hist + 6 * kRadix;
-        band_flag_kernel<<<hist_grid * 2, 256, 0, stream>>>(N, means2d, radii, radii_is_float, depths, p, flags,
-                                                            keys_full, hist2, w.n_band);
-        BSPLAT_LAUNCH_CHECK();
-        band_fix_hist_kernel<<<1, 1, 0, stream>>>(N, hist2);
-        BSPLAT_LAUNCH_CHECK();
-        rc = onesweep_pass_u32(N, nullptr, flags, nullptr, nullptr, w.perm, 0, 1, hist2, 0, w.tickets + 6,
-                               w.status_n + (size_t)4 * tn * kRadix, nullptr, stream);
-        if (rc != BSPLAT_OK) return rc;
-        band_gather_hist_kernel<<<hist_grid, 256, 0, stream>>>(w.n_band, w.perm, keys_full, w.dkeys, w.hist);
+    if (compact) {
+        const int64_t cb = ceil_div(N, kCompactChunk);
+        bin_compact_kernel<<<(unsigned)(cb < 148 * 2 ? cb : 148 * 2), kCompactThreads, 0, stream>>>(
+            N, w.rects_in, w.dkeys_alt, p.row_begin, p.row_end, w.dkeys, w.perm, w.hist, w.n_band, w.tickets + 8,
+            w.compact_status);
         BSPLAT_LAUNCH_CHECK();
         n_dev = reinterpret_cast<const uint64_t*>(w.n_band);
         vsrc = w.perm;
-    } else {
-        depth_key_hist_kernel<<<hist_grid, 256, 0, stream>>>(N, depths, w.dkeys, w.hist);
-        BSPLAT_LAUNCH_CHECK();
     }
     const uint32_t* ksrc = w.dkeys; uint32_t* kdst = w.dkeys_alt;
     int32_t* vdst = w.perm_alt;
@@ -483,66 +717,70 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
         vsrc = vdst; vdst = (vdst == w.perm_alt) ? w.perm : w.perm_alt;
     }
     // after 4 passes the sorted permutation is in w.perm (passes 1 and 3 write w.perm)
-    return bin_count_scan_launch(N, w.perm, means2d, radii, radii_is_float, depths, p, w.offsets, w.info,
-                                 w.scan_ws, /*finalize_key_range=*/false, stream, w.rects,
-                                 reinterpret_cast<const unsigned long long*>(n_dev));
+    const unsigned grid = (unsigned)ceil_div(N, kScan2Chunk);
+    bin_count_scan2_kernel<<<grid, kScan2Threads, 0, stream>>>(
+        N, reinterpret_cast<const unsigned long long*>(n_dev), w.perm, w.rects_in, p.row_begin, p.row_end, w.offsets,
+        w.info, static_cast<unsigned long long*>(w.scan_ws), w.rects);
+    BSPLAT_LAUNCH_CHECK();
+    return BSPLAT_OK;
 }
 
 // device_m: M is a capacity; the real count is read on the device from the bin info (n_isect) written by
 // prepare -- no host read-back between prepare and finish (sync-free / graph-capturable frames).
-int bin2_finish(int64_t N, int64_t M, bool device_m, const float* means2d, const void* radii, int radii_is_float,
-                const BinParams& p, void* workspace, size_t workspace_bytes, int32_t* sorted_ids,
-                int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream) {
+int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* workspace, size_t workspace_bytes,
+                int32_t* sorted_ids, int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream, bool compact) {
     const int n_tiles = p.tiles_w * p.tiles_h;
     Bin2Ws w = carve_bin2(workspace, N, M, n_tiles);
     if (!workspace || workspace_bytes < w.total) return BSPLAT_E_WORKSPACE;
+    compact = compact || is_band(p);
     bsplat_bin_info* info_dev = device_m ? w.info : nullptr;
     const uint64_t* m_dev = device_m ? reinterpret_cast<const uint64_t*>(w.info) : nullptr;
+    // status words of the tile passes, the per-tile counters and the finish scratch are contiguous: one memset
+    BSPLAT_CUDA_TRY(cudaMemsetAsync(w.status_m, 0, w.zero_m_bytes, stream));
+    const int first = p.row_begin * p.tiles_w, n_order = (p.row_end - p.row_begin) * p.tiles_w;
     if (M == 0) {
-        BSPLAT_CUDA_TRY(cudaMemsetAsync(tile_ranges, 0, (size_t)n_tiles * 2 * sizeof(int32_t), stream));
-        if (tile_order)
-            return tile_finish_launch(n_tiles, p.row_begin * p.tiles_w, (p.row_end - p.row_begin) * p.tiles_w,
-                                      nullptr, tile_ranges, tile_order, stream);
-        return BSPLAT_OK;
+        if (!tile_order) {
+            BSPLAT_CUDA_TRY(cudaMemsetAsync(tile_ranges, 0, (size_t)n_tiles * 2 * sizeof(int32_t), stream));
+            return BSPLAT_OK;
+        }
+        return tile_finish_launch(n_tiles, first, n_order, nullptr, tile_ranges, tile_order, w.fin_scratch, stream);
     }
-    // status words of the two passes and the per-tile counters are contiguous: one memset
-    BSPLAT_CUDA_TRY(cudaMemsetAsync(w.status_m, 0, w.status_m_bytes + (size_t)n_tiles * sizeof(uint32_t), stream));
-    const int tb = tile_bits_of(p);
-    const int lo_bits = tb > 8 ? (tb + 1) / 2 : tb;  // split the tile id evenly over <= 2 passes
-    const int hi_bits = tb - lo_bits;
+    const TilePasses tp = tile_passes_of(n_tiles);
     // one warp per task of kEmitTask pairs; M is the capacity in sync-free frames
     const int64_t emit_ctas = ceil_div(ceil_div(M, (int64_t)kEmitTask), kEmit2Threads / 32);
-    const bool band = p.row_begin > 0 || p.row_end < p.tiles_h;  // prepare compacted the depth order to the band
     bin_emit2_kernel<<<(unsigned)(emit_ctas < 148 * 8 ? emit_ctas : 148 * 8), kEmit2Threads, 0, stream>>>(
-        N, band ? w.n_band : nullptr, w.perm, w.rects, p.tiles_w, w.offsets, lo_bits, w.tkeys, w.ids,
+        N, compact ? w.n_band : nullptr, w.perm, w.rects, p.tiles_w, w.offsets, tp, w.tkeys, w.ids,
         w.hist + 4 * kRadix, info_dev, M);
     BSPLAT_LAUNCH_CHECK();
-    int rc = BSPLAT_OK;
     const int64_t tm = sort_tiles_u32(M);
-    if (hi_bits > 0) {
-        rc = onesweep_pass_u32(M, m_dev, w.tkeys, w.tkeys_alt, w.ids, w.ids_alt, 0, lo_bits, w.hist + 4 * kRadix,
-                               0, w.tickets + 4, w.status_m, nullptr, stream);
-        if (rc != BSPLAT_OK) return rc;
+    const uint32_t* ksrc = w.tkeys; uint32_t* kdst = w.tkeys_alt;
+    const int32_t* vsrc = w.ids; int32_t* vdst = w.ids_alt;
+    for (int q = 0; q < tp.n; ++q) {
+        const bool last = q == tp.n - 1;
         // last pass: sorted tile ids are not written; per-tile counts come out of the pass instead
-        rc = onesweep_pass_u32(M, m_dev, w.tkeys_alt, nullptr, w.ids_alt, sorted_ids, lo_bits, hi_bits,
-                               w.hist + 5 * kRadix, 0, w.tickets + 5, w.status_m + (size_t)tm * kRadix,
-                               w.tile_counts, stream);
-    } else {
-        rc = onesweep_pass_u32(M, m_dev, w.tkeys, nullptr, w.ids, sorted_ids, 0, lo_bits, w.hist + 4 * kRadix,
-                               0, w.tickets + 4, w.status_m, w.tile_counts, stream);
+        const int rc = onesweep_pass_u32(M, m_dev, ksrc, last ? nullptr : kdst, vsrc, last ? sorted_ids : vdst,
+                                         tp.shift[q], tp.bits[q], w.hist + (size_t)(4 + q) * kRadix, 0,
+                                         w.tickets + 4 + q, w.status_m + (size_t)q * tm * kRadix,
+                                         last ? w.tile_counts : nullptr, stream);
+        if (rc != BSPLAT_OK) return rc;
+        ksrc = kdst; kdst = (kdst == w.tkeys_alt) ? w.tkeys : w.tkeys_alt;
+        vsrc = vdst; vdst = (vdst == w.ids_alt) ? w.ids : w.ids_alt;
     }
-    if (rc != BSPLAT_OK) return rc;
-    return tile_finish_launch(n_tiles, p.row_begin * p.tiles_w, (p.row_end - p.row_begin) * p.tiles_w,
-                              w.tile_counts, tile_ranges, tile_order, stream);
+    return tile_finish_launch(n_tiles, first, n_order, w.tile_counts, tile_ranges, tile_order, w.fin_scratch, stream);
 }
 
 size_t bin2_workspace_bytes(int64_t N, int64_t M, int64_t n_tiles) { return carve_bin2(nullptr, N, M, n_tiles).total; }
+// depth-ordered list of the compacted frame's Gaussians + their count (device)
 void bin2_band_list(void* workspace, int64_t N, const int32_t** perm, const unsigned long long** n_band) {
     const Bin2Ws w = carve_bin2(workspace, N, 0, 0);
     *perm = w.perm;
     *n_band = w.n_band;
 }
 bsplat_bin_info* bin2_info_ptr(void* workspace, int64_t N) { return carve_bin2(workspace, N, 0, 0).info; }
+// one spare word of the finish scratch: zero from bin2_finish's memset on (grid barrier of the rasterizer's pre-pass)
+uint32_t* bin2_spare_counter(void* workspace, int64_t N, int64_t M, int64_t n_tiles) {
+    return carve_bin2(workspace, N, M, n_tiles).fin_scratch + 700;
+}
 
 }  // namespace bsplat
 
@@ -553,7 +791,7 @@ extern "C" size_t bsplat_bin2_workspace_bytes(int64_t N, int64_t M_capacity, int
     return bin2_workspace_bytes(N, M_capacity, n_tiles);
 }
 
-// Phase 1: depth-sort the Gaussians, tile rects + prefix sum in depth order. Afterwards *info_out
+// Phase 1: rectangles + depth keys, depth-sort the Gaussians, count + scan in depth order. Afterwards *info_out
 // (device, 32 bytes) holds M; the caller reads it back (the stage's single read-back), sizes
 // sorted_ids and calls phase 2 with the same workspace.
 extern "C" int bsplat_bin2_prepare(int64_t N, const float* means2d, const void* radii, int32_t radii_is_float,
@@ -563,11 +801,12 @@ extern "C" int bsplat_bin2_prepare(int64_t N, const float* means2d, const void* 
                                    void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     BinParams p;
-    int rc = make_bin_params(width, height, tile_size, tile_row_begin, tile_row_end, semantics, &p);
+    int rc = make_bin_params(width, height, tile_size, tile_row_begin, tile_row_end, semantics & 0xff, &p);
     if (rc != BSPLAT_OK) return rc;
     if (N < 0 || !info_out) return BSPLAT_E_ARG;
     if (N > 0 && (!means2d || !radii || !depths)) return BSPLAT_E_ARG;
-    rc = bin2_prepare(N, means2d, radii, radii_is_float, depths, p, workspace, workspace_bytes, stream);
+    rc = bin2_prepare(N, means2d, radii, radii_is_float, depths, p, workspace, workspace_bytes, stream, false,
+                      (semantics & BSPLAT_BIN_PACKED) != 0);
     if (rc != BSPLAT_OK) return rc;
     const bsplat_bin_info* src = bin2_info_ptr(workspace, N);
     if (info_out != src)
@@ -581,13 +820,14 @@ extern "C" int bsplat_bin2_finish(int64_t N, int64_t M, const float* means2d, co
                                   int32_t tile_row_begin, int32_t tile_row_end, int32_t semantics,
                                   void* workspace, size_t workspace_bytes, int32_t* sorted_ids,
                                   int32_t* tile_ranges, int32_t* tile_order, void* stream_) {
+    (void)means2d; (void)radii; (void)radii_is_float;  // phase 1 kept everything phase 2 needs in the workspace
     cudaStream_t stream = (cudaStream_t)stream_;
     BinParams p;
-    int rc = make_bin_params(width, height, tile_size, tile_row_begin, tile_row_end, semantics, &p);
+    int rc = make_bin_params(width, height, tile_size, tile_row_begin, tile_row_end, semantics & 0xff, &p);
     if (rc != BSPLAT_OK) return rc;
     if (N < 0 || M < 0 || !tile_ranges) return BSPLAT_E_ARG;
     if (M >= (int64_t)kStatMask) return BSPLAT_E_OVERFLOW;
-    if (M > 0 && (!means2d || !radii || !sorted_ids)) return BSPLAT_E_ARG;
-    return bin2_finish(N, M, false, means2d, radii, radii_is_float, p, workspace, workspace_bytes, sorted_ids,
-                       tile_ranges, tile_order, stream);
+    if (M > 0 && !sorted_ids) return BSPLAT_E_ARG;
+    return bin2_finish(N, M, false, p, workspace, workspace_bytes, sorted_ids, tile_ranges, tile_order, stream,
+                       (semantics & BSPLAT_BIN_PACKED) != 0);
 }

@@ -6,24 +6,30 @@
 #include "binning.cuh"
 
 namespace bsplat {
+int bin2_begin(int64_t N, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+void bin2_prep_targets(void* workspace, int64_t N, bool compact, uint2** rects_in, uint32_t** dkeys, uint32_t** hist);
 int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_is_float, const float* depths,
-                 const BinParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream);
-int bin2_finish(int64_t N, int64_t M, bool device_m, const float* means2d, const void* radii, int radii_is_float,
-                const BinParams& p, void* workspace, size_t workspace_bytes, int32_t* sorted_ids,
-                int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream);
+                 const BinParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream, bool have_prep,
+                 bool compact);
+int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* workspace, size_t workspace_bytes,
+                int32_t* sorted_ids, int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream, bool compact);
 int project_fwd_launch(int64_t N, const float* means3d, const float* log_scales, const float* quats,
                        const float* opacities, const bsplat_camera& cam, float eps2d, int semantics,
                        float* means2d, float* conics, float* depths, int32_t* radii, cudaStream_t stream,
-                       const bsplat_camera* cam_dev = nullptr);
+                       const bsplat_camera* cam_dev, const ProjExtra* extra, bool allow_fma);
 int rasterize_launch(int64_t N, int channels, const float* means2d, const float* conics, const float* colors,
                      const float* opacities, const float* background_dev, const int32_t* tile_ranges,
                      const int32_t* tile_order, const int32_t* sorted_ids, int W, int H, int tile_size,
                      int row_begin, int row_end, int mode, float* image, unsigned long long* stats,
                      const unsigned long long* m_dev, void* rec_ws, cudaStream_t stream,
                      const PeerImages* peers = nullptr, const int32_t* rec_list = nullptr,
-                     const unsigned long long* rec_list_n = nullptr);
+                     const unsigned long long* rec_list_n = nullptr, bool rec_ready = false,
+                     int32_t* surv = nullptr, uint32_t* chunk_cnt = nullptr, uint32_t* long_barrier = nullptr);
+uint32_t* bin2_spare_counter(void* workspace, int64_t N, int64_t M, int64_t n_tiles);
 void bin2_band_list(void* workspace, int64_t N, const int32_t** perm, const unsigned long long** n_band);
 size_t raster_workspace_bytes(int64_t N);
+size_t raster_long_surv_bytes(int64_t M_cap);
+size_t raster_long_cnt_bytes(int64_t M_cap, int64_t n_tiles);
 int tile_order_launch(int first_tile, int n_tiles, const int32_t* tile_ranges, int32_t* order,
                       cudaStream_t stream);
 }  // namespace bsplat
@@ -138,7 +144,9 @@ struct RenderWs {
     float* means2d; float* conics; float* depths; int32_t* radii;
     int32_t* tile_ranges; int32_t* tile_order; int32_t* sorted_ids;
     bsplat_camera* cam_dev;  // indirect camera of captured frames
-    void* raster_rec;        // 48 B per Gaussian: raster records (raster_prep_kernel)
+    void* raster_rec;        // 80 B per Gaussian: raster records (projection epilogue / raster_pair_prep_kernel)
+    int32_t* long_surv;      // [M] survivor ids of the long-list pre-pass
+    uint32_t* long_cnt;      // per-chunk survivor counts of the long-list pre-pass
     void* bin_ws; size_t bin_bytes;
     size_t total;
 };
@@ -162,8 +170,64 @@ RenderWs carve_render(void* base, int64_t N, int64_t M, int W, int H, int tile_s
     w.bin_bytes = single_level ? carve_bin1(nullptr, N, M).total : bin2_workspace_bytes(N, M, (int64_t)tiles_w * tiles_h);
     w.bin_ws = take(w.bin_bytes);
     w.sorted_ids = (int32_t*)take(m * sizeof(int32_t));
+    w.long_surv = (int32_t*)take(raster_long_surv_bytes(M));
+    w.long_cnt = (uint32_t*)take(raster_long_cnt_bytes(M, (int64_t)tiles_w * tiles_h));
     w.total = off;
     return w;
+}
+
+inline bool fast_raster_for(int raster_mode, int tile_size, int channels) {
+    return (raster_mode == BSPLAT_RASTER_FAST || raster_mode == BSPLAT_RASTER_FAST_NOCULL) && tile_size == 16 &&
+           channels == 3;
+}
+
+// CUDA events of the per-stage timing; destroyed on every exit path
+struct StageEvents {
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool on = false;
+    int create() {
+        on = true;
+        for (auto& e : ev) BSPLAT_CUDA_TRY(cudaEventCreate(&e));
+        return BSPLAT_OK;
+    }
+    int record(int k, cudaStream_t s) {
+        if (on) BSPLAT_CUDA_TRY(cudaEventRecord(ev[k], s));
+        return BSPLAT_OK;
+    }
+    ~StageEvents() {
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+};
+
+// Front half of a two-level frame: control words zeroed, projection with the fused epilogue (tile rectangles, depth
+// keys + histograms, raster records), [compaction,] depth sort, count + scan.  write_stage_outputs: also store the
+// reference's four projection outputs (needed by the faithful rasterizer, the aux outputs and nobody else).
+int frame_front(int64_t N, const float* means3d, const float* log_scales, const float* quats, const float* opacities,
+                const float* colors, const bsplat_camera& cam, const bsplat_camera* cam_dev, int tile_size,
+                int semantics, int flags, int row0, int row1, bool want_rec, float* o_means2d, float* o_conics,
+                float* o_depths, int32_t* o_radii, const RenderWs& w, cudaStream_t stream,
+                cudaEvent_t ev_after_projection = nullptr) {
+    const int W = cam.width, H = cam.height;
+    BinParams p;
+    int rc = make_bin_params(W, H, tile_size, row0, row1, semantics, &p);
+    if (rc != BSPLAT_OK) return rc;
+    const bool compact = (flags & BSPLAT_FLAG_PACKED) != 0 || p.row_begin > 0 || p.row_end < p.tiles_h;
+    rc = bin2_begin(N, w.bin_ws, w.bin_bytes, stream);
+    if (rc != BSPLAT_OK) return rc;
+    ProjExtra ex;
+    bin2_prep_targets(w.bin_ws, N, compact, &ex.rects, &ex.dkeys, &ex.hist);
+    ex.rec = want_rec ? w.raster_rec : nullptr;
+    ex.colors = colors;
+    ex.opac = opacities;
+    ex.tile_size = tile_size;
+    ex.rec_row_begin = p.row_begin;
+    ex.rec_row_end = p.row_end;
+    rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, cam, 0.3f, semantics, o_means2d, o_conics,
+                            o_depths, o_radii, stream, cam_dev, &ex, (flags & BSPLAT_FLAG_PROJ_FMA) != 0);
+    if (rc != BSPLAT_OK) return rc;
+    if (ev_after_projection) BSPLAT_CUDA_TRY(cudaEventRecord(ev_after_projection, stream));
+    return bin2_prepare(N, nullptr, nullptr, 0, nullptr, p, w.bin_ws, w.bin_bytes, stream, /*have_prep=*/true, compact);
 }
 
 }  // namespace
@@ -186,6 +250,7 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     if (!cam || !image || !background || N < 0 || channels <= 0 || tile_size <= 0 || tile_size > 32)
         return BSPLAT_E_ARG;
     if (N > 0 && (!means3d || !log_scales || !quats || !opacities || !colors)) return BSPLAT_E_ARG;
+    if (semantics != BSPLAT_SEM_TORCH && semantics != BSPLAT_SEM_GSPLAT) return BSPLAT_E_ARG;
     const int W = cam->width, H = cam->height;
     if (W <= 0 || H <= 0) return BSPLAT_E_ARG;
     const int raster_mode = flags & 0xff;
@@ -203,54 +268,60 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
         BSPLAT_CUDA_TRY(cudaMemsetAsync(image, 0, image_bytes, stream));
         return BSPLAT_OK;
     }
-    const bool timing = aux && aux->timing;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    auto drop_events = [&]() { if (timing) for (auto& e : ev) if (e) cudaEventDestroy(e); };
-    if (timing) {
-        for (auto& e : ev) BSPLAT_CUDA_TRY(cudaEventCreate(&e));
-        BSPLAT_CUDA_TRY(cudaEventRecord(ev[0], stream));
+    StageEvents te;
+    if (aux && aux->timing) {
+        int rc0 = te.create();
+        if (rc0 != BSPLAT_OK) return rc0;
     }
+    int rc = te.record(0, stream);
+    if (rc != BSPLAT_OK) return rc;
+    const bool fast_raster = fast_raster_for(raster_mode, tile_size, channels);
+    const bool want_aux = aux && (aux->means2d || aux->conics || aux->depths || aux->radii);
+    // the reference's four projection outputs are only stored when somebody reads them
+    const bool stage_outputs = single_level || !fast_raster || want_aux;
     float* d_means2d = (aux && aux->means2d) ? aux->means2d : w.means2d;
     float* d_conics = (aux && aux->conics) ? aux->conics : w.conics;
     float* d_depths = (aux && aux->depths) ? aux->depths : w.depths;
     int32_t* d_radii = (aux && aux->radii) ? aux->radii : w.radii;
     int32_t* d_ranges = (aux && aux->tile_ranges) ? aux->tile_ranges : w.tile_ranges;
 
-    int rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, *cam, 0.3f, semantics, d_means2d,
-                                d_conics, d_depths, d_radii, stream);
-    if (rc != BSPLAT_OK) { drop_events(); return rc; }
-    if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[1], stream));
-
     const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
     bsplat_bin_info* d_info;
     Bin1Ws b1 = carve_bin1(w.bin_ws, N, 0);
+    bool rec_ready = false;
     if (single_level) {
+        rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, *cam, 0.3f, semantics, d_means2d, d_conics,
+                                d_depths, d_radii, stream, nullptr, nullptr, (flags & BSPLAT_FLAG_PROJ_FMA) != 0);
+        if (rc != BSPLAT_OK) return rc;
+        rc = te.record(1, stream);
+        if (rc != BSPLAT_OK) return rc;
         rc = bsplat_bin_count_scan(N, d_means2d, d_radii, 0, d_depths, W, H, tile_size, 0, tiles_h, semantics,
                                    b1.offsets, b1.info, b1.scan_ws, b1.scan_bytes, stream);
         d_info = b1.info;
     } else {
         d_info = bin2_info_ptr(w.bin_ws, N);
-        rc = bsplat_bin2_prepare(N, d_means2d, d_radii, 0, d_depths, W, H, tile_size, 0, tiles_h, semantics,
-                                 w.bin_ws, w.bin_bytes, d_info, stream);
+        rec_ready = fast_raster;
+        rc = frame_front(N, means3d, log_scales, quats, opacities, colors, *cam, nullptr, tile_size, semantics, flags,
+                         0, tiles_h, fast_raster, stage_outputs ? d_means2d : nullptr,
+                         stage_outputs ? d_conics : nullptr, stage_outputs ? d_depths : nullptr,
+                         stage_outputs ? d_radii : nullptr, w, stream, te.on ? te.ev[1] : nullptr);
     }
-    if (rc != BSPLAT_OK) { drop_events(); return rc; }
+    if (rc != BSPLAT_OK) return rc;
     bsplat_bin_info info;
     BSPLAT_CUDA_TRY(cudaMemcpyAsync(&info, d_info, sizeof(info), cudaMemcpyDeviceToHost, stream));
     BSPLAT_CUDA_TRY(cudaStreamSynchronize(stream));  // the single read-back of the frame (M, key range)
     const int64_t M = (int64_t)info.n_isect;
-    if (aux) { aux->n_isect = M; aux->n_launches = single_level ? 3 : 7; }
-    if (M >= (1ll << 30)) { drop_events(); return BSPLAT_E_OVERFLOW; }
+    if (aux) { aux->n_isect = M; aux->n_launches = single_level ? 3 : 6; }
+    if (M >= (1ll << 30)) return BSPLAT_E_OVERFLOW;
     if (M == 0) {
         // render.py:73-76: no overlaps => black image (not the background)
         BSPLAT_CUDA_TRY(cudaMemsetAsync(image, 0, image_bytes, stream));
         BSPLAT_CUDA_TRY(cudaMemsetAsync(d_ranges, 0, (size_t)tiles_w * tiles_h * 2 * sizeof(int32_t), stream));
-        drop_events();
         return BSPLAT_OK;
     }
     w = carve_render(workspace, N, M, W, H, tile_size, single_level);
     if (workspace_bytes < w.total) {
         if (needed_bytes) *needed_bytes = bsplat_render_workspace_bytes(N, M + M / 4, W, H, tile_size);
-        drop_events();
         return BSPLAT_E_WORKSPACE;
     }
     const int32_t* sorted_ids = nullptr;
@@ -260,57 +331,68 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
         const bsplat_key_layout layout = bsplat_make_key_layout(&info, W, H, tile_size);
         rc = bsplat_bin_emit(N, d_means2d, d_radii, 0, d_depths, W, H, tile_size, 0, tiles_h, semantics,
                              b1.offsets, layout, b1.keys, b1.ids, stream);
-        if (rc != BSPLAT_OK) { drop_events(); return rc; }
-        if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[2], stream));
+        if (rc != BSPLAT_OK) return rc;
+        rc = te.record(2, stream);
+        if (rc != BSPLAT_OK) return rc;
         int in_alt = 0;
         rc = bsplat_radix_sort_pairs(M, b1.keys, b1.keys_alt, b1.ids, b1.ids_alt, 0,
                                      layout.depth_bits + layout.tile_bits, b1.sort_ws, b1.sort_bytes, &in_alt, stream);
-        if (rc != BSPLAT_OK) { drop_events(); return rc; }
+        if (rc != BSPLAT_OK) return rc;
         sorted_ids = in_alt ? b1.ids_alt : b1.ids;
         rc = bsplat_tile_ranges(M, in_alt ? b1.keys_alt : b1.keys, layout.depth_bits, tiles_w * tiles_h, d_ranges,
                                 stream);
-        if (rc != BSPLAT_OK) { drop_events(); return rc; }
+        if (rc != BSPLAT_OK) return rc;
         if (aux) {
             aux->key_bits = layout.depth_bits + layout.tile_bits;
             aux->sort_passes = (aux->key_bits + 7) / 8;
             aux->n_launches = 3 + 1 + 2 + aux->sort_passes + 1 + 1;
         }
     } else {
-        if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[2], stream));
-        rc = bsplat_bin2_finish(N, M, d_means2d, d_radii, 0, W, H, tile_size, 0, tiles_h, semantics, w.bin_ws,
-                                w.bin_bytes, w.sorted_ids, d_ranges, w.tile_order, stream);
-        if (rc != BSPLAT_OK) { drop_events(); return rc; }
+        // stage_ms: [0] projection (+ epilogue), [1] depth sort + count/scan (+ the M read-back), [2] emit + tile sort +
+        // ranges, [3] rasterizer (+ long-list pre-pass)
+        rc = te.record(2, stream);
+        if (rc != BSPLAT_OK) return rc;
+        BinParams p;
+        rc = make_bin_params(W, H, tile_size, 0, tiles_h, semantics, &p);
+        if (rc != BSPLAT_OK) return rc;
+        rc = bin2_finish(N, M, false, p, w.bin_ws, w.bin_bytes, w.sorted_ids, d_ranges, w.tile_order, stream,
+                         (flags & BSPLAT_FLAG_PACKED) != 0);
+        if (rc != BSPLAT_OK) return rc;
         sorted_ids = w.sorted_ids;
         have_order = true;
         if (aux) {
             int tb = 1;
             while ((1 << tb) < tiles_w * tiles_h) ++tb;
+            const int tile_passes = (tb + 7) / 8;
             aux->key_bits = 32 + tb;
-            aux->sort_passes = 4 + (tb > 8 ? 2 : 1);  // 4 over N items, the rest over M items
-            // project, depth hist, 4 passes, count_scan | emit, 1-2 passes, tile_finish, raster
-            aux->n_launches = 7 + 1 + (tb > 8 ? 2 : 1) + 1 + 1;
+            aux->sort_passes = 4 + tile_passes;  // 4 over N items, the rest over M items
+            // project (+ epilogue), [compact,] 4 passes, count_scan | emit, tile passes, tile_finish
+            aux->n_launches = 1 + ((flags & BSPLAT_FLAG_PACKED) ? 1 : 0) + 4 + 1 + 1 + tile_passes + 1;
         }
     }
-    const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
-    if (aux && fast_raster && raster_mode != BSPLAT_RASTER_SINGLE) aux->n_launches += 1;  // raster record prep kernel
     if (fast_raster && !have_order) {
         rc = tile_order_launch(0, tiles_w * tiles_h, d_ranges, w.tile_order, stream);
-        if (rc != BSPLAT_OK) { drop_events(); return rc; }
+        if (rc != BSPLAT_OK) return rc;
         if (aux) aux->n_launches += 1;
     }
-    if (timing) BSPLAT_CUDA_TRY(cudaEventRecord(ev[3], stream));
+    if (aux && fast_raster) aux->n_launches += rec_ready ? 1 : 2;  // [record kernel,] long-list pre-pass
+    if (aux) aux->n_launches += 1;                                   // rasterizer
+    rc = te.record(3, stream);
+    if (rc != BSPLAT_OK) return rc;
     rc = rasterize_launch(N, channels, d_means2d, d_conics, colors, opacities, background, d_ranges,
                           fast_raster ? w.tile_order : nullptr, sorted_ids, W, H, tile_size, 0, tiles_h, raster_mode,
-                          image, nullptr, nullptr, w.raster_rec, stream);
-    if (rc != BSPLAT_OK) { drop_events(); return rc; }
+                          image, nullptr, nullptr, w.raster_rec, stream, nullptr, nullptr, nullptr, rec_ready,
+                          w.long_surv, w.long_cnt,
+                          single_level ? nullptr : bin2_spare_counter(w.bin_ws, N, M, (int64_t)tiles_w * tiles_h));
+    if (rc != BSPLAT_OK) return rc;
     if (aux && aux->sorted_ids && aux->sorted_ids_capacity >= M)
         BSPLAT_CUDA_TRY(cudaMemcpyAsync(aux->sorted_ids, sorted_ids, (size_t)M * sizeof(int32_t),
                                         cudaMemcpyDeviceToDevice, stream));
-    if (timing) {
-        BSPLAT_CUDA_TRY(cudaEventRecord(ev[4], stream));
-        BSPLAT_CUDA_TRY(cudaEventSynchronize(ev[4]));
-        for (int s = 0; s < 4; ++s) cudaEventElapsedTime(&aux->stage_ms[s], ev[s], ev[s + 1]);
-        drop_events();
+    if (te.on) {
+        rc = te.record(4, stream);
+        if (rc != BSPLAT_OK) return rc;
+        BSPLAT_CUDA_TRY(cudaEventSynchronize(te.ev[4]));
+        for (int s = 0; s < 4; ++s) cudaEventElapsedTime(&aux->stage_ms[s], te.ev[s], te.ev[s + 1]);
     }
     return BSPLAT_OK;
 }
@@ -318,7 +400,7 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
 // ------------------------------------------------------------------------------------------
 // split-phase frame: begin = project + depth sort + count/scan (N-scale, latency-bound) and an async
 // copy of M into pinned host memory; end = emit + tile sort + ranges + order + raster (M-scale).
-// A two-stream pipeline overlaps begin(k+1) with end(k) (mojosplat_b200/parallel.py).
+// A two-stream pipeline overlaps begin(k+1) with end(k) (mojosplat_b200/pipeline.py).
 // ------------------------------------------------------------------------------------------
 extern "C" int bsplat_render_begin(int64_t N, const float* means3d, const float* log_scales, const float* quats,
                                    const float* opacities, const bsplat_camera* cam, int32_t tile_size,
@@ -327,18 +409,17 @@ extern "C" int bsplat_render_begin(int64_t N, const float* means3d, const float*
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!cam || !info_host_pinned || N <= 0 || tile_size <= 0 || tile_size > 32) return BSPLAT_E_ARG;
     if (!means3d || !log_scales || !quats) return BSPLAT_E_ARG;
+    if (semantics != BSPLAT_SEM_TORCH && semantics != BSPLAT_SEM_GSPLAT) return BSPLAT_E_ARG;
     const int W = cam->width, H = cam->height;
     if (W <= 0 || H <= 0) return BSPLAT_E_ARG;
     RenderWs w = carve_render(workspace, N, 0, W, H, tile_size, false);
     if (!workspace || workspace_bytes < w.total) return BSPLAT_E_WORKSPACE;
-    int rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, *cam, 0.3f, semantics, w.means2d, w.conics,
-                                w.depths, w.radii, stream);
-    if (rc != BSPLAT_OK) return rc;
     const int tiles_h = (H + tile_size - 1) / tile_size;
-    bsplat_bin_info* d_info = bin2_info_ptr(w.bin_ws, N);
-    rc = bsplat_bin2_prepare(N, w.means2d, w.radii, 0, w.depths, W, H, tile_size, 0, tiles_h, semantics, w.bin_ws,
-                             w.bin_bytes, d_info, stream);
+    // (colours arrive with bsplat_render_end: the raster records are built there, from the stage outputs kept here)
+    int rc = frame_front(N, means3d, log_scales, quats, opacities, nullptr, *cam, nullptr, tile_size, semantics, 0, 0,
+                         tiles_h, false, w.means2d, w.conics, w.depths, w.radii, w, stream);
     if (rc != BSPLAT_OK) return rc;
+    bsplat_bin_info* d_info = bin2_info_ptr(w.bin_ws, N);
     BSPLAT_CUDA_TRY(cudaMemcpyAsync(info_host_pinned, d_info, sizeof(bsplat_bin_info), cudaMemcpyDeviceToHost, stream));
     return BSPLAT_OK;
 }
@@ -349,11 +430,14 @@ extern "C" int bsplat_render_end(int64_t N, int64_t M, const float* colors, cons
                                  size_t workspace_bytes, size_t* needed_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!cam || !image || !background || N <= 0 || M < 0 || channels <= 0) return BSPLAT_E_ARG;
+    if (tile_size <= 0 || tile_size > 32) return BSPLAT_E_ARG;
     if (!colors || !opacities) return BSPLAT_E_ARG;
+    if (semantics != BSPLAT_SEM_TORCH && semantics != BSPLAT_SEM_GSPLAT) return BSPLAT_E_ARG;
     if (M >= (1ll << 30)) return BSPLAT_E_OVERFLOW;
     const int W = cam->width, H = cam->height;
+    if (W <= 0 || H <= 0) return BSPLAT_E_ARG;
     const int raster_mode = flags & 0xff;
-    const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
+    const int tiles_h = (H + tile_size - 1) / tile_size;
     if (M == 0) {
         BSPLAT_CUDA_TRY(cudaMemsetAsync(image, 0, (size_t)W * H * channels * sizeof(float), stream));
         return BSPLAT_OK;
@@ -363,13 +447,17 @@ extern "C" int bsplat_render_end(int64_t N, int64_t M, const float* colors, cons
         if (needed_bytes) *needed_bytes = w.total;
         return BSPLAT_E_WORKSPACE;
     }
-    int rc = bsplat_bin2_finish(N, M, w.means2d, w.radii, 0, W, H, tile_size, 0, tiles_h, semantics, w.bin_ws,
-                                w.bin_bytes, w.sorted_ids, w.tile_ranges, w.tile_order, stream);
+    BinParams p;
+    int rc = make_bin_params(W, H, tile_size, 0, tiles_h, semantics, &p);
     if (rc != BSPLAT_OK) return rc;
-    const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
+    rc = bin2_finish(N, M, false, p, w.bin_ws, w.bin_bytes, w.sorted_ids, w.tile_ranges, w.tile_order, stream, false);
+    if (rc != BSPLAT_OK) return rc;
+    const bool fast_raster = fast_raster_for(raster_mode, tile_size, channels);
     return rasterize_launch(N, channels, w.means2d, w.conics, colors, opacities, background, w.tile_ranges,
                             fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, 0, tiles_h,
-                            raster_mode, image, nullptr, nullptr, w.raster_rec, stream);
+                            raster_mode, image, nullptr, nullptr, w.raster_rec, stream, nullptr, nullptr, nullptr,
+                            /*rec_ready=*/false, w.long_surv, w.long_cnt,
+                            bin2_spare_counter(w.bin_ws, N, M, (int64_t)p.tiles_w * p.tiles_h));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -436,6 +524,7 @@ extern "C" int bsplat_render_enqueue_band_p2p(int64_t N, const float* means3d, c
         tile_size > 32)
         return BSPLAT_E_ARG;
     if (!means3d || !log_scales || !quats || !opacities || !colors) return BSPLAT_E_ARG;
+    if (semantics != BSPLAT_SEM_TORCH && semantics != BSPLAT_SEM_GSPLAT) return BSPLAT_E_ARG;
     if (M_capacity >= (1ll << 30)) return BSPLAT_E_OVERFLOW;
     if (sr != sb && !event_bin_done) return BSPLAT_E_ARG;
     const int W = cam->width, H = cam->height;
@@ -446,48 +535,60 @@ extern "C" int bsplat_render_enqueue_band_p2p(int64_t N, const float* means3d, c
         if (needed_bytes) *needed_bytes = w.total;
         return BSPLAT_E_WORKSPACE;
     }
+    const int tiles_h = (H + tile_size - 1) / tile_size;
+    const int row0 = tile_row_begin < 0 ? 0 : tile_row_begin;
+    const int row1 = tile_row_end > tiles_h ? tiles_h : tile_row_end;
+    bsplat_bin_info* d_info = bin2_info_ptr(w.bin_ws, N);
+    if (row1 <= row0) {
+        // empty band: nothing to write, but the caller's status protocol still holds -- a zeroed info and the event
+        BSPLAT_CUDA_TRY(cudaMemsetAsync(d_info, 0, sizeof(bsplat_bin_info), sb));
+        if (info_host_pinned)
+            BSPLAT_CUDA_TRY(cudaMemcpyAsync(info_host_pinned, d_info, sizeof(bsplat_bin_info), cudaMemcpyDeviceToHost, sb));
+        if (sr != sb) {
+            BSPLAT_CUDA_TRY(cudaEventRecord((cudaEvent_t)event_bin_done, sb));
+            BSPLAT_CUDA_TRY(cudaStreamWaitEvent(sr, (cudaEvent_t)event_bin_done, 0));
+        }
+        return BSPLAT_OK;
+    }
     const bsplat_camera* cam_dev = nullptr;
     if (flags & BSPLAT_FLAG_CAMERA_INDIRECT) {
         // `cam` is pinned host (or managed) memory: copied when the stream gets here, i.e. at every replay
         BSPLAT_CUDA_TRY(cudaMemcpyAsync(w.cam_dev, cam, sizeof(bsplat_camera), cudaMemcpyDefault, sb));
         cam_dev = w.cam_dev;
     }
-    int rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, *cam, 0.3f, semantics, w.means2d, w.conics,
-                                w.depths, w.radii, sb, cam_dev);
+    const bool fast_raster = fast_raster_for(raster_mode, tile_size, channels);
+    // the faithful rasterizer reads the stage outputs; the fast one only needs the records of the projection epilogue
+    int rc = frame_front(N, means3d, log_scales, quats, opacities, colors, *cam, cam_dev, tile_size, semantics, flags,
+                         row0, row1, fast_raster, fast_raster ? nullptr : w.means2d, fast_raster ? nullptr : w.conics,
+                         fast_raster ? nullptr : w.depths, fast_raster ? nullptr : w.radii, w, sb);
     if (rc != BSPLAT_OK) return rc;
-    const int tiles_h = (H + tile_size - 1) / tile_size;
-    const int row0 = tile_row_begin < 0 ? 0 : tile_row_begin;
-    const int row1 = tile_row_end > tiles_h ? tiles_h : tile_row_end;
-    if (row1 <= row0) return BSPLAT_OK;  // empty band: nothing to write
     BinParams p;
     rc = make_bin_params(W, H, tile_size, row0, row1, semantics, &p);
     if (rc != BSPLAT_OK) return rc;
-    rc = bin2_prepare(N, w.means2d, w.radii, 0, w.depths, p, w.bin_ws, w.bin_bytes, sb);
+    rc = bin2_finish(N, M_capacity, /*device_m=*/true, p, w.bin_ws, w.bin_bytes, w.sorted_ids, w.tile_ranges,
+                     w.tile_order, sb, (flags & BSPLAT_FLAG_PACKED) != 0);
     if (rc != BSPLAT_OK) return rc;
-    rc = bin2_finish(N, M_capacity, /*device_m=*/true, w.means2d, w.radii, 0, p, w.bin_ws, w.bin_bytes, w.sorted_ids,
-                     w.tile_ranges, w.tile_order, sb);
-    if (rc != BSPLAT_OK) return rc;
-    bsplat_bin_info* d_info = bin2_info_ptr(w.bin_ws, N);
     if (info_host_pinned)
         BSPLAT_CUDA_TRY(cudaMemcpyAsync(info_host_pinned, d_info, sizeof(bsplat_bin_info), cudaMemcpyDeviceToHost, sb));
     if (sr != sb) {
         BSPLAT_CUDA_TRY(cudaEventRecord((cudaEvent_t)event_bin_done, sb));
         BSPLAT_CUDA_TRY(cudaStreamWaitEvent(sr, (cudaEvent_t)event_bin_done, 0));
     }
-    const bool fast_raster = (raster_mode != BSPLAT_RASTER_FAITHFUL) && tile_size == 16 && channels == 3;
-    // a band that is not the whole image: raster records only for the band's Gaussians (the depth-sorted list of
-    // the band-compacted binning)
+    // "no intersections at all => all-zero image" (render.py:73-76) is a whole-frame rule: a partial band decides it
+    // from the number of Gaussians that own a tile anywhere in the frame (counted by the compaction pass)
     const bool band_partial = row0 > 0 || row1 < tiles_h;
-    const int32_t* band_list = nullptr;
-    const unsigned long long* band_n = nullptr;
-    // (gathering by the depth-ordered list is scattered: it only pays when the band is a small part of the frame)
-    if (band_partial && 3 * (row1 - row0) <= tiles_h) bin2_band_list(w.bin_ws, N, &band_list, &band_n);
+    const unsigned long long* m_dev = reinterpret_cast<const unsigned long long*>(d_info);
+    if (band_partial) {
+        const int32_t* perm;
+        const unsigned long long* n_band;
+        bin2_band_list(w.bin_ws, N, &perm, &n_band);
+        m_dev = n_band + 1;
+    }
     return rasterize_launch(N, channels, w.means2d, w.conics, colors, opacities, background, w.tile_ranges,
                             fast_raster ? w.tile_order : nullptr, w.sorted_ids, W, H, tile_size, row0, row1,
-                            raster_mode, image, nullptr,
-                            // "no intersections at all => zero image" is a whole-frame rule: a band cannot decide it
-                            band_partial ? nullptr : reinterpret_cast<const unsigned long long*>(d_info),
-                            w.raster_rec, sr, &peers, band_list, band_n);
+                            raster_mode, image, nullptr, m_dev, w.raster_rec, sr, &peers, nullptr, nullptr,
+                            /*rec_ready=*/fast_raster, w.long_surv, w.long_cnt,
+                            bin2_spare_counter(w.bin_ws, N, M_capacity, (int64_t)p.tiles_w * p.tiles_h));
 }
 
 extern "C" size_t bsplat_render_host_scratch_bytes(int64_t N, int32_t channels, int32_t width, int32_t height) {
@@ -512,11 +613,10 @@ extern "C" int bsplat_render_fwd_host(int64_t N, const float* means3d, const flo
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!cam || !image_host || !background || N < 0 || channels <= 0) return BSPLAT_E_ARG;
     const int W = cam->width, H = cam->height;
-    const size_t need = bsplat_render_host_scratch_bytes(N, channels, W, H);
-    if (!device_scratch || scratch_bytes < need) {
-        if (needed_bytes) *needed_bytes = need;
-        return BSPLAT_E_WORKSPACE;
-    }
+    if (W <= 0 || H <= 0) return BSPLAT_E_ARG;
+    // the scratch size is a pure function of the arguments (bsplat_render_host_scratch_bytes): a short buffer is a
+    // caller error; *needed_bytes / BSPLAT_E_WORKSPACE always refer to the render workspace
+    if (!device_scratch || scratch_bytes < bsplat_render_host_scratch_bytes(N, channels, W, H)) return BSPLAT_E_ARG;
     const size_t n = (size_t)(N > 0 ? N : 1);
     char* p = static_cast<char*>(device_scratch);
     size_t off = 0;

@@ -32,6 +32,19 @@ struct PeerImages {
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Optional epilogue products of the projection kernel inside a fused frame (any pointer may be null):
+// what the binning stage and the rasterizer would otherwise compute in passes of their own.
+struct ProjExtra {
+    uint2* rects;         // [N] full-frame tile rectangle: x0 | y0 << 16, w | h << 16 (rules of `semantics`)
+    uint32_t* dkeys;      // [N] monotone depth keys
+    uint32_t* hist;       // [4][256] digit histograms of the depth keys (caller-zeroed)
+    void* rec;            // [N][5] float4 raster records (needs colors and opac)
+    const float* colors;  // [N,3]
+    const float* opac;    // [N] raw opacities
+    int tile_size;
+    int rec_row_begin, rec_row_end;  // (with rects) records only for Gaussians with a tile in these rows; 0, 0 = all
+};
+
 // Monotone float -> uint32 map: ascending float order, -0.0 == +0.0, NaN last.
 // Canonical depth order of the binning stage (reference: torch.argsort of float depths,
 // binning.py:223).
@@ -101,6 +114,52 @@ __device__ inline TileRect tile_rect(float mx, float my, float rx, float ry, int
     if (r.y1 < r.y0) r.y1 = r.y0;
     if (r.x1 < r.x0) r.x1 = r.x0;
     return r;
+}
+
+// Full-frame tile rectangle; inv_tile_size != 0 (power-of-two tile sizes only): x * (1 / tile_size) is then
+// exactly x / tile_size, and the four IEEE divisions become multiplications.
+__device__ inline TileRect tile_rect_inv(float mx, float my, float rx, float ry, int W, int H, float tile_size_f,
+                                         float inv_tile_size, int tiles_w, int tiles_h, int semantics) {
+    if (inv_tile_size == 0.0f)
+        return tile_rect(mx, my, rx, ry, W, H, tile_size_f, tiles_w, tiles_h, semantics, 0, tiles_h);
+    TileRect r;
+    if (semantics == BSPLAT_SEM_TORCH) {
+        const float ax = clamp_torch(mx - rx, 0.0f, (float)(W - 1));
+        const float bx = clamp_torch(mx + rx, 0.0f, (float)(W - 1));
+        const float ay = clamp_torch(my - ry, 0.0f, (float)(H - 1));
+        const float by = clamp_torch(my + ry, 0.0f, (float)(H - 1));
+        r.x0 = clampi(__float2int_rz(__fmul_rn(ax, inv_tile_size)), 0, tiles_w - 1);
+        r.x1 = clampi(__float2int_rz(__fmul_rn(bx, inv_tile_size)), 0, tiles_w - 1) + 1;
+        r.y0 = clampi(__float2int_rz(__fmul_rn(ay, inv_tile_size)), 0, tiles_h - 1);
+        r.y1 = clampi(__float2int_rz(__fmul_rn(by, inv_tile_size)), 0, tiles_h - 1) + 1;
+    } else {
+        if (!(rx > 0.0f) || !(ry > 0.0f)) {
+            r.x0 = r.x1 = r.y0 = r.y1 = 0;
+            return r;
+        }
+        const float fx0 = floorf(__fmul_rn(mx - rx, inv_tile_size));
+        const float fx1 = ceilf(__fmul_rn(mx + rx, inv_tile_size));
+        const float fy0 = floorf(__fmul_rn(my - ry, inv_tile_size));
+        const float fy1 = ceilf(__fmul_rn(my + ry, inv_tile_size));
+        r.x0 = (int)fminf(fmaxf(fx0, 0.0f), (float)tiles_w);
+        r.x1 = (int)fminf(fmaxf(fx1, 0.0f), (float)tiles_w);
+        r.y0 = (int)fminf(fmaxf(fy0, 0.0f), (float)tiles_h);
+        r.y1 = (int)fminf(fmaxf(fy1, 0.0f), (float)tiles_h);
+    }
+    if (r.y1 < r.y0) r.y1 = r.y0;
+    if (r.x1 < r.x0) r.x1 = r.x0;
+    return r;
+}
+
+// Packed tile rectangle (x0 | y0 << 16, w | h << 16) clipped to the tile rows [row_begin, row_end).
+__device__ inline uint2 clip_rect_rows(const uint2 rc, const int row_begin, const int row_end) {
+    int y0 = (int)(rc.x >> 16), h = (int)(rc.y >> 16);
+    const int w = (int)(rc.y & 0xffffu);
+    int y1 = y0 + h;
+    y0 = y0 < row_begin ? row_begin : y0;
+    y1 = y1 > row_end ? row_end : y1;
+    h = y1 > y0 ? y1 - y0 : 0;
+    return make_uint2((rc.x & 0xffffu) | ((uint32_t)y0 << 16), (uint32_t)(h > 0 ? w : 0) | ((uint32_t)h << 16));
 }
 
 __device__ inline uint32_t lane_id() { return threadIdx.x & 31u; }

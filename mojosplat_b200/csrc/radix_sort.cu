@@ -68,7 +68,12 @@ __global__ void __launch_bounds__(kRadix) radix_scan_kernel(uint32_t* __restrict
 // the tile's aggregate -> scatter key/payload into shared memory in tile-sorted order (registers are
 // free from here on) -> decoupled look-back, kLookback predecessors in flight per round trip ->
 // contiguous per-digit runs to global.
-template <typename KeyT, int ITEMS, int BITS>
+// LOOKBACK: predecessors fetched per look-back round trip.  When every tile of a pass is resident at once (the
+// N-scale depth passes: ~245 tiles), all tiles publish their aggregates at the same time and the last tile has to
+// walk back through ALL of them -- tiles / LOOKBACK dependent round trips of ~1 us each bound the pass, so those
+// launches use a 64-wide window (4 round trips instead of 15); the M-scale passes run in waves, find inclusive
+// prefixes a few tiles back and keep the 16-wide window.
+template <typename KeyT, int ITEMS, int BITS, int LOOKBACK = kLookback>
 __global__ void __launch_bounds__(kSortThreads, 3)
 onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const KeyT* __restrict__ keys_in,
                 KeyT* __restrict__ keys_out, const int32_t* __restrict__ vals_in,
@@ -263,13 +268,13 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
                 --j;
                 if (j < 0) break;
                 // the ones behind it are older and almost surely published: fetch a window at once
-                uint32_t v[kLookback];
+                uint32_t v[LOOKBACK];
 #pragma unroll
-                for (int w = 0; w < kLookback; ++w)
+                for (int w = 0; w < LOOKBACK; ++w)
                     v[w] = (j - w >= 0) ? ld_relaxed_u32(status + (size_t)(j - w) * kRadix + tid) : kStatPrefix;
                 int consumed = 0;
 #pragma unroll
-                for (int w = 0; w < kLookback; ++w) {
+                for (int w = 0; w < LOOKBACK; ++w) {
                     if ((v[w] & ~kStatMask) == 0) break;  // not published yet: go back to the polite wait
                     prev += v[w] & kStatMask;
                     ++consumed;
@@ -326,6 +331,13 @@ int onesweep_pass_u32(int64_t M, const uint64_t* m_dev, const uint32_t* keys_in,
                       int hist_is_scanned, uint32_t* ticket, uint32_t* status, uint32_t* key_counts,
                       cudaStream_t stream) {
     const int64_t n_tiles = sort_tiles_u32(M);
+    if (bits == 8 && n_tiles <= 3 * 148) {  // every tile resident at once (3 CTAs per SM): wide look-back window
+        onesweep_kernel<uint32_t, kSortItems32, 8, 64><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
+            M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,
+            key_counts);
+        BSPLAT_LAUNCH_CHECK();
+        return BSPLAT_OK;
+    }
     switch (bits) {
         case 8: BSPLAT_ONESWEEP32(8); break;
         case 7: BSPLAT_ONESWEEP32(7); break;

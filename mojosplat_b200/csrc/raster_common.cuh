@@ -54,4 +54,35 @@ __device__ __forceinline__ void cull_constants(const float a, const float b, con
     hx = pd ? __fdividef(-B, 2.0f * A) : 0.0f;
 }
 
+constexpr int kPairRec = 5;  // float4 per raster record
+
+// The rasterizer's record of one Gaussian (5 x float4; every operand of the packed-pair walk stored duplicated):
+//   q0 = {mx, mx, my, my}  q1 = {-A, -A, -B, -B}  q2 = {-C, -C, L, L}  q3 = {r, g, b, tau}  q4 = {hy, hx, special, Lt}
+// One definition for the in-kernel staging, the record kernel and the projection epilogue, so that every path
+// composites bit-identical values (products of two or three factors only: nothing here can be contracted).
+__device__ __forceinline__ void pair_record_from(const float mx, const float my, const float ca, const float cb,
+                                                 const float cc, const float op, const float cr, const float cg,
+                                                 const float cbl, float4& q0, float4& q1, float4& q2, float4& q3,
+                                                 float4& q4) {
+    const float A = __fmul_rn(__fmul_rn(0.5f, kLog2e), ca), B = __fmul_rn(kLog2e, cb),
+                C = __fmul_rn(__fmul_rn(0.5f, kLog2e), cc);
+    // MUFU.LG2 (abs. error ~2^-22): alpha = 2^(L - q) stays within 1e-6 of o*exp(-sigma)
+    const float L = (op > 0.0f) ? __log2f(op) : -INFINITY;
+    const bool pd = (A > 0.0f) && (C > 0.0f) && (__fsub_rn(__fmul_rn(__fmul_rn(4.0f, A), C), __fmul_rn(B, B)) > 0.0f);
+    float tau = pd ? __fsub_rn(L, kLog2AlphaThreshold) : INFINITY;
+    if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
+    q0 = make_float4(mx, mx, my, my);
+    q1 = make_float4(-A, -A, -B, -B);
+    q2 = make_float4(-C, -C, L, L);
+    q3 = make_float4(cr, cg, cbl, tau);
+    // "plain" Gaussians (positive-definite conic, opacity <= 0.99, no NaN) have q >= 0 and alpha <= opacity by
+    // construction: the walk may skip the sigma < 0 test and the 0.999 clamp (0.99, not 0.999: ex2.approx may
+    // overshoot by an ulp).  q4.w is the bound of the sigma >= 0 test of the full walk: +inf for plain Gaussians,
+    // so both walks treat them identically.  The edge minimisers hy, hx feed the conservative culling bound only:
+    // approximate division is inside its slack.
+    const bool plain = pd && (op <= 0.99f);
+    q4 = make_float4(pd ? __fdividef(-B, __fmul_rn(2.0f, C)) : 0.0f, pd ? __fdividef(-B, __fmul_rn(2.0f, A)) : 0.0f,
+                     plain ? 0.f : 1.f, plain ? INFINITY : L);
+}
+
 }  // namespace bsplat

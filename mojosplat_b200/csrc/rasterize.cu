@@ -11,14 +11,17 @@
 //   raster_faithful_kernel  any tile size <= 32 and any channel count; arithmetic in the exact
 //       operation order of the Mojo kernel (separately rounded products, expf).  Parity anchor
 //       and fallback for non-default shapes.
-//   raster_fast_kernel      16x16 tiles, RGB.  One warp owns an 8x4 pixel block; staged Gaussians
-//       carry log2-folded conics so a pixel costs 2 FADD + 2 FMUL + 3 FFMA + 1 MUFU.EX2; each warp
-//       first tests 32 staged Gaussians at once (one per lane) against its 8x4 block with an exact
-//       conservative ellipse/rectangle bound and then only walks the survivors (warp ballot),
-//       warps retire when all 32 pixels are saturated, the CTA retires on __syncthreads_count,
-//       the tile is written with 128-bit stores.  Skipping is exact: a skipped Gaussian has
+//   raster_pair_kernel      16x16 tiles, RGB: packed FP32 pairs (two pixels per lane), log2-folded
+//       conics (a pixel costs a handful of FFMA2/FADD2/FMUL2 + 1 MUFU.EX2), cp.async staging of
+//       per-Gaussian records one batch ahead, per-warp culling of 32 staged Gaussians at a time against
+//       the warp's 8x8 block with an exact conservative bound, warp / CTA early exit on saturation,
+//       128-bit image stores (also into the peers' images in the fused row-band exchange), and a
+//       multi-SM compaction pre-pass for very long lists.  Skipping is exact: a skipped Gaussian has
 //       alpha < 1/255 on every pixel of the block, so the composited result is unchanged.
 // No tensor cores: no stage of this path is a dense contraction.
+#include <stdlib.h>
+#include <string.h>
+
 #include <type_traits>
 
 #include "raster_common.cuh"
@@ -130,207 +133,33 @@ __global__ void __launch_bounds__(1024) raster_faithful_kernel(const int64_t N, 
 }
 
 // ------------------------------------------------------------------------------------------
-// fast kernel (tile 16, RGB)
-// ------------------------------------------------------------------------------------------
-constexpr int kFastTile = 16;
-constexpr int kFastThreads = 256;
-constexpr int kFastBatch = 256;
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// Staged Gaussian t (log2-folded, 48 B): s_g[3t] = {mx, my, A, B}, s_g[3t+1] = {C, L, hy, hx},
-// s_g[3t+2] = {r, g, b, tau} with A = 0.5 a log2e, B = b log2e, C = 0.5 c log2e, L = log2(opacity),
-// hy = -B/(2C), hx = -B/(2A) (edge minimisers of the quadratic), tau = L - log2(1/255)
-// (+inf: never cull, -inf: not a Gaussian).  alpha = 2^(L - (A dx^2 + B dx dy + C dy^2)).
-template <bool kCull>
-__global__ void __launch_bounds__(kFastThreads)
-raster_fast_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
-                   const float* __restrict__ colors, const float* __restrict__ opacities,
-                   const float* __restrict__ background, const int32_t* __restrict__ tile_ranges,
-                   const int32_t* __restrict__ tile_order, const int first_tile,
-                   const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
-                   float* __restrict__ image, const int vec_store,
-                   const unsigned long long* __restrict__ m_dev) {
-    __shared__ float4 s_g[kFastBatch * 3];
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    // heavy tiles first (tile_order, longest lists first) so that no long list starts at the tail
-    const int tile = tile_order ? __ldg(tile_order + blockIdx.x) : first_tile + (int)blockIdx.x;
-    const int tile_y = tile / tiles_w, tile_x = tile - tile_y * tiles_w;
-    // warp -> 8x4 pixel block inside the tile; lane -> pixel inside the block
-    const int bx = tile_x * kFastTile + (warp & 1) * 8;
-    const int by = tile_y * kFastTile + (warp >> 1) * 4;
-    const int j = bx + (lane & 7);
-    const int i = by + (lane >> 3);
-    const bool inside = (i < H) && (j < W);
-    // a finished pixel gets an infinite x: every later Gaussian then fails the alpha test by itself,
-    // and "done" is simply px == inf (no separate flag to maintain in the inner loop)
-    float px = inside ? (float)j + 0.5f : INFINITY;
-    const float py = (float)i + 0.5f;
-    // pixel-centre extent of this warp's block (clipped blocks only get more conservative)
-    const float X0 = (float)bx + 0.5f, X1 = (float)bx + 7.5f;
-    const float Y0 = (float)by + 0.5f, Y1 = (float)by + 3.5f;
-
-    const int32_t r0 = tile_ranges[2 * tile], r1 = tile_ranges[2 * tile + 1];
-    float T = 1.0f, accr = 0.0f, accg = 0.0f, accb = 0.0f;
-
-    for (int32_t b0 = r0; b0 < r1; b0 += kFastBatch) {
-        if (__syncthreads_count(!(px < INFINITY)) >= kFastThreads) break;
-        const int32_t idx = b0 + tid;
-        if (idx < r1) {
-            const int32_t g = __ldg(sorted_ids + idx);
-            float4 ga, gb, gc;
-            if (g >= 0 && (int64_t)g < N) {
-                const float2 m = __ldg(reinterpret_cast<const float2*>(means2d) + g);
-                const float ca = __ldg(conics + 3 * (int64_t)g), cb = __ldg(conics + 3 * (int64_t)g + 1),
-                            cc = __ldg(conics + 3 * (int64_t)g + 2);
-                const float op = __ldg(opacities + g);
-                const float A = 0.5f * kLog2e * ca, B = kLog2e * cb, C = 0.5f * kLog2e * cc;
-                // accurate log2 keeps alpha = 2^(L - q) within a few ulp of o*exp(-sigma)
-                const float L = (op > 0.0f) ? log2f(op) : -INFINITY;
-                const bool pd = (A > 0.0f) && (C > 0.0f) && (4.0f * A * C - B * B > 0.0f);
-                ga = make_float4(m.x, m.y, A, B);
-                gb = make_float4(C, L, pd ? -B / (2.0f * C) : 0.0f, pd ? -B / (2.0f * A) : 0.0f);
-                float tau = pd ? (L - kLog2AlphaThreshold) : INFINITY;
-                if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
-                gc = make_float4(__ldg(colors + 3 * (int64_t)g), __ldg(colors + 3 * (int64_t)g + 1),
-                                 __ldg(colors + 3 * (int64_t)g + 2), tau);
-            } else {
-                ga = make_float4(0.f, 0.f, 0.f, 0.f);
-                gb = make_float4(0.f, -INFINITY, 0.f, 0.f);
-                gc = make_float4(0.f, 0.f, 0.f, -INFINITY);
-            }
-            s_g[3 * tid] = ga; s_g[3 * tid + 1] = gb; s_g[3 * tid + 2] = gc;
-        }
-        __syncthreads();
-
-        const int bs = min(kFastBatch, (int)(r1 - b0));
-        // warp-uniform loop; a warp whose 32 pixels are all saturated just falls through
-        for (int c0 = 0; c0 < bs; c0 += 32) {
-            if (__all_sync(0xffffffffu, !(px < INFINITY))) break;
-            unsigned int mask;
-            if (kCull) {
-                bool hit = false;
-                // lane l tests Gaussian c0 + 31 - l: the earliest Gaussian is the HIGHEST ballot bit, so the
-                // walk below needs a single FLO (clz) per survivor instead of BREV + FLO
-                const int gi = c0 + 31 - lane;
-                if (gi < bs) {
-                    const float4 a = s_g[3 * gi];
-                    const float4 b = s_g[3 * gi + 1];
-                    const float tau = s_g[3 * gi + 2].w;
-                    // u = mx - x over the block, v = my - y
-                    const float u0 = a.x - X1, u1 = a.x - X0;
-                    const float v0 = a.y - Y1, v1 = a.y - Y0;
-                    const bool zu = (u0 <= 0.0f) && (u1 >= 0.0f);
-                    const bool zv = (v0 <= 0.0f) && (v1 >= 0.0f);
-                    // min of q over the block = min over the (<= 2) edges facing the mean; along the edge
-                    // u = ue the quadratic is D ue^2 + C (v - hy ue)^2 with D = A - B^2/(4C) = A + B hy / 2
-                    // (and symmetrically E = C + B hx / 2), so each edge costs a clamp and two FMAs.
-                    float qmin = 0.0f;
-                    if (!(zu && zv)) {
-                        float q1 = INFINITY, q2 = INFINITY;
-                        if (!zu) {
-                            const float ue = (u0 > 0.0f) ? u0 : u1;
-                            const float vstar = b.z * ue;
-                            const float dv = vstar - fminf(fmaxf(vstar, v0), v1);
-                            q1 = fmaf(fmaf(0.5f * a.w, b.z, a.z) * ue, ue, b.x * dv * dv);
-                        }
-                        if (!zv) {
-                            const float ve = (v0 > 0.0f) ? v0 : v1;
-                            const float ustar = b.w * ve;
-                            const float du = ustar - fminf(fmaxf(ustar, u0), u1);
-                            q2 = fmaf(fmaf(0.5f * a.w, b.w, b.x) * ve, ve, a.z * du * du);
-                        }
-                        qmin = fminf(q1, q2);
-                    }
-                    const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
-                    const float slack = 4e-6f * (a.z * um * um + b.x * vm * vm) + 1e-3f;
-                    hit = !(qmin > tau + slack);  // NaN-safe: anything odd counts as a hit
-                }
-                mask = __ballot_sync(0xffffffffu, hit);
-            } else {
-                const int rem = bs - c0;
-                mask = rem >= 32 ? 0xffffffffu : ~(0xffffffffu >> rem);  // Gaussian c0+k <-> bit 31-k
-            }
-            const float4* rec_hi = s_g + 3 * (c0 + 31);  // record of ballot bit 0; bit b is 3*b records earlier
-            while (mask) {
-                // highest set bit = next Gaussian, front to back (bfind -> a single FLO; written in PTX
-                // because nvcc rewrites 31 - clz(x) into a longer clz-based sequence)
-                unsigned int b_hi;
-                asm("bfind.u32 %0, %1;" : "=r"(b_hi) : "r"(mask));
-                mask ^= 1u << b_hi;
-                const float4* r = rec_hi - 3 * (int)b_hi;
-                const float4 a = r[0];
-                const float2 b = *reinterpret_cast<const float2*>(r + 1);
-                const float4 c = r[2];
-                const float dx = a.x - px, dy = a.y - py;
-                const float t1 = fmaf(a.w, dy, a.z * dx);
-                const float q = fmaf(b.x * dy, dy, t1 * dx);
-                const float power = b.y - q;
-                // branch-free body: selects instead of divergent paths (90 % of the walked Gaussians
-                // contribute to at least one pixel of the block, so a skip branch saves nothing)
-                const bool pass = (q >= 0.0f) && (power >= kLog2AlphaThreshold);
-                const float alpha = fminf(0.999f, ex2_approx(power));
-                const float next_T = T * (1.0f - alpha);
-                const bool live = next_T > 1e-4f;
-                const float vis = (pass && live) ? alpha * T : 0.0f;
-                accr = fmaf(c.x, vis, accr);
-                accg = fmaf(c.y, vis, accg);
-                accb = fmaf(c.z, vis, accb);
-                T = (pass && live) ? next_T : T;
-                // saturated: this Gaussian is not added (rasterization.mojo:146-150) and the pixel retires
-                px = (pass && !live) ? INFINITY : px;
-            }
-        }
-    }
-
-    // ---- write the tile: through shared memory as 128-bit rows when the layout allows ----
-    // sync-free frames: no intersections at all => all-zero image (render.py:73-76), decided on the device
-    const float bgs = (m_dev != nullptr && *m_dev == 0ull) ? 0.0f : 1.0f;
-    const float outr = fmaf(T, bgs * __ldg(background), accr), outg = fmaf(T, bgs * __ldg(background + 1), accg),
-                outb = fmaf(T, bgs * __ldg(background + 2), accb);
-    const bool full_tile = (tile_x * kFastTile + kFastTile <= W) && (tile_y * kFastTile + kFastTile <= H);
-    if (vec_store && full_tile) {
-        __syncthreads();  // staging buffers are dead from here on
-        float* s_out = reinterpret_cast<float*>(s_g);  // 16 rows x 48 floats = 3 KB
-        const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
-        s_out[(ly * kFastTile + lx) * 3 + 0] = outr;
-        s_out[(ly * kFastTile + lx) * 3 + 1] = outg;
-        s_out[(ly * kFastTile + lx) * 3 + 2] = outb;
-        __syncthreads();
-        if (tid < 16 * 12) {
-            const int row = tid / 12, c4 = tid % 12;
-            const float4 v = reinterpret_cast<const float4*>(s_out)[row * 12 + c4];
-            float* dst = image + ((int64_t)(tile_y * kFastTile + row) * W + tile_x * kFastTile) * 3;
-            reinterpret_cast<float4*>(dst)[c4] = v;
-        }
-    } else if (inside) {
-        float* dst = image + ((int64_t)i * W + j) * 3;
-        dst[0] = outr; dst[1] = outg; dst[2] = outb;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// pair kernel (tile 16, RGB): the default fast path.
+// pair kernel (tile 16, RGB): the fast path.
 // sm_100 executes packed FP32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot, two lanes of work), and the
 // rasterizer is bound by instruction issue, not by the FP32 pipe.  So each lane owns TWO pixels -- (x, y) and
 // (x, y + 4) of the warp's 8x8 block -- and the whole quadratic runs as f32x2 instructions on
 // register pairs.  Staged records keep every per-Gaussian operand duplicated {v, v}, so the pairs come
 // straight out of LDS.128 with no packing moves.  4 warps (128 threads) per 16x16 tile.
 //   record t (80 B): s[5t] = {mx, mx, my, my}  s[5t+1] = {-A, -A, -B, -B}  s[5t+2] = {-C, -C, L, L}
-//                    s[5t+3] = {r, g, b, tau}  s[5t+4] = {hy, hx, -, -}
+//                    s[5t+3] = {r, g, b, tau}  s[5t+4] = {hy, hx, special, Lt}
+//   with A = 0.5 a log2e, B = b log2e, C = 0.5 c log2e, L = log2(opacity), hy = -B/(2C), hx = -B/(2A) (edge
+//   minimisers of the quadratic), tau = L - log2(1/255) (+inf: never cull, -inf: not a Gaussian)
 //   power = L - (A dx^2 + B dx dy + C dy^2) as  fma2(fma2(-A, dx, -B dy), dx, fma2(-C dy, dy, L))
-// A finished pixel carries -x = -inf (every later power is -inf or NaN and fails the alpha test).
-// Same culling as above on the 8x8 block; a skipped Gaussian has alpha < 1/255 on all 64 pixels.
+// A finished pixel carries -x = -inf (every later power is -inf or NaN and fails the alpha test by itself -- no
+// flag in the inner loop).  Each warp first tests 32 staged Gaussians at once (one per lane) against its 8x8
+// block with an exact conservative ellipse / rectangle bound and then only walks the survivors (warp ballot);
+// a skipped Gaussian has alpha < 1/255 on all 64 pixels, so the composited result is unchanged.
+// (Three earlier variants -- one pixel per lane, independent warps with per-warp staging, an mbarrier
+// full/empty pipeline instead of the per-batch barrier -- were measured slower and removed: DESIGN.md section 9.)
 // ------------------------------------------------------------------------------------------
+constexpr int kFastTile = 16;
 constexpr int kPairThreads = 128;
 constexpr int kPairBatch = 256;
-constexpr int kPairRec = 5;  // float4 per staged Gaussian
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) {
@@ -357,44 +186,40 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     return r;
 }
 
-constexpr int kLongTile = 2048;  // lists longer than this get a tile-level pre-test (see the kernel)
+// Lists longer than kLongTile are mostly Gaussians that cannot touch the tile at all (under the torch binning rules
+// every culled Gaussian is clamped into a border tile: ~10 k entries in each corner tile at config 3, ~350 k at
+// config 5).  Walking such a list is a serial chain of thousands of batches inside ONE CTA.  Two remedies:
+//   * len > kLongTile: the four warps of the tile share ONE test of every staged Gaussian against the whole 16x16 tile
+//     (64 entries per warp instead of 256 each) before the per-warp 8x8 tests -- still one CTA, ~4x shorter chain;
+//   * len > kPrepassMin (fused frames): the tile-level test, which is embarrassingly parallel, runs as a pre-pass over
+//     all SMs (raster_long_compact_kernel) and leaves a compacted private copy of the list; the rasterizer walks only
+//     the survivors.  This is what bounds a frame once it is split across GPUs (0.35 ms chains at config 5).
+// sorted_ids / tile_ranges, the API-visible lists, are untouched.
+constexpr int kLongTile = 2048;
+constexpr int kPrepassMin = 16384;     // shorter lists: the in-kernel tile test hides behind the rest of the frame
+constexpr int kLongChunk = 4096;       // entries per pre-pass work item
+constexpr int kMaxLongChunks = 256;    // longer lists (> 1 M entries) keep the in-kernel tile test
+constexpr int kMaxLongSlots = 256;     // at most this many long tiles are compacted (the longest ones)
+constexpr int kLongThreads = 1024;     // 4 entries per thread: every gather of a chunk is in flight at once
 
 struct LoopConsts {
     unsigned int one_u;
     float one_f, mone_f;
 };
 
-// The staged record of one Gaussian (5 x float4, layout above).  One definition for the in-kernel staging and for
-// raster_pair_prep_kernel, so both paths composite bit-identical values.
 __device__ __forceinline__ void pair_record(const int64_t g, const float* __restrict__ means2d,
                                             const float* __restrict__ conics, const float* __restrict__ colors,
                                             const float* __restrict__ opacities, float4& q0, float4& q1, float4& q2,
                                             float4& q3, float4& q4) {
     const float2 m = __ldg(reinterpret_cast<const float2*>(means2d) + g);
-    const float ca = __ldg(conics + 3 * g), cb = __ldg(conics + 3 * g + 1), cc = __ldg(conics + 3 * g + 2);
-    const float op = __ldg(opacities + g);
-    const float A = 0.5f * kLog2e * ca, B = kLog2e * cb, C = 0.5f * kLog2e * cc;
-    // MUFU.LG2 (abs. error ~2^-22): alpha = 2^(L - q) stays within 1e-6 of o*exp(-sigma)
-    const float L = (op > 0.0f) ? __log2f(op) : -INFINITY;
-    const bool pd = (A > 0.0f) && (C > 0.0f) && (4.0f * A * C - B * B > 0.0f);
-    float tau = pd ? (L - kLog2AlphaThreshold) : INFINITY;
-    if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
-    q0 = make_float4(m.x, m.x, m.y, m.y);
-    q1 = make_float4(-A, -A, -B, -B);
-    q2 = make_float4(-C, -C, L, L);
-    q3 = make_float4(__ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), tau);
-    // "plain" Gaussians (positive-definite conic, opacity <= 0.99, no NaN) have q >= 0 and alpha <= opacity by
-    // construction: the walk may skip the sigma < 0 test and the 0.999 clamp (0.99, not 0.999: ex2.approx may
-    // overshoot by an ulp).  q4.w is the bound of the sigma >= 0 test of the full walk: +inf for plain Gaussians,
-    // so both walks treat them identically.  The edge minimisers hy, hx feed the conservative culling bound only:
-    // approximate division is inside its slack.
-    const bool plain = pd && (op <= 0.99f);
-    q4 = make_float4(pd ? __fdividef(-B, 2.0f * C) : 0.0f, pd ? __fdividef(-B, 2.0f * A) : 0.0f, plain ? 0.f : 1.f,
-                     plain ? INFINITY : L);
+    pair_record_from(m.x, m.y, __ldg(conics + 3 * g), __ldg(conics + 3 * g + 1), __ldg(conics + 3 * g + 2),
+                     __ldg(opacities + g), __ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2),
+                     q0, q1, q2, q3, q4);
 }
 
 // Records of ALL Gaussians, once per frame (80 B each): with them the rasterizer's staging is a pure gather that
-// cp.async can run one batch ahead, and the per-(tile, Gaussian) staging arithmetic disappears.
+// cp.async can run one batch ahead, and the per-(tile, Gaussian) staging arithmetic disappears.  (Fused frames get
+// the records from the projection kernel's epilogue instead; this kernel serves the stage-level entry point.)
 // With a list (row-band frames: the band's Gaussians in depth order, count on the device) only those get a record.
 __global__ void __launch_bounds__(256)
 raster_pair_prep_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
@@ -413,6 +238,168 @@ raster_pair_prep_kernel(const int64_t N, const float* __restrict__ means2d, cons
     d[0] = q0; d[1] = q1; d[2] = q2; d[3] = q3; d[4] = q4;
 }
 
+// Scratch of the pre-pass (uint32 words): [0, kMaxLongSlots) survivors per compacted slot (slot = position in
+// tile_order), then the per-chunk survivor counts: tiles own disjoint, tile-ordered list ranges, so
+// (r0 / chunk) + tile + c never collides between tiles (floor(a) + floor(b) <= floor(a + b)).
+__device__ __forceinline__ int64_t long_chunk_index(const int32_t r0, const int tile, const int c) {
+    return (int64_t)kMaxLongSlots + (int64_t)(r0 / kLongChunk) + tile + c;
+}
+
+// Tile-level test of one chunk: ballots[k] = hits of this warp's 32 entries of round k; ids[k] = this thread's entry.
+__device__ __forceinline__ void long_test_chunk(const int64_t N, const float4* __restrict__ rec,
+                                                const int32_t* __restrict__ sorted_ids, const int32_t e0,
+                                                const int32_t r1, const float TX0, const float TX1, const float TY0,
+                                                const float TY1, int32_t (&ids)[kLongChunk / kLongThreads],
+                                                unsigned int (&ballots)[kLongChunk / kLongThreads]) {
+    constexpr int kRounds = kLongChunk / kLongThreads;
+#pragma unroll
+    for (int k = 0; k < kRounds; ++k) {
+        const int32_t e = e0 + k * kLongThreads + (int)threadIdx.x;
+        ids[k] = (e < r1) ? __ldg(sorted_ids + e) : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < kRounds; ++k) {
+        bool hit = false;
+        const int32_t g = ids[k];
+        if (g >= 0 && (int64_t)g < N) {
+            const float4* r = rec + kPairRec * (int64_t)g;
+            const float4 p0 = __ldg(r), p1 = __ldg(r + 1);
+            const float nC = __ldg(reinterpret_cast<const float*>(r + 2));
+            const float tau = __ldg(reinterpret_cast<const float*>(r + 3) + 3);
+            const float2 hh = __ldg(reinterpret_cast<const float2*>(r + 4));
+            hit = pair_cull_hit(p0.x, p0.z, -p1.x, -p1.z, -nC, tau, hh.x, hh.y, TX0, TX1, TY0, TY1);
+        }
+        ballots[k] = __ballot_sync(0xffffffffu, hit);
+    }
+}
+
+// Pre-pass for very long lists (see kPrepassMin).  Work items = (long tile, chunk of kLongChunk entries), found by
+// every CTA on its own from the head of tile_order (longest lists first, so the long tiles are a prefix of it).
+// Phase 1 counts the survivors of every chunk, a grid-wide barrier follows (the grid is one CTA per SM: co-resident),
+// phase 2 repeats the test and writes the survivors, in list order, at the chunk's offset inside the tile's compacted
+// list surv[r0 ...); scratch[slot] = number of survivors of the tile.  `barrier` is a zeroed counter.
+__global__ void __launch_bounds__(kLongThreads)
+raster_long_compact_kernel(const int64_t N, const float4* __restrict__ rec, const int32_t* __restrict__ tile_ranges,
+                           const int32_t* __restrict__ tile_order, const int n_order,
+                           const int32_t* __restrict__ sorted_ids, const int tiles_w,
+                           int32_t* __restrict__ surv, uint32_t* __restrict__ scratch, uint32_t* __restrict__ barrier) {
+    __shared__ int s_pref[kMaxLongSlots + 1];   // exclusive prefix of chunk counts over the long tiles
+    __shared__ int s_wsum[kLongThreads / 32];
+    __shared__ int s_grp[kLongChunk / 32];      // survivors per (round, warp) group of a chunk
+    __shared__ int s_red[kLongThreads / 32];
+    static_assert(kMaxLongSlots <= kLongThreads && kMaxLongChunks <= kLongThreads, "one thread per slot / chunk");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kRounds = kLongChunk / kLongThreads;
+    constexpr int kGroups = kRounds * (kLongThreads / 32);
+    static_assert(kGroups % 32 == 0 && kGroups <= kLongThreads, "group prefix layout");
+    // ---- work discovery: chunks of slot `tid` ----
+    int chunks = 0;
+    if (tid < n_order && tid < kMaxLongSlots) {
+        const int tile = __ldg(tile_order + tid);
+        const int len = __ldg(tile_ranges + 2 * tile + 1) - __ldg(tile_ranges + 2 * tile);
+        const int nc = (len + kLongChunk - 1) / kLongChunk;
+        if (len > kPrepassMin && nc <= kMaxLongChunks) chunks = nc;
+    }
+    int incl = chunks;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += s_wsum[w];
+    if (tid < kMaxLongSlots) s_pref[tid] = wbase + incl - chunks;
+    if (tid == kMaxLongSlots - 1) s_pref[kMaxLongSlots] = wbase + incl;
+    __syncthreads();
+    const int total = s_pref[kMaxLongSlots];
+    if (total == 0) return;  // (the same decision in every CTA: nobody waits at the barrier below)
+
+    for (int phase = 0; phase < 2; ++phase) {
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            // slot of this item: the largest s with s_pref[s] <= item (zero-chunk slots are skipped by construction)
+            int lo = 0, hi = kMaxLongSlots;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_pref[mid] <= item) lo = mid; else hi = mid;
+            }
+            const int c = item - s_pref[lo];
+            const int nc = s_pref[lo + 1] - s_pref[lo];
+            const int tile = __ldg(tile_order + lo);
+            const int32_t r0 = __ldg(tile_ranges + 2 * tile), r1 = __ldg(tile_ranges + 2 * tile + 1);
+            const int tile_y = tile / tiles_w, tile_x = tile - tile_y * tiles_w;
+            const float TX0 = (float)(tile_x * kFastTile) + 0.5f, TX1 = TX0 + 15.0f;
+            const float TY0 = (float)(tile_y * kFastTile) + 0.5f, TY1 = TY0 + 15.0f;
+            const int32_t e0 = r0 + c * kLongChunk;
+            int32_t ids[kRounds];
+            unsigned int ballots[kRounds];
+            long_test_chunk(N, rec, sorted_ids, e0, r1, TX0, TX1, TY0, TY1, ids, ballots);
+#pragma unroll
+            for (int k = 0; k < kRounds; ++k)
+                if (lane == 0) s_grp[k * (kLongThreads / 32) + warp] = __popc(ballots[k]);
+            __syncthreads();
+            // exclusive prefix over the (round, warp) groups: one warp scan per 32 groups, totals in s_wsum
+            if (tid < kGroups) {
+                const int v = s_grp[tid];
+                int in2 = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, in2, d);
+                    if (lane >= d) in2 += u;
+                }
+                s_grp[tid] = in2 - v;
+                if (lane == 31) s_wsum[warp] = in2;
+            }
+            __syncthreads();
+            int gtot[kGroups / 32], total_surv = 0;  // survivors of each run of 32 groups
+#pragma unroll
+            for (int w = 0; w < kGroups / 32; ++w) { gtot[w] = s_wsum[w]; total_surv += gtot[w]; }
+            const int64_t cidx = long_chunk_index(r0, tile, 0);
+            if (phase == 0) {
+                if (tid == 0) scratch[cidx + c] = (uint32_t)total_surv;
+            } else {
+                // offset of this chunk inside the tile's compacted list: survivors of the chunks before it
+                int before = (tid < c) ? (int)__ldcg(scratch + cidx + tid) : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
+                if (lane == 0) s_red[warp] = before;
+                __syncthreads();
+                int base0 = 0;
+#pragma unroll
+                for (int w = 0; w < kLongThreads / 32; ++w) base0 += s_red[w];
+#pragma unroll
+                for (int k = 0; k < kRounds; ++k) {
+                    const int gi = k * (kLongThreads / 32) + warp;
+                    int base = base0 + s_grp[gi];
+#pragma unroll
+                    for (int w = 0; w < kGroups / 32; ++w)
+                        if (w < gi / 32) base += gtot[w];
+                    const unsigned int bl = ballots[k];
+                    if ((bl >> lane) & 1u) surv[r0 + base + __popc(bl & ((1u << lane) - 1u))] = ids[k];
+                }
+                if (c == nc - 1 && tid == 0) scratch[lo] = (uint32_t)(base0 + total_surv);
+            }
+            __syncthreads();  // s_grp / s_wsum / s_red are reused by the next item
+        }
+        if (phase == 0) {
+            // grid-wide barrier: every chunk count is visible before any offset is summed
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                atomicAdd(barrier, 1u);
+                unsigned ns = 32;
+                while (ld_relaxed_u32(barrier) < gridDim.x) {
+                    __nanosleep(ns);
+                    if (ns < 256) ns <<= 1;
+                }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
@@ -420,39 +407,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// kRec: the Gaussians come as prepared records (raster_pair_prep_kernel); batches of 128 are gathered by sorted id
-// with cp.async into the two halves of the staging buffer, one batch ahead of the walk (ids two batches ahead),
-// one barrier per batch.  !kRec: workspace-free staging of 256 per batch from the raw arrays.
-// kMbar (with kRec): no CTA barrier in the loop at all.  Three stages; the cp.async copies of a batch arrive on an
-// mbarrier by themselves ("full": the batch has landed, whatever the issuing threads are doing meanwhile), each
-// warp arrives on a second mbarrier when it has consumed a stage ("empty"), and a thread waits for "empty" of
-// batch b-1 before it gathers batch b+2 into the same stage -- so a warp with little to walk runs up to two batches
-// ahead of the slowest one instead of waiting for it at every batch.
-__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_cp_async_arrive(unsigned long long* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
-    unsigned int ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (!ok) __nanosleep(40);  // polite: a waiting warp must not take issue slots from the walking ones
-    } while (!ok);
-}
-
-constexpr int kMbarStages = 3;
-constexpr int kMbarBatch = 96;  // entries per stage (3 x 96 x 80 B = 23 KB: keeps 8-9 CTAs per SM)
-
-template <bool kCull, bool kRec, bool kMbar = false>
+// kRec: the Gaussians come as prepared records; batches of 128 are gathered by sorted id with cp.async into the two
+// halves of the staging buffer, one batch ahead of the walk (ids two batches ahead), one barrier per batch.
+// !kRec: workspace-free staging of 256 per batch from the raw arrays (same arithmetic, bit-identical image).
+template <bool kCull, bool kRec>
 __global__ void __launch_bounds__(kPairThreads)
 raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float* __restrict__ means2d, const float* __restrict__ conics,
                    const float* __restrict__ colors, const float* __restrict__ opacities,
@@ -460,12 +418,10 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                    const int32_t* __restrict__ tile_order, const int first_tile,
                    const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
                    float* __restrict__ image, const int vec_store,
-                   const unsigned long long* __restrict__ m_dev, const PeerImages peers, const LoopConsts consts) {
-    __shared__ float4 s_g[(kMbar ? kMbarStages * kMbarBatch : kPairBatch) * kPairRec];
-    __shared__ unsigned int s_tmask[kPairBatch / 32];  // long tiles: survivors of the tile-level test
-    __shared__ unsigned long long s_full[kMbarStages], s_empty[kMbarStages];
-    __shared__ int s_done_warps;
-
+                   const unsigned long long* __restrict__ m_dev, const PeerImages peers, const LoopConsts consts,
+                   const int32_t* __restrict__ surv, const uint32_t* __restrict__ chunk_cnt) {
+    __shared__ float4 s_g[kPairBatch * kPairRec];
+    __shared__ unsigned int s_tmask[kPairBatch / 32];  // long tiles without a pre-pass: survivors of the tile-level test
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int tile = tile_order ? __ldg(tile_order + blockIdx.x) : first_tile + (int)blockIdx.x;
@@ -483,12 +439,22 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     const float Y0 = (float)by + 0.5f, Y1 = (float)by + 7.5f;
 
     const int32_t r0 = tile_ranges[2 * tile], r1 = tile_ranges[2 * tile + 1];
-    // Very long lists are mostly Gaussians that cannot touch the tile at all (under the torch binning rules every
-    // culled Gaussian is clamped into a border tile: ~10 k entries in each corner tile at config 3, ~350 k at
-    // config 5).  For those tiles the four warps first share ONE test of every staged Gaussian against the whole
-    // 16x16 tile (64 entries per warp instead of 256), and a warp only runs its own 8x8 test on the survivors:
-    // the serial walk of such a list, which bounds the kernel once a frame is split across GPUs, gets ~4x shorter.
-    const bool long_tile = kCull && !kMbar && (r1 - r0 > kLongTile);  // (needs a CTA barrier per batch)
+    // the list as the loop sees it: entries [v0, v1) of `ids` -- sorted_ids, or the compacted private copy the
+    // pre-pass left for a very long list (same ids, same order, minus those that cannot reach the tile)
+    const int32_t* __restrict__ ids = sorted_ids;
+    int32_t v0 = r0, v1 = r1;
+    bool compacted = false;
+    if constexpr (kRec && kCull) {
+        if (surv != nullptr && tile_order != nullptr && (int)blockIdx.x < kMaxLongSlots && r1 - r0 > kPrepassMin &&
+            (r1 - r0 + kLongChunk - 1) / kLongChunk <= kMaxLongChunks) {
+            compacted = true;
+            ids = surv;
+            v1 = r0 + (int32_t)__ldg(chunk_cnt + blockIdx.x);
+        }
+    }
+    // long list without a pre-pass (stage-level entry point, or a list beyond the pre-pass limits): the four warps
+    // share ONE test of every staged Gaussian against the whole tile (64 entries per warp instead of 256 each)
+    const bool long_tile = kCull && !compacted && (r1 - r0 > kLongTile);
     const float TX0 = (float)(tile_x * kFastTile) + 0.5f, TX1 = TX0 + 15.0f;
     const float TY0 = (float)(tile_y * kFastTile) + 0.5f, TY1 = TY0 + 15.0f;
     float T0 = 1.0f, T1 = 1.0f;
@@ -498,9 +464,9 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     const unsigned int bit_one = consts.one_u;
     const f32x2 one2 = pk2(consts.one_f, consts.one_f), mone2 = pk2(consts.mone_f, consts.mone_f);
 
-    constexpr int kBatch = kMbar ? kMbarBatch : (kRec ? kPairThreads : kPairBatch);
+    constexpr int kBatch = kRec ? kPairThreads : kPairBatch;
     constexpr int kPer = kBatch / kPairThreads;  // staged entries per thread and batch
-    auto load_id = [&](int32_t at) { return (at < r1) ? __ldg(sorted_ids + at) : -1; };
+    auto load_id = [&](int32_t at) { return (at < v1) ? __ldg(ids + at) : -1; };
     auto gather = [&](int half, int32_t id) {  // kRec: this thread's entry of a batch -> record buffer `half`
         float4* dst = s_g + (half * kPairThreads + tid) * kPairRec;
         if (id >= 0 && (int64_t)id < N) {
@@ -517,61 +483,18 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
         cp_async_commit();
     };
     int32_t id_next = -1;
-    bool warp_done = false;  // kMbar: this warp's 64 pixels are saturated (it keeps gathering and arriving)
-    if (kMbar) {
-        if (tid == 0) {
-#pragma unroll
-            for (int st = 0; st < kMbarStages; ++st) { mbar_init(&s_full[st], kMbarBatch); mbar_init(&s_empty[st], kPairThreads / 32); }
-            s_done_warps = 0;
-        }
-        __syncthreads();
-    }
-    // kMbar: this thread's entry of batch b -> stage b % 3; the copies (or the sentinel store) arrive on "full"
-    auto gather_mbar = [&](int b, int32_t id) {
-        const int st = b % kMbarStages;
-        if (tid >= kMbarBatch) return;  // the last warp has no entry to fetch
-        float4* dst = s_g + (st * kMbarBatch + tid) * kPairRec;
-        if (id >= 0 && (int64_t)id < N) {
-            const float4* src = rec + kPairRec * (int64_t)id;
-#pragma unroll
-            for (int q = 0; q < kPairRec; ++q) cp_async16(dst + q, src + q);
-            mbar_cp_async_arrive(&s_full[st]);
-        } else {
-            dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            dst[1] = dst[0];
-            dst[2] = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
-            dst[3] = make_float4(0.f, 0.f, 0.f, -INFINITY);
-            dst[4] = dst[0];
-            mbar_arrive(&s_full[st]);
-        }
-    };
-    const int n_batches = (int)((r1 - r0 + kBatch - 1) / kBatch);
-    if (kMbar) {
-        if (n_batches > 0) gather_mbar(0, load_id(r0 + tid));
-        if (n_batches > 1) gather_mbar(1, load_id(r0 + kBatch + tid));
-        id_next = load_id(r0 + 2 * kBatch + tid);
-    } else if (kRec && r0 < r1) {
-        gather(0, load_id(r0 + tid));
-        id_next = load_id(r0 + kBatch + tid);
+    if (kRec && v0 < v1) {
+        gather(0, load_id(v0 + tid));
+        id_next = load_id(v0 + kBatch + tid);
     }
     int batch = 0;
-    for (int32_t b0 = r0; b0 < r1; b0 += kBatch, ++batch) {
+    for (int32_t b0 = v0; b0 < v1; b0 += kBatch, ++batch) {
         const bool fin = !(npx0 > -INFINITY) && !(npx1 > -INFINITY);
         const float4* s_rec = s_g;
-        if (kMbar) {
-            if (*reinterpret_cast<volatile int*>(&s_done_warps) >= kPairThreads / 32) break;  // every warp is done
-            if (batch + 2 < n_batches) {
-                // stage (batch + 2) % 3 was last read for batch - 1: wait until all four warps have consumed it
-                if (batch >= 1) mbar_wait(&s_empty[(batch - 1) % kMbarStages], ((batch - 1) / kMbarStages) & 1);
-                gather_mbar(batch + 2, id_next);
-                id_next = load_id(b0 + 3 * kBatch + tid);
-            }
-            mbar_wait(&s_full[batch % kMbarStages], (batch / kMbarStages) & 1);  // batch has landed
-            s_rec = s_g + (batch % kMbarStages) * kMbarBatch * kPairRec;
-        } else if (kRec) {
+        if (kRec) {
             cp_async_wait_all();  // this thread's part of batch `batch` has landed ...
             if (__syncthreads_count(fin) >= kPairThreads) break;  // ... everyone's has; batch - 1 is fully consumed
-            if (b0 + kBatch < r1) gather((batch + 1) & 1, id_next);  // next batch flies during this walk
+            if (b0 + kBatch < v1) gather((batch + 1) & 1, id_next);  // next batch flies during this walk
             id_next = load_id(b0 + 2 * kBatch + tid);
             s_rec = s_g + (batch & 1) * kPairThreads * kPairRec;
         } else {
@@ -580,8 +503,8 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             for (int h = 0; h < kPer; ++h) {
                 const int t = tid + h * kPairThreads;
                 const int32_t idx = b0 + t;
-                if (idx < r1) {
-                    const int32_t g = __ldg(sorted_ids + idx);
+                if (idx < v1) {
+                    const int32_t g = __ldg(ids + idx);
                     float4 q0, q1, q2, q3, q4;
                     if (g >= 0 && (int64_t)g < N) {
                         pair_record(g, means2d, conics, colors, opacities, q0, q1, q2, q3, q4);
@@ -599,7 +522,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             __syncthreads();
         }
 
-        const int bs = min(kBatch, (int)(r1 - b0));
+        const int bs = min(kBatch, (int)(v1 - b0));
         if (long_tile) {
 #pragma unroll
             for (int h = 0; h < kPer; ++h) {
@@ -624,10 +547,12 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                 if (tword == 0u) continue;  // nothing of this chunk reaches the tile
             }
             unsigned int mask;
-            bool special = false;  // this lane's Gaussian needs the full alpha test (see staging)
+            bool special = false;  // this lane's Gaussian needs the full alpha test (see pair_record_from)
             if (kCull) {
                 bool hit = false;
-                const int gi = c0 + 31 - lane;  // earliest Gaussian = highest ballot bit
+                // lane l tests Gaussian c0 + 31 - l: the earliest Gaussian is the HIGHEST ballot bit, so the
+                // walk below needs a single FLO (bfind) per survivor instead of BREV + FLO
+                const int gi = c0 + 31 - lane;
                 if (gi < bs && ((tword >> (31 - lane)) & 1u)) {
                     const float4* r = s_rec + kPairRec * gi;
                     const float4 p0 = r[0], p1 = r[1], p2 = r[2];
@@ -641,16 +566,18 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                 special = special && hit;
             } else {
                 const int rem = bs - c0;
-                mask = rem >= 32 ? 0xffffffffu : ~(0xffffffffu >> rem);
+                mask = rem >= 32 ? 0xffffffffu : ~(0xffffffffu >> rem);  // Gaussian c0+k <-> bit 31-k
                 special = true;
             }
             const bool any_special = __any_sync(0xffffffffu, special);
-            const float4* rec_hi = s_rec + kPairRec * (c0 + 31);
+            const float4* rec_hi = s_rec + kPairRec * (c0 + 31);  // record of ballot bit 0; bit b is 5 b float4 earlier
             // two copies of the walk: chunks whose survivors are all "plain" (the common case) run without the
             // sigma < 0 test and without the 0.999 clamp (4 of 47 instructions)
             auto walk = [&](auto plain_tag) {
                 constexpr bool kPlain = decltype(plain_tag)::value;
                 while (mask) {
+                    // highest set bit = next Gaussian, front to back (bfind -> a single FLO; written in PTX
+                    // because nvcc rewrites 31 - clz(x) into a longer clz-based sequence)
                     unsigned int b_hi;
                     asm("bfind.u32 %0, %1;" : "=r"(b_hi) : "r"(mask));
                     mask ^= bit_one << b_hi;
@@ -687,6 +614,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                     vis1 = (pass1 && live1) ? vis1 : 0.0f;
                     T0 = (pass0 && live0) ? nT0 : T0;
                     T1 = (pass1 && live1) ? nT1 : T1;
+                    // saturated: this Gaussian is not added (rasterization.mojo:146-150) and the pixel retires
                     npx0 = (pass0 && !live0) ? -INFINITY : npx0;
                     npx1 = (pass1 && !live1) ? -INFINITY : npx1;
                     ar0 = fmaf(c.x, vis0, ar0); ag0 = fmaf(c.y, vis0, ag0); ab0 = fmaf(c.z, vis0, ab0);
@@ -696,21 +624,10 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             if (any_special) walk(std::false_type{});
             else walk(std::true_type{});
         }
-        if (kMbar) {
-            // a warp that is done says so BEFORE it releases the stage: whoever sees the release also sees the count
-            if (!warp_done && __all_sync(0xffffffffu, !(npx0 > -INFINITY) && !(npx1 > -INFINITY))) {
-                warp_done = true;
-                if (lane == 0) atomicAdd(&s_done_warps, 1);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                mbar_arrive(&s_empty[batch % kMbarStages]);  // this warp has consumed the stage
-            }
-        }
     }
 
     if (kRec) cp_async_wait_all();  // nothing may still be landing in shared memory when it is reused below
+    // sync-free frames: no intersections at all => all-zero image (render.py:73-76), decided on the device
     const float bgs = (m_dev != nullptr && *m_dev == 0ull) ? 0.0f : 1.0f;
     const float bgr = bgs * __ldg(background), bgg = bgs * __ldg(background + 1), bgb = bgs * __ldg(background + 2);
     const float o0r = fmaf(T0, bgr, ar0), o0g = fmaf(T0, bgg, ag0), o0b = fmaf(T0, bgb, ab0);
@@ -743,217 +660,6 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             if (in0) { float* dst = img + ((int64_t)i0 * W + j) * 3; dst[0] = o0r; dst[1] = o0g; dst[2] = o0b; }
             if (in1) { float* dst = img + ((int64_t)i1 * W + j) * 3; dst[0] = o1r; dst[1] = o1g; dst[2] = o1b; }
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// warp kernel (tile 16, RGB, needs a 48 B/Gaussian record workspace): the default fast path.
-// Same packed-pair arithmetic as raster_pair_kernel, but the four warps of a tile never meet:
-//   * raster_prep_kernel turns every Gaussian ONCE per frame into a 48-byte raster record
-//     {mx, my, -A, -B | -C, L, hy, hx | r, g, b, tau} (log2-folded conic, culling constants),
-//     instead of once per (tile, Gaussian) inside the rasterizer;
-//   * each warp walks the tile's list by itself in chunks of 32: the records of chunk k+1 are gathered
-//     by sorted id with cp.async (16 B x 3 per lane) into the warp's own staging slot while chunk k is
-//     composited; lane l tests Gaussian l of the chunk against the warp's 8x8 block, the survivors are
-//     compacted (ballot prefix) into the warp's survivor slot in the duplicated {v, v} layout and walked
-//     front to back.  No __syncthreads in the loop: a warp whose 64 pixels are saturated just leaves.
-// ------------------------------------------------------------------------------------------
-constexpr int kWarpKStages = 3;  // chunk k is consumed while k+1 and k+2 are in flight
-
-__global__ void __launch_bounds__(256)
-raster_prep_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
-                   const float* __restrict__ colors, const float* __restrict__ opacities,
-                   float4* __restrict__ rec) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= N) return;
-    const float mx = __ldg(means2d + 2 * g), my = __ldg(means2d + 2 * g + 1);
-    const float ca = __ldg(conics + 3 * g), cb = __ldg(conics + 3 * g + 1), cc = __ldg(conics + 3 * g + 2);
-    const float op = __ldg(opacities + g);
-    const float A = 0.5f * kLog2e * ca, B = kLog2e * cb, C = 0.5f * kLog2e * cc;
-    // accurate log2 keeps alpha = 2^(L - q) within a few ulp of o*exp(-sigma)
-    const float L = (op > 0.0f) ? __log2f(op) : -INFINITY;  // same arithmetic as the pair kernel's staging
-    const bool pd = (A > 0.0f) && (C > 0.0f) && (4.0f * A * C - B * B > 0.0f);
-    float tau = pd ? (L - kLog2AlphaThreshold) : INFINITY;
-    if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
-    rec[3 * g] = make_float4(mx, my, -A, -B);
-    rec[3 * g + 1] = make_float4(-C, L, pd ? __fdividef(-B, 2.0f * C) : 0.0f, pd ? __fdividef(-B, 2.0f * A) : 0.0f);
-    rec[3 * g + 2] = make_float4(__ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2), tau);
-}
-
-template <bool kCull>
-__global__ void __launch_bounds__(32, 32)
-raster_warp_kernel(const int64_t N, const float4* __restrict__ rec, const float* __restrict__ background,
-                   const int32_t* __restrict__ tile_ranges, const int32_t* __restrict__ tile_order,
-                   const int first_tile, const int32_t* __restrict__ sorted_ids, const int W, const int H,
-                   const int tiles_w, float* __restrict__ image, const int vec_store,
-                   const unsigned long long* __restrict__ m_dev) {
-    __shared__ float4 s_stage1[kWarpKStages][32 * 3];  // gathered records, a ring
-    __shared__ float4 s_surv1[32 * kPairRec];          // compacted survivors, {v, v} layout
-    float4 (*const s_stage)[32 * 3] = s_stage1;
-
-    // one warp per CTA: the four 8x8 blocks of a tile are scheduled (and retire) independently
-    const int lane = threadIdx.x;
-    const int warp = (int)blockIdx.x & 3;
-    const int tile_slot = (int)blockIdx.x >> 2;
-    const int tile = tile_order ? __ldg(tile_order + tile_slot) : first_tile + tile_slot;
-    const int tile_y = tile / tiles_w, tile_x = tile - tile_y * tiles_w;
-    const int bx = tile_x * kFastTile + (warp & 1) * 8;
-    const int by = tile_y * kFastTile + (warp >> 1) * 8;
-    const int j = bx + (lane & 7);
-    const int i0 = by + (lane >> 3), i1 = i0 + 4;
-    const bool in0 = (i0 < H) && (j < W), in1 = (i1 < H) && (j < W);
-    float npx0 = in0 ? -((float)j + 0.5f) : -INFINITY;  // negated x per pixel; -inf = finished
-    float npx1 = in1 ? -((float)j + 0.5f) : -INFINITY;
-    const f32x2 npy = pk2(-((float)i0 + 0.5f), -((float)i1 + 0.5f));
-    const float X0 = (float)bx + 0.5f, X1 = (float)bx + 7.5f;
-    const float Y0 = (float)by + 0.5f, Y1 = (float)by + 7.5f;
-
-    const int32_t r0 = tile_ranges[2 * tile], r1 = tile_ranges[2 * tile + 1];
-    float T0 = 1.0f, T1 = 1.0f;
-    float ar0 = 0.f, ag0 = 0.f, ab0 = 0.f, ar1 = 0.f, ag1 = 0.f, ab1 = 0.f;
-    const f32x2 one2 = pk2(1.0f, 1.0f), mone2 = pk2(-1.0f, -1.0f);
-    const unsigned int lt = (1u << lane) - 1u;
-    float4* const surv = s_surv1;
-
-    // gather of one chunk: lane l fetches the record of list entry (chunk base + l) into stage[buf]
-    auto gather = [&](int buf, int32_t id) {
-        float4* dst = &s_stage[buf][lane * 3];
-        if (id >= 0 && (int64_t)id < N) {
-            const float4* src = rec + 3 * (int64_t)id;
-            cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
-        } else {
-            // past the end of the list / invalid id (rasterization.mojo:109 guard): can never hit
-            dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            dst[1] = make_float4(0.f, -INFINITY, 0.f, 0.f);
-            dst[2] = make_float4(0.f, 0.f, 0.f, -INFINITY);
-        }
-        cp_async_commit();
-    };
-
-    // Software pipeline: list ids are fetched 3 chunks ahead of their gather, records 2 chunks ahead of their
-    // use, so that a run of chunks without survivors (the culled Gaussians that the torch binning rules pile
-    // up in the corner tiles: ~10 k entries, 300 chunks per warp) advances at the speed of the test, not of
-    // an L2 round trip per chunk.
-    auto load_id = [&](int32_t at) { return (at < r1) ? __ldg(sorted_ids + at) : -1; };
-    int32_t id_a = -1, id_b = -1, id_c = -1;  // ids of this lane's entries in chunks k+2, k+3, k+4
-    if (r0 < r1) {
-        const int32_t id0 = load_id(r0 + lane), id1 = load_id(r0 + 32 + lane);
-        id_a = load_id(r0 + 64 + lane); id_b = load_id(r0 + 96 + lane); id_c = load_id(r0 + 128 + lane);
-        gather(0, id0);
-        gather(1, id1);
-    }
-    int buf = 0;
-    for (int32_t base = r0; base < r1; base += 32, buf = (buf + 1 == kWarpKStages) ? 0 : buf + 1) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");  // chunk k has landed (k+1 may still fly)
-        __syncwarp();
-        const float4* st = &s_stage[buf][lane * 3];
-        const float4 p0 = st[0], p1 = st[1], p2 = st[2];
-        // chunk k+2 goes into the slot chunk k-1 was read from (all lanes passed the vote that ended k-1)
-        gather((buf + 2 >= kWarpKStages) ? buf + 2 - kWarpKStages : buf + 2, id_a);
-        id_a = id_b; id_b = id_c;
-        id_c = load_id(base + 160 + lane);
-
-        bool hit;
-        if (kCull) {
-            const float A = -p0.z, B = -p0.w, C = -p1.x, tau = p2.w;
-            const float u0 = p0.x - X1, u1 = p0.x - X0;
-            const float v0 = p0.y - Y1, v1 = p0.y - Y0;
-            const bool zu = (u0 <= 0.0f) && (u1 >= 0.0f);
-            const bool zv = (v0 <= 0.0f) && (v1 >= 0.0f);
-            // min of q over the block = min over the (<= 2) edges facing the mean (see raster_fast_kernel)
-            float qmin = 0.0f;
-            if (!(zu && zv)) {
-                float q1 = INFINITY, q2 = INFINITY;
-                if (!zu) {
-                    const float ue = (u0 > 0.0f) ? u0 : u1;
-                    const float vstar = p1.z * ue;
-                    const float dv = vstar - fminf(fmaxf(vstar, v0), v1);
-                    q1 = fmaf(fmaf(0.5f * B, p1.z, A) * ue, ue, C * dv * dv);
-                }
-                if (!zv) {
-                    const float ve = (v0 > 0.0f) ? v0 : v1;
-                    const float ustar = p1.w * ve;
-                    const float du = ustar - fminf(fmaxf(ustar, u0), u1);
-                    q2 = fmaf(fmaf(0.5f * B, p1.w, C) * ve, ve, A * du * du);
-                }
-                qmin = fminf(q1, q2);
-            }
-            const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
-            const float slack = 4e-6f * (A * um * um + C * vm * vm) + 1e-3f;
-            hit = !(qmin > tau + slack);  // NaN-safe: anything odd counts as a hit
-        } else {
-            hit = !(p2.w == -INFINITY);  // every real Gaussian
-        }
-        const unsigned int mask = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-            float4* d = surv + kPairRec * __popc(mask & lt);
-            d[0] = make_float4(p0.x, p0.x, p0.y, p0.y);
-            d[1] = make_float4(p0.z, p0.z, p0.w, p0.w);
-            d[2] = make_float4(p1.x, p1.x, p1.y, p1.y);
-            d[3] = p2;
-        }
-        __syncwarp();
-        const float4* r = surv;
-        const float4* const r_end = surv + kPairRec * __popc(mask);
-        for (; r != r_end; r += kPairRec) {
-            const float4 q0 = r[0], q1 = r[1], q2 = r[2];
-            const f32x2 dx = add2(pk2(q0.x, q0.y), pk2(npx0, npx1));
-            const f32x2 dy = add2(pk2(q0.z, q0.w), npy);
-            const f32x2 nbdy = mul2(pk2(q1.z, q1.w), dy);
-            const f32x2 ncdy = mul2(pk2(q2.x, q2.y), dy);
-            const f32x2 lmc = fma2(ncdy, dy, pk2(q2.z, q2.w));
-            const f32x2 t = fma2(pk2(q1.x, q1.y), dx, nbdy);
-            const f32x2 pw = fma2(t, dx, lmc);
-            float pw0, pw1;
-            upk2(pw, pw0, pw1);
-            const float L = q2.z;
-            const bool pass0 = (pw0 <= L) && (pw0 >= kLog2AlphaThreshold);
-            const bool pass1 = (pw1 <= L) && (pw1 >= kLog2AlphaThreshold);
-            const float a0 = fminf(0.999f, ex2_approx(pw0)), a1 = fminf(0.999f, ex2_approx(pw1));
-            const f32x2 a2 = pk2(a0, a1), T2 = pk2(T0, T1);
-            const f32x2 nT2 = mul2(T2, fma2(a2, mone2, one2));
-            const f32x2 vis2 = mul2(a2, T2);
-            float nT0, nT1, vis0, vis1;
-            upk2(nT2, nT0, nT1);
-            upk2(vis2, vis0, vis1);
-            const bool live0 = nT0 > 1e-4f, live1 = nT1 > 1e-4f;
-            const float4 c = r[3];
-            vis0 = (pass0 && live0) ? vis0 : 0.0f;
-            vis1 = (pass1 && live1) ? vis1 : 0.0f;
-            T0 = (pass0 && live0) ? nT0 : T0;
-            T1 = (pass1 && live1) ? nT1 : T1;
-            // saturated: this Gaussian is not added (rasterization.mojo:146-150) and the pixel retires
-            npx0 = (pass0 && !live0) ? -INFINITY : npx0;
-            npx1 = (pass1 && !live1) ? -INFINITY : npx1;
-            ar0 = fmaf(c.x, vis0, ar0); ag0 = fmaf(c.y, vis0, ag0); ab0 = fmaf(c.z, vis0, ab0);
-            ar1 = fmaf(c.x, vis1, ar1); ag1 = fmaf(c.y, vis1, ag1); ab1 = fmaf(c.z, vis1, ab1);
-        }
-        if (__all_sync(0xffffffffu, !(npx0 > -INFINITY) && !(npx1 > -INFINITY))) break;  // also orders surv reuse
-    }
-    cp_async_wait_all();  // nothing may still be landing in shared memory when it is reused below
-
-    const float bgs = (m_dev != nullptr && *m_dev == 0ull) ? 0.0f : 1.0f;
-    const float bgr = bgs * __ldg(background), bgg = bgs * __ldg(background + 1), bgb = bgs * __ldg(background + 2);
-    const float o0r = fmaf(T0, bgr, ar0), o0g = fmaf(T0, bgg, ag0), o0b = fmaf(T0, bgb, ab0);
-    const float o1r = fmaf(T1, bgr, ar1), o1g = fmaf(T1, bgg, ag1), o1b = fmaf(T1, bgb, ab1);
-    const bool full_block = (bx + 8 <= W) && (by + 8 <= H);
-    if (vec_store && full_block) {
-        __syncwarp();  // the survivor slot is dead from here on
-        float* s_out = reinterpret_cast<float*>(surv);  // 8 rows x 24 floats
-        float* d0 = s_out + ((lane >> 3) * 8 + (lane & 7)) * 3;
-        float* d1 = d0 + 4 * 8 * 3;
-        d0[0] = o0r; d0[1] = o0g; d0[2] = o0b;
-        d1[0] = o1r; d1[1] = o1g; d1[2] = o1b;
-        __syncwarp();
-        for (int v = lane; v < 8 * 6; v += 32) {  // 8 rows of 96 contiguous bytes
-            const int row = v / 6, c4 = v % 6;
-            const float4 val = reinterpret_cast<const float4*>(s_out)[row * 6 + c4];
-            float* dst = image + ((int64_t)(by + row) * W + bx) * 3;
-            reinterpret_cast<float4*>(dst)[c4] = val;
-        }
-    } else {
-        if (in0) { float* dst = image + ((int64_t)i0 * W + j) * 3; dst[0] = o0r; dst[1] = o0g; dst[2] = o0b; }
-        if (in1) { float* dst = image + ((int64_t)i1 * W + j) * 3; dst[0] = o1r; dst[1] = o1g; dst[2] = o1b; }
     }
 }
 
@@ -1008,19 +714,25 @@ static int launch_faithful(int64_t N, int cdim, int c0, const float* means2d, co
 
 namespace bsplat {
 // shared with capi.cu.  mode 0 = fast (pair kernel; with a record workspace: records + cp.async staging),
-// 2 = the same without sub-tile culling (exactness A/B), 3 = warp kernel (independent warps, needs the record
-// workspace; pair kernel without it), 4 = one pixel per lane (first fast kernel), 1 = faithful.  On config 3 the three fast kernels are within 3 % of each other
-// (0.29-0.30 ms): 264 M / 211 M / 187 M warp instructions, but the lighter ones issue less densely
-// (profiles/r01_raster_*): the pair kernel is the default.
+// 2 = the same without sub-tile culling (exactness A/B), 1 = faithful.
 size_t raster_workspace_bytes(int64_t N) { return (size_t)(N > 0 ? N : 1) * kPairRec * sizeof(float4); }
+// long-list pre-pass scratch of a fused frame: survivor ids [M_cap] + per-chunk counts
+size_t raster_long_surv_bytes(int64_t M_cap) { return (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(int32_t); }
+size_t raster_long_cnt_bytes(int64_t M_cap, int64_t n_tiles) {
+    return (size_t)(kMaxLongSlots + (M_cap > 0 ? M_cap : 1) / kLongChunk + n_tiles + 2) * sizeof(uint32_t);
+}
 
+// rec_ready: the records in rec_ws are already written (projection epilogue); otherwise the record kernel runs here.
+// surv / chunk_cnt / long_barrier (optional, fused frames): scratch of the long-list pre-pass; long_barrier is one
+// uint32 that is zero when the stream gets here.
 int rasterize_launch(int64_t N, int channels, const float* means2d, const float* conics, const float* colors,
                      const float* opacities, const float* background_dev,
                      const int32_t* tile_ranges, const int32_t* tile_order, const int32_t* sorted_ids, int W,
                      int H, int tile_size, int row_begin, int row_end, int mode, float* image,
                      unsigned long long* stats, const unsigned long long* m_dev, void* rec_ws,
                      cudaStream_t stream, const PeerImages* peers_in, const int32_t* rec_list,
-                     const unsigned long long* rec_list_n) {
+                     const unsigned long long* rec_list_n, bool rec_ready, int32_t* surv, uint32_t* chunk_cnt,
+                     uint32_t* long_barrier) {
     PeerImages peers;
     peers.n = 0;
     if (peers_in) peers = *peers_in;
@@ -1031,12 +743,14 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
     if (row_begin < 0) row_begin = 0;
     if (row_end > tiles_h) row_end = tiles_h;
     if (row_end <= row_begin) return BSPLAT_OK;  // empty band
-    if (peers.n > 0 && !(mode == BSPLAT_RASTER_FAST && tile_size == kFastTile && channels == 3 && stats == nullptr &&
-                         (reinterpret_cast<uintptr_t>(means2d) & 7u) == 0))
+    const bool fast_mode = (mode == BSPLAT_RASTER_FAST || mode == BSPLAT_RASTER_FAST_NOCULL);
+    if (mode != BSPLAT_RASTER_FAITHFUL && !fast_mode) return BSPLAT_E_ARG;
+    // (the raw-array staging reads means2d as float2: an unaligned view falls back to the faithful kernel)
+    const bool inputs_ok = (means2d != nullptr && (reinterpret_cast<uintptr_t>(means2d) & 7u) == 0) ||
+                           (rec_ready && rec_ws != nullptr);
+    const bool fast_ok = fast_mode && tile_size == kFastTile && channels == 3 && stats == nullptr && inputs_ok;
+    if (peers.n > 0 && !(fast_ok && mode == BSPLAT_RASTER_FAST))
         return BSPLAT_E_ARG;  // the fused exchange exists in the default 16x16 RGB kernel only
-    const bool fast_ok = (mode == BSPLAT_RASTER_FAST || (mode >= 2 && mode <= 5)) && tile_size == kFastTile &&
-                         channels == 3 && stats == nullptr &&
-                         (reinterpret_cast<uintptr_t>(means2d) & 7u) == 0;
     if (fast_ok) {
         const float* bg = background_dev;
         const int vec = ((reinterpret_cast<uintptr_t>(image) & 15u) == 0 && (W % 4) == 0) ? 1 : 0;
@@ -1045,42 +759,49 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         const LoopConsts loop_consts = {1u, 1.0f, -1.0f};
         const bool have_rec = rec_ws != nullptr && N > 0 && (reinterpret_cast<uintptr_t>(rec_ws) & 15u) == 0;
         float4* recp = static_cast<float4*>(rec_ws);
-        if (mode == 3 && have_rec) {
-            raster_prep_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(N, means2d, conics, colors, opacities, recp);
-            BSPLAT_LAUNCH_CHECK();
-            raster_warp_kernel<true><<<grid * 4, 32, 0, stream>>>(N, recp, bg, tile_ranges, tile_order,
-                                                                  first_tile, sorted_ids, W, H, tiles_w,
-                                                                  image, vec, m_dev);
-        } else if (mode == 4) {
-            raster_fast_kernel<true><<<grid, kFastThreads, 0, stream>>>(N, means2d, conics, colors, opacities, bg,
-                                                                        tile_ranges, tile_order, first_tile, sorted_ids,
-                                                                        W, H, tiles_w, image, vec, m_dev);
-        } else if (have_rec) {
-            // default: records once per frame, then the cp.async-staged pair kernel
-            raster_pair_prep_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(N, means2d, conics, colors,
-                                                                                    opacities, recp, rec_list,
-                                                                                    rec_list_n);
-            BSPLAT_LAUNCH_CHECK();
-            if (mode == 5)
-                raster_pair_kernel<true, true, true><<<grid, kPairThreads, 0, stream>>>(
-                    N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
-                    tiles_w, image, vec, m_dev, peers, loop_consts);
-            else if (mode == 2)
+        if (have_rec) {
+            if (!rec_ready) {
+                if (!means2d || !conics || !colors || !opacities || (reinterpret_cast<uintptr_t>(means2d) & 7u) != 0)
+                    return BSPLAT_E_ARG;
+                raster_pair_prep_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(N, means2d, conics, colors,
+                                                                                        opacities, recp, rec_list,
+                                                                                        rec_list_n);
+                BSPLAT_LAUNCH_CHECK();
+            }
+            // BSPLAT_DEBUG (A/B measurements only, not part of the interface): "noprepass" / "roworder"
+            static const char* dbg = getenv("BSPLAT_DEBUG");
+            if (dbg && strstr(dbg, "roworder")) tile_order = nullptr;
+            const bool prepass = mode == BSPLAT_RASTER_FAST && surv != nullptr && chunk_cnt != nullptr &&
+                                 long_barrier != nullptr && tile_order != nullptr &&
+                                 !(dbg && strstr(dbg, "noprepass"));
+            if (prepass) {
+                // one CTA per SM: the grid-wide barrier inside needs every CTA resident
+                raster_long_compact_kernel<<<148, kLongThreads, 0, stream>>>(N, recp, tile_ranges, tile_order, (int)grid,
+                                                                             sorted_ids, tiles_w, surv, chunk_cnt,
+                                                                             long_barrier);
+                BSPLAT_LAUNCH_CHECK();
+            }
+            if (mode == BSPLAT_RASTER_FAST_NOCULL)
                 raster_pair_kernel<false, true><<<grid, kPairThreads, 0, stream>>>(
                     N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
-                    tiles_w, image, vec, m_dev, peers, loop_consts);
+                    tiles_w, image, vec, m_dev, peers, loop_consts, nullptr, nullptr);
             else
                 raster_pair_kernel<true, true><<<grid, kPairThreads, 0, stream>>>(
                     N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
-                    tiles_w, image, vec, m_dev, peers, loop_consts);
-        } else if (mode == 2) {
-            raster_pair_kernel<false, false><<<grid, kPairThreads, 0, stream>>>(
-                N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
-                tiles_w, image, vec, m_dev, peers, loop_consts);
+                    tiles_w, image, vec, m_dev, peers, loop_consts, prepass ? surv : nullptr,
+                    prepass ? chunk_cnt : nullptr);
         } else {
-            raster_pair_kernel<true, false><<<grid, kPairThreads, 0, stream>>>(
-                N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
-                tiles_w, image, vec, m_dev, peers, loop_consts);
+            if (N > 0 && (!means2d || !conics || !colors || !opacities ||
+                          (reinterpret_cast<uintptr_t>(means2d) & 7u) != 0))
+                return BSPLAT_E_ARG;
+            if (mode == BSPLAT_RASTER_FAST_NOCULL)
+                raster_pair_kernel<false, false><<<grid, kPairThreads, 0, stream>>>(
+                    N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W,
+                    H, tiles_w, image, vec, m_dev, peers, loop_consts, nullptr, nullptr);
+            else
+                raster_pair_kernel<true, false><<<grid, kPairThreads, 0, stream>>>(
+                    N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W,
+                    H, tiles_w, image, vec, m_dev, peers, loop_consts, nullptr, nullptr);
         }
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;

@@ -329,9 +329,15 @@ extern "C" int bsplat_rasterize_fwd_train(int64_t N, int32_t channels, const flo
     const int nthreads = round_up32(tile_size * tile_size);
     const dim3 grid(tiles_w, tiles_h);
     const size_t smem = (size_t)nthreads * (9 + channels) * sizeof(float);
+    // tile sizes 31 / 32 need more than the 48 KB a kernel gets without opting in
 #define BSPLAT_TRAIN_FWD(CH)                                                                                    \
-    raster_train_fwd_kernel<CH><<<grid, nthreads, smem, stream>>>(N, means2d, conics, colors, opacities,       \
-        background, tile_ranges, sorted_ids, width, height, tile_size, tiles_w, image, final_T, last_idx)
+    do {                                                                                                        \
+        if (smem + 256 > 48 * 1024) /* (+ the kernel's static shared memory) */                                 \
+            BSPLAT_CUDA_TRY(cudaFuncSetAttribute(raster_train_fwd_kernel<CH>,                                   \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        raster_train_fwd_kernel<CH><<<grid, nthreads, smem, stream>>>(N, means2d, conics, colors, opacities,   \
+            background, tile_ranges, sorted_ids, width, height, tile_size, tiles_w, image, final_T, last_idx);  \
+    } while (0)
     switch (channels) {
         case 1: BSPLAT_TRAIN_FWD(1); break;
         case 2: BSPLAT_TRAIN_FWD(2); break;
@@ -363,9 +369,14 @@ extern "C" int bsplat_rasterize_bwd(int64_t N, int32_t channels, const float* me
     const dim3 grid(tiles_w, tiles_h);
     const size_t smem = (size_t)nthreads * (10 + channels) * sizeof(float);
 #define BSPLAT_BWD(CH)                                                                                          \
-    raster_bwd_kernel<CH><<<grid, nthreads, smem, stream>>>(N, means2d, conics, colors, opacities, background,  \
-        tile_ranges, sorted_ids, width, height, tile_size, tiles_w, final_T, last_idx, grad_image, grad_means2d, \
-        grad_conics, grad_colors, grad_opacities)
+    do {                                                                                                        \
+        if (smem + 256 > 48 * 1024) /* (+ the kernel's static shared memory) */                                 \
+            BSPLAT_CUDA_TRY(cudaFuncSetAttribute(raster_bwd_kernel<CH>,                                         \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        raster_bwd_kernel<CH><<<grid, nthreads, smem, stream>>>(N, means2d, conics, colors, opacities,         \
+            background, tile_ranges, sorted_ids, width, height, tile_size, tiles_w, final_T, last_idx,          \
+            grad_image, grad_means2d, grad_conics, grad_colors, grad_opacities);                                \
+    } while (0)
     switch (channels) {
         case 1: BSPLAT_BWD(1); break;
         case 2: BSPLAT_BWD(2); break;

@@ -12,8 +12,7 @@ from . import _lib
 from .projection import CUDA_BACKENDS, _reference_module
 from .utils import Camera
 
-RASTER_MODES = {"fast": _lib.RASTER_FAST, "faithful": _lib.RASTER_FAITHFUL,
-                "fast_nocull": _lib.RASTER_FAST_NOCULL, "warp": _lib.RASTER_WARP, "single": _lib.RASTER_SINGLE, "mbar": _lib.RASTER_MBAR}
+RASTER_MODES = {"fast": _lib.RASTER_FAST, "faithful": _lib.RASTER_FAITHFUL, "fast_nocull": _lib.RASTER_FAST_NOCULL}
 
 
 def rasterize_gaussians(
@@ -78,7 +77,7 @@ def rasterize_gaussians_cuda(means2d, conics, colors, opacities, background_colo
             _lib.check(L.bsplat_tile_order(r0 * tw, order.numel(), _lib.ptr(tile_ranges), _lib.ptr(order),
                                            _lib.stream_ptr(dev)), "bsplat_tile_order")
         ws = None
-        if order is not None and mode in ("fast", "warp", "mbar"):
+        if order is not None and mode in ("fast", "fast_nocull"):
             ws = _lib.workspace.get(dev, "raster_rec", L.bsplat_rasterize_workspace_bytes(N))
         rc = L.bsplat_rasterize_fwd(N, C, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
                                     _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),

@@ -95,8 +95,11 @@ _last_M: dict = {}
 
 def render_fused(means3d, scales, quats, opacities, colors, camera, background, tile_size=TILE_SIZE,
                  semantics=_lib.SEM_TORCH, raster_mode="fast", return_aux=False, timing=False,
-                 bin_algo="two_level"):
-    """One C call per frame (include/bsplat.h: bsplat_render_fwd). Device tensors in, image out."""
+                 bin_algo="two_level", packed=False, proj_fma=False):
+    """One C call per frame (include/bsplat.h: bsplat_render_fwd). Device tensors in, image out.
+    ``packed``: gsplat's packed layout -- Gaussians that own no tile are compacted away right after projection
+    (same image and lists; only pays under the gsplat rule set, where culled Gaussians own no tile).
+    ``proj_fma``: the A/B build of the projection kernel with FMA contraction allowed."""
     dev = means3d.device
     L = _lib.require_device(dev)
     means3d = _lib.as_f32(means3d, "means3d"); scales = _lib.as_f32(scales, "scales")
@@ -128,6 +131,7 @@ def render_fused(means3d, scales, quats, opacities, colors, camera, background, 
             aux.sorted_ids, aux.sorted_ids_capacity = outs["sorted_ids"].data_ptr(), cap
     needed = c_size_t(0)
     flags = RASTER_MODES[raster_mode] | (_lib.FLAG_BIN_SINGLE_LEVEL if bin_algo == "single" else 0)
+    flags |= (_lib.FLAG_PACKED if packed else 0) | (_lib.FLAG_PROJ_FMA if proj_fma else 0)
     with torch.cuda.device(dev):
         for _attempt in range(3):
             rc = L.bsplat_render_fwd(N, _lib.ptr(means3d), _lib.ptr(scales), _lib.ptr(quats),
@@ -144,7 +148,8 @@ def render_fused(means3d, scales, quats, opacities, colors, camera, background, 
     _last_M[key] = max(M, 1)
     if M == 0:
         warnings.warn("No Gaussian overlaps found; returning a black image (render.py:73-76)")
-    if return_aux:
+    if return_aux or timing:
+        outs = outs if outs is not None else {}
         outs["n_isect"] = M
         outs["n_launches"] = int(aux.n_launches)
         outs["sort_passes"] = int(aux.sort_passes)
@@ -152,6 +157,8 @@ def render_fused(means3d, scales, quats, opacities, colors, camera, background, 
         if "sorted_ids" in outs:
             outs["sorted_ids"] = outs["sorted_ids"][:M] if outs["sorted_ids"].numel() >= M else None
         if timing:
+            # [0] projection (+ fused epilogue), [1] depth sort + count/scan + the M read-back, [2] emit + tile sort +
+            # ranges, [3] rasterizer (+ long-list pre-pass); the stage outputs are only stored with return_aux
             outs["stage_ms"] = [float(v) for v in aux.stage_ms]
         return image, outs
     return image

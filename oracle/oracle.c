@@ -15,16 +15,22 @@
  *
  * Pinning status:
  *   - projection + binning: PINNED against outputs of the unmodified reference torch
- *     backend run in the build container (oracle/make_golden.py -> tests/golden/*.npz).
+ *     backend run in the build container (oracle/make_golden.py -> tests/golden/*.npz):
+ *     means2d, depths, radii, tile ranges bit for bit; conics bit for bit except where MKL's exp is
+ *     1 ulp off the correctly rounded value (~3 % of the rows; within 1e-4 + 1e-4 |ref| there).
  *   - rasterization: the reference has no CPU rasterizer and gsplat is not installable
  *     offline, so gsplat parity is UNPINNED; the restatement is pinned only to the
  *     backend-independent known-answer checks of the reference's tests
  *     (tests/test_rasterization.py:154-248, tests/test_render.py:60-119) and to an
  *     independent numpy restatement (oracle/oracle_np.py).
  *
+ * Error budgets: oracle_project_f64 / oracle_rasterize_f64 evaluate the same
+ * algorithms in double precision from the fp32 inputs; oracle_raster_audit explains out-of-tolerance pixels by
+ * forced alpha-threshold / saturation flips.
+ *
  * Build: oracle/build.sh  (gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC).
  * -ffp-contract=off keeps every multiply and add separately rounded, like the eager
- * torch ops the reference issues.
+ * torch ops the reference issues; where the reference's matmul kernels fuse, fmaf() is written out.
  */
 #include <math.h>
 #include <stdint.h>
@@ -52,6 +58,26 @@ void oracle_set_num_threads(int n) {
     (void)n;
 #endif
 }
+
+/* How the reference's torch ops round (found by bisecting the unmodified reference against tests/golden, torch
+ * 2.11 CPU; oracle/make_golden.py regenerates the evidence):
+ *   - element-wise ops (quat -> R, R * s, the Jacobian entries, det, conic, radii): one rounding per operation;
+ *   - einsum that lowers to the matmul kernel -- R . mu, (R Sigma) R^T, K . mu_c: a dot product is
+ *     c = a0 b0; c = fma(a1, b1, c); c = fma(a2, b2, c);
+ *   - einsum that lowers to product + sum -- M M^T ("ij,kj->ik") and (J Sigma_c) J^T: every product and every sum
+ *     rounded, left to right;
+ *   - torch.exp (MKL VML, high accuracy): the correctly rounded result for 98.9 % of the arguments, 1 ulp off
+ *     otherwise -- not reproducible without MKL; exp_torch returns the correctly rounded value.
+ * With these rules means2d, depths and radii of the oracle equal the reference's bit for bit on every fixture, and
+ * so do the conics of every Gaussian whose three scales got the correctly rounded exp (tests/test_oracle_golden.py). */
+static inline float dot3_mm(float a0, float b0, float a1, float b1, float a2, float b2) {
+    float c = a0 * b0;
+    c = fmaf(a1, b1, c);
+    c = fmaf(a2, b2, c);
+    return c;
+}
+
+static inline float exp_torch(float x) { return (float)exp((double)x); }
 
 /* ------------------------------------------------------------------------------------
  * Projection.  projection.py:285-346 (wrapper), :72-102 (covariance), :51-69 (quat->R),
@@ -99,10 +125,10 @@ void oracle_project(
         const float* ls = log_scales + 3 * i;
         const float* q = quats + 4 * i;
 
-        /* world -> camera mean, projection.py:190-192 */
+        /* world -> camera mean, projection.py:190-192 (einsum -> matmul kernel: FMA chain, then `+ t`) */
         float mc[3];
         for (int r = 0; r < 3; ++r)
-            mc[r] = (Rv[r][0] * mu[0] + Rv[r][1] * mu[1] + Rv[r][2] * mu[2]) + tv[r];
+            mc[r] = dot3_mm(Rv[r][0], mu[0], Rv[r][1], mu[1], Rv[r][2], mu[2]) + tv[r];
 
         if (semantics == ORACLE_SEM_GSPLAT) {
             /* projection.mojo:59-87 */
@@ -125,8 +151,8 @@ void oracle_project(
             {2.0f * (x * y + w * z), 1.0f - 2.0f * (x * x + z * z), 2.0f * (y * z - w * x)},
             {2.0f * (x * z - w * y), 2.0f * (y * z + w * x), 1.0f - 2.0f * (x * x + y * y)}};
 
-        /* M = R * s ; Sigma = M M^T, projection.py:86-87 */
-        const float s[3] = {expf(ls[0]), expf(ls[1]), expf(ls[2])};
+        /* M = R * s ; Sigma = M M^T, projection.py:86-87 ("ij,kj->ik": product + sum, every operation rounded) */
+        const float s[3] = {exp_torch(ls[0]), exp_torch(ls[1]), exp_torch(ls[2])};
         float M[3][3], S[3][3];
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) M[r][c] = R[r][c] * s[c];
@@ -134,14 +160,15 @@ void oracle_project(
             for (int c = 0; c < 3; ++c)
                 S[r][c] = M[r][0] * M[c][0] + M[r][1] * M[c][1] + M[r][2] * M[c][2];
 
-        /* Sigma_c = Rv Sigma Rv^T, projection.py:193-195 */
+        /* Sigma_c = (Rv Sigma) Rv^T, projection.py:193-195 (three-operand einsum, left to right, both products
+         * through the matmul kernel: FMA chains) */
         float A[3][3], Sc[3][3];
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c)
-                A[r][c] = Rv[r][0] * S[0][c] + Rv[r][1] * S[1][c] + Rv[r][2] * S[2][c];
+                A[r][c] = dot3_mm(Rv[r][0], S[0][c], Rv[r][1], S[1][c], Rv[r][2], S[2][c]);
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c)
-                Sc[r][c] = A[r][0] * Rv[c][0] + A[r][1] * Rv[c][1] + A[r][2] * Rv[c][2];
+                Sc[r][c] = dot3_mm(A[r][0], Rv[c][0], A[r][1], Rv[c][1], A[r][2], Rv[c][2]);
 
         /* pinhole Jacobian, projection.py:134-159 */
         const float tz = mc[2];
@@ -160,9 +187,9 @@ void oracle_project(
         float c10 = JS[1][0] * J[0][0] + JS[1][1] * J[0][1] + JS[1][2] * J[0][2];
         float c11 = JS[1][0] * J[1][0] + JS[1][1] * J[1][1] + JS[1][2] * J[1][2];
 
-        /* means2d = (K[:2,:3] . mu_c) / z, projection.py:156-159 */
-        const float m2x = (fx * mc[0] + 0.0f * mc[1] + cx * mc[2]) / tz;
-        const float m2y = (0.0f * mc[0] + fy * mc[1] + cy * mc[2]) / tz;
+        /* means2d = (K[:2,:3] . mu_c) / z, projection.py:156-159 (matmul kernel: FMA chain) */
+        const float m2x = dot3_mm(fx, mc[0], 0.0f, mc[1], cx, mc[2]) / tz;
+        const float m2y = dot3_mm(0.0f, mc[0], fy, mc[1], cy, mc[2]) / tz;
 
         c00 += eps2d; /* projection.py:242 */
         c11 += eps2d;
@@ -416,4 +443,236 @@ void oracle_rasterize(
         }
     }
     if (stats) { stats[0] += e_all; stats[1] += e_pass; }
+}
+
+/* ------------------------------------------------------------------------------------
+ * fp64 variants: the same algorithms evaluated in double precision
+ * from the same fp32 inputs.  They are the yardstick of the error-budget tests: the error of
+ * a GPU kernel against these must not exceed the error the reference's own fp32 arithmetic has
+ * against them.  Thresholds are the reference's constants (rasterization.mojo:143-150).
+ * ---------------------------------------------------------------------------------- */
+void oracle_project_f64(
+    int64_t N, const float* means3d, const float* log_scales, const float* quats,
+    const float* viewmat, double fx, double fy, double cx, double cy, int W, int H,
+    double near_plane, double far_plane, double eps2d,
+    double* means2d, double* conics, double* depths, double* radii_real /* [N,2] 3.33 sqrt(c), 0 if culled */)
+{
+    const double Rv[3][3] = {
+        {viewmat[0], viewmat[1], viewmat[2]},
+        {viewmat[4], viewmat[5], viewmat[6]},
+        {viewmat[8], viewmat[9], viewmat[10]}};
+    const double tv[3] = {viewmat[3], viewmat[7], viewmat[11]};
+    const double tan_fovx = 0.5 * (double)W / fx, tan_fovy = 0.5 * (double)H / fy;
+    const double lim_x_pos = ((double)W - cx) / fx + 0.3 * tan_fovx, lim_x_neg = cx / fx + 0.3 * tan_fovx;
+    const double lim_y_pos = ((double)H - cy) / fy + 0.3 * tan_fovy, lim_y_neg = cy / fy + 0.3 * tan_fovy;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+        const float* mu = means3d + 3 * i;
+        const float* ls = log_scales + 3 * i;
+        const float* q = quats + 4 * i;
+        double mc[3];
+        for (int r = 0; r < 3; ++r) mc[r] = Rv[r][0] * mu[0] + Rv[r][1] * mu[1] + Rv[r][2] * mu[2] + tv[r];
+        double nrm = sqrt((double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2] + (double)q[3] * q[3]);
+        if (nrm < 1e-12) nrm = 1e-12;
+        const double w = q[0] / nrm, x = q[1] / nrm, y = q[2] / nrm, z = q[3] / nrm;
+        const double R[3][3] = {
+            {1.0 - 2.0 * (y * y + z * z), 2.0 * (x * y - w * z), 2.0 * (x * z + w * y)},
+            {2.0 * (x * y + w * z), 1.0 - 2.0 * (x * x + z * z), 2.0 * (y * z - w * x)},
+            {2.0 * (x * z - w * y), 2.0 * (y * z + w * x), 1.0 - 2.0 * (x * x + y * y)}};
+        const double s[3] = {exp((double)ls[0]), exp((double)ls[1]), exp((double)ls[2])};
+        double M[3][3], S[3][3], A[3][3], Sc[3][3];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) M[r][c] = R[r][c] * s[c];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+            S[r][c] = M[r][0] * M[c][0] + M[r][1] * M[c][1] + M[r][2] * M[c][2];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+            A[r][c] = Rv[r][0] * S[0][c] + Rv[r][1] * S[1][c] + Rv[r][2] * S[2][c];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+            Sc[r][c] = A[r][0] * Rv[c][0] + A[r][1] * Rv[c][1] + A[r][2] * Rv[c][2];
+        const double tz = mc[2], tz2 = tz * tz;
+        double rx = mc[0] / tz, ry = mc[1] / tz;
+        rx = fmin(fmax(rx, -lim_x_neg), lim_x_pos);
+        ry = fmin(fmax(ry, -lim_y_neg), lim_y_pos);
+        const double tx = tz * rx, ty = tz * ry;
+        const double J[2][3] = {{fx / tz, 0.0, -fx * tx / tz2}, {0.0, fy / tz, -fy * ty / tz2}};
+        double JS[2][3];
+        for (int r = 0; r < 2; ++r) for (int c = 0; c < 3; ++c)
+            JS[r][c] = J[r][0] * Sc[0][c] + J[r][1] * Sc[1][c] + J[r][2] * Sc[2][c];
+        double c00 = JS[0][0] * J[0][0] + JS[0][1] * J[0][1] + JS[0][2] * J[0][2];
+        const double c01 = JS[0][0] * J[1][0] + JS[0][1] * J[1][1] + JS[0][2] * J[1][2];
+        const double c10 = JS[1][0] * J[0][0] + JS[1][1] * J[0][1] + JS[1][2] * J[0][2];
+        double c11 = JS[1][0] * J[1][0] + JS[1][1] * J[1][1] + JS[1][2] * J[1][2];
+        const double m2x = (fx * mc[0] + cx * mc[2]) / tz, m2y = (fy * mc[1] + cy * mc[2]) / tz;
+        c00 += eps2d; c11 += eps2d;
+        double det = c00 * c11 - c01 * c10;
+        if (!(det >= 1e-10)) det = (det != det) ? det : 1e-10;
+        means2d[2 * i] = m2x; means2d[2 * i + 1] = m2y;
+        conics[3 * i] = c11 / det; conics[3 * i + 1] = -(c01 + c10) / 2.0 / det; conics[3 * i + 2] = c00 / det;
+        depths[i] = tz;
+        double r_x = 3.33 * sqrt(c00), r_y = 3.33 * sqrt(c11);
+        const int valid = (det > 0.0) && (tz > near_plane) && (tz < far_plane);
+        if (!valid) { r_x = 0.0; r_y = 0.0; }
+        const int inside = (m2x + ceil(r_x) > 0.0) && (m2x - ceil(r_x) < (double)W) &&
+                           (m2y + ceil(r_y) > 0.0) && (m2y - ceil(r_y) < (double)H);
+        if (!inside) { r_x = 0.0; r_y = 0.0; }
+        radii_real[2 * i] = r_x; radii_real[2 * i + 1] = r_y;
+    }
+}
+
+/* The rasterizer in double precision, fp32 inputs (kernels/rasterization.mojo:138-162). */
+void oracle_rasterize_f64(
+    int64_t N, int CDIM, const float* means2d, const float* conics, const float* colors,
+    const float* opacities, const float* background, const int32_t* tile_ranges,
+    const int32_t* sorted_ids, int W, int H, int tile_size, double* image)
+{
+    const int tiles_w = (W + tile_size - 1) / tile_size, tiles_h = (H + tile_size - 1) / tile_size;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int t = 0; t < tiles_w * tiles_h; ++t) {
+        const int tr = t / tiles_w, tc = t % tiles_w;
+        const int32_t r0 = tile_ranges[2 * t], r1 = tile_ranges[2 * t + 1];
+        double pix[CDIM > 0 ? CDIM : 1];
+        for (int ii = 0; ii < tile_size; ++ii) {
+            const int i = tr * tile_size + ii;
+            if (i >= H) break;
+            for (int jj = 0; jj < tile_size; ++jj) {
+                const int j = tc * tile_size + jj;
+                if (j >= W) break;
+                const double px = (double)j + 0.5, py = (double)i + 0.5;
+                double T = 1.0;
+                for (int c = 0; c < CDIM; ++c) pix[c] = 0.0;
+                for (int32_t k = r0; k < r1; ++k) {
+                    const int32_t g = sorted_ids[k];
+                    if (g < 0 || g >= N) continue;
+                    const double dx = (double)means2d[2 * g] - px, dy = (double)means2d[2 * g + 1] - py;
+                    const double a = conics[3 * g], b = conics[3 * g + 1], cc = conics[3 * g + 2];
+                    const double sigma = 0.5 * (a * dx * dx + cc * dy * dy) + b * dx * dy;
+                    double alpha = (double)opacities[g] * exp(-sigma);
+                    if (alpha > 0.999) alpha = 0.999;
+                    if (sigma < 0.0 || alpha < (1.0 / 255.0)) continue;
+                    const double next_T = T * (1.0 - alpha);
+                    if (next_T <= 1e-4) break;
+                    const double vis = alpha * T;
+                    for (int c = 0; c < CDIM; ++c) pix[c] += (double)colors[(int64_t)g * CDIM + c] * vis;
+                    T = next_T;
+                }
+                double* out = image + ((int64_t)i * W + j) * CDIM;
+                for (int c = 0; c < CDIM; ++c) out[c] = pix[c] + T * (double)background[c];
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * Outlier audit.  The alpha >= 1/255 test and the T (1 - alpha) <= 1e-4 stop make a pixel
+ * discontinuous in exp(): two correct fp32 implementations may take a different branch when a value sits
+ * within rounding distance of a threshold, and the pixel then differs by up to alpha T colour.  That is the
+ * ONLY legitimate cause of a value outside the tolerance.  For every listed pixel this routine re-composites
+ * the pixel (fp32, the oracle's arithmetic) with each borderline decision forced the other way -- one flip at
+ * a time, then pairs -- and reports whether some variant reproduces the observed value within atol + rtol |v|.
+ * A decision is borderline when |alpha - 1/255| <= rel_window / 255 or |next_T - 1e-4| <= 10 rel_window * 1e-4
+ * (or sigma within rel_window of 0).
+ *   pixels[n][2] = (row, col); observed[n][CDIM]; explained[n] (out) = 0 unexplained, 1 one flip, 2 two flips,
+ *   3 = the unflipped oracle value is already within tolerance; n_borderline[n] (out).
+ * ---------------------------------------------------------------------------------- */
+#define AUDIT_MAX_BORDER 24
+
+static void audit_composite(
+    int CDIM, const float* means2d, const float* conics, const float* colors, const float* opacities,
+    const float* background, const int32_t* sorted_ids, int64_t N, int32_t r0, int32_t r1, float px, float py,
+    const int32_t* flip_at, int n_flip, float rel_window, int32_t* border, int* n_border, float* out)
+{
+    float T = 1.0f;
+    float pix[16];
+    for (int c = 0; c < CDIM; ++c) pix[c] = 0.0f;
+    int nb = 0;
+    for (int32_t k = r0; k < r1; ++k) {
+        const int32_t g = sorted_ids[k];
+        if (g < 0 || g >= N) continue;
+        const float dx = means2d[2 * g] - px, dy = means2d[2 * g + 1] - py;
+        const float a = conics[3 * g], b = conics[3 * g + 1], cc = conics[3 * g + 2];
+        const float sigma = 0.5f * (a * dx * dx + cc * dy * dy) + b * dx * dy;
+        float alpha = opacities[g] * expf(-sigma);
+        if (alpha > 0.999f) alpha = 0.999f;
+        int skip = (sigma < 0.0f || alpha < (1.0f / 255.0f));
+        const int near_alpha = fabsf(alpha - (1.0f / 255.0f)) <= rel_window * (1.0f / 255.0f) ||
+                               fabsf(sigma) <= rel_window;
+        int flipped = 0;
+        for (int f = 0; f < n_flip; ++f) if (flip_at[f] == k) flipped = 1;
+        if (near_alpha) {
+            if (border && nb < AUDIT_MAX_BORDER) border[nb] = k;
+            ++nb;
+            if (flipped) { skip = !skip; flipped = 0; }
+        }
+        if (skip) continue;
+        const float next_T = T * (1.0f - alpha);
+        int stop = next_T <= 1e-4f;
+        const int near_T = fabsf(next_T - 1e-4f) <= 10.0f * rel_window * 1e-4f;  /* T carries the error of every earlier alpha */
+        if (near_T) {
+            if (!near_alpha) {  /* (a Gaussian borderline on both tests is listed once) */
+                if (border && nb < AUDIT_MAX_BORDER) border[nb] = k;
+                ++nb;
+            }
+            if (flipped) stop = !stop;
+        }
+        if (stop) break;
+        const float vis = alpha * T;
+        for (int c = 0; c < CDIM; ++c) pix[c] += colors[(int64_t)g * CDIM + c] * vis;
+        T = next_T;
+    }
+    for (int c = 0; c < CDIM; ++c) out[c] = pix[c] + T * background[c];
+    if (n_border) *n_border = nb;
+}
+
+void oracle_raster_audit(
+    int64_t N, int CDIM, const float* means2d, const float* conics, const float* colors,
+    const float* opacities, const float* background, const int32_t* tile_ranges,
+    const int32_t* sorted_ids, int W, int H, int tile_size,
+    int64_t n_pixels, const int32_t* pixels, const float* observed, float atol, float rtol, float rel_window,
+    int32_t* explained, int32_t* n_borderline)
+{
+    (void)H;
+    const int tiles_w = (W + tile_size - 1) / tile_size;
+    if (CDIM > 16) { for (int64_t n = 0; n < n_pixels; ++n) { explained[n] = 0; n_borderline[n] = -1; } return; }
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t n = 0; n < n_pixels; ++n) {
+        const int i = pixels[2 * n], j = pixels[2 * n + 1];
+        const int t = (i / tile_size) * tiles_w + (j / tile_size);
+        const int32_t r0 = tile_ranges[2 * t], r1 = tile_ranges[2 * t + 1];
+        const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+        const float* obs = observed + n * CDIM;
+        int32_t border[AUDIT_MAX_BORDER];
+        int nb = 0;
+        float out[16];
+        audit_composite(CDIM, means2d, conics, colors, opacities, background, sorted_ids, N, r0, r1, px, py,
+                        NULL, 0, rel_window, border, &nb, out);
+        n_borderline[n] = nb;
+        int ok = 1;
+        for (int c = 0; c < CDIM; ++c) if (fabsf(out[c] - obs[c]) > atol + rtol * fabsf(obs[c])) ok = 0;
+        if (ok) { explained[n] = 3; continue; }
+        explained[n] = 0;
+        const int m = nb < AUDIT_MAX_BORDER ? nb : AUDIT_MAX_BORDER;
+        for (int f = 0; f < m && !explained[n]; ++f) {
+            audit_composite(CDIM, means2d, conics, colors, opacities, background, sorted_ids, N, r0, r1, px, py,
+                            &border[f], 1, rel_window, NULL, NULL, out);
+            ok = 1;
+            for (int c = 0; c < CDIM; ++c) if (fabsf(out[c] - obs[c]) > atol + rtol * fabsf(obs[c])) ok = 0;
+            if (ok) explained[n] = 1;
+        }
+        /* a flip can make a later decision borderline that was not before (T changed): pairs re-enumerate */
+        for (int f = 0; f < m && !explained[n]; ++f) {
+            int32_t border2[AUDIT_MAX_BORDER];
+            int nb2 = 0;
+            audit_composite(CDIM, means2d, conics, colors, opacities, background, sorted_ids, N, r0, r1, px, py,
+                            &border[f], 1, rel_window, border2, &nb2, out);
+            const int m2 = nb2 < AUDIT_MAX_BORDER ? nb2 : AUDIT_MAX_BORDER;
+            for (int f2 = 0; f2 < m2 && !explained[n]; ++f2) {
+                if (border2[f2] == border[f]) continue;
+                int32_t two[2] = {border[f], border2[f2]};
+                audit_composite(CDIM, means2d, conics, colors, opacities, background, sorted_ids, N, r0, r1, px, py,
+                                two, 2, rel_window, NULL, NULL, out);
+                ok = 1;
+                for (int c = 0; c < CDIM; ++c) if (fabsf(out[c] - obs[c]) > atol + rtol * fabsf(obs[c])) ok = 0;
+                if (ok) explained[n] = 2;
+            }
+        }
+    }
 }

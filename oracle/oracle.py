@@ -131,6 +131,62 @@ def rasterize(means2d, conics, colors, opacities, background, tile_ranges, sorte
     return image
 
 
+def project_f64(means3d, log_scales, quats, viewmat, fx, fy, cx, cy, W, H, near=0.1, far=100.0, eps2d=0.3):
+    """Torch-rule projection evaluated in double precision from the fp32 inputs (error-budget yardstick).
+    -> (means2d[N,2], conics[N,3], depths[N], radii_real[N,2]) float64; radii_real = 3.33 sqrt(c) before ceil."""
+    means3d, log_scales, quats = _f32(means3d), _f32(log_scales), _f32(quats)
+    viewmat = _f32(viewmat).reshape(16)
+    N = means3d.shape[0]
+    means2d = np.zeros((N, 2), np.float64)
+    conics = np.zeros((N, 3), np.float64)
+    depths = np.zeros((N,), np.float64)
+    radii = np.zeros((N, 2), np.float64)
+    d = ctypes.c_double
+    lib().oracle_project_f64(ctypes.c_int64(N), _ptr(means3d), _ptr(log_scales), _ptr(quats), _ptr(viewmat),
+                             d(fx), d(fy), d(cx), d(cy), ctypes.c_int(W), ctypes.c_int(H), d(near), d(far), d(eps2d),
+                             _ptr(means2d), _ptr(conics), _ptr(depths), _ptr(radii))
+    return means2d, conics, depths, radii
+
+
+def rasterize_f64(means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, W, H, tile_size=16):
+    """The rasterizer in double precision on the fp32 inputs -> image[H,W,C] float64."""
+    means2d, conics, colors = _f32(means2d), _f32(conics), _f32(colors)
+    opacities = _f32(opacities).reshape(-1)
+    background = _f32(background).reshape(-1)
+    N, C = colors.shape
+    ranges = np.ascontiguousarray(np.asarray(tile_ranges, dtype=np.int32))
+    ids = np.ascontiguousarray(np.asarray(sorted_ids, dtype=np.int32))
+    image = np.zeros((H, W, C), np.float64)
+    lib().oracle_rasterize_f64(ctypes.c_int64(N), ctypes.c_int(C), _ptr(means2d), _ptr(conics), _ptr(colors),
+                               _ptr(opacities), _ptr(background), _ptr(ranges), _ptr(ids), ctypes.c_int(W),
+                               ctypes.c_int(H), ctypes.c_int(tile_size), _ptr(image))
+    return image
+
+
+def raster_audit(means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, W, H, tile_size,
+                 pixels, observed, atol=1e-4, rtol=1e-4, rel_window=1e-4):
+    """SURVEY H4 audit of out-of-tolerance pixels (see oracle.c: oracle_raster_audit).
+    pixels [n,2] (row, col), observed [n,C] -> (explained[n] in {0: no, 1: one flip, 2: two flips, 3: already
+    within tolerance}, n_borderline[n])."""
+    means2d, conics, colors = _f32(means2d), _f32(conics), _f32(colors)
+    opacities = _f32(opacities).reshape(-1)
+    background = _f32(background).reshape(-1)
+    N, C = colors.shape
+    ranges = np.ascontiguousarray(np.asarray(tile_ranges, dtype=np.int32))
+    ids = np.ascontiguousarray(np.asarray(sorted_ids, dtype=np.int32))
+    pixels = np.ascontiguousarray(np.asarray(pixels, dtype=np.int32)).reshape(-1, 2)
+    observed = _f32(observed).reshape(-1, C)
+    n = pixels.shape[0]
+    explained = np.zeros((n,), np.int32)
+    nb = np.zeros((n,), np.int32)
+    f = ctypes.c_float
+    lib().oracle_raster_audit(ctypes.c_int64(N), ctypes.c_int(C), _ptr(means2d), _ptr(conics), _ptr(colors),
+                              _ptr(opacities), _ptr(background), _ptr(ranges), _ptr(ids), ctypes.c_int(W),
+                              ctypes.c_int(H), ctypes.c_int(tile_size), ctypes.c_int64(n), _ptr(pixels),
+                              _ptr(observed), f(atol), f(rtol), f(rel_window), _ptr(explained), _ptr(nb))
+    return explained, nb
+
+
 def render(means3d, log_scales, quats, opacities, colors, viewmat, fx, fy, cx, cy, W, H,
            near=0.1, far=100.0, background=None, tile_size=16, semantics=SEM_TORCH,
            return_all=False):

@@ -79,3 +79,23 @@ def test_product_never_imports_oracle():
         assert "import oracle" not in src and "from oracle" not in src, p
     for p in (ROOT / "mojosplat_b200" / "csrc").glob("*.cu*"):
         assert "oracle" not in p.read_text(), p
+
+
+def test_camera_struct_reads_intrinsics_from_Ks():
+    """Like the reference (projection.py:137-140, 156-159), the intrinsics come from camera.Ks."""
+    import pytest
+    import torch
+
+    import mojosplat_b200 as ms
+    from mojosplat_b200 import _lib
+    cam = ms.Camera(R=torch.eye(3), T=torch.zeros(3), H=48, W=64, fx=100.0, fy=100.0, cx=32.0, cy=24.0)
+    c = _lib.camera_struct(cam)
+    assert (c.fx, c.fy, c.cx, c.cy, c.width, c.height) == (100.0, 100.0, 32.0, 24.0, 64, 48)
+    cam2 = ms.Camera(R=torch.eye(3), T=torch.zeros(3), H=48, W=64, fx=1.0, fy=1.0, cx=0.0, cy=0.0,
+                     Ks=torch.tensor([[120.0, 0.0, 30.0], [0.0, 110.0, 20.0], [0.0, 0.0, 1.0]]))
+    c2 = _lib.camera_struct(cam2)
+    assert (c2.fx, c2.fy, c2.cx, c2.cy) == (120.0, 110.0, 30.0, 20.0)
+    cam3 = ms.Camera(R=torch.eye(3), T=torch.zeros(3), H=48, W=64, fx=1.0, fy=1.0, cx=0.0, cy=0.0,
+                     Ks=torch.tensor([[120.0, 0.5, 30.0], [0.0, 110.0, 20.0], [0.0, 0.0, 1.0]]))
+    with pytest.raises(ValueError, match="pinhole"):
+        _lib.camera_struct(cam3)

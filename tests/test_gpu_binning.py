@@ -151,3 +151,47 @@ def test_binning_mixed_huge_and_tiny_rectangles(cuda_device, W, H, ts, sem):
     assert np.array_equal(ranges.cpu().numpy(), o_ranges)
     assert np.array_equal(ids.cpu().numpy(), o_ids)
     assert ids.numel() > 20 * N  # the huge ones dominate
+
+
+@pytest.mark.parametrize("W,H,ts,N", [(1920, 1080, 4, 20_000),      # 480 x 270 = 129 600 tiles: 17 tile bits, 3 passes
+                                       (3840, 2160, 4, 4_000),       # 960 x 540 = 518 400 tiles: 19 bits
+                                       (4096, 4096, 1, 300)])        # 16.8 M tiles: 24 bits, 3 passes of 8
+def test_binning_more_than_65536_tiles(cuda_device, W, H, ts, N):
+    """Tile ids wider than two 8-bit digits (8K frames, small tiles): the tile sort takes ceil(bits / 8) passes.
+    Both algorithms against the oracle, bit for bit."""
+    g = torch.Generator().manual_seed(W + ts)
+    m2 = torch.stack([torch.rand(N, generator=g) * (W + 40) - 20, torch.rand(N, generator=g) * (H + 40) - 20], 1)
+    rad = torch.randint(0, 9 * ts, (N, 2), generator=g, dtype=torch.int32)
+    dep = torch.rand(N, generator=g) * 20 + 0.1
+    dep[::7] = dep[3]  # ties
+    o_ids, o_ranges = oracle.bin_tiles(m2.numpy(), rad.numpy(), dep.numpy(), H, W, ts)
+    assert o_ranges.shape[0] * o_ranges.shape[1] > 65536
+    for algo in ("two_level", "single"):
+        ids, ranges = binning.bin_gaussians_to_tiles_cuda(m2.to(cuda_device), rad.to(cuda_device), dep.to(cuda_device),
+                                                          H, W, ts, algo=algo)
+        assert np.array_equal(ranges.cpu().numpy(), o_ranges), algo
+        assert np.array_equal(ids.cpu().numpy(), o_ids), algo
+
+
+@pytest.mark.parametrize("cfg,N", [("config1_1k_256", None), ("config3_1m_1080p", 300_000)])
+def test_packed_layout_identical_lists_and_image(cuda_device, cfg, N):
+    """gsplat's packed (culled-compacted) layout (projection.mojo:73-87,213-244; tests/test_projection_mojo.py:238-247):
+    Gaussians without a tile leave the frame before the depth sort.  Lists and image must not change."""
+    sc = synthetic.make_scene(cfg, N=N)
+    sc.opacities[::9] = 0.001   # opacity cull
+    g = [t.to(cuda_device) for t in sc.gaussians()]
+    cam = sc.camera.to(cuda_device)
+    bg = sc.background.to(cuda_device)
+    for sem in (_lib.SEM_TORCH, _lib.SEM_GSPLAT):
+        a, aux_a = ms.render_fused(*g, cam, bg, semantics=sem, return_aux=True)
+        a, aux_a = ms.render_fused(*g, cam, bg, semantics=sem, return_aux=True)  # (second call returns sorted_ids)
+        b, aux_b = ms.render_fused(*g, cam, bg, semantics=sem, return_aux=True, packed=True)
+        assert torch.equal(a, b)
+        assert aux_a["n_isect"] == aux_b["n_isect"] and torch.equal(aux_a["tile_ranges"], aux_b["tile_ranges"])
+        assert torch.equal(aux_a["sorted_ids"], aux_b["sorted_ids"])
+        # the stage-level entry point too
+        ids, ranges = binning.bin_gaussians_to_tiles_cuda(aux_a["means2d"], aux_a["radii"], aux_a["depths"], cam.H,
+                                                          cam.W, 16, semantics=sem, packed=True)
+        assert torch.equal(ids, aux_a["sorted_ids"]) and torch.equal(ranges, aux_a["tile_ranges"])
+    culled = (aux_b["radii"] == 0).all(-1)
+    assert culled[::9].all()      # the torch rules keep them in border tiles; the gsplat rules drop them

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import mojosplat_b200 as ms
-from helpers import image_gate, scene_on
+from helpers import audit_inputs, image_gate, scene_on
 from mojosplat_b200 import synthetic
 from oracle import oracle
 
@@ -23,8 +23,9 @@ def test_config5_6m_4k_vs_oracle(cuda_device):
     img, aux = ms.render_fused(m, s, q, o, c, camd, sc.background.to(cuda_device), return_aux=True)
     M_ref = ref["sorted_ids"].shape[0]
     assert abs(aux["n_isect"] - M_ref) <= 64 and abs(M_ref - 58_024_036) <= 64  # SURVEY 8d probe
-    r = image_gate(img.cpu().numpy(), ref["image"], frac_allowed=2e-4)
+    r = image_gate(img.cpu().numpy(), ref["image"], frac_allowed=2e-4, audit=audit_inputs(ref, sc))
     assert r["ok"], r
+    print(f"\n[parity config5] fused frame vs oracle: {r}")
     if np.array_equal(aux["radii"].cpu().numpy(), ref["radii"]) and \
             np.array_equal(aux["means2d"].cpu().numpy(), ref["means2d"]):
         assert np.array_equal(aux["tile_ranges"].cpu().numpy(), ref["tile_ranges"])

@@ -65,7 +65,10 @@ def small_scene(N, HW, seed, C=3, opacity_lo=0.3):
 
 @pytest.mark.parametrize("N,HW,ts,C,seed", [(1, 32, 16, 3, 0), (40, 48, 16, 3, 1), (150, 64, 16, 3, 2),
                                             (60, 40, 10, 3, 3), (80, 48, 16, 1, 4), (80, 48, 16, 4, 5),
-                                            (400, 32, 16, 3, 6)])
+                                            (400, 32, 16, 3, 6),
+                                            # tile sizes 31 / 32: > 48 KB of dynamic shared memory (opt-in attribute)
+                                            (60, 64, 32, 3, 7), (60, 64, 32, 4, 8), (60, 62, 31, 3, 9),
+                                            (60, 64, 32, 2, 10)])
 def test_backward_matches_torch_autograd(cuda_device, N, HW, ts, C, seed):
     cam, m2, con, dep, rad, o, c = small_scene(N, HW, seed, C)
     ids, ranges = oracle.bin_tiles(m2, rad, dep, HW, HW, ts)
@@ -164,3 +167,65 @@ def test_backward_empty_and_linearity(cuda_device):
     img.sum().backward()
     assert float((img - 0.25).abs().max()) == 0.0
     assert all(float(x.grad.abs().max()) == 0.0 for x in t)
+
+
+def test_backward_100k_gaussians_vs_finite_differences(cuda_device):
+    """Backward at scale (100 k Gaussians @1080p, M ~ 8 M) against central finite differences of the forward pass, on a
+    random subset of parameters.  The loss is a fixed random projection of the image; the forward used for the
+    differences is the train forward in fp32, so the step is chosen large enough for its rounding noise (1e-7
+    relative on a sum of ~6 M terms) and parameters whose two-sided difference crosses a threshold decision (alpha
+    1/255, saturation: the loss is discontinuous there) are recognised by a mismatch between the h and h/2
+    differences and skipped."""
+    from mojosplat_b200 import synthetic
+    sc = synthetic.make_scene("config2_100k_1080p")
+    cam = sc.camera
+    g = [t.to(cuda_device) for t in sc.gaussians()]
+    bg = sc.background.to(cuda_device)
+    _, aux = ms.render_fused(*g, cam.to(cuda_device), bg, return_aux=True)
+    _, aux = ms.render_fused(*g, cam.to(cuda_device), bg, return_aux=True)
+    ids, ranges = aux["sorted_ids"], aux["tile_ranges"]
+    assert ids is not None and ids.numel() > 5_000_000
+    gen = torch.Generator().manual_seed(5)
+    gimg = torch.randn(cam.H, cam.W, 3, generator=gen).to(cuda_device)
+    base = [aux["means2d"].double(), aux["conics"].double(), g[4].double(), g[3].double()]
+
+    def loss(params):
+        img = rasterization.rasterize_gaussians_diff(params[0].float(), params[1].float(), params[2].float(),
+                                                     params[3].float(), bg, ranges, ids, cam, 16)
+        return float((img.double() * gimg.double()).sum())
+
+    t = [x.float().clone().requires_grad_(True) for x in base]
+    img = rasterization.rasterize_gaussians_diff(*t, bg, ranges, ids, cam, 16)
+    (img * gimg).sum().backward()
+    torch.cuda.synchronize()
+    # visible Gaussians with a sizeable gradient
+    vis = torch.nonzero((aux["radii"] > 0).all(-1)).flatten().cpu()
+    pick = vis[torch.randperm(vis.numel(), generator=gen)[:12]]
+    # The alpha >= 1/255 ring of a Gaussian is ~60 pixels long: a step moves a few of them across the threshold and each
+    # crossing jumps the loss by ~T c / 255.  Their contribution to the difference quotient falls like 1 / sqrt(h)
+    # while the truncation error of a ~3 px wide Gaussian is (h / sigma)^2 / 6: fairly large steps are the accurate ones.
+    steps = {0: 0.25, 1: None, 2: 5e-2, 3: 5e-2}   # means2d (px), conics (relative), colours, opacities
+    checked = 0
+    for which, name in enumerate(["means2d", "conics", "colors", "opacities"]):
+        for gi in pick.tolist():
+            comp = 0 if which == 3 else int(gi) % base[which].shape[1]
+            analytic = float(t[which].grad[gi] if which == 3 else t[which].grad[gi, comp])
+            x0 = float(base[which][gi] if which == 3 else base[which][gi, comp])
+            h = steps[which] if steps[which] is not None else 0.05 * abs(x0) + 1e-5
+            fd = []
+            for hh in (h, h / 2):
+                vals = []
+                for sgn in (+1, -1):
+                    p = [x.clone() for x in base]
+                    if which == 3:
+                        p[which][gi] = x0 + sgn * hh
+                    else:
+                        p[which][gi, comp] = x0 + sgn * hh
+                    vals.append(loss(p))
+                fd.append((vals[0] - vals[1]) / (2 * hh))
+            scale = max(abs(fd[0]), abs(fd[1]), abs(analytic), 1e-6)
+            if abs(fd[0] - fd[1]) > 0.1 * scale:
+                continue   # threshold crossings dominate inside [x - h, x + h]: no derivative to compare with
+            checked += 1
+            assert abs(analytic - fd[0]) <= 0.1 * scale + 2e-3, (name, gi, comp, analytic, fd)
+    assert checked >= 24, checked

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import mojosplat_b200 as ms
-from helpers import image_gate, scene_on
+from helpers import audit_inputs, image_gate, scene_on
 from mojosplat_b200 import synthetic
 from oracle import oracle
 
@@ -26,7 +26,9 @@ def test_render_end_to_end_vs_oracle(cuda_device, cfg, N):
     (m, s, q, o, c), cam = scene_on(sc, cuda_device)
     img = ms.render_gaussians(m, s, q, o, c, cam, background_color=sc.background.to(cuda_device), backend="cuda")
     assert img.shape == (cam.H, cam.W, 3) and img.dtype == torch.float32 and img.device.type == "cuda"
-    r = image_gate(img.cpu().numpy(), ref["image"], frac_allowed=2e-4)
+    # end to end the projected values differ from the oracle's in the last bits (libdevice vs glibc expf, conic
+    # reciprocal), so a few more threshold decisions flip than with identical raster inputs: every one is audited
+    r = image_gate(img.cpu().numpy(), ref["image"], frac_allowed=2e-4, audit=audit_inputs(ref, sc))
     assert r["ok"], r
     # stage outputs of the fused path: binning must be bit-exact when the projected inputs agree
     img2, aux = ms.render_fused(m, s, q, o, c, cam, sc.background.to(cuda_device), return_aux=True)

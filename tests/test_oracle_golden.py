@@ -21,19 +21,27 @@ def project_case(g, semantics=oracle.SEM_TORCH):
                           fx, fy, cx, cy, W, H, near, far, 0.3, semantics)
 
 
+def bits_equal(a, b):
+    """Element-wise bit equality of two float32 arrays, NaNs of any payload counted equal."""
+    a = np.asarray(a, np.float32); b = np.asarray(b, np.float32)
+    return (a == b) | ((a != a) & (b != b))
+
+
 @pytest.mark.parametrize("name", FULL_CASES)
 def test_projection_matches_reference(name):
+    """The oracle follows the rounding of the reference's torch ops (oracle.c: matmul einsums as FMA chains,
+    product + sum einsums and element-wise ops rounded per operation, correctly rounded exp): means2d, depths and
+    radii equal the unmodified reference's output BIT FOR BIT; so do the conics wherever MKL's exp returned the
+    correctly rounded scale (~97 % of the rows), the rest stays within the reference's own tolerance."""
     g = load_golden(name)
     m2, con, dep, rad = project_case(g)
+    assert bits_equal(m2, g["means2d"]).all()
+    assert bits_equal(dep, g["depths"]).all()
+    assert np.array_equal(rad, g["radii"])
+    rows = bits_equal(con, g["conics"]).all(-1)
+    assert rows.mean() >= 0.95, rows.mean()
     # SURVEY H3: the reference's own convention atol + rtol*|ref| (test_rasterization.py:110)
-    np.testing.assert_allclose(m2, g["means2d"], atol=1e-4, rtol=1e-4)
     np.testing.assert_allclose(con, g["conics"], atol=1e-4, rtol=1e-4)
-    np.testing.assert_allclose(dep, g["depths"], atol=1e-4, rtol=1e-4)
-    diff = np.abs(rad.astype(np.int64) - g["radii"].astype(np.int64))
-    # ceil() flips by one at integer crossings; culling decisions must agree
-    assert diff.max() <= 1
-    assert (diff > 0).sum() <= max(1, rad.shape[0] // 2000)
-    assert np.array_equal((rad > 0).all(-1), (g["radii"] > 0).all(-1))
 
 
 @pytest.mark.parametrize("name", FULL_CASES + BIN_CASES)
