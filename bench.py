@@ -82,9 +82,9 @@ def ncu_traffic(key):
     if not p.exists():
         return None, None
     d = json.loads(p.read_text()).get(key)
-    if not d:
+    if not d or d.get("dram_bytes") is None:
         return None, None
-    return d["dram_bytes"], d["source"]
+    return d["dram_bytes"], d.get("source")
 
 
 class ClockSampler:

@@ -130,11 +130,11 @@ class OverlappedPipeline:
 
     def __init__(self, device, N: int, W: int, H: int, channels: int = 3, tile_size: int = 16,
                  semantics: int = _lib.SEM_TORCH, slots: int = 3, m_capacity: int | None = None,
-                 raster_mode: str = "fast", bin_streams: int = 2):
+                 raster_mode: str = "fast", bin_streams: int = 2, packed: bool = False):
         self.dev = torch.device(device)
         self.L = _lib.require_device(self.dev)
         self.N, self.W, self.H, self.C, self.ts = int(N), int(W), int(H), int(channels), int(tile_size)
-        self.semantics, self.flags = semantics, RASTER_MODES[raster_mode]
+        self.semantics, self.flags = semantics, RASTER_MODES[raster_mode] | (_lib.FLAG_PACKED if packed else 0)
         self.slots = slots
         self.n_bin = max(1, min(bin_streams, slots))
         self.m_cap = int(m_capacity) if m_capacity else 8 * self.N + 4096
@@ -346,20 +346,30 @@ class HostFramePipeline:
 
     @torch.no_grad()
     def render(self, host_scenes, cameras: Sequence[Camera], background_host: torch.Tensor,
-               out_host: torch.Tensor, upload: str = "every_frame") -> torch.Tensor:
+               out_host: torch.Tensor, upload: str = "every_frame", timeline: bool = False) -> torch.Tensor:
         """host_scenes: callable k -> 5 contiguous float32 CPU tensors (pinned for full speed);
         out_host: pinned [n or ring, H, W, C].  Returns out_host after a final synchronisation.
         upload="once": the scene of frame 0 is uploaded once and stays resident (a static scene seen from many
-        poses); every frame still sends its camera and downloads its image."""
+        poses); every frame still sends its camera and downloads its image.
+        timeline=True: per-frame device times (ms since the first enqueue) of (rasterizer end, download start,
+        download end) in ``self.last_timeline``; ``self.last_host_enqueue_s`` is the host time spent enqueueing."""
+        import time
         core = self.core
         n = len(cameras)
         cams = [_lib.camera_struct(c) for c in cameras]
         infos = torch.zeros((max(n, 1), 32), dtype=torch.uint8).pin_memory()
+        mk = (lambda: torch.cuda.Event(enable_timing=True)) if timeline else torch.cuda.Event
         ev_in = [torch.cuda.Event() for _ in range(n)]
-        ev_used = [torch.cuda.Event() for _ in range(n)]   # frame k no longer reads its input slot
-        ev_ras = [torch.cuda.Event() for _ in range(n)]
-        ev_out = [torch.cuda.Event() for _ in range(n)]
+        ev_used = [None] * n                               # frame k no longer reads its input slot
+        ev_ras = [mk() for _ in range(n)]
+        ev_dl = [mk() for _ in range(n)] if timeline else None
+        ev_out = [mk() for _ in range(n)]
+        t_host = time.perf_counter()
         with torch.cuda.device(self.dev):
+            ev0 = None
+            if timeline:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(self.s_in):
                 self.bg_dev.copy_(background_host.reshape(-1), non_blocking=True)
             for k in range(n):
@@ -385,11 +395,19 @@ class HostFramePipeline:
                 core._enqueue(oslot, self.g_dev[islot], cams[k], self.bg_dev, self.img_dev[oslot], infos[k], sb)
                 ev_ras[k].record(core.s_ras)   # rasterizer read colours/opacities: inputs are free after it
                 ev_used[k] = ev_ras[k]
+                # download on its own stream (plain stream calls: no context-manager overhead per frame)
+                self.s_out.wait_event(ev_ras[k])
+                if timeline:
+                    ev_dl[k].record(self.s_out)
                 with torch.cuda.stream(self.s_out):
-                    self.s_out.wait_event(ev_ras[k])
                     out_host[k % out_host.shape[0]].copy_(self.img_dev[oslot], non_blocking=True)
-                    ev_out[k].record(self.s_out)
+                ev_out[k].record(self.s_out)
+        self.last_host_enqueue_s = time.perf_counter() - t_host
         torch.cuda.synchronize(self.dev)
+        self.last_timeline = None
+        if timeline:
+            self.last_timeline = [(ev0.elapsed_time(ev_ras[k]), ev0.elapsed_time(ev_dl[k]), ev0.elapsed_time(ev_out[k]))
+                                  for k in range(n)]
         for k in range(n):
             info = _lib.BsplatBinInfo.from_buffer_copy(infos[k].numpy().tobytes())
             if info.reserved[1]:
