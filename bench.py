@@ -258,6 +258,12 @@ def run_b200(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     L = _lib.require_device(dev)  # fails loudly without the .so / an sm_100 device
+    # multi-GPU boxes: run this rank, and allocate its pinned host buffers, on the GPU's own NUMA node (best effort;
+    # the outcome is reported in e2e.numa -- containers often confine every rank to node 0)
+    numa = None
+    if world > 1:
+        from mojosplat_b200 import hostmem
+        numa = hostmem.bind_to_device_node(local_rank)
     sem = _lib.SEM_TORCH if args.semantics == "torch" else _lib.SEM_GSPLAT
 
     # ---- scene: rank 0 draws it, everyone else receives it over NCCL (one broadcast, at load) ----
@@ -601,6 +607,7 @@ def run_b200(args, rank, world, local_rank):
                 "resident_scene_value": e2e_resident,
                 "resident_scene_note": "same pipeline with the Gaussians uploaded once per batch (static scene): per frame "
                                        "only the camera goes up and the image (d2h_bytes_per_step) comes down",
+                "numa": numa, "host_cores_visible": host_cores(),
                 "single_call_ms": e2e_single_call_ms,
                 "single_call_api": "mojosplat_b200.render_gaussians_host (copy in -> render -> copy out -> sync)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,

@@ -447,7 +447,8 @@ __device__ __forceinline__ int fin_bucket(const uint32_t cc) { return (int)(255u
 
 __global__ void __launch_bounds__(kFinThreads)
 tile_finish2_kernel(const int n_tiles, const int first, const int n_order, const uint32_t* __restrict__ counts,
-                    int32_t* __restrict__ ranges, int32_t* __restrict__ order, uint32_t* __restrict__ scratch) {
+                    int32_t* __restrict__ ranges, int32_t* __restrict__ order, uint32_t* __restrict__ scratch,
+                    const bsplat_bin_info* __restrict__ info_dev, bsplat_bin_info* __restrict__ info_host) {
     __shared__ int s_cnt[256];
     __shared__ int s_res[256];
     __shared__ uint32_t s_w[kFinThreads / 32];
@@ -474,6 +475,12 @@ tile_finish2_kernel(const int n_tiles, const int first, const int n_order, const
         return s;
     };
     for (int i = tid; i < 256; i += kFinThreads) s_cnt[i] = 0;
+    // The frame's status (M, overflow flag) goes to the caller's pinned host block with a plain store over PCIe --
+    // not a cudaMemcpyAsync: a 32-byte copy would queue in the device-to-host copy engine behind a 25 MB image
+    // download of an earlier frame and stall the whole binning stream for its duration (measured: a 0.44 ms bubble
+    // every third frame of the host-buffer pipeline).
+    if (info_host != nullptr && b == 0 && tid < (int)(sizeof(bsplat_bin_info) / sizeof(uint32_t)))
+        reinterpret_cast<volatile uint32_t*>(info_host)[tid] = reinterpret_cast<const uint32_t*>(info_dev)[tid];
     __syncthreads();
     // ---- phase 1: block total + bucket histogram of this CTA's tiles ----
     uint32_t mine = 0;
@@ -549,10 +556,12 @@ tile_finish2_kernel(const int n_tiles, const int first, const int n_order, const
 }
 
 int tile_finish_launch(int n_tiles, int first, int n_order, const uint32_t* counts, int32_t* ranges,
-                       int32_t* order, uint32_t* scratch, cudaStream_t stream) {
+                       int32_t* order, uint32_t* scratch, const bsplat_bin_info* info_dev,
+                       bsplat_bin_info* info_host, cudaStream_t stream) {
     const int by_size = (n_tiles + 63) / 64;
     const int G = by_size < 1 ? 1 : (by_size > kFinMaxCtas ? kFinMaxCtas : by_size);
-    tile_finish2_kernel<<<G, kFinThreads, 0, stream>>>(n_tiles, first, n_order, counts, ranges, order, scratch);
+    tile_finish2_kernel<<<G, kFinThreads, 0, stream>>>(n_tiles, first, n_order, counts, ranges, order, scratch,
+                                                       info_dev, info_host);
     BSPLAT_LAUNCH_CHECK();
     return BSPLAT_OK;
 }
@@ -727,8 +736,10 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
 
 // device_m: M is a capacity; the real count is read on the device from the bin info (n_isect) written by
 // prepare -- no host read-back between prepare and finish (sync-free / graph-capturable frames).
+// info_host (optional): device-accessible pinned host block that receives the frame's bin info from the last kernel.
 int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* workspace, size_t workspace_bytes,
-                int32_t* sorted_ids, int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream, bool compact) {
+                int32_t* sorted_ids, int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream, bool compact,
+                bsplat_bin_info* info_host) {
     const int n_tiles = p.tiles_w * p.tiles_h;
     Bin2Ws w = carve_bin2(workspace, N, M, n_tiles);
     if (!workspace || workspace_bytes < w.total) return BSPLAT_E_WORKSPACE;
@@ -743,7 +754,8 @@ int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* w
             BSPLAT_CUDA_TRY(cudaMemsetAsync(tile_ranges, 0, (size_t)n_tiles * 2 * sizeof(int32_t), stream));
             return BSPLAT_OK;
         }
-        return tile_finish_launch(n_tiles, first, n_order, nullptr, tile_ranges, tile_order, w.fin_scratch, stream);
+        return tile_finish_launch(n_tiles, first, n_order, nullptr, tile_ranges, tile_order, w.fin_scratch, w.info,
+                                  info_host, stream);
     }
     const TilePasses tp = tile_passes_of(n_tiles);
     // one warp per task of kEmitTask pairs; M is the capacity in sync-free frames
@@ -766,7 +778,8 @@ int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* w
         ksrc = kdst; kdst = (kdst == w.tkeys_alt) ? w.tkeys : w.tkeys_alt;
         vsrc = vdst; vdst = (vdst == w.ids_alt) ? w.ids : w.ids_alt;
     }
-    return tile_finish_launch(n_tiles, first, n_order, w.tile_counts, tile_ranges, tile_order, w.fin_scratch, stream);
+    return tile_finish_launch(n_tiles, first, n_order, w.tile_counts, tile_ranges, tile_order, w.fin_scratch, w.info,
+                              info_host, stream);
 }
 
 size_t bin2_workspace_bytes(int64_t N, int64_t M, int64_t n_tiles) { return carve_bin2(nullptr, N, M, n_tiles).total; }
@@ -829,5 +842,5 @@ extern "C" int bsplat_bin2_finish(int64_t N, int64_t M, const float* means2d, co
     if (M >= (int64_t)kStatMask) return BSPLAT_E_OVERFLOW;
     if (M > 0 && !sorted_ids) return BSPLAT_E_ARG;
     return bin2_finish(N, M, false, p, workspace, workspace_bytes, sorted_ids, tile_ranges, tile_order, stream,
-                       (semantics & BSPLAT_BIN_PACKED) != 0);
+                       (semantics & BSPLAT_BIN_PACKED) != 0, nullptr);
 }

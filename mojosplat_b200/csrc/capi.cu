@@ -12,7 +12,8 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
                  const BinParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream, bool have_prep,
                  bool compact);
 int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* workspace, size_t workspace_bytes,
-                int32_t* sorted_ids, int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream, bool compact);
+                int32_t* sorted_ids, int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream, bool compact,
+                bsplat_bin_info* info_host = nullptr);
 int project_fwd_launch(int64_t N, const float* means3d, const float* log_scales, const float* quats,
                        const float* opacities, const bsplat_camera& cam, float eps2d, int semantics,
                        float* means2d, float* conics, float* depths, int32_t* radii, cudaStream_t stream,
@@ -565,10 +566,21 @@ extern "C" int bsplat_render_enqueue_band_p2p(int64_t N, const float* means3d, c
     BinParams p;
     rc = make_bin_params(W, H, tile_size, row0, row1, semantics, &p);
     if (rc != BSPLAT_OK) return rc;
+    // the bin info reaches the host as a store from the last binning kernel when the block is device-accessible
+    // (pinned memory under UVA); a copy-engine transfer would queue behind image downloads of earlier frames
+    bool info_direct = false;
+    if (info_host_pinned) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, info_host_pinned) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer == (void*)info_host_pinned)
+            info_direct = true;
+        else
+            (void)cudaGetLastError();
+    }
     rc = bin2_finish(N, M_capacity, /*device_m=*/true, p, w.bin_ws, w.bin_bytes, w.sorted_ids, w.tile_ranges,
-                     w.tile_order, sb, (flags & BSPLAT_FLAG_PACKED) != 0);
+                     w.tile_order, sb, (flags & BSPLAT_FLAG_PACKED) != 0, info_direct ? info_host_pinned : nullptr);
     if (rc != BSPLAT_OK) return rc;
-    if (info_host_pinned)
+    if (info_host_pinned && !info_direct)
         BSPLAT_CUDA_TRY(cudaMemcpyAsync(info_host_pinned, d_info, sizeof(bsplat_bin_info), cudaMemcpyDeviceToHost, sb));
     if (sr != sb) {
         BSPLAT_CUDA_TRY(cudaEventRecord((cudaEvent_t)event_bin_done, sb));
