@@ -521,9 +521,9 @@ def run_b200(args, rank, world, local_rank):
     achieved = flops / raster_s / 1e12
     n_tiles = math.ceil(H / 16) * math.ceil(W / 16)
     proj_bytes = 72 * N
-    # the fused kernel reads colours + opacity too (56 B) and writes the tile rectangle, the depth key and the 80-byte
-    # raster record instead of the four stage outputs (92 B): work the separate record / depth-key passes used to do
-    proj_fused_bytes = (56 + 92) * N
+    # the fused kernel reads colours + opacity too (56 B) and writes the tile rectangle, the depth key and the 48-byte
+    # raster record instead of the four stage outputs (60 B): work the separate record / depth-key passes used to do
+    proj_fused_bytes = (56 + 60) * N
     bin_bytes = 52 * N + (28 + 24 * P) * M + 8 * n_tiles
     bin_traffic, bin_traffic_src = ncu_traffic("binning")
     stages = {
@@ -534,7 +534,7 @@ def run_b200(args, rank, world, local_rank):
                              "frac_hbm": proj_fused_bytes / (stage[0] * 1e-3) / 1e9 / hbm_peak,
                              "bytes": proj_fused_bytes,
                              "kernel": "project_kernel inside a frame: epilogue writes tile rectangles, depth keys + "
-                                       "digit histograms and raster records (148 B per Gaussian) instead of the stage "
+                                       "digit histograms and raster records (116 B per Gaussian) instead of the stage "
                                        "outputs"},
         "binning": {"ms": stage[1] + stage[2], "depth_sort_count_scan_ms": stage[1], "emit_tile_sort_ranges_ms": stage[2],
                     "GB/s": bin_bytes / ((stage[1] + stage[2]) * 1e-3) / 1e9,

@@ -55,4 +55,5 @@ print(json.dumps({"config": cfg, "projection_alone_ms": round(float(np.median(tp
                   "M": info["n_isect"], "stage_ms": [round(float(x), 4) for x in stage],
                   "frame_ms": round(float(stage.sum()), 4),
                   "standalone_raster_call_ms (tile order + record kernel + raster)": round(float(np.median(ts)), 4),
-                  "same_image": bool(torch.equal(img, img2))}))
+                  "same_image": bool(torch.equal(img, img2)),
+                  "image_sha1": __import__("hashlib").sha1(img.cpu().numpy().tobytes()).hexdigest()[:16]}))

@@ -182,7 +182,7 @@ int bsplat_tile_order(int32_t first_tile, int32_t n_tiles, const int32_t* tile_r
  * tile_order may be NULL (row-major tile order). Only tile rows [tile_row_begin, tile_row_end) are
  * rasterized and written (pass 0 and tiles_h for the whole frame; a row band for the multi-GPU split --
  * tile_order, if given, must then list exactly the band's tiles).
- * workspace (optional, bsplat_rasterize_workspace_bytes(N) = 80 B per Gaussian, 16-byte aligned): holds the
+ * workspace (optional, bsplat_rasterize_workspace_bytes(N) = 48 B per Gaussian, 16-byte aligned): holds the
  * per-Gaussian raster records, written once per call; with it the fast kernel stages its batches with
  * cp.async one batch ahead (faster, identical results); without it it stages from the raw arrays.
  * mode: BSPLAT_RASTER_FAST / _FAITHFUL / _FAST_NOCULL (anything else: BSPLAT_E_ARG). */

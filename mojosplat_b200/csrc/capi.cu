@@ -145,7 +145,7 @@ struct RenderWs {
     float* means2d; float* conics; float* depths; int32_t* radii;
     int32_t* tile_ranges; int32_t* tile_order; int32_t* sorted_ids;
     bsplat_camera* cam_dev;  // indirect camera of captured frames
-    void* raster_rec;        // 80 B per Gaussian: raster records (projection epilogue / raster_pair_prep_kernel)
+    void* raster_rec;        // 48 B per Gaussian: raster records (projection epilogue / raster_pair_prep_kernel)
     int32_t* long_surv;      // [M] survivor ids of the long-list pre-pass
     uint32_t* long_cnt;      // per-chunk survivor counts of the long-list pre-pass
     void* bin_ws; size_t bin_bytes;

@@ -18,23 +18,20 @@ __device__ __forceinline__ bool pair_cull_hit(const float mx, const float my, co
     const float v0 = my - Y1, v1 = my - Y0;
     const bool zu = (u0 <= 0.0f) && (u1 >= 0.0f);
     const bool zv = (v0 <= 0.0f) && (v1 >= 0.0f);
-    float qmin = 0.0f;
-    if (!(zu && zv)) {
-        float q1 = INFINITY, q2 = INFINITY;
-        if (!zu) {
-            const float ue = (u0 > 0.0f) ? u0 : u1;
-            const float vstar = hy * ue;
-            const float dv = vstar - fminf(fmaxf(vstar, v0), v1);
-            q1 = fmaf(fmaf(0.5f * B, hy, A) * ue, ue, C * dv * dv);
-        }
-        if (!zv) {
-            const float ve = (v0 > 0.0f) ? v0 : v1;
-            const float ustar = hx * ve;
-            const float du = ustar - fminf(fmaxf(ustar, u0), u1);
-            q2 = fmaf(fmaf(0.5f * B, hx, C) * ve, ve, A * du * du);
-        }
-        qmin = fminf(q1, q2);
-    }
+    // branch-free (lanes of a warp test different Gaussians: divergent branches here cost more than the arithmetic)
+    const float hB = 0.5f * B;
+    const float ue = (u0 > 0.0f) ? u0 : u1;
+    const float vstar = hy * ue;
+    const float dv = vstar - fminf(fmaxf(vstar, v0), v1);
+    float q1 = fmaf(fmaf(hB, hy, A) * ue, ue, C * dv * dv);
+    const float ve = (v0 > 0.0f) ? v0 : v1;
+    const float ustar = hx * ve;
+    const float du = ustar - fminf(fmaxf(ustar, u0), u1);
+    float q2 = fmaf(fmaf(hB, hx, C) * ve, ve, A * du * du);
+    q1 = zu ? INFINITY : q1;
+    q2 = zv ? INFINITY : q2;
+    float qmin = fminf(q1, q2);
+    qmin = (zu && zv) ? 0.0f : qmin;
     const float um = fmaxf(fabsf(u0), fabsf(u1)), vm = fmaxf(fabsf(v0), fabsf(v1));
     const float slack = 4e-6f * (A * um * um + C * vm * vm) + 1e-3f;
     return !(qmin > tau + slack);
@@ -54,16 +51,20 @@ __device__ __forceinline__ void cull_constants(const float a, const float b, con
     hx = pd ? __fdividef(-B, 2.0f * A) : 0.0f;
 }
 
-constexpr int kPairRec = 5;  // float4 per raster record
+constexpr int kPairRec = 3;  // float4 per raster record (48 B: a 12-word stride keeps per-lane LDS.128 conflict-free)
 
-// The rasterizer's record of one Gaussian (5 x float4; every operand of the packed-pair walk stored duplicated):
-//   q0 = {mx, mx, my, my}  q1 = {-A, -A, -B, -B}  q2 = {-C, -C, L, L}  q3 = {r, g, b, tau}  q4 = {hy, hx, special, Lt}
+// The rasterizer's record of one Gaussian (3 x float4), operands stored ONCE: sm_100's packed FP32 instructions take a
+// scalar register broadcast to both halves (`FFMA2 R, R.F32x2, R.F32, R.F32x2`), so the two-pixel walk needs no
+// duplicated operands.
+//   q0 = {mx, my, -A, -B}  q1 = {-C, L, r, g}  q2 = {b, tau*, hy, hx}
+// tau* = tau with the lowest mantissa bit carrying the "special" flag (tau only feeds the conservative culling bound,
+// whose slack is 1e-3; tau = +inf -- never cull -- only occurs for special Gaussians and becomes a NaN, which the
+// NaN-safe bound also counts as a hit).
 // One definition for the in-kernel staging, the record kernel and the projection epilogue, so that every path
 // composites bit-identical values (products of two or three factors only: nothing here can be contracted).
 __device__ __forceinline__ void pair_record_from(const float mx, const float my, const float ca, const float cb,
                                                  const float cc, const float op, const float cr, const float cg,
-                                                 const float cbl, float4& q0, float4& q1, float4& q2, float4& q3,
-                                                 float4& q4) {
+                                                 const float cbl, float4& q0, float4& q1, float4& q2) {
     const float A = __fmul_rn(__fmul_rn(0.5f, kLog2e), ca), B = __fmul_rn(kLog2e, cb),
                 C = __fmul_rn(__fmul_rn(0.5f, kLog2e), cc);
     // MUFU.LG2 (abs. error ~2^-22): alpha = 2^(L - q) stays within 1e-6 of o*exp(-sigma)
@@ -71,18 +72,34 @@ __device__ __forceinline__ void pair_record_from(const float mx, const float my,
     const bool pd = (A > 0.0f) && (C > 0.0f) && (__fsub_rn(__fmul_rn(__fmul_rn(4.0f, A), C), __fmul_rn(B, B)) > 0.0f);
     float tau = pd ? __fsub_rn(L, kLog2AlphaThreshold) : INFINITY;
     if (!(op == op)) tau = INFINITY;  // NaN opacity: evaluate, never cull
-    q0 = make_float4(mx, mx, my, my);
-    q1 = make_float4(-A, -A, -B, -B);
-    q2 = make_float4(-C, -C, L, L);
-    q3 = make_float4(cr, cg, cbl, tau);
     // "plain" Gaussians (positive-definite conic, opacity <= 0.99, no NaN) have q >= 0 and alpha <= opacity by
     // construction: the walk may skip the sigma < 0 test and the 0.999 clamp (0.99, not 0.999: ex2.approx may
-    // overshoot by an ulp).  q4.w is the bound of the sigma >= 0 test of the full walk: +inf for plain Gaussians,
-    // so both walks treat them identically.  The edge minimisers hy, hx feed the conservative culling bound only:
+    // overshoot by an ulp).  The full walk applies the sigma >= 0 test (power <= L) to special Gaussians only, so
+    // both walks treat plain ones identically.  The edge minimisers hy, hx feed the conservative culling bound only:
     // approximate division is inside its slack.
     const bool plain = pd && (op <= 0.99f);
-    q4 = make_float4(pd ? __fdividef(-B, __fmul_rn(2.0f, C)) : 0.0f, pd ? __fdividef(-B, __fmul_rn(2.0f, A)) : 0.0f,
-                     plain ? 0.f : 1.f, plain ? INFINITY : L);
+    const uint32_t tb = (__float_as_uint(tau) & ~1u) | (plain ? 0u : 1u);
+    q0 = make_float4(mx, my, -A, -B);
+    q1 = make_float4(-C, L, cr, cg);
+    q2 = make_float4(cbl, __uint_as_float(tb), pd ? __fdividef(-B, __fmul_rn(2.0f, C)) : 0.0f,
+                     pd ? __fdividef(-B, __fmul_rn(2.0f, A)) : 0.0f);
+}
+
+// A record that can never hit (past the end of a list / invalid id, rasterization.mojo:109 guard): tau = -inf
+__device__ __forceinline__ void pair_record_none(float4& q0, float4& q1, float4& q2) {
+    q0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    q1 = make_float4(0.f, -INFINITY, 0.f, 0.f);
+    q2 = make_float4(0.f, -INFINITY, 0.f, 0.f);
+}
+
+// The culling test on a record (global or shared memory): block = pixel-centre rectangle [X0, X1] x [Y0, Y1].
+__device__ __forceinline__ bool pair_record_hit(const float4* r, const float X0, const float X1, const float Y0,
+                                                const float Y1, bool* special) {
+    const float4 p0 = r[0];
+    const float nC = reinterpret_cast<const float*>(r + 1)[0];
+    const float4 p2 = r[2];
+    if (special) *special = (__float_as_uint(p2.y) & 1u) != 0u;
+    return pair_cull_hit(p0.x, p0.y, -p0.z, -p0.w, -nC, p2.y, p2.z, p2.w, X0, X1, Y0, Y1);
 }
 
 }  // namespace bsplat

@@ -136,16 +136,16 @@ __global__ void __launch_bounds__(1024) raster_faithful_kernel(const int64_t N, 
 // pair kernel (tile 16, RGB): the fast path.
 // sm_100 executes packed FP32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot, two lanes of work), and the
 // rasterizer is bound by instruction issue, not by the FP32 pipe.  So each lane owns TWO pixels -- (x, y) and
-// (x, y + 4) of the warp's 8x8 block -- and the whole quadratic runs as f32x2 instructions on
-// register pairs.  Staged records keep every per-Gaussian operand duplicated {v, v}, so the pairs come
-// straight out of LDS.128 with no packing moves.  4 warps (128 threads) per 16x16 tile.
-//   record t (80 B): s[5t] = {mx, mx, my, my}  s[5t+1] = {-A, -A, -B, -B}  s[5t+2] = {-C, -C, L, L}
-//                    s[5t+3] = {r, g, b, tau}  s[5t+4] = {hy, hx, special, Lt}
+// (x, y + 4) of the warp's 8x8 block -- and the whole quadratic, the transmittance update and the colour
+// accumulation run as f32x2 instructions on register pairs; the per-Gaussian operands enter as scalar registers
+// broadcast to both halves (`R.F32` operands), so records hold every value once.  4 warps (128 threads) per tile.
+//   record t (48 B): s[3t] = {mx, my, -A, -B}  s[3t+1] = {-C, L, r, g}  s[3t+2] = {b, tau*, hy, hx}
 //   with A = 0.5 a log2e, B = b log2e, C = 0.5 c log2e, L = log2(opacity), hy = -B/(2C), hx = -B/(2A) (edge
-//   minimisers of the quadratic), tau = L - log2(1/255) (+inf: never cull, -inf: not a Gaussian)
+//   minimisers of the quadratic), tau = L - log2(1/255) (+inf: never cull, -inf: not a Gaussian; lowest bit = special)
 //   power = L - (A dx^2 + B dx dy + C dy^2) as  fma2(fma2(-A, dx, -B dy), dx, fma2(-C dy, dy, L))
-// A finished pixel carries -x = -inf (every later power is -inf or NaN and fails the alpha test by itself -- no
-// flag in the inner loop).  Each warp first tests 32 staged Gaussians at once (one per lane) against its 8x8
+// alpha is zeroed when it fails the threshold, so T (1 - alpha) = T and alpha T = 0 need no selects; the walk only
+// branches (rarely) when a pixel saturates.  A finished pixel carries -x = -inf (every later power is -inf or NaN
+// and fails the alpha test by itself -- no flag in the inner loop).  Each warp first tests 32 staged Gaussians at once (one per lane) against its 8x8
 // block with an exact conservative ellipse / rectangle bound and then only walks the survivors (warp ballot);
 // a skipped Gaussian has alpha < 1/255 on all 64 pixels, so the composited result is unchanged.
 // (Three earlier variants -- one pixel per lane, independent warps with per-warp staging, an mbarrier
@@ -153,7 +153,16 @@ __global__ void __launch_bounds__(1024) raster_faithful_kernel(const int64_t N, 
 // ------------------------------------------------------------------------------------------
 constexpr int kFastTile = 16;
 constexpr int kPairThreads = 128;
-constexpr int kPairBatch = 256;
+constexpr int kPairBatch = 256;   // staged entries per batch without records
+#ifndef BSPLAT_REC_BATCH
+#define BSPLAT_REC_BATCH 128
+#endif
+#ifndef BSPLAT_REC_STAGES
+#define BSPLAT_REC_STAGES 2
+#endif
+constexpr int kRecBatch = BSPLAT_REC_BATCH;    // with records: entries per batch (a multiple of 32) ...
+constexpr int kRecStages = BSPLAT_REC_STAGES;  // ... in a ring of this many buffers: the gather runs kRecStages - 1 batches ahead
+static_assert(kRecBatch % 32 == 0 && kRecStages >= 2 && kRecStages <= 4, "record staging ring");
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -161,29 +170,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
+// packed FP32 pairs: the sm_100 intrinsics on float2 (register pairs; FFMA2 / FADD2 / FMUL2)
+__device__ __forceinline__ float2 dup2(const float v) { return make_float2(v, v); }  // becomes an `R.F32` operand
+__device__ __forceinline__ bool pair_finished(const float2 npx) {  // both halves are -inf
+    return !(npx.x > -INFINITY) && !(npx.y > -INFINITY);
 }
 
 // Lists longer than kLongTile are mostly Gaussians that cannot touch the tile at all (under the torch binning rules
@@ -202,22 +192,17 @@ constexpr int kMaxLongChunks = 256;    // longer lists (> 1 M entries) keep the 
 constexpr int kMaxLongSlots = 256;     // at most this many long tiles are compacted (the longest ones)
 constexpr int kLongThreads = 1024;     // 4 entries per thread: every gather of a chunk is in flight at once
 
-struct LoopConsts {
-    unsigned int one_u;
-    float one_f, mone_f;
-};
 
 __device__ __forceinline__ void pair_record(const int64_t g, const float* __restrict__ means2d,
                                             const float* __restrict__ conics, const float* __restrict__ colors,
-                                            const float* __restrict__ opacities, float4& q0, float4& q1, float4& q2,
-                                            float4& q3, float4& q4) {
+                                            const float* __restrict__ opacities, float4& q0, float4& q1, float4& q2) {
     const float2 m = __ldg(reinterpret_cast<const float2*>(means2d) + g);
     pair_record_from(m.x, m.y, __ldg(conics + 3 * g), __ldg(conics + 3 * g + 1), __ldg(conics + 3 * g + 2),
                      __ldg(opacities + g), __ldg(colors + 3 * g), __ldg(colors + 3 * g + 1), __ldg(colors + 3 * g + 2),
-                     q0, q1, q2, q3, q4);
+                     q0, q1, q2);
 }
 
-// Records of ALL Gaussians, once per frame (80 B each): with them the rasterizer's staging is a pure gather that
+// Records of ALL Gaussians, once per frame (48 B each): with them the rasterizer's staging is a pure gather that
 // cp.async can run one batch ahead, and the per-(tile, Gaussian) staging arithmetic disappears.  (Fused frames get
 // the records from the projection kernel's epilogue instead; this kernel serves the stage-level entry point.)
 // With a list (row-band frames: the band's Gaussians in depth order, count on the device) only those get a record.
@@ -232,10 +217,10 @@ raster_pair_prep_kernel(const int64_t N, const float* __restrict__ means2d, cons
         g = __ldg(list + g);
     }
     if (g < 0 || g >= N) return;
-    float4 q0, q1, q2, q3, q4;
-    pair_record(g, means2d, conics, colors, opacities, q0, q1, q2, q3, q4);
+    float4 q0, q1, q2;
+    pair_record(g, means2d, conics, colors, opacities, q0, q1, q2);
     float4* d = rec + kPairRec * g;
-    d[0] = q0; d[1] = q1; d[2] = q2; d[3] = q3; d[4] = q4;
+    d[0] = q0; d[1] = q1; d[2] = q2;
 }
 
 // Scratch of the pre-pass (uint32 words): [0, kMaxLongSlots) survivors per compacted slot (slot = position in
@@ -263,11 +248,9 @@ __device__ __forceinline__ void long_test_chunk(const int64_t N, const float4* _
         const int32_t g = ids[k];
         if (g >= 0 && (int64_t)g < N) {
             const float4* r = rec + kPairRec * (int64_t)g;
-            const float4 p0 = __ldg(r), p1 = __ldg(r + 1);
-            const float nC = __ldg(reinterpret_cast<const float*>(r + 2));
-            const float tau = __ldg(reinterpret_cast<const float*>(r + 3) + 3);
-            const float2 hh = __ldg(reinterpret_cast<const float2*>(r + 4));
-            hit = pair_cull_hit(p0.x, p0.z, -p1.x, -p1.z, -nC, tau, hh.x, hh.y, TX0, TX1, TY0, TY1);
+            const float4 p0 = __ldg(r), p2 = __ldg(r + 2);
+            const float nC = __ldg(reinterpret_cast<const float*>(r + 1));
+            hit = pair_cull_hit(p0.x, p0.y, -p0.z, -p0.w, -nC, p2.y, p2.z, p2.w, TX0, TX1, TY0, TY1);
         }
         ballots[k] = __ballot_sync(0xffffffffu, hit);
     }
@@ -406,6 +389,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 // kRec: the Gaussians come as prepared records; batches of 128 are gathered by sorted id with cp.async into the two
 // halves of the staging buffer, one batch ahead of the walk (ids two batches ahead), one barrier per batch.
@@ -418,10 +403,14 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                    const int32_t* __restrict__ tile_order, const int first_tile,
                    const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
                    float* __restrict__ image, const int vec_store,
-                   const unsigned long long* __restrict__ m_dev, const PeerImages peers, const LoopConsts consts,
+                   const unsigned long long* __restrict__ m_dev, const PeerImages peers,
                    const int32_t* __restrict__ surv, const uint32_t* __restrict__ chunk_cnt) {
-    __shared__ float4 s_g[kPairBatch * kPairRec];
-    __shared__ unsigned int s_tmask[kPairBatch / 32];  // long tiles without a pre-pass: survivors of the tile-level test
+    // staging: with records a ring of kRecStages batches, without one batch; the output tile (16 x 48 floats) reuses it.
+    // (Kept as small as possible: what shared memory does not take stays L1, which the record gathers live on.)
+    constexpr int kStageRecs = kRec ? kRecStages * kRecBatch : kPairBatch;
+    static_assert(kStageRecs * kPairRec * sizeof(float4) >= 16 * 48 * sizeof(float), "output tile fits the staging buffer");
+    __shared__ float4 s_g[kStageRecs * kPairRec];
+    __shared__ unsigned int s_tmask[(kRec ? kRecBatch : kPairBatch) / 32];  // long tiles without a pre-pass: survivors of the tile-level test
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int tile = tile_order ? __ldg(tile_order + blockIdx.x) : first_tile + (int)blockIdx.x;
@@ -432,9 +421,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     const int j = bx + (lane & 7);
     const int i0 = by + (lane >> 3), i1 = i0 + 4;
     const bool in0 = (i0 < H) && (j < W), in1 = (i1 < H) && (j < W);
-    float npx0 = in0 ? -((float)j + 0.5f) : -INFINITY;  // negated x per pixel; -inf = finished
-    float npx1 = in1 ? -((float)j + 0.5f) : -INFINITY;
-    const f32x2 npy = pk2(-((float)i0 + 0.5f), -((float)i1 + 0.5f));
+    const float2 npy = make_float2(-((float)i0 + 0.5f), -((float)i1 + 0.5f));
     const float X0 = (float)bx + 0.5f, X1 = (float)bx + 7.5f;
     const float Y0 = (float)by + 0.5f, Y1 = (float)by + 7.5f;
 
@@ -457,46 +444,60 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     const bool long_tile = kCull && !compacted && (r1 - r0 > kLongTile);
     const float TX0 = (float)(tile_x * kFastTile) + 0.5f, TX1 = TX0 + 15.0f;
     const float TY0 = (float)(tile_y * kFastTile) + 0.5f, TY1 = TY0 + 15.0f;
-    float T0 = 1.0f, T1 = 1.0f;
-    float ar0 = 0.f, ag0 = 0.f, ab0 = 0.f, ar1 = 0.f, ag1 = 0.f, ab1 = 0.f;
-    // loop constants come in as kernel parameters (constant bank operands): ptxas otherwise re-materialises
-    // literal constants with a MOV in every iteration of the walk, which is bound by issue slots
-    const unsigned int bit_one = consts.one_u;
-    const f32x2 one2 = pk2(consts.one_f, consts.one_f), mone2 = pk2(consts.mone_f, consts.mone_f);
+    float2 T2 = make_float2(1.0f, 1.0f);
+    float2 acc_r = make_float2(0.f, 0.f), acc_g = acc_r, acc_b = acc_r;  // {pixel 0, pixel 1} per channel
+    // negated x per pixel; -inf = finished
+    float2 npx2 = make_float2(in0 ? -((float)j + 0.5f) : -INFINITY, in1 ? -((float)j + 0.5f) : -INFINITY);
+    const float2 one2 = dup2(1.0f);
 
-    constexpr int kBatch = kRec ? kPairThreads : kPairBatch;
-    constexpr int kPer = kBatch / kPairThreads;  // staged entries per thread and batch
-    auto load_id = [&](int32_t at) { return (at < v1) ? __ldg(ids + at) : -1; };
-    auto gather = [&](int half, int32_t id) {  // kRec: this thread's entry of a batch -> record buffer `half`
-        float4* dst = s_g + (half * kPairThreads + tid) * kPairRec;
-        if (id >= 0 && (int64_t)id < N) {
-            const float4* src = rec + kPairRec * (int64_t)id;
+    constexpr int kBatch = kRec ? kRecBatch : kPairBatch;
+    constexpr int kPer = (kBatch + kPairThreads - 1) / kPairThreads;  // staged entries per thread and batch
+    struct IdSet { int32_t v[kPer]; };
+    auto load_ids = [&](int32_t at) {  // this thread's entries of the batch starting at list position `at`
+        IdSet o;
 #pragma unroll
-            for (int q = 0; q < kPairRec; ++q) cp_async16(dst + q, src + q);
-        } else {  // past the end of the list / invalid id (rasterization.mojo:109 guard): can never hit
-            dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            dst[1] = dst[0];
-            dst[2] = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
-            dst[3] = make_float4(0.f, 0.f, 0.f, -INFINITY);
-            dst[4] = dst[0];
+        for (int h = 0; h < kPer; ++h) {
+            const int32_t e = at + h * kPairThreads + tid;
+            o.v[h] = (e < v1 && h * kPairThreads + tid < kBatch) ? __ldg(ids + e) : -1;
+        }
+        return o;
+    };
+    auto gather = [&](int half, const IdSet& id) {  // kRec: this thread's entries of a batch -> record buffer `half`
+#pragma unroll
+        for (int h = 0; h < kPer; ++h) {
+            if (h * kPairThreads + tid >= kBatch) break;  // (batches smaller than the CTA: the first warps gather)
+            float4* dst = s_g + (half * kBatch + h * kPairThreads + tid) * kPairRec;
+            if (id.v[h] >= 0 && (int64_t)id.v[h] < N) {
+                const float4* src = rec + kPairRec * (int64_t)id.v[h];
+#pragma unroll
+                for (int q = 0; q < kPairRec; ++q) cp_async16(dst + q, src + q);
+            } else {  // past the end of the list / invalid id (rasterization.mojo:109 guard): can never hit
+                pair_record_none(dst[0], dst[1], dst[2]);
+            }
         }
         cp_async_commit();
     };
-    int32_t id_next = -1;
-    if (kRec && v0 < v1) {
-        gather(0, load_id(v0 + tid));
-        id_next = load_id(v0 + kBatch + tid);
+    IdSet id_next;
+#pragma unroll
+    for (int h = 0; h < kPer; ++h) id_next.v[h] = -1;
+    if (kRec && v0 < v1) {  // prologue: the first kRecStages - 1 batches are in flight, the ids of the next one loaded
+#pragma unroll
+        for (int st = 0; st < kRecStages - 1; ++st) gather(st, load_ids(v0 + st * kBatch));
+        id_next = load_ids(v0 + (kRecStages - 1) * kBatch);
     }
     int batch = 0;
     for (int32_t b0 = v0; b0 < v1; b0 += kBatch, ++batch) {
-        const bool fin = !(npx0 > -INFINITY) && !(npx1 > -INFINITY);
+        const bool fin = pair_finished(npx2);
         const float4* s_rec = s_g;
         if (kRec) {
-            cp_async_wait_all();  // this thread's part of batch `batch` has landed ...
+            cp_async_wait_group<kRecStages - 2>();  // this thread's part of batch `batch` has landed ...
             if (__syncthreads_count(fin) >= kPairThreads) break;  // ... everyone's has; batch - 1 is fully consumed
-            if (b0 + kBatch < v1) gather((batch + 1) & 1, id_next);  // next batch flies during this walk
-            id_next = load_id(b0 + 2 * kBatch + tid);
-            s_rec = s_g + (batch & 1) * kPairThreads * kPairRec;
+            // the buffer batch - 1 used is refilled kRecStages - 1 batches ahead of the walk (an empty group past the
+            // end of the list keeps the group count in step)
+            if (b0 + (kRecStages - 1) * kBatch < v1) gather((batch + kRecStages - 1) % kRecStages, id_next);
+            else cp_async_commit();
+            id_next = load_ids(b0 + kRecStages * kBatch);
+            s_rec = s_g + (batch % kRecStages) * kBatch * kPairRec;
         } else {
             if (__syncthreads_count(fin) >= kPairThreads) break;
 #pragma unroll
@@ -505,18 +506,14 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                 const int32_t idx = b0 + t;
                 if (idx < v1) {
                     const int32_t g = __ldg(ids + idx);
-                    float4 q0, q1, q2, q3, q4;
+                    float4 q0, q1, q2;
                     if (g >= 0 && (int64_t)g < N) {
-                        pair_record(g, means2d, conics, colors, opacities, q0, q1, q2, q3, q4);
+                        pair_record(g, means2d, conics, colors, opacities, q0, q1, q2);
                     } else {
-                        q0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        q1 = q0;
-                        q2 = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
-                        q3 = make_float4(0.f, 0.f, 0.f, -INFINITY);
-                        q4 = q0;
+                        pair_record_none(q0, q1, q2);
                     }
                     float4* dst = s_g + kPairRec * t;
-                    dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3; dst[4] = q4;
+                    dst[0] = q0; dst[1] = q1; dst[2] = q2;
                 }
             }
             __syncthreads();
@@ -528,19 +525,14 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             for (int h = 0; h < kPer; ++h) {
                 const int e = warp * (32 * kPer) + h * 32 + lane;
                 bool hit = false;
-                if (e < bs) {
-                    const float4* r = s_rec + kPairRec * e;
-                    const float4 p0 = r[0], p1 = r[1], p2 = r[2];
-                    const float4 hh4 = r[4];
-                    hit = pair_cull_hit(p0.x, p0.z, -p1.x, -p1.z, -p2.x, r[3].w, hh4.x, hh4.y, TX0, TX1, TY0, TY1);
-                }
+                if (e < bs) hit = pair_record_hit(s_rec + kPairRec * e, TX0, TX1, TY0, TY1, nullptr);
                 const unsigned int word = __ballot_sync(0xffffffffu, hit);  // bit l <-> entry chunk base + l
                 if (lane == 0) s_tmask[warp * kPer + h] = word;
             }
             __syncthreads();
         }
         for (int c0 = 0; c0 < bs; c0 += 32) {
-            if (__all_sync(0xffffffffu, !(npx0 > -INFINITY) && !(npx1 > -INFINITY))) break;
+            if (__all_sync(0xffffffffu, pair_finished(npx2))) break;
             unsigned int tword = 0xffffffffu;
             if (long_tile) {
                 tword = s_tmask[c0 >> 5];
@@ -553,15 +545,8 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                 // lane l tests Gaussian c0 + 31 - l: the earliest Gaussian is the HIGHEST ballot bit, so the
                 // walk below needs a single FLO (bfind) per survivor instead of BREV + FLO
                 const int gi = c0 + 31 - lane;
-                if (gi < bs && ((tword >> (31 - lane)) & 1u)) {
-                    const float4* r = s_rec + kPairRec * gi;
-                    const float4 p0 = r[0], p1 = r[1], p2 = r[2];
-                    const float tau = r[3].w;
-                    const float4 hh4 = r[4];
-                    const float2 hh = make_float2(hh4.x, hh4.y);
-                    special = hh4.z != 0.0f;
-                    hit = pair_cull_hit(p0.x, p0.z, -p1.x, -p1.z, -p2.x, tau, hh.x, hh.y, X0, X1, Y0, Y1);
-                }
+                if (gi < bs && ((tword >> (31 - lane)) & 1u))
+                    hit = pair_record_hit(s_rec + kPairRec * gi, X0, X1, Y0, Y1, &special);
                 mask = __ballot_sync(0xffffffffu, hit);
                 special = special && hit;
             } else {
@@ -570,55 +555,67 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                 special = true;
             }
             const bool any_special = __any_sync(0xffffffffu, special);
-            const float4* rec_hi = s_rec + kPairRec * (c0 + 31);  // record of ballot bit 0; bit b is 5 b float4 earlier
+            const float4* rec_hi = s_rec + kPairRec * (c0 + 31);  // record of ballot bit 0; bit b is 3 b float4 earlier
             // two copies of the walk: chunks whose survivors are all "plain" (the common case) run without the
-            // sigma < 0 test and without the 0.999 clamp (4 of 47 instructions)
-            auto walk = [&](auto plain_tag) {
+            // sigma < 0 test and without the 0.999 clamp
+            // alpha of one Gaussian on this lane's two pixels; a failed alpha test gives alpha = 0 (then T (1 - 0) = T and
+            // 0 T = 0 exactly: the compositing below needs no select for it)
+            auto alpha_of = [&](auto plain_tag, const float4* r, const float4 p0, const float4 p1) -> float2 {
                 constexpr bool kPlain = decltype(plain_tag)::value;
+                const float2 dx = __fadd2_rn(dup2(p0.x), npx2);
+                const float2 dy = __fadd2_rn(dup2(p0.y), npy);
+                const float2 nbdy = __fmul2_rn(dup2(p0.w), dy);
+                const float2 ncdy = __fmul2_rn(dup2(p1.x), dy);
+                const float2 lmc = __ffma2_rn(ncdy, dy, dup2(p1.y));
+                const float2 t = __ffma2_rn(dup2(p0.z), dx, nbdy);
+                const float2 pw = __ffma2_rn(t, dx, lmc);
+                bool pass0 = pw.x >= kLog2AlphaThreshold, pass1 = pw.y >= kLog2AlphaThreshold;
+                if (!kPlain) {
+                    // sigma >= 0  <=>  power <= L: tested for special Gaussians only (plain ones pass by
+                    // construction and must be treated exactly as in the plain walk)
+                    const float tau = reinterpret_cast<const float*>(r + 2)[1];
+                    const float Lt = (__float_as_uint(tau) & 1u) ? p1.y : INFINITY;
+                    pass0 = pass0 && (pw.x <= Lt);
+                    pass1 = pass1 && (pw.y <= Lt);
+                }
+                float2 a2 = make_float2(0.0f, 0.0f);
+                if (pass0) a2.x = kPlain ? ex2_approx(pw.x) : fminf(0.999f, ex2_approx(pw.x));
+                if (pass1) a2.y = kPlain ? ex2_approx(pw.y) : fminf(0.999f, ex2_approx(pw.y));
+                return a2;
+            };
+            // compositing of one Gaussian.  Saturation (T (1 - alpha) <= 1e-4, once per pixel): the Gaussian is not
+            // added (rasterization.mojo:146-150) and the pixel retires with its T unchanged -- alpha := 0, -x := -inf.
+            // Branch-free: a lane that left the walk for a rare path would make its warp walk the chunk twice.
+            auto composite = [&](float2 a2, const float cr, const float cg, const float cb) {
+                float2 oma = __fadd2_rn(one2, make_float2(-a2.x, -a2.y));  // 1 - alpha
+                const float2 nT = __fmul2_rn(T2, oma);
+                const bool dead0 = !(nT.x > 1e-4f), dead1 = !(nT.y > 1e-4f);
+                a2.x = dead0 ? 0.0f : a2.x;
+                a2.y = dead1 ? 0.0f : a2.y;
+                npx2.x = dead0 ? -INFINITY : npx2.x;
+                npx2.y = dead1 ? -INFINITY : npx2.y;
+                oma.x = dead0 ? 1.0f : oma.x;
+                oma.y = dead1 ? 1.0f : oma.y;
+                const float2 vis2 = __fmul2_rn(a2, T2);
+                T2 = __fmul2_rn(T2, oma);
+                acc_r = __ffma2_rn(dup2(cr), vis2, acc_r);
+                acc_g = __ffma2_rn(dup2(cg), vis2, acc_g);
+                acc_b = __ffma2_rn(dup2(cb), vis2, acc_b);
+            };
+            // two copies of the walk: chunks whose survivors are all "plain" (the common case) run without the
+            // sigma < 0 test and without the 0.999 clamp
+            auto walk = [&](auto plain_tag) {
                 while (mask) {
                     // highest set bit = next Gaussian, front to back (bfind -> a single FLO; written in PTX
                     // because nvcc rewrites 31 - clz(x) into a longer clz-based sequence)
-                    unsigned int b_hi;
+                    unsigned int b_hi, below;
                     asm("bfind.u32 %0, %1;" : "=r"(b_hi) : "r"(mask));
-                    mask ^= bit_one << b_hi;
+                    asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(below) : "r"(b_hi));  // bits below b_hi
+                    mask &= below;
                     const float4* r = rec_hi - kPairRec * (int)b_hi;
-                    const float4 p0 = r[0], p1 = r[1], p2 = r[2];
-                    const f32x2 dx = add2(pk2(p0.x, p0.y), pk2(npx0, npx1));
-                    const f32x2 dy = add2(pk2(p0.z, p0.w), npy);
-                    const f32x2 nbdy = mul2(pk2(p1.z, p1.w), dy);
-                    const f32x2 ncdy = mul2(pk2(p2.x, p2.y), dy);
-                    const f32x2 L2 = pk2(p2.z, p2.w);
-                    const f32x2 lmc = fma2(ncdy, dy, L2);
-                    const f32x2 t = fma2(pk2(p1.x, p1.y), dx, nbdy);
-                    const f32x2 pw = fma2(t, dx, lmc);
-                    float pw0, pw1;
-                    upk2(pw, pw0, pw1);
-                    bool pass0 = pw0 >= kLog2AlphaThreshold, pass1 = pw1 >= kLog2AlphaThreshold;
-                    float a0 = ex2_approx(pw0), a1 = ex2_approx(pw1);
-                    if (!kPlain) {
-                        const float Lt = r[4].w;  // sigma >= 0  <=>  power <= L (never fails for plain Gaussians)
-                        pass0 = pass0 && (pw0 <= Lt);
-                        pass1 = pass1 && (pw1 <= Lt);
-                        a0 = fminf(0.999f, a0);
-                        a1 = fminf(0.999f, a1);
-                    }
-                    const f32x2 a2 = pk2(a0, a1), T2 = pk2(T0, T1);
-                    const f32x2 nT2 = mul2(T2, fma2(a2, mone2, one2));
-                    const f32x2 vis2 = mul2(a2, T2);
-                    float nT0, nT1, vis0, vis1;
-                    upk2(nT2, nT0, nT1);
-                    upk2(vis2, vis0, vis1);
-                    const bool live0 = nT0 > 1e-4f, live1 = nT1 > 1e-4f;
-                    const float4 c = r[3];
-                    vis0 = (pass0 && live0) ? vis0 : 0.0f;
-                    vis1 = (pass1 && live1) ? vis1 : 0.0f;
-                    T0 = (pass0 && live0) ? nT0 : T0;
-                    T1 = (pass1 && live1) ? nT1 : T1;
-                    // saturated: this Gaussian is not added (rasterization.mojo:146-150) and the pixel retires
-                    npx0 = (pass0 && !live0) ? -INFINITY : npx0;
-                    npx1 = (pass1 && !live1) ? -INFINITY : npx1;
-                    ar0 = fmaf(c.x, vis0, ar0); ag0 = fmaf(c.y, vis0, ag0); ab0 = fmaf(c.z, vis0, ab0);
-                    ar1 = fmaf(c.x, vis1, ar1); ag1 = fmaf(c.y, vis1, ag1); ab1 = fmaf(c.z, vis1, ab1);
+                    const float4 p0 = r[0], p1 = r[1];
+                    const float cb = reinterpret_cast<const float*>(r + 2)[0];
+                    composite(alpha_of(plain_tag, r, p0, p1), p1.z, p1.w, cb);
                 }
             };
             if (any_special) walk(std::false_type{});
@@ -630,6 +627,8 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     // sync-free frames: no intersections at all => all-zero image (render.py:73-76), decided on the device
     const float bgs = (m_dev != nullptr && *m_dev == 0ull) ? 0.0f : 1.0f;
     const float bgr = bgs * __ldg(background), bgg = bgs * __ldg(background + 1), bgb = bgs * __ldg(background + 2);
+    const float T0 = T2.x, T1 = T2.y, ar0 = acc_r.x, ar1 = acc_r.y, ag0 = acc_g.x, ag1 = acc_g.y, ab0 = acc_b.x,
+                ab1 = acc_b.y;
     const float o0r = fmaf(T0, bgr, ar0), o0g = fmaf(T0, bgg, ag0), o0b = fmaf(T0, bgb, ab0);
     const float o1r = fmaf(T1, bgr, ar1), o1g = fmaf(T1, bgg, ag1), o1b = fmaf(T1, bgb, ab1);
     const bool full_tile = (tile_x * kFastTile + kFastTile <= W) && (tile_y * kFastTile + kFastTile <= H);
@@ -756,7 +755,6 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         const int vec = ((reinterpret_cast<uintptr_t>(image) & 15u) == 0 && (W % 4) == 0) ? 1 : 0;
         const unsigned grid = (unsigned)(tiles_w * (row_end - row_begin));
         const int first_tile = row_begin * tiles_w;
-        const LoopConsts loop_consts = {1u, 1.0f, -1.0f};
         const bool have_rec = rec_ws != nullptr && N > 0 && (reinterpret_cast<uintptr_t>(rec_ws) & 15u) == 0;
         float4* recp = static_cast<float4*>(rec_ws);
         if (have_rec) {
@@ -784,11 +782,11 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
             if (mode == BSPLAT_RASTER_FAST_NOCULL)
                 raster_pair_kernel<false, true><<<grid, kPairThreads, 0, stream>>>(
                     N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
-                    tiles_w, image, vec, m_dev, peers, loop_consts, nullptr, nullptr);
+                    tiles_w, image, vec, m_dev, peers, nullptr, nullptr);
             else
                 raster_pair_kernel<true, true><<<grid, kPairThreads, 0, stream>>>(
                     N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
-                    tiles_w, image, vec, m_dev, peers, loop_consts, prepass ? surv : nullptr,
+                    tiles_w, image, vec, m_dev, peers, prepass ? surv : nullptr,
                     prepass ? chunk_cnt : nullptr);
         } else {
             if (N > 0 && (!means2d || !conics || !colors || !opacities ||
@@ -797,11 +795,11 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
             if (mode == BSPLAT_RASTER_FAST_NOCULL)
                 raster_pair_kernel<false, false><<<grid, kPairThreads, 0, stream>>>(
                     N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W,
-                    H, tiles_w, image, vec, m_dev, peers, loop_consts, nullptr, nullptr);
+                    H, tiles_w, image, vec, m_dev, peers, nullptr, nullptr);
             else
                 raster_pair_kernel<true, false><<<grid, kPairThreads, 0, stream>>>(
                     N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W,
-                    H, tiles_w, image, vec, m_dev, peers, loop_consts, nullptr, nullptr);
+                    H, tiles_w, image, vec, m_dev, peers, nullptr, nullptr);
         }
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
