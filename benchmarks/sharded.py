@@ -83,7 +83,7 @@ def run_config5(dev, rank, world, n_gaussians=None, steps=6, exchanges=("nccl", 
     bg = sc.background.to(dev)
     ref = ms.render_fused(*g, cam0, bg, 16) if rank == 0 else None
     out = {"workload": name, "N": N, "n_gpus": world, "broadcast_ms": bcast_ms,
-           "timing": "CUDA events around one sync-free band frame (project all, bin + rasterize the band) + the band "
+           "timing": "CUDA events around one sync-free band frame (pre-test, project the candidates, bin + rasterize the band) + the band "
                      "exchange, max over ranks, best of repeats"}
     t1 = None
     if rank == 0:
@@ -100,6 +100,8 @@ def run_config5(dev, rank, world, n_gaussians=None, steps=6, exchanges=("nccl", 
         rb = parallel.RowBandRenderer(N, cam0, exchange=ex if world > 1 else "nccl")
         bands = rb.rebalance(g[0], g[1], g[2], g[3], cam0)   # once per sequence, not per frame
         img = rb.render(*g, cam0, bg); rb.check()            # warm-up
+        bands = rb.tune_bands(*g, cam0, bg)                  # ... refined with measured band times (3 frames)
+        img = rb.render(*g, cam0, bg); rb.check()
         ts = []
         for _ in range(steps):
             if world > 1:

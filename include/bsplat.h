@@ -81,6 +81,9 @@ extern "C" {
                                                (projection.mojo:73-87,213-244; gsplat packed=True).  Same image and
                                                lists.  A no-op under BSPLAT_SEM_TORCH, where every Gaussian owns a tile */
 #define BSPLAT_FLAG_PROJ_FMA 0x800          /* the BSPLAT_PROJ_ALLOW_FMA projection inside a fused frame */
+#define BSPLAT_FLAG_NO_BAND_PRETEST 0x1000  /* row-band frames: project every Gaussian instead of only those a
+                                             * conservative pre-test cannot rule out of the band (A/B and tests:
+                                             * both ways give bit-identical lists and images) */
 
 /* Pinhole camera, world->camera. Mirrors mojosplat/utils.py:5-31 (Camera.view_matrix, Ks, H, W,
  * near, far) as a POD. viewmat is row-major 4x4. */

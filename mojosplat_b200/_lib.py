@@ -28,6 +28,7 @@ FLAG_BIN_SINGLE_LEVEL = 0x100
 FLAG_CAMERA_INDIRECT = 0x200
 FLAG_PACKED = 0x400
 FLAG_PROJ_FMA = 0x800
+FLAG_NO_BAND_PRETEST = 0x1000
 PROJ_ALLOW_FMA = 0x100  # or-ed into `semantics` of bsplat_project_fwd
 BIN_PACKED = 0x100      # or-ed into `semantics` of bsplat_bin2_prepare / bsplat_bin2_finish
 

@@ -69,6 +69,44 @@ bin_prep_kernel(const int64_t N, const float* __restrict__ means2d, const void* 
     }
 }
 
+// Decoupled look-back of one warp: exclusive prefix of chunk `chunk` = sum of the aggregates of its predecessors back
+// to (and including) the nearest published inclusive prefix.  Four windows of 32 predecessors are fetched per round
+// trip: when a whole wave of chunks publishes its aggregates at the same time (persistent grids: every resident CTA),
+// a chunk deep in the wave otherwise walks back 32 links per ~1 us.
+__device__ __forceinline__ unsigned long long lookback_prefix(const unsigned long long* __restrict__ status,
+                                                              const int64_t chunk, const int lane) {
+    constexpr int kWin = 4;
+    unsigned long long prefix = 0;
+    int64_t j = chunk - 1;
+    while (true) {
+        unsigned long long v[kWin];
+#pragma unroll
+        for (int u = 0; u < kWin; ++u) {
+            const int64_t idx = j - 32 * u - lane;  // lane 0 of window 0 = nearest predecessor
+            v[u] = idx >= 0 ? ld_relaxed_u64(status + idx) : kFlagPrefix;
+        }
+        bool done = false, stalled = false;
+#pragma unroll
+        for (int u = 0; u < kWin; ++u) {
+            if (done || stalled) break;
+            const unsigned ready = __ballot_sync(0xffffffffu, (v[u] & ~kValueMask) != 0);
+            const unsigned pref = __ballot_sync(0xffffffffu, (v[u] & kFlagPrefix) != 0);
+            const unsigned first_pref = pref ? (unsigned)(__ffs(pref) - 1) : 32u;
+            const unsigned need = first_pref == 32u ? 0xffffffffu : ((2u << first_pref) - 1u);
+            if ((ready & need) != need) { stalled = true; break; }  // not published yet
+            unsigned long long contrib = ((unsigned)lane <= first_pref) ? (v[u] & kValueMask) : 0ull;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+            prefix += contrib;
+            if (first_pref != 32u) done = true;
+            else j -= 32;
+        }
+        if (done) break;
+        if (stalled) __nanosleep(64);  // polite re-poll from the first window that was not ready
+    }
+    return prefix;
+}
+
 // ---- 0b. stable compaction of the Gaussians that own >= 1 tile of the band -------------------------------
 // Row-band frames (every rank of a band split would otherwise depth-sort all N Gaussians) and packed frames
 // (gsplat rules: culled Gaussians own no tile; projection.mojo:73-87, 213-244).  One pass: persistent CTAs take
@@ -80,41 +118,186 @@ constexpr int kCompactThreads = 256;
 constexpr int kCompactItems = 8;
 constexpr int kCompactChunk = kCompactThreads * kCompactItems;
 
-__global__ void __launch_bounds__(kCompactThreads)
-bin_compact_kernel(const int64_t N, const uint2* __restrict__ rects_in, const uint32_t* __restrict__ keys_full,
-                   const int row_begin, const int row_end, uint32_t* __restrict__ keys, int32_t* __restrict__ perm,
-                   uint32_t* __restrict__ hist /* [4][256] */, unsigned long long* __restrict__ n_out,
-                   uint32_t* __restrict__ ticket, unsigned long long* __restrict__ status) {
-    __shared__ uint32_t s_hist[4][kRadix];
-    __shared__ unsigned int s_chunk;
-    __shared__ unsigned int s_warp_sum[kCompactThreads / 32];
-    __shared__ unsigned long long s_prefix;
-    __shared__ unsigned int s_whole;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 4 * kRadix; i += kCompactThreads) (&s_hist[0][0])[i] = 0;
-    if (tid == 0) s_whole = 0;
-    const int64_t n_chunks = ceil_div(N, kCompactChunk);
-    while (true) {
-        __syncthreads();  // previous chunk is done with s_chunk / s_prefix / s_warp_sum (and the zeroing above)
-        if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
-        __syncthreads();
-        const int64_t chunk = s_chunk;
-        if (chunk >= n_chunks) break;
-        const int64_t base = chunk * kCompactChunk + (int64_t)tid * kCompactItems;
-        uint32_t key[kCompactItems];
-        unsigned int flags = 0, whole = 0;
+// kPre (row-band frames under the torch rules): the same stable compaction, but BEFORE the projection -- the flag is a
+// cheap conservative test "can this Gaussian's tile rectangle reach the band's rows at all?" on the camera-space mean
+// and the largest scale (BandPretest below), the output the list of candidate indices; only those are projected, and
+// the exact compaction afterwards runs over that list (`list` / `list_n`) instead of over all N.
+struct BandPretest {
+    float r1[3], r2[3], t1, t2;   // rows 1 and 2 of the world -> camera transform
+    float fy, cy;
+    float jn2;                    // 1 + max(lim_y_neg, lim_y_pos)^2: |J row 1|^2 <= (fy / z)^2 jn2
+    float gain2;                  // 9 |Rv|_2^2 (1 + 1e-3): |R(q)|_2 <= 3 for any |q| <= 1 (= 1 for unit q)
+    float eps2d;
+    float y_lo, y_hi;             // the band in pixels, widened by a pixel; -inf / +inf at the image border
+};
+
+// Flags of one thread's kCompactItems consecutive slots (bit k <-> slot base + k); `whole` counts the slots whose
+// full-frame rectangle is non-empty (exact mode).
+template <bool kPre>
+__device__ __forceinline__ unsigned int compact_flags(const int64_t N, const int64_t base,
+                                                      const int32_t* __restrict__ list,
+                                                      const uint2* __restrict__ rects_in, const int row_begin,
+                                                      const int row_end, const float* __restrict__ means3d,
+                                                      const float* __restrict__ log_scales, const BandPretest& pt,
+                                                      unsigned int& whole) {
+    unsigned int flags = 0;
+    if (base >= N) return 0u;
+    if constexpr (kPre) {
+        // a thread's 8 Gaussians are 96 contiguous bytes of each input array: six 128-bit loads instead of 24 scalar
+        // ones when the slots are all valid and the arrays are 16-byte aligned
+        static_assert((3 * kCompactItems) % 4 == 0, "vector loads of a thread's rows");
+        float pre_m[3 * kCompactItems], pre_s[3 * kCompactItems];
+        const bool vec = base + kCompactItems <= N &&
+                         ((reinterpret_cast<uintptr_t>(means3d) | reinterpret_cast<uintptr_t>(log_scales)) & 15u) == 0;
+        if (vec) {
+            const float4* vm = reinterpret_cast<const float4*>(means3d + 3 * base);
+            const float4* vs = reinterpret_cast<const float4*>(log_scales + 3 * base);
+#pragma unroll
+            for (int v = 0; v < 3 * kCompactItems / 4; ++v) {
+                const float4 a = __ldg(vm + v), b = __ldg(vs + v);
+                pre_m[4 * v] = a.x; pre_m[4 * v + 1] = a.y; pre_m[4 * v + 2] = a.z; pre_m[4 * v + 3] = a.w;
+                pre_s[4 * v] = b.x; pre_s[4 * v + 1] = b.y; pre_s[4 * v + 2] = b.z; pre_s[4 * v + 3] = b.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 3 * kCompactItems; ++e) {
+                const bool in = base + e / 3 < N;
+                pre_m[e] = in ? __ldg(means3d + 3 * base + e) : 0.0f;
+                pre_s[e] = in ? __ldg(log_scales + 3 * base + e) : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kCompactItems; ++k) {
+            if (base + k >= N) break;
+            // conservative: the exact projection computes the same camera-space mean; its radius is 0 or
+            // ceil(3.33 sqrt(c11)) with c11 <= |J row 1|^2 |Rv|^2 |R(q)|^2 smax^2 + eps2d.  Anything not provably
+            // outside the band stays (NaN / inf compare false).
+            const float mx = pre_m[3 * k], my = pre_m[3 * k + 1], mz = pre_m[3 * k + 2];
+            const float l0 = pre_s[3 * k], l1 = pre_s[3 * k + 1], l2 = pre_s[3 * k + 2];
+            const float lmax = fmaxf(fmaxf(l0, l1), l2);
+            const float mcy = __fmaf_rn(pt.r1[2], mz, __fmaf_rn(pt.r1[1], my, __fmul_rn(pt.r1[0], mx))) + pt.t1;
+            const float mcz = __fmaf_rn(pt.r2[2], mz, __fmaf_rn(pt.r2[1], my, __fmul_rn(pt.r2[0], mx))) + pt.t2;
+            const float ny = __fmaf_rn(pt.cy, mcz, __fmul_rn(pt.fy, mcy));
+            // approximate quotients and no square root: everything below carries a relative margin of 1e-4 or
+            // more, and the radius enters squared
+            const float rz = __frcp_rn(mcz);  // (inf for z = 0: nothing is skipped)
+            const float m2y = ny * rz;
+            const float smax = __expf(lmax);
+            const float fz = pt.fy * rz;
+            // (3.33 sqrt(c11) 1.0001)^2 with c11 <= (fy / z)^2 jn2 gain2 smax^2 (1 + 1e-3) + eps2d
+            const float r2 = 11.0889f * 1.002f * (fz * fz * pt.jn2 * pt.gain2 * smax * smax * 1.001f + pt.eps2d);
+            const float slack = 1e-4f * fabsf(m2y) + 2.0f;  // (the ceil and a pixel of rounding)
+            const float da = pt.y_lo - m2y - slack;          // room above the band: skip if radius < da
+            const float db = m2y - pt.y_hi - slack;          // room below the band
+            const bool above = da > 0.0f && r2 < da * da;
+            const bool below = db > 0.0f && r2 < db * db;
+            const bool nan_in = !(l0 == l0) || !(l1 == l1) || !(l2 == l2);  // (fmaxf drops NaNs)
+            if (!(above || below) || nan_in) flags |= 1u << k;
+        }
+    } else {
+        int32_t gidx[kCompactItems];
 #pragma unroll
         for (int k = 0; k < kCompactItems; ++k) {
             const int64_t i = base + k;
-            key[k] = 0;
-            if (i < N) {
-                const uint2 rc = __ldg(rects_in + i);
-                key[k] = __ldg(keys_full + i);
-                const uint2 cl = clip_rect_rows(rc, row_begin, row_end);
-                if ((cl.y & 0xffffu) != 0u && (cl.y >> 16) != 0u) flags |= 1u << k;
-                if ((rc.y & 0xffffu) != 0u && (rc.y >> 16) != 0u) ++whole;
-            }
+            gidx[k] = (i < N) ? (list ? __ldg(list + i) : (int32_t)i) : -1;
         }
+        uint2 rc[kCompactItems];
+#pragma unroll
+        for (int k = 0; k < kCompactItems; ++k) rc[k] = gidx[k] >= 0 ? __ldg(rects_in + gidx[k]) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int k = 0; k < kCompactItems; ++k) {
+            const uint2 cl = clip_rect_rows(rc[k], row_begin, row_end);
+            if ((cl.y & 0xffffu) != 0u && (cl.y >> 16) != 0u) flags |= 1u << k;
+            if ((rc[k].y & 0xffffu) != 0u && (rc[k].y >> 16) != 0u) ++whole;
+        }
+    }
+    return flags;
+}
+
+// Stable compaction in two launches without any dependency between CTAs (a single-pass chained scan left every CTA
+// waiting at a barrier for its look-back -- 46 % of the stall samples, 88 us for 6 M Gaussians):
+//   A. flags of every slot (one byte per thread), the survivors per chunk of 2 048; the CTA that finishes last
+//      turns the chunk counts into exclusive offsets and publishes the total (n_out[0]);
+//   B. scatter: block scan of the flag bytes + the chunk offset; exact mode also moves the depth keys and
+//      accumulates their digit histograms.
+// n_out[1] (exact mode) = Gaussians with a non-empty FULL-FRAME rectangle (+ whole_extra).
+template <bool kPre>
+__global__ void __launch_bounds__(kCompactThreads)
+bin_compact_flags_kernel(const int64_t N_host, const int32_t* __restrict__ list,
+                         const unsigned long long* __restrict__ list_n, const uint2* __restrict__ rects_in,
+                         const int row_begin, const int row_end, const float* __restrict__ means3d,
+                         const float* __restrict__ log_scales, const BandPretest pt,
+                         uint8_t* __restrict__ flag_bytes, uint32_t* __restrict__ counts,
+                         uint32_t* __restrict__ offs, uint32_t* __restrict__ done,
+                         unsigned long long* __restrict__ n_out, const unsigned long long whole_extra) {
+    __shared__ unsigned int s_cnt[kCompactThreads / 32], s_whole[kCompactThreads / 32];
+    __shared__ bool s_last;
+    const int64_t N = list_n ? (int64_t)(*list_n) : N_host;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t base = (int64_t)blockIdx.x * kCompactChunk + (int64_t)tid * kCompactItems;
+    unsigned int whole = 0;
+    const unsigned int flags = compact_flags<kPre>(N, base, list, rects_in, row_begin, row_end, means3d, log_scales, pt,
+                                                   whole);
+    flag_bytes[(int64_t)blockIdx.x * kCompactThreads + tid] = (uint8_t)flags;
+    unsigned int cnt = __popc(flags);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    whole = __reduce_add_sync(0xffffffffu, whole);
+    if (lane == 0) { s_cnt[warp] = cnt; s_whole[warp] = whole; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int c = 0, wsum = 0;
+#pragma unroll
+        for (int w = 0; w < kCompactThreads / 32; ++w) { c += s_cnt[w]; wsum += s_whole[w]; }
+        counts[blockIdx.x] = c;
+        if (!kPre && wsum) atomicAdd(n_out + 1, (unsigned long long)wsum);
+        __threadfence();
+        s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // ---- the last CTA: exclusive scan of the chunk counts ----
+    __threadfence();
+    const int n_chunks = (int)gridDim.x;
+    const int per = (n_chunks + kCompactThreads - 1) / kCompactThreads;
+    const int c0 = tid * per;
+    unsigned int sum = 0;
+    for (int q = 0; q < per; ++q)
+        if (c0 + q < n_chunks) sum += __ldcg(counts + c0 + q);
+    unsigned int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_cnt[warp] = incl;
+    __syncthreads();
+    unsigned int run = incl - sum;
+    for (int w = 0; w < warp; ++w) run += s_cnt[w];
+    for (int q = 0; q < per; ++q)
+        if (c0 + q < n_chunks) {
+            offs[c0 + q] = run;
+            run += __ldcg(counts + c0 + q);
+        }
+    if (tid == kCompactThreads - 1) {
+        n_out[0] = run;
+        if (!kPre && whole_extra) atomicAdd(n_out + 1, whole_extra);
+    }
+}
+
+template <bool kPre>
+__global__ void __launch_bounds__(kCompactThreads)
+bin_compact_scatter_kernel(const int64_t n_chunks, const int32_t* __restrict__ list,
+                           const uint8_t* __restrict__ flag_bytes, const uint32_t* __restrict__ offs,
+                           const uint32_t* __restrict__ keys_full, uint32_t* __restrict__ keys,
+                           int32_t* __restrict__ perm, uint32_t* __restrict__ hist /* [4][256] */) {
+    __shared__ uint32_t s_hist[kPre ? 1 : 4][kRadix];
+    __shared__ unsigned int s_warp_sum[kCompactThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!kPre)
+        for (int i = tid; i < 4 * kRadix; i += kCompactThreads) (&s_hist[0][0])[i] = 0;
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        __syncthreads();  // s_warp_sum of the previous chunk is consumed (and the zeroing above is done)
+        const unsigned int flags = flag_bytes[chunk * kCompactThreads + tid];
         const unsigned int cnt = __popc(flags);
         unsigned int incl = cnt;
 #pragma unroll
@@ -122,70 +305,35 @@ bin_compact_kernel(const int64_t N, const uint2* __restrict__ rects_in, const ui
             const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += v;
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) whole += __shfl_xor_sync(0xffffffffu, whole, d);
         if (lane == 31) s_warp_sum[warp] = incl;
-        if (lane == 0 && whole) atomicAdd(&s_whole, whole);
         __syncthreads();
-        unsigned int warp_excl = 0, block_total = 0;
-#pragma unroll
-        for (int w = 0; w < kCompactThreads / 32; ++w) {
-            const unsigned int v = s_warp_sum[w];
-            if (w < warp) warp_excl += v;
-            block_total += v;
-        }
-        // decoupled look-back over the previous chunks: warp 0 inspects 32 predecessors per round trip
-        if (warp == 0) {
-            unsigned long long prefix = 0;
-            if (chunk == 0) {
-                if (lane == 0) st_relaxed_u64(status + 0, kFlagPrefix | (unsigned long long)block_total);
-            } else {
-                if (lane == 0) st_relaxed_u64(status + chunk, kFlagAgg | (unsigned long long)block_total);
-                int64_t j = chunk - 1;
-                while (true) {
-                    const int64_t idx = j - lane;  // lane 0 = nearest predecessor
-                    const unsigned long long v = idx >= 0 ? ld_relaxed_u64(status + idx) : kFlagPrefix;
-                    const unsigned ready = __ballot_sync(0xffffffffu, (v & ~kValueMask) != 0);
-                    const unsigned pref = __ballot_sync(0xffffffffu, (v & kFlagPrefix) != 0);
-                    const unsigned first_pref = pref ? (unsigned)(__ffs(pref) - 1) : 32u;
-                    const unsigned need = first_pref == 32u ? 0xffffffffu : ((2u << first_pref) - 1u);
-                    if ((ready & need) != need) { __nanosleep(64); continue; }  // not published yet: polite re-poll
-                    unsigned long long contrib = ((unsigned)lane <= first_pref) ? (v & kValueMask) : 0ull;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-                    prefix += contrib;
-                    if (first_pref != 32u) break;
-                    j -= 32;
-                }
-                if (lane == 0) st_relaxed_u64(status + chunk, kFlagPrefix | (prefix + block_total));
-            }
-            if (lane == 0) {
-                s_prefix = prefix;
-                if (chunk == n_chunks - 1) n_out[0] = prefix + block_total;  // the last chunk publishes the total
-            }
-        }
-        __syncthreads();
-        unsigned long long pos = s_prefix + warp_excl + incl - cnt;
+        unsigned int pos = __ldg(offs + chunk) + incl - cnt;
+        for (int w = 0; w < warp; ++w) pos += s_warp_sum[w];
+        const int64_t base = chunk * kCompactChunk + (int64_t)tid * kCompactItems;
 #pragma unroll
         for (int k = 0; k < kCompactItems; ++k) {
             if ((flags >> k) & 1u) {
-                const uint32_t kk = key[k];
-                keys[pos] = kk;
-                perm[pos] = (int32_t)(base + k);
+                const int32_t gi = list ? __ldg(list + base + k) : (int32_t)(base + k);
+                perm[pos] = gi;
+                if (!kPre) {
+                    const uint32_t kk = __ldg(keys_full + gi);
+                    keys[pos] = kk;
+                    atomicAdd(&s_hist[0][kk & 0xffu], 1u);
+                    atomicAdd(&s_hist[1][(kk >> 8) & 0xffu], 1u);
+                    atomicAdd(&s_hist[2][(kk >> 16) & 0xffu], 1u);
+                    atomicAdd(&s_hist[3][kk >> 24], 1u);
+                }
                 ++pos;
-                atomicAdd(&s_hist[0][kk & 0xffu], 1u);
-                atomicAdd(&s_hist[1][(kk >> 8) & 0xffu], 1u);
-                atomicAdd(&s_hist[2][(kk >> 16) & 0xffu], 1u);
-                atomicAdd(&s_hist[3][kk >> 24], 1u);
             }
         }
     }
-    // (every thread left the loop through the same break, after a barrier)
-    for (int i = tid; i < 4 * kRadix; i += kCompactThreads) {
-        const uint32_t v = (&s_hist[0][0])[i];
-        if (v) atomicAdd(hist + i, v);
+    if constexpr (!kPre) {
+        __syncthreads();
+        for (int i = tid; i < 4 * kRadix; i += kCompactThreads) {
+            const uint32_t v = (&s_hist[0][0])[i];
+            if (v) atomicAdd(hist + i, v);
+        }
     }
-    if (tid == 0 && s_whole) atomicAdd(n_out + 1, (unsigned long long)s_whole);
 }
 
 // ---- 2. count + scan in depth order ----------------------------------------------------------
@@ -202,8 +350,16 @@ __global__ void __launch_bounds__(kScan2Threads)
 bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_dev,
                        const int32_t* __restrict__ perm, const uint2* __restrict__ rects_in, const int row_begin,
                        const int row_end, uint32_t* __restrict__ offsets, bsplat_bin_info* __restrict__ info,
-                       unsigned long long* __restrict__ ws, uint2* __restrict__ rects) {
+                       unsigned long long* __restrict__ ws, uint2* __restrict__ rects,
+                       uint32_t* __restrict__ hist_xy /* [2][256] or null */, const int tiles_w) {
     __shared__ unsigned int s_chunk;
+    // 2-D tile keys (hist_xy != null): the digit histograms of the two tile-sort passes are the column and row
+    // coverage counts -- a rectangle adds h to each of its w columns and w to each of its h rows, i.e. four updates of
+    // two difference arrays per Gaussian (prefix-summed once per CTA), instead of one update per pair in the emitter
+    __shared__ uint32_t s_diff[2][kRadix + 1];
+    if (hist_xy != nullptr) {
+        for (int i = threadIdx.x; i < 2 * (kRadix + 1); i += kScan2Threads) (&s_diff[0][0])[i] = 0u;
+    }
     __shared__ unsigned long long s_warp_sum[kScan2Threads / 32];
     __shared__ unsigned long long s_prefix;
 
@@ -240,6 +396,46 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
         if (jj < N) rects[jj] = cl;
         thread_sum += cnt[k];
     }
+    if (hist_xy != nullptr) {
+        // (s_diff was zeroed before the first barrier above; uint32 wrap-around carries the negative steps.)  Runs of
+        // identical rectangles in a thread's depth-consecutive slots -- the culled Gaussians that the torch rules clamp
+        // into a corner tile -- are merged first: they would all hit the same four words.
+        // Rectangles clipped at an image (or band) border all update the same word: those four words are summed in
+        // registers and reduced over the warp instead (a same-address shared-memory atomic serialises its lanes).
+        uint32_t px = 0xffffffffu, py = 0u, mult = 0u;
+        uint32_t edge_l = 0u, edge_r = 0u, edge_t = 0u, edge_b = 0u;
+        const uint32_t x_end = (uint32_t)tiles_w, y_beg = (uint32_t)row_begin, y_end = (uint32_t)row_end;
+        auto flush = [&]() {
+            if (mult == 0u) return;
+            const uint32_t x0 = px & 0xffffu, y0 = px >> 16, w = py & 0xffffu, h = py >> 16;
+            if (x0 == 0u) edge_l += h * mult; else atomicAdd(&s_diff[0][x0], h * mult);
+            if (x0 + w == x_end) edge_r += h * mult; else atomicAdd(&s_diff[0][x0 + w], 0u - h * mult);
+            if (y0 == y_beg) edge_t += w * mult; else atomicAdd(&s_diff[1][y0], w * mult);
+            if (y0 + h == y_end) edge_b += w * mult; else atomicAdd(&s_diff[1][y0 + h], 0u - w * mult);
+        };
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (cnt[k] == 0u) continue;
+            const uint2 cl = clip_rect_rows(rc[k], row_begin, row_end);
+            if (cl.x == px && cl.y == py) {
+                ++mult;
+            } else {
+                flush();
+                px = cl.x; py = cl.y; mult = 1u;
+            }
+        }
+        flush();
+        edge_l = __reduce_add_sync(0xffffffffu, edge_l);
+        edge_r = __reduce_add_sync(0xffffffffu, edge_r);
+        edge_t = __reduce_add_sync(0xffffffffu, edge_t);
+        edge_b = __reduce_add_sync(0xffffffffu, edge_b);
+        if ((tid & 31) == 0) {
+            if (edge_l) atomicAdd(&s_diff[0][0], edge_l);
+            if (edge_r) atomicAdd(&s_diff[0][x_end], 0u - edge_r);
+            if (edge_t) atomicAdd(&s_diff[1][y_beg], edge_t);
+            if (edge_b) atomicAdd(&s_diff[1][y_end], 0u - edge_b);
+        }
+    }
     const int lane = tid & 31, warp = tid >> 5;
     unsigned long long incl = thread_sum;
 #pragma unroll
@@ -257,28 +453,32 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
         block_total += s;
     }
     const unsigned long long thread_excl = warp_excl + incl - thread_sum;
+    if (hist_xy != nullptr && tid >= kScan2Threads - 2 * kRadix) {
+        // inclusive prefix of the difference arrays = coverage per column (first 256 of these threads) / row (last
+        // 256); every s_diff update precedes the barrier above.  The upper half of the CTA does this (and the global
+        // flush) while warp 0 is in the look-back.
+        const int t2 = tid - (kScan2Threads - 2 * kRadix);
+        const int which = t2 >> 8, b = t2 & (kRadix - 1);
+        uint32_t v = s_diff[which][b];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += u;
+        }
+        __shared__ uint32_t s_wtot[2 * kRadix / 32];
+        if (lane == 31) s_wtot[t2 >> 5] = v;
+        asm volatile("bar.sync 1, %0;" ::"n"(2 * kRadix));  // (the 512 threads of this branch)
+        const int w0 = which * (kRadix / 32);
+        for (int q = w0; q < (t2 >> 5); ++q) v += s_wtot[q];
+        if (v) atomicAdd(hist_xy + which * kRadix + b, v);
+    }
     if (warp == 0) {
         unsigned long long prefix = 0;
         if (chunk == 0) {
             if (lane == 0) st_relaxed_u64(status + 0, kFlagPrefix | block_total);
         } else {
             if (lane == 0) st_relaxed_u64(status + chunk, kFlagAgg | block_total);
-            int64_t j = (int64_t)chunk - 1;
-            while (true) {
-                const int64_t idx = j - lane;  // lane 0 = nearest predecessor
-                const unsigned long long v = idx >= 0 ? ld_relaxed_u64(status + idx) : kFlagPrefix;
-                const unsigned ready = __ballot_sync(0xffffffffu, (v & ~kValueMask) != 0);
-                const unsigned pref = __ballot_sync(0xffffffffu, (v & kFlagPrefix) != 0);
-                const unsigned first_pref = pref ? (unsigned)(__ffs(pref) - 1) : 32u;
-                const unsigned need = first_pref == 32u ? 0xffffffffu : ((2u << first_pref) - 1u);
-                if ((ready & need) != need) { __nanosleep(64); continue; }  // not published yet: polite re-poll
-                unsigned long long contrib = ((unsigned)lane <= first_pref) ? (v & kValueMask) : 0ull;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-                prefix += contrib;
-                if (first_pref != 32u) break;
-                j -= 32;
-            }
+            prefix = lookback_prefix(status, (int64_t)chunk, lane);
             if (lane == 0) st_relaxed_u64(status + chunk, kFlagPrefix | (prefix + block_total));
         }
         if (lane == 0) s_prefix = prefix;
@@ -320,6 +520,10 @@ struct TilePasses {
     int bits[kMaxTilePasses];
 };
 
+// kSep: 2-D tile keys (row << 16 | column; images of at most 256 x 256 tiles).  The digit histograms then come from the
+// count + scan kernel (column / row coverage), the key needs no multiplication, and k / w is an exact multiply-high
+// with a per-width constant (k w^2 < 2^32 holds for such rectangles).  Otherwise: linear tile ids, histograms on the fly.
+template <bool kSep>
 __global__ void __launch_bounds__(kEmit2Threads)
 bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_dev,
                  const int32_t* __restrict__ perm, const uint2* __restrict__ rects,
@@ -333,11 +537,16 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
         if (blockIdx.x == 0 && threadIdx.x == 0) info_dev->reserved[1] = 1u;
         return;
     }
-    __shared__ uint32_t s_hist[kMaxTilePasses][kRadix];
+    __shared__ uint32_t s_hist[kSep ? 1 : kMaxTilePasses][kRadix];  // kSep: ceil(2^32 / w) for w = 1 .. 256 instead
     const int64_t N = n_dev ? (int64_t)(*n_dev) : N_host;  // compacted depth order: the count is on the device
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
-    for (int i = tid; i < kMaxTilePasses * kRadix; i += kEmit2Threads) (&s_hist[0][0])[i] = 0;
+    if (kSep) {
+        // s_hist[0][w - 1] = ceil(2^32 / w) (w = 1: 2^32 does not fit -- handled where it is used)
+        for (int i = tid; i < kRadix; i += kEmit2Threads) s_hist[0][i] = i == 0 ? 0u : 0xffffffffu / (uint32_t)(i + 1) + 1u;
+    } else {
+        for (int i = tid; i < kMaxTilePasses * kRadix; i += kEmit2Threads) (&s_hist[0][0])[i] = 0;
+    }
     __syncthreads();
     const int top = tp.n - 1;
     const int top_shift = tp.n == 1 ? tp.shift[0] : (tp.n == 2 ? tp.shift[1] : (tp.n == 3 ? tp.shift[2] : tp.shift[3]));
@@ -376,7 +585,8 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
                 off = __ldg(offsets + jg);
             }
             const uint32_t w = rc.y & 0xffffu, cnt = w * (rc.y >> 16);
-            const float inv_w = 1.0f / (float)(w ? w : 1u);
+            // kSep: the reciprocal is the integer magic of w (bit pattern carried in the same register)
+            const float inv_w = kSep ? __uint_as_float(s_hist[0][(w ? w : 1u) - 1u]) : 1.0f / (float)(w ? w : 1u);
             // pairs covered by this window: [off of lane 0, end of the last live lane)
             const int n_live = (int)min((int64_t)32, N - jg0);
             const uint32_t win_end = __shfl_sync(0xffffffffu, off + cnt, n_live - 1);
@@ -398,30 +608,44 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
                 const float iw = __shfl_sync(0xffffffffu, inv_w, ol);
                 const int32_t go = __shfl_sync(0xffffffffu, g, ol);
                 uint32_t tile = 0;
-                if (valid) {
-                    const uint32_t k = pidx - eo;
-                    // k / w through the reciprocal, corrected to be exact (k < 2^24: a rectangle has < 2^24 tiles
-                    // whenever the image has, which tile ids as 32-bit keys already require)
-                    uint32_t dy = (uint32_t)__float2int_rz(__fmul_rn((float)k, iw));
-                    if (dy * wo > k) --dy;
-                    else if ((dy + 1u) * wo <= k) ++dy;
-                    const uint32_t dx = k - dy * wo;
-                    tile = ((xy >> 16) + dy) * tw + (xy & 0xffffu) + dx;
-                    tile_keys[pidx] = tile;
-                    ids[pidx] = go;
+                if (kSep) {
+                    if (valid) {
+                        const uint32_t k = pidx - eo;
+                        // k / w = hi(k * ceil(2^32 / w)), exact while k (w ceil(2^32 / w) - 2^32) < 2^32, i.e. for
+                        // k w < 2^32: rectangles of at most 256 x 256 tiles have k < 2^16 and w <= 2^8
+                        const uint32_t dy = wo == 1u ? k : __umulhi(k, __float_as_uint(iw));
+                        const uint32_t dx = k - dy * wo;
+                        tile_keys[pidx] = xy + (dy << 16) + dx;   // (row << 16 | column), the layout of rc.x
+                        ids[pidx] = go;
+                    }
+                } else {
+                    if (valid) {
+                        const uint32_t k = pidx - eo;
+                        // k / w through the reciprocal, corrected to be exact (k < 2^24: a rectangle has < 2^24
+                        // tiles whenever the image has, which tile ids as 32-bit keys already require)
+                        uint32_t dy = (uint32_t)__float2int_rz(__fmul_rn((float)k, iw));
+                        if (dy * wo > k) --dy;
+                        else if ((dy + 1u) * wo <= k) ++dy;
+                        const uint32_t dx = k - dy * wo;
+                        tile = ((xy >> 16) + dy) * tw + (xy & 0xffffu) + dx;
+                        tile_keys[pidx] = tile;
+                        ids[pidx] = go;
 #pragma unroll
-                    for (int q = 0; q < kMaxTilePasses - 1; ++q)  // (constant indices keep tp in the parameter bank)
-                        if (q < top) atomicAdd(&s_hist[q][(tile >> tp.shift[q]) & ((1u << tp.bits[q]) - 1u)], 1u);
+                        for (int q = 0; q < kMaxTilePasses - 1; ++q)  // (constant indices keep tp in the parameter bank)
+                            if (q < top) atomicAdd(&s_hist[q][(tile >> tp.shift[q]) & ((1u << tp.bits[q]) - 1u)], 1u);
+                    }
+                    const uint32_t td = valid ? (tile >> top_shift) : 0x100u;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, td);
+                    if (valid && lane == (uint32_t)(__ffs(peers) - 1))
+                        atomicAdd(&s_hist[top][td], (uint32_t)__popc(peers));
                 }
-                const uint32_t td = valid ? (tile >> top_shift) : 0x100u;
-                const uint32_t peers = __match_any_sync(0xffffffffu, td);
-                if (valid && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[top][td], (uint32_t)__popc(peers));
             }
             cur = stop;
             jg0 += 32;
             // (a window whose last Gaussian reaches beyond E ends the task; one that ends before E continues)
         }
     }
+    if (kSep) return;
     __syncthreads();
     for (int i = tid; i < tp.n * kRadix; i += kEmit2Threads) {
         const uint32_t v = (&s_hist[0][0])[i];
@@ -577,6 +801,19 @@ static int tile_bits_of(int64_t n_tiles) {
 }
 
 // ceil(bits / 8) passes of (nearly) equal width: 13 bits -> 7 + 6, 17 bits -> 6 + 6 + 5, never more than 8 per pass
+// 2-D tile keys (row << 16 | column): used when the linear tile id needs two passes anyway and both coordinates fit
+// a digit.  One pass per coordinate, columns first.
+static bool tile_keys_2d(const BinParams& p) {
+    return p.tiles_w <= kRadix && p.tiles_h <= kRadix && tile_bits_of((int64_t)p.tiles_w * p.tiles_h) > kRadixBits;
+}
+static TilePasses tile_passes_2d(const BinParams& p) {
+    TilePasses tp;
+    tp.n = 2;
+    for (int q = 0; q < kMaxTilePasses; ++q) { tp.shift[q] = 0; tp.bits[q] = 0; }
+    tp.shift[0] = 0; tp.bits[0] = tile_bits_of(p.tiles_w);
+    tp.shift[1] = 16; tp.bits[1] = tile_bits_of(p.tiles_h);
+    return tp;
+}
 static TilePasses tile_passes_of(int64_t n_tiles) {
     TilePasses tp;
     const int tb = tile_bits_of(n_tiles);
@@ -592,7 +829,7 @@ static TilePasses tile_passes_of(int64_t n_tiles) {
 }
 
 constexpr int kHistRows = 4 + kMaxTilePasses;   // 4 depth passes + the tile passes
-constexpr int kTickets = 16;                    // [0..3] depth, [4..7] tile passes, [8] compaction
+constexpr int kTickets = 16;                    // [0..3] depth, [4..7] tile passes, [8] compaction, [9] band pre-test
 
 struct Bin2Ws {
     // N part (lives from prepare to finish)
@@ -602,6 +839,11 @@ struct Bin2Ws {
     uint32_t* tickets;   // [kTickets]
     unsigned long long* n_band;  // [0] Gaussians with >= 1 tile in the band, [1] with >= 1 tile in the frame
     unsigned long long* compact_status;
+    int32_t* cand;                      // row-band pre-test: candidate indices (index order), [N]
+    unsigned long long* cand_n;         // [0] number of candidates
+    unsigned long long* cand_status;    // pre-test compaction: chunk counts, then chunk offsets (uint32 each)
+    uint8_t* cand_flags;                // one flag byte per thread of the pre-test compaction
+    uint8_t* compact_flags;             // ... and of the exact compaction
     uint32_t* status_n;  // [4][tilesN][256]
     size_t zero_begin, zero_end_n;  // byte range zeroed by begin
     size_t n_bytes;
@@ -626,6 +868,9 @@ static Bin2Ws carve_bin2(void* base, int64_t N, int64_t M, int64_t n_tiles) {
     w.offsets = (uint32_t*)take((n + 1) * 4);
     w.rects = (uint2*)take(n * sizeof(uint2));
     w.rects_in = (uint2*)take(n * sizeof(uint2));
+    w.cand = (int32_t*)take(n * 4);
+    w.cand_flags = (uint8_t*)take((size_t)ceil_div((int64_t)n, kCompactChunk) * kCompactThreads);
+    w.compact_flags = (uint8_t*)take((size_t)ceil_div((int64_t)n, kCompactChunk) * kCompactThreads);
     w.zero_begin = off;
     w.info = (bsplat_bin_info*)take(sizeof(bsplat_bin_info));
     w.scan_bytes = bsplat_bin_scan_workspace_bytes(N);
@@ -634,6 +879,8 @@ static Bin2Ws carve_bin2(void* base, int64_t N, int64_t M, int64_t n_tiles) {
     w.tickets = (uint32_t*)take(kTickets * 4);
     w.n_band = (unsigned long long*)take(16);
     w.compact_status = (unsigned long long*)take((size_t)(ceil_div((int64_t)n, kCompactChunk) + 1) * 8);
+    w.cand_n = (unsigned long long*)take(16);
+    w.cand_status = (unsigned long long*)take((size_t)(ceil_div((int64_t)n, kCompactChunk) + 1) * 8);
     w.status_n = (uint32_t*)take(sort_status_words(sort_tiles_u32(N), 4) * 4);
     w.zero_end_n = off;
     w.n_bytes = off;
@@ -679,9 +926,55 @@ void bin2_prep_targets(void* workspace, int64_t N, bool compact, uint2** rects_i
 
 // have_prep: bin2_begin ran and step 0 is done (fused frames); otherwise both happen here from the stage inputs.
 // compact: sort only the Gaussians that own a tile of the band (always for partial bands).
+// Row-band frames under the torch rules: list of the Gaussians whose tile rectangle can reach the band at all
+// (conservative pre-test on the raw inputs, BandPretest), in index order, count on the device.  Call between bin2_begin
+// and the projection; hand the list to the projection (ProjExtra::list) and to bin2_prepare (use_candidates).
+int bin2_band_candidates(int64_t N, const float* means3d, const float* log_scales, const bsplat_camera& cam,
+                         float eps2d, const BinParams& p, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream, const int32_t** list, const unsigned long long** list_n) {
+    Bin2Ws w = carve_bin2(workspace, N, 0, 0);
+    if (!workspace || workspace_bytes < w.n_bytes) return BSPLAT_E_WORKSPACE;
+    if (p.semantics != BSPLAT_SEM_TORCH || !is_band(p) || N <= 0) return BSPLAT_E_ARG;
+    BandPretest pt;
+    double a[3][3];  // Rv^T Rv: its largest eigenvalue (<= the largest absolute row sum) bounds |Rv|_2^2
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            a[r][c] = 0.0;
+            for (int k = 0; k < 3; ++k) a[r][c] += (double)cam.viewmat[4 * k + r] * (double)cam.viewmat[4 * k + c];
+        }
+    double rv2 = 0.0;
+    for (int r = 0; r < 3; ++r) {
+        const double rs = fabs(a[r][0]) + fabs(a[r][1]) + fabs(a[r][2]);
+        rv2 = rs > rv2 ? rs : rv2;
+    }
+    for (int k = 0; k < 3; ++k) { pt.r1[k] = cam.viewmat[4 + k]; pt.r2[k] = cam.viewmat[8 + k]; }
+    pt.t1 = cam.viewmat[7]; pt.t2 = cam.viewmat[11];
+    pt.fy = cam.fy; pt.cy = cam.cy;
+    const float Hf = (float)cam.height, tan_fovy = 0.5f * Hf / cam.fy;
+    const float lim_pos = (Hf - cam.cy) / cam.fy + 0.3f * tan_fovy, lim_neg = cam.cy / cam.fy + 0.3f * tan_fovy;
+    const float lim = fmaxf(fabsf(lim_pos), fabsf(lim_neg));
+    pt.jn2 = (1.0f + lim * lim) * 1.001f;
+    pt.gain2 = (float)(9.0 * rv2 * 1.001);
+    pt.eps2d = eps2d;
+    pt.y_lo = p.row_begin <= 0 ? -INFINITY : (float)p.row_begin * p.tile_size_f - 1.0f;
+    pt.y_hi = p.row_end >= p.tiles_h ? INFINITY : (float)p.row_end * p.tile_size_f + 1.0f;
+    const int64_t cb = ceil_div(N, kCompactChunk);
+    uint32_t* counts = reinterpret_cast<uint32_t*>(w.cand_status);
+    bin_compact_flags_kernel<true><<<(unsigned)cb, kCompactThreads, 0, stream>>>(
+        N, nullptr, nullptr, nullptr, p.row_begin, p.row_end, means3d, log_scales, pt, w.cand_flags, counts, counts + cb,
+        w.tickets + 9, w.cand_n, 0ull);
+    BSPLAT_LAUNCH_CHECK();
+    bin_compact_scatter_kernel<true><<<(unsigned)(cb < 148 * 8 ? cb : 148 * 8), kCompactThreads, 0, stream>>>(
+        cb, nullptr, w.cand_flags, counts + cb, nullptr, nullptr, w.cand, nullptr);
+    BSPLAT_LAUNCH_CHECK();
+    *list = w.cand;
+    *list_n = w.cand_n;
+    return BSPLAT_OK;
+}
+
 int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_is_float, const float* depths,
                  const BinParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream, bool have_prep,
-                 bool compact) {
+                 bool compact, bool use_candidates) {
     Bin2Ws w = carve_bin2(workspace, N, 0, 0);
     if (!workspace || workspace_bytes < w.n_bytes) return BSPLAT_E_WORKSPACE;
     compact = compact || is_band(p);
@@ -707,9 +1000,17 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
     const int32_t* vsrc = nullptr;
     if (compact) {
         const int64_t cb = ceil_div(N, kCompactChunk);
-        bin_compact_kernel<<<(unsigned)(cb < 148 * 2 ? cb : 148 * 2), kCompactThreads, 0, stream>>>(
-            N, w.rects_in, w.dkeys_alt, p.row_begin, p.row_end, w.dkeys, w.perm, w.hist, w.n_band, w.tickets + 8,
-            w.compact_status);
+        // use_candidates: only the pre-tested Gaussians were projected; under the torch rules every Gaussian owns a
+        // tile somewhere in the frame, so the whole-frame count is N
+        uint32_t* counts = reinterpret_cast<uint32_t*>(w.compact_status);
+        const int32_t* list = use_candidates ? w.cand : nullptr;
+        bin_compact_flags_kernel<false><<<(unsigned)cb, kCompactThreads, 0, stream>>>(
+            N, list, use_candidates ? w.cand_n : nullptr, w.rects_in, p.row_begin, p.row_end, nullptr, nullptr,
+            BandPretest(), w.compact_flags, counts, counts + cb, w.tickets + 8, w.n_band,
+            use_candidates ? (unsigned long long)N : 0ull);
+        BSPLAT_LAUNCH_CHECK();
+        bin_compact_scatter_kernel<false><<<(unsigned)(cb < 148 * 4 ? cb : 148 * 4), kCompactThreads, 0, stream>>>(
+            cb, list, w.compact_flags, counts + cb, w.dkeys_alt, w.dkeys, w.perm, w.hist);
         BSPLAT_LAUNCH_CHECK();
         n_dev = reinterpret_cast<const uint64_t*>(w.n_band);
         vsrc = w.perm;
@@ -729,7 +1030,8 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
     const unsigned grid = (unsigned)ceil_div(N, kScan2Chunk);
     bin_count_scan2_kernel<<<grid, kScan2Threads, 0, stream>>>(
         N, reinterpret_cast<const unsigned long long*>(n_dev), w.perm, w.rects_in, p.row_begin, p.row_end, w.offsets,
-        w.info, static_cast<unsigned long long*>(w.scan_ws), w.rects);
+        w.info, static_cast<unsigned long long*>(w.scan_ws), w.rects, tile_keys_2d(p) ? w.hist + 4 * kRadix : nullptr,
+        p.tiles_w);
     BSPLAT_LAUNCH_CHECK();
     return BSPLAT_OK;
 }
@@ -757,12 +1059,19 @@ int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* w
         return tile_finish_launch(n_tiles, first, n_order, nullptr, tile_ranges, tile_order, w.fin_scratch, w.info,
                                   info_host, stream);
     }
-    const TilePasses tp = tile_passes_of(n_tiles);
+    const bool keys2d = tile_keys_2d(p);
+    const TilePasses tp = keys2d ? tile_passes_2d(p) : tile_passes_of(n_tiles);
     // one warp per task of kEmitTask pairs; M is the capacity in sync-free frames
     const int64_t emit_ctas = ceil_div(ceil_div(M, (int64_t)kEmitTask), kEmit2Threads / 32);
-    bin_emit2_kernel<<<(unsigned)(emit_ctas < 148 * 8 ? emit_ctas : 148 * 8), kEmit2Threads, 0, stream>>>(
-        N, compact ? w.n_band : nullptr, w.perm, w.rects, p.tiles_w, w.offsets, tp, w.tkeys, w.ids,
-        w.hist + 4 * kRadix, info_dev, M);
+    const unsigned emit_grid = (unsigned)(emit_ctas < 148 * 8 ? emit_ctas : 148 * 8);
+    if (keys2d)
+        bin_emit2_kernel<true><<<emit_grid, kEmit2Threads, 0, stream>>>(
+            N, compact ? w.n_band : nullptr, w.perm, w.rects, p.tiles_w, w.offsets, tp, w.tkeys, w.ids,
+            w.hist + 4 * kRadix, info_dev, M);
+    else
+        bin_emit2_kernel<false><<<emit_grid, kEmit2Threads, 0, stream>>>(
+            N, compact ? w.n_band : nullptr, w.perm, w.rects, p.tiles_w, w.offsets, tp, w.tkeys, w.ids,
+            w.hist + 4 * kRadix, info_dev, M);
     BSPLAT_LAUNCH_CHECK();
     const int64_t tm = sort_tiles_u32(M);
     const uint32_t* ksrc = w.tkeys; uint32_t* kdst = w.tkeys_alt;
@@ -773,7 +1082,7 @@ int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* w
         const int rc = onesweep_pass_u32(M, m_dev, ksrc, last ? nullptr : kdst, vsrc, last ? sorted_ids : vdst,
                                          tp.shift[q], tp.bits[q], w.hist + (size_t)(4 + q) * kRadix, 0,
                                          w.tickets + 4 + q, w.status_m + (size_t)q * tm * kRadix,
-                                         last ? w.tile_counts : nullptr, stream);
+                                         last ? w.tile_counts : nullptr, stream, keys2d ? p.tiles_w : 0);
         if (rc != BSPLAT_OK) return rc;
         ksrc = kdst; kdst = (kdst == w.tkeys_alt) ? w.tkeys : w.tkeys_alt;
         vsrc = vdst; vdst = (vdst == w.ids_alt) ? w.ids : w.ids_alt;
@@ -819,7 +1128,7 @@ extern "C" int bsplat_bin2_prepare(int64_t N, const float* means2d, const void* 
     if (N < 0 || !info_out) return BSPLAT_E_ARG;
     if (N > 0 && (!means2d || !radii || !depths)) return BSPLAT_E_ARG;
     rc = bin2_prepare(N, means2d, radii, radii_is_float, depths, p, workspace, workspace_bytes, stream, false,
-                      (semantics & BSPLAT_BIN_PACKED) != 0);
+                      (semantics & BSPLAT_BIN_PACKED) != 0, false);
     if (rc != BSPLAT_OK) return rc;
     const bsplat_bin_info* src = bin2_info_ptr(workspace, N);
     if (info_out != src)

@@ -10,7 +10,10 @@ int bin2_begin(int64_t N, void* workspace, size_t workspace_bytes, cudaStream_t 
 void bin2_prep_targets(void* workspace, int64_t N, bool compact, uint2** rects_in, uint32_t** dkeys, uint32_t** hist);
 int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_is_float, const float* depths,
                  const BinParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream, bool have_prep,
-                 bool compact);
+                 bool compact, bool use_candidates);
+int bin2_band_candidates(int64_t N, const float* means3d, const float* log_scales, const bsplat_camera& cam,
+                         float eps2d, const BinParams& p, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream, const int32_t** list, const unsigned long long** list_n);
 int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* workspace, size_t workspace_bytes,
                 int32_t* sorted_ids, int32_t* tile_ranges, int32_t* tile_order, cudaStream_t stream, bool compact,
                 bsplat_bin_info* info_host = nullptr);
@@ -224,11 +227,23 @@ int frame_front(int64_t N, const float* means3d, const float* log_scales, const 
     ex.tile_size = tile_size;
     ex.rec_row_begin = p.row_begin;
     ex.rec_row_end = p.row_end;
+    // Row bands under the torch rules (and nobody asking for the stage outputs): a cheap conservative pre-test on
+    // the raw inputs first lists the Gaussians whose rectangle can reach the band at all; only those are projected
+    // and compacted.  (What every rank of a band split repeats shrinks from all N to its candidates.)
+    const bool band = p.row_begin > 0 || p.row_end < p.tiles_h;
+    const bool pretest = band && semantics == BSPLAT_SEM_TORCH && cam_dev == nullptr && o_means2d == nullptr &&
+                         (flags & BSPLAT_FLAG_NO_BAND_PRETEST) == 0 && N > 0;
+    if (pretest) {
+        rc = bin2_band_candidates(N, means3d, log_scales, cam, 0.3f, p, w.bin_ws, w.bin_bytes, stream, &ex.list,
+                                  &ex.list_n);
+        if (rc != BSPLAT_OK) return rc;
+    }
     rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, cam, 0.3f, semantics, o_means2d, o_conics,
                             o_depths, o_radii, stream, cam_dev, &ex, (flags & BSPLAT_FLAG_PROJ_FMA) != 0);
     if (rc != BSPLAT_OK) return rc;
     if (ev_after_projection) BSPLAT_CUDA_TRY(cudaEventRecord(ev_after_projection, stream));
-    return bin2_prepare(N, nullptr, nullptr, 0, nullptr, p, w.bin_ws, w.bin_bytes, stream, /*have_prep=*/true, compact);
+    return bin2_prepare(N, nullptr, nullptr, 0, nullptr, p, w.bin_ws, w.bin_bytes, stream, /*have_prep=*/true, compact,
+                        pretest);
 }
 
 }  // namespace

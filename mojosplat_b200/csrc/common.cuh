@@ -38,11 +38,14 @@ struct ProjExtra {
     uint2* rects;         // [N] full-frame tile rectangle: x0 | y0 << 16, w | h << 16 (rules of `semantics`)
     uint32_t* dkeys;      // [N] monotone depth keys
     uint32_t* hist;       // [4][256] digit histograms of the depth keys (caller-zeroed)
-    void* rec;            // [N][5] float4 raster records (needs colors and opac)
+    void* rec;            // [N][3] float4 raster records (needs colors and opac)
     const float* colors;  // [N,3]
     const float* opac;    // [N] raw opacities
     int tile_size;
     int rec_row_begin, rec_row_end;  // (with rects) records only for Gaussians with a tile in these rows; 0, 0 = all
+    // optional (fused-only launches): project list[0 .. *list_n) instead of all N Gaussians (device pointers)
+    const int32_t* list = nullptr;
+    const unsigned long long* list_n = nullptr;
 };
 
 // Monotone float -> uint32 map: ascending float order, -0.0 == +0.0, NaN last.

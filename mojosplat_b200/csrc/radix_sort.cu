@@ -79,7 +79,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
                 KeyT* __restrict__ keys_out, const int32_t* __restrict__ vals_in,
                 int32_t* __restrict__ vals_out, const int shift, const int bits_rt,
                 const uint32_t* __restrict__ hist, const int hist_is_scanned, uint32_t* __restrict__ ticket,
-                uint32_t* __restrict__ status, uint32_t* __restrict__ key_counts) {
+                uint32_t* __restrict__ status, uint32_t* __restrict__ key_counts, const int key_row_stride) {
     constexpr int TILE = kSortThreads * ITEMS;
     // BITS > 0: digit width known at compile time (branch-free ballot loop with constant masks)
     const int bits = BITS > 0 ? BITS : bits_rt;
@@ -307,9 +307,15 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
                 // key_counts[key] += run length (uint32 wrap-around arithmetic).
                 const bool first = (j == 0) || (s_keys[j - 1] != kk);
                 const bool last = (j == n_valid - 1) || (s_keys[j + 1] != kk);
-                if (first && last) atomicAdd(key_counts + kk, 1u);
-                else if (first) atomicAdd(key_counts + kk, (uint32_t)(0 - j));
-                else if (last) atomicAdd(key_counts + kk, (uint32_t)(j + 1));
+                if (first || last) {
+                    // key_row_stride > 0: 2-D keys (row << 16 | column) counted under row * stride + column
+                    const uint32_t ki = key_row_stride > 0
+                                            ? (uint32_t)(kk >> 16) * (uint32_t)key_row_stride + ((uint32_t)kk & 0xffffu)
+                                            : (uint32_t)kk;
+                    if (first && last) atomicAdd(key_counts + ki, 1u);
+                    else if (first) atomicAdd(key_counts + ki, (uint32_t)(0 - j));
+                    else atomicAdd(key_counts + ki, (uint32_t)(j + 1));
+                }
             }
         }
     }
@@ -324,17 +330,17 @@ size_t sort_status_words(int64_t n_tiles, int passes) { return (size_t)passes * 
 #define BSPLAT_ONESWEEP32(B)                                                                              \
     onesweep_kernel<uint32_t, kSortItems32, B><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(               \
         M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,    \
-        key_counts)
+        key_counts, key_row_stride)
 
 int onesweep_pass_u32(int64_t M, const uint64_t* m_dev, const uint32_t* keys_in, uint32_t* keys_out,
                       const int32_t* vals_in, int32_t* vals_out, int shift, int bits, const uint32_t* hist,
                       int hist_is_scanned, uint32_t* ticket, uint32_t* status, uint32_t* key_counts,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int key_row_stride) {
     const int64_t n_tiles = sort_tiles_u32(M);
     if (bits == 8 && n_tiles <= 3 * 148) {  // every tile resident at once (3 CTAs per SM): wide look-back window
         onesweep_kernel<uint32_t, kSortItems32, 8, 64><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
             M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,
-            key_counts);
+            key_counts, key_row_stride);
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
     }
@@ -415,7 +421,7 @@ extern "C" int bsplat_radix_sort_pairs(int64_t M, uint64_t* keys, uint64_t* keys
         const int bits = (end_bit - shift) < kRadixBits ? (end_bit - shift) : kRadixBits;
         onesweep_kernel<uint64_t, kSortItems64, 0><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
             M, nullptr, ksrc, kdst, vsrc, vdst, shift, bits, w.hist + (size_t)p * kRadix, 1, w.tickets + p,
-            w.status + (size_t)p * n_tiles * kRadix, nullptr);
+            w.status + (size_t)p * n_tiles * kRadix, nullptr, 0);
         BSPLAT_LAUNCH_CHECK();
         uint64_t* tk = ksrc; ksrc = kdst; kdst = tk;
         int32_t* tv = vsrc; vsrc = vdst; vdst = tv;

@@ -218,8 +218,9 @@ def assemble_bands(image: torch.Tensor, bands, tile_size: int, rank: int, world:
 class RowBandRenderer:
     """One huge frame per step, split into tile-row bands across the ranks (BASELINE.json config 5).
 
-    Per frame and rank: ONE sync-free C call (bsplat_render_enqueue_band: project all N, bin + rasterize the
-    band only, write the band rows) followed by the exchange of the bands.  Bands are balanced by
+    Per frame and rank: ONE sync-free C call (bsplat_render_enqueue_band: list the Gaussians that can reach the band
+    with a conservative pre-test, project those, bin + rasterize the band only, write the band rows) followed by the
+    exchange of the bands.  pretest=False projects all N instead (A/B; bit-identical result).  Bands are balanced by
     intersection count; they are computed once (``rebalance``) and reused -- consecutive frames of a
     sequence have near-identical row costs -- instead of per frame.  The assembled image equals the
     single-GPU image bit for bit (per-tile lists do not depend on the split).
@@ -231,13 +232,15 @@ class RowBandRenderer:
     """
 
     def __init__(self, N: int, camera: Camera, channels: int = 3, tile_size: int = TILE_SIZE,
-                 semantics=_lib.SEM_TORCH, group=None, m_capacity: int | None = None, exchange: str = "nccl"):
+                 semantics=_lib.SEM_TORCH, group=None, m_capacity: int | None = None, exchange: str = "nccl",
+                 pretest: bool = True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self.L = _lib.require_device(self.dev)
         self.N, self.C, self.ts, self.semantics = int(N), int(channels), int(tile_size), semantics
+        self.raster_flags = _lib.RASTER_FAST | (0 if pretest else _lib.FLAG_NO_BAND_PRETEST)
         self.H, self.W = int(camera.H), int(camera.W)
         self.th = math.ceil(self.H / self.ts)
         self.m_cap = int(m_capacity) if m_capacity else 4 * self.N + 4096
@@ -270,11 +273,47 @@ class RowBandRenderer:
         if self.world > 1:
             dist.broadcast(cost, src=0, group=self.group)
         cost_list = cost.tolist()
+        self._row_cost = cost_list
         self.bands = balanced_row_bands(cost_list, self.world)
         self._pad = None
         # size the pair buffers for this rank's band (the cost is the torch-rule intersection count per row)
         b0, b1 = self.bands[self.rank]
         self._resize(int(1.25 * sum(cost_list[b0:b1])) + 65536)
+        return self.bands
+
+    def tune_bands(self, means3d, scales, quats, opacities, features, camera: Camera, background,
+                   iters: int = 3) -> list:
+        """Refine the bands of ``rebalance`` with measured times (once per sequence): the intersection count is a good
+        cost model for the inner bands but not for the first and last one, whose corner tiles hold the Gaussians the
+        torch rules clamp into them (cheap per pair, plus a pre-pass).  Each round renders one frame, all-gathers the
+        ranks' device times of the band call, spreads every band's time over its rows in proportion to their pair
+        counts and re-cuts the rows into bands of equal time."""
+        if self.world == 1 or not hasattr(self, "_row_cost"):
+            return self.bands
+        cost = self._row_cost
+        for _ in range(iters):
+            self._time_band = True
+            self.render(means3d, scales, quats, opacities, features, camera, background)
+            self._time_band = False
+            try:
+                self.check()
+            except RuntimeError:
+                continue  # (capacity grown; measure again)
+            t = torch.tensor([self._ev[0].elapsed_time(self._ev[1])], dtype=torch.float32, device=self.dev)
+            ts = torch.empty(self.world, dtype=torch.float32, device=self.dev)
+            dist.all_gather_into_tensor(ts, t, group=self.group)
+            ts = ts.tolist()
+            dens = [0.0] * len(cost)
+            mean_rate = sum(ts) / max(sum(cost), 1.0)
+            for r, (b0, b1) in enumerate(self.bands):
+                c = sum(cost[b0:b1])
+                rate = ts[r] / c if c > 0 else mean_rate
+                for row in range(b0, b1):
+                    dens[row] = cost[row] * rate
+            self.bands = balanced_row_bands(dens, self.world)
+            self._pad = None
+            b0, b1 = self.bands[self.rank]
+            self._resize(int(1.25 * sum(cost[b0:b1])) + 65536)
         return self.bands
 
     def _resize(self, m_cap: int) -> None:
@@ -291,24 +330,35 @@ class RowBandRenderer:
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         needed = c_size_t(0)
         import ctypes
+        timed = getattr(self, "_time_band", False)
+        if timed:
+            self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         if self.exchange == "p2p":
             # nobody may still be reading the previous frame out of a buffer this frame writes into
             self._hdl.barrier(channel=0)
+            if timed:
+                self._ev[0].record()
             rc = self.L.bsplat_render_enqueue_band_p2p(
                 self.N, _lib.ptr(means3d), _lib.ptr(scales), _lib.ptr(quats), _lib.ptr(opacities),
                 _lib.ptr(features), self.C, ctypes.addressof(cam), _lib.ptr(background), self.ts, self.semantics,
-                _lib.RASTER_FAST, b0, b1, _lib.ptr(self.image), self._peer_arr, len(self._peer_arr),
+                self.raster_flags, b0, b1, _lib.ptr(self.image), self._peer_arr, len(self._peer_arr),
                 _lib.ptr(self.ws), self.ws.numel(), self.m_cap, byref(needed), self.info.data_ptr(), stream,
                 None, None)
             _lib.check(rc, "bsplat_render_enqueue_band_p2p")
+            if timed:
+                self._ev[1].record()
             self._hdl.barrier(channel=1)  # every rank's tiles have landed everywhere
             return self.image
+        if timed:
+            self._ev[0].record()
         rc = self.L.bsplat_render_enqueue_band(
             self.N, _lib.ptr(means3d), _lib.ptr(scales), _lib.ptr(quats), _lib.ptr(opacities), _lib.ptr(features),
-            self.C, ctypes.addressof(cam), _lib.ptr(background), self.ts, self.semantics, _lib.RASTER_FAST, b0, b1,
+            self.C, ctypes.addressof(cam), _lib.ptr(background), self.ts, self.semantics, self.raster_flags, b0, b1,
             _lib.ptr(self.image), _lib.ptr(self.ws), self.ws.numel(), self.m_cap, byref(needed),
             self.info.data_ptr(), stream, None, None)
         _lib.check(rc, "bsplat_render_enqueue_band")
+        if timed:
+            self._ev[1].record()
         if self.exchange == "nccl":
             rows = [(min(a * self.ts, self.H), min(b * self.ts, self.H)) for a, b in self.bands]
             n_max = max(e - s for s, e in rows)

@@ -182,6 +182,46 @@ def test_row_band_renderer_bands_reassemble(cuda_device, cfg, N, world):
     assert total == aux["n_isect"]  # every (Gaussian, tile) pair lands in exactly one band
 
 
+@pytest.mark.parametrize("pretest", [True, False])
+def test_band_pretest_is_conservative(cuda_device, pretest):
+    """Row-band frames only project the Gaussians a cheap pre-test cannot rule out of the band.  Adversarial inputs
+    (huge / tiny / NaN / inf scales, zero and unnormalised quaternions, means behind and on the camera plane, far
+    outside the frustum, non-finite means): every band must still hold exactly the pairs of the single-GPU frame."""
+    g = torch.Generator().manual_seed(7)
+    sc = synthetic.make_scene("config3_1m_1080p", N=120_000)
+    (m, s, q, o, c), cam = scene_on(sc, cuda_device)
+    m, s, q = m.clone(), s.clone(), q.clone()
+    n = sc.N
+    pick = lambda k: torch.randperm(n, generator=g)[:k].to(cuda_device)
+    s[pick(2000)] += 3.0                       # e^3 larger: rectangles spanning many bands
+    s[pick(2000), 1] = 6.0                     # one huge axis
+    s[pick(500)] = -30.0                       # vanishing
+    s[pick(50), 0] = float("nan")
+    s[pick(50), 2] = float("inf")
+    q[pick(300)] = 0.0                         # degenerate quaternion (normalisation clamp)
+    q[pick(300)] *= 1e-14
+    q[pick(300)] *= 1e6                        # unnormalised
+    q[pick(20), 1] = float("nan")
+    m[pick(3000), 2] *= -1.0                   # mirrored through the origin plane: many land behind the camera
+    m[pick(200)] *= 50.0                       # far outside the frustum
+    m[pick(20), 1] = float("inf")
+    m[pick(20), 0] = float("nan")
+    bg = sc.background.to(cuda_device)
+    full, aux = ms.render_fused(m, s, q, o, c, cam, bg, return_aux=True)
+    with torch.cuda.device(cuda_device):
+        rb = parallel.RowBandRenderer(sc.N, cam, m_capacity=200 * sc.N, pretest=pretest)
+    th = (cam.H + 15) // 16
+    cuts = [0, 1, 7, th // 3, th // 2, th - 9, th - 1, th]
+    rb.image.fill_(-1.0)
+    total = 0
+    for b0, b1 in zip(cuts[:-1], cuts[1:]):
+        rb.bands = [(b0, b1)]
+        rb.render(m, s, q, o, c, cam, bg)
+        total += rb.check()
+    assert total == aux["n_isect"]
+    assert torch.equal(rb.image.nan_to_num(nan=-7.0), full.nan_to_num(nan=-7.0))
+
+
 @pytest.mark.parametrize("cfg,N,W,H,f", [("config3_1m_1080p", 150_000, 800, 450, 420.0), ("config2_100k_1080p", 3_000, 640, 360, 170.0),
                                          ("config1_1k_256", 1_000, 256, 256, 66.7)])
 def test_sync_free_paths_gsplat_rules(cuda_device, cfg, N, W, H, f):
