@@ -43,19 +43,20 @@ for cfg, N, sem in [("config1_1k_256", None, "cuda"), ("config3_1m_1080p", 8000 
          g[4].clone().requires_grad_(True), g[3].clone().requires_grad_(True)]
     out = rasterization.rasterize_gaussians_diff(*t, bg, aux["tile_ranges"], aux["sorted_ids"], sc.camera, 16)
     out.sum().backward()
-    pipe = OverlappedPipeline(dev, sc.N, sc.camera.W, sc.camera.H, semantics=semv)
+    pipe = OverlappedPipeline(dev, sc.N, sc.camera.W, sc.camera.H, semantics=semv, m_capacity=200 * sc.N + 4096)
     cams = synthetic.orbit_cameras(4, sc.camera.W, sc.camera.H, sc.camera.fx)
     pipe.render(*g, cams, bg); pipe.check()
     tiny = OverlappedPipeline(dev, sc.N, sc.camera.W, sc.camera.H, m_capacity=500)
     tiny.render(*g, cams[:2], bg); tiny.check()
-    gr = GraphRenderer(*g, sc.camera, bg, semantics=semv)
+    gr = GraphRenderer(*g, sc.camera, bg, semantics=semv, m_capacity=200 * sc.N + 4096)
     gr.render(cams[1]); gr.check()
     full = ms.render_fused(*g, sc.camera, bg, 16, semantics=semv)
     assert torch.equal(parallel.render_frame_row_split(*g, sc.camera, bg, semantics=semv), full)
     rb_img = torch.zeros_like(full)
     th = (sc.camera.H + 15) // 16
-    for band in ((0, th // 3), (th // 3, th // 3), (th // 3, th)):   # (one empty band)
-        rb = parallel.RowBandRenderer(sc.N, sc.camera, semantics=semv)
+    for bi, band in enumerate(((0, th // 3), (th // 3, th // 3), (th // 3, th // 2), (th // 2, th))):   # (one empty band)
+        # (torch rules: bands 0..2 through the band pre-test + candidate-list projection, the last one without)
+        rb = parallel.RowBandRenderer(sc.N, sc.camera, semantics=semv, pretest=bi < 3, m_capacity=200 * sc.N + 4096)
         rb.bands = [band]
         rb.render(*g, sc.camera, bg); rb.check()
         r0, r1 = band[0] * 16, min(band[1] * 16, sc.camera.H)

@@ -314,6 +314,7 @@ bin_compact_scatter_kernel(const int64_t n_chunks, const int32_t* __restrict__ l
         for (int k = 0; k < kCompactItems; ++k) {
             if ((flags >> k) & 1u) {
                 const int32_t gi = list ? __ldg(list + base + k) : (int32_t)(base + k);
+                BSPLAT_DASSERT(gi >= 0 && (int64_t)pos < n_chunks * kCompactChunk);
                 perm[pos] = gi;
                 if (!kPre) {
                     const uint32_t kk = __ldg(keys_full + gi);
@@ -396,7 +397,8 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
         if (jj < N) rects[jj] = cl;
         thread_sum += cnt[k];
     }
-    if (hist_xy != nullptr) {
+    const int lane = tid & 31, warp = tid >> 5;
+    auto add_coverage = [&]() {
         // (s_diff was zeroed before the first barrier above; uint32 wrap-around carries the negative steps.)  Runs of
         // identical rectangles in a thread's depth-consecutive slots -- the culled Gaussians that the torch rules clamp
         // into a corner tile -- are merged first: they would all hit the same four words.
@@ -408,6 +410,7 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
         auto flush = [&]() {
             if (mult == 0u) return;
             const uint32_t x0 = px & 0xffffu, y0 = px >> 16, w = py & 0xffffu, h = py >> 16;
+            BSPLAT_DASSERT(x0 + w <= (uint32_t)kRadix && y0 + h <= (uint32_t)kRadix && x0 + w <= x_end && y0 + h <= y_end);
             if (x0 == 0u) edge_l += h * mult; else atomicAdd(&s_diff[0][x0], h * mult);
             if (x0 + w == x_end) edge_r += h * mult; else atomicAdd(&s_diff[0][x0 + w], 0u - h * mult);
             if (y0 == y_beg) edge_t += w * mult; else atomicAdd(&s_diff[1][y0], w * mult);
@@ -435,8 +438,10 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
             if (edge_t) atomicAdd(&s_diff[1][y_beg], edge_t);
             if (edge_b) atomicAdd(&s_diff[1][y_end], 0u - edge_b);
         }
-    }
-    const int lane = tid & 31, warp = tid >> 5;
+    };
+    // warp 0 (which goes into the look-back below) adds its coverage now; the other 31 warps do it while warp 0 waits
+    // for its predecessors, so the chunk's aggregate is published without waiting for the histogram work
+    if (hist_xy != nullptr && warp == 0) add_coverage();
     unsigned long long incl = thread_sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -453,10 +458,13 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
         block_total += s;
     }
     const unsigned long long thread_excl = warp_excl + incl - thread_sum;
+    if (hist_xy != nullptr && warp != 0) {
+        add_coverage();
+        asm volatile("bar.sync 2, %0;" ::"n"(kScan2Threads - 32));  // warps 1 .. 31: every update is in s_diff
+    }
     if (hist_xy != nullptr && tid >= kScan2Threads - 2 * kRadix) {
         // inclusive prefix of the difference arrays = coverage per column (first 256 of these threads) / row (last
-        // 256); every s_diff update precedes the barrier above.  The upper half of the CTA does this (and the global
-        // flush) while warp 0 is in the look-back.
+        // 256).  The upper half of the CTA does this (and the global flush) while warp 0 is in the look-back.
         const int t2 = tid - (kScan2Threads - 2 * kRadix);
         const int which = t2 >> 8, b = t2 & (kRadix - 1);
         uint32_t v = s_diff[which][b];
@@ -611,6 +619,8 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
                 if (kSep) {
                     if (valid) {
                         const uint32_t k = pidx - eo;
+                        BSPLAT_DASSERT((int64_t)pidx < m_cap && pidx >= eo && wo >= 1u && wo <= (uint32_t)kRadix &&
+                                       k / wo == (wo == 1u ? k : __umulhi(k, __float_as_uint(iw))) && (xy >> 16) + k / wo < 256u);
                         // k / w = hi(k * ceil(2^32 / w)), exact while k (w ceil(2^32 / w) - 2^32) < 2^32, i.e. for
                         // k w < 2^32: rectangles of at most 256 x 256 tiles have k < 2^16 and w <= 2^8
                         const uint32_t dy = wo == 1u ? k : __umulhi(k, __float_as_uint(iw));

@@ -12,6 +12,24 @@
         if (_e != cudaSuccess) return static_cast<int>(_e);    \
     } while (0)
 
+// Checked build (make checked -> libbsplat_checked.so, -DBSPLAT_CHECKED): device-side bounds / invariant checks at
+// the indexing hot spots (staging rings, shared-memory scatters, scatter positions, list bounds).  A failed check
+// prints its location and traps.  compute-sanitizer is not available on every pool; benchmarks/selfcheck.py runs the
+// whole kernel inventory under this build, with canaries around every buffer, and repeats frames for run-to-run
+// determinism.
+#ifdef BSPLAT_CHECKED
+#include <cstdio>
+#define BSPLAT_DASSERT(cond)                                                                    \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            printf("BSPLAT_DASSERT failed: %s  (%s:%d)\n", #cond, __FILE__, __LINE__);           \
+            __trap();                                                                           \
+        }                                                                                       \
+    } while (0)
+#else
+#define BSPLAT_DASSERT(cond) ((void)0)
+#endif
+
 #define BSPLAT_LAUNCH_CHECK()                                  \
     do {                                                       \
         cudaError_t _e = cudaGetLastError();                   \

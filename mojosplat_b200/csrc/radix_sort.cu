@@ -240,6 +240,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
         for (int it = 0; it < ITEMS; ++it) {
             const uint32_t d = (uint32_t)(key[it] >> shift) & digit_mask;
             const uint32_t pos = s_local_off[d] + s_whist[warp][d] + rank[it];  // padding slots: pos >= n_valid
+            BSPLAT_DASSERT(d < (uint32_t)kRadix && pos < (uint32_t)TILE);
             s_keys[pos] = key[it];
             s_vals[pos] = val[it];
         }
@@ -298,6 +299,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
             const KeyT kk = s_keys[j];
             const uint32_t d = (uint32_t)(kk >> shift) & digit_mask;
             const uint32_t dst = s_gbase[d] + (uint32_t)j;
+            BSPLAT_DASSERT((int64_t)dst < M);
             if (write_keys) keys_out[dst] = kk;
             vals_out[dst] = s_vals[j];
             if (count_keys) {

@@ -359,6 +359,7 @@ raster_long_compact_kernel(const int64_t N, const float4* __restrict__ rec, cons
                     for (int w = 0; w < kGroups / 32; ++w)
                         if (w < gi / 32) base += gtot[w];
                     const unsigned int bl = ballots[k];
+                    BSPLAT_DASSERT(!((bl >> lane) & 1u) || r0 + base + (int)__popc(bl & ((1u << lane) - 1u)) < r1);
                     if ((bl >> lane) & 1u) surv[r0 + base + __popc(bl & ((1u << lane) - 1u))] = ids[k];
                 }
                 if (c == nc - 1 && tid == 0) scratch[lo] = (uint32_t)(base0 + total_surv);
@@ -437,6 +438,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             compacted = true;
             ids = surv;
             v1 = r0 + (int32_t)__ldg(chunk_cnt + blockIdx.x);
+            BSPLAT_DASSERT(v1 >= r0 && v1 <= r1);
         }
     }
     // long list without a pre-pass (stage-level entry point, or a list beyond the pre-pass limits): the four warps
@@ -467,6 +469,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
         for (int h = 0; h < kPer; ++h) {
             if (h * kPairThreads + tid >= kBatch) break;  // (batches smaller than the CTA: the first warps gather)
             float4* dst = s_g + (half * kBatch + h * kPairThreads + tid) * kPairRec;
+            BSPLAT_DASSERT(half >= 0 && (half * kBatch + h * kPairThreads + tid + 1) * kPairRec <= kStageRecs * kPairRec);
             if (id.v[h] >= 0 && (int64_t)id.v[h] < N) {
                 const float4* src = rec + kPairRec * (int64_t)id.v[h];
 #pragma unroll
@@ -613,6 +616,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                     asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(below) : "r"(b_hi));  // bits below b_hi
                     mask &= below;
                     const float4* r = rec_hi - kPairRec * (int)b_hi;
+                    BSPLAT_DASSERT(r >= s_g && r + kPairRec <= s_g + kStageRecs * kPairRec && c0 + 31 - (int)b_hi < bs);
                     const float4 p0 = r[0], p1 = r[1];
                     const float cb = reinterpret_cast<const float*>(r + 2)[0];
                     composite(alpha_of(plain_tag, r, p0, p1), p1.z, p1.w, cb);
