@@ -14,4 +14,4 @@ cd "$(dirname "$0")/.."
 python benchmarks/ncu_src.py $rep raster_pair 48 > profiles/${tag}_raster_hot_sass.txt 2>&1 || true
 ncu -i $rep --page details --kernel-name regex:raster_pair_kernel 2>/dev/null | awk '/raster_pair_kernel/{n++} n<=1' > profiles/${tag}_raster_details.txt
 ncu -i $rep --page details --kernel-name regex:project_kernel 2>/dev/null | awk '/project_kernel/{n++} n<=1' > profiles/${tag}_projection_details.txt
-python benchmarks/ncu_traffic.py $rep profiles/ncu_traffic.json
+python benchmarks/ncu_traffic.py $rep profiles/ncu_traffic.json profiles/${tag}_frame_summary.txt

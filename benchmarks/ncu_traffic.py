@@ -8,6 +8,7 @@ import subprocess
 import sys
 
 rep, out = sys.argv[1], sys.argv[2]
+label = sys.argv[3] if len(sys.argv) > 3 else rep  # what the JSON cites (the committed summary of the capture)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
@@ -28,9 +29,14 @@ for r in rows[2:]:
                     "dram_read": val(r, "dram__bytes_read.sum"), "dram_write": val(r, "dram__bytes_write.sum")})
 
 
+n_frames = max(1, sum(1 for k in kernels if "raster_pair_kernel" in k["kernel"]))
+
+
 def group(pred):
+    """Kernels of ONE frame (the last captured one) and their DRAM bytes averaged over the captured frames."""
     sel = [k for k in kernels if pred(k["kernel"])]
-    return sel, sum(k["dram_read"] + k["dram_write"] for k in sel)
+    per_frame = sum(k["dram_read"] + k["dram_write"] for k in sel) / n_frames
+    return sel[-(len(sel) // n_frames):], per_frame
 
 
 frame = [k for k in kernels if "bsplat" in k["kernel"] or "proj_" in k["kernel"]]
@@ -39,7 +45,8 @@ proj = [k for k in frame if "project_kernel" in k["kernel"]]
 fused_proj, alone_proj = proj[0], proj[-1]
 ras, ras_b = group(lambda n: "raster_" in n)
 binn, bin_b = group(lambda n: any(t in n for t in ("onesweep", "bin_", "tile_finish")))
-src = f"{rep} (ncu --set full --clock-control none, benchmarks/one_frame.py config3_1m_1080p, one frame)"
+src = (f"{label} (ncu --set full --clock-control none, benchmarks/one_frame.py config3_1m_1080p; bytes per frame, "
+       f"averaged over the {n_frames} captured frames)")
 res = {
     "raster": {"kernel": " + ".join(sorted({k['kernel'] for k in ras})), "dram_bytes": ras_b,
                "per_kernel": ras, "source": src},

@@ -230,6 +230,7 @@ bin_compact_flags_kernel(const int64_t N_host, const int32_t* __restrict__ list,
                          uint8_t* __restrict__ flag_bytes, uint32_t* __restrict__ counts,
                          uint32_t* __restrict__ offs, uint32_t* __restrict__ done,
                          unsigned long long* __restrict__ n_out, const unsigned long long whole_extra) {
+    pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
     __shared__ unsigned int s_cnt[kCompactThreads / 32], s_whole[kCompactThreads / 32];
     __shared__ bool s_last;
     const int64_t N = list_n ? (int64_t)(*list_n) : N_host;
@@ -290,6 +291,7 @@ bin_compact_scatter_kernel(const int64_t n_chunks, const int32_t* __restrict__ l
                            const uint8_t* __restrict__ flag_bytes, const uint32_t* __restrict__ offs,
                            const uint32_t* __restrict__ keys_full, uint32_t* __restrict__ keys,
                            int32_t* __restrict__ perm, uint32_t* __restrict__ hist /* [4][256] */) {
+    pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
     __shared__ uint32_t s_hist[kPre ? 1 : 4][kRadix];
     __shared__ unsigned int s_warp_sum[kCompactThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -353,6 +355,7 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
                        const int row_end, uint32_t* __restrict__ offsets, bsplat_bin_info* __restrict__ info,
                        unsigned long long* __restrict__ ws, uint2* __restrict__ rects,
                        uint32_t* __restrict__ hist_xy /* [2][256] or null */, const int tiles_w) {
+    pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
     __shared__ unsigned int s_chunk;
     // 2-D tile keys (hist_xy != null): the digit histograms of the two tile-sort passes are the column and row
     // coverage counts -- a rectangle adds h to each of its w columns and w to each of its h rows, i.e. four updates of
@@ -492,6 +495,7 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
         if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
+    pdl_trigger();  // only the output is left: the next kernel of the stream may be staged now
     unsigned long long run = s_prefix + thread_excl;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
@@ -539,6 +543,7 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
                  uint32_t* __restrict__ tile_keys, int32_t* __restrict__ ids,
                  uint32_t* __restrict__ hist /* [kMaxTilePasses][256] */,
                  bsplat_bin_info* __restrict__ info_dev, const int64_t m_cap) {
+    pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
     // sync-free frames: the pair buffers hold m_cap entries; if this frame produced more, emit nothing,
     // raise the overflow flag (reserved[1]) and let the later passes see it (they skip too)
     if (info_dev != nullptr && (int64_t)info_dev->n_isect > m_cap) {
@@ -655,6 +660,7 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
             // (a window whose last Gaussian reaches beyond E ends the task; one that ends before E continues)
         }
     }
+    pdl_trigger();
     if (kSep) return;
     __syncthreads();
     for (int i = tid; i < tp.n * kRadix; i += kEmit2Threads) {
@@ -683,6 +689,7 @@ __global__ void __launch_bounds__(kFinThreads)
 tile_finish2_kernel(const int n_tiles, const int first, const int n_order, const uint32_t* __restrict__ counts,
                     int32_t* __restrict__ ranges, int32_t* __restrict__ order, uint32_t* __restrict__ scratch,
                     const bsplat_bin_info* __restrict__ info_dev, bsplat_bin_info* __restrict__ info_host) {
+    pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
     __shared__ int s_cnt[256];
     __shared__ int s_res[256];
     __shared__ uint32_t s_w[kFinThreads / 32];
@@ -794,7 +801,7 @@ int tile_finish_launch(int n_tiles, int first, int n_order, const uint32_t* coun
                        bsplat_bin_info* info_host, cudaStream_t stream) {
     const int by_size = (n_tiles + 63) / 64;
     const int G = by_size < 1 ? 1 : (by_size > kFinMaxCtas ? kFinMaxCtas : by_size);
-    tile_finish2_kernel<<<G, kFinThreads, 0, stream>>>(n_tiles, first, n_order, counts, ranges, order, scratch,
+    BSPLAT_LAUNCH_PDL((tile_finish2_kernel), G, kFinThreads, 0, stream, n_tiles, first, n_order, counts, ranges, order, scratch,
                                                        info_dev, info_host);
     BSPLAT_LAUNCH_CHECK();
     return BSPLAT_OK;
@@ -970,12 +977,10 @@ int bin2_band_candidates(int64_t N, const float* means3d, const float* log_scale
     pt.y_hi = p.row_end >= p.tiles_h ? INFINITY : (float)p.row_end * p.tile_size_f + 1.0f;
     const int64_t cb = ceil_div(N, kCompactChunk);
     uint32_t* counts = reinterpret_cast<uint32_t*>(w.cand_status);
-    bin_compact_flags_kernel<true><<<(unsigned)cb, kCompactThreads, 0, stream>>>(
-        N, nullptr, nullptr, nullptr, p.row_begin, p.row_end, means3d, log_scales, pt, w.cand_flags, counts, counts + cb,
+    BSPLAT_LAUNCH_PDL((bin_compact_flags_kernel<true>), (unsigned)cb, kCompactThreads, 0, stream, N, nullptr, nullptr, nullptr, p.row_begin, p.row_end, means3d, log_scales, pt, w.cand_flags, counts, counts + cb,
         w.tickets + 9, w.cand_n, 0ull);
     BSPLAT_LAUNCH_CHECK();
-    bin_compact_scatter_kernel<true><<<(unsigned)(cb < 148 * 8 ? cb : 148 * 8), kCompactThreads, 0, stream>>>(
-        cb, nullptr, w.cand_flags, counts + cb, nullptr, nullptr, w.cand, nullptr);
+    BSPLAT_LAUNCH_PDL((bin_compact_scatter_kernel<true>), (unsigned)(cb < 148 * 8 ? cb : 148 * 8), kCompactThreads, 0, stream, cb, nullptr, w.cand_flags, counts + cb, nullptr, nullptr, w.cand, nullptr);
     BSPLAT_LAUNCH_CHECK();
     *list = w.cand;
     *list_n = w.cand_n;
@@ -1014,13 +1019,11 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
         // tile somewhere in the frame, so the whole-frame count is N
         uint32_t* counts = reinterpret_cast<uint32_t*>(w.compact_status);
         const int32_t* list = use_candidates ? w.cand : nullptr;
-        bin_compact_flags_kernel<false><<<(unsigned)cb, kCompactThreads, 0, stream>>>(
-            N, list, use_candidates ? w.cand_n : nullptr, w.rects_in, p.row_begin, p.row_end, nullptr, nullptr,
+        BSPLAT_LAUNCH_PDL((bin_compact_flags_kernel<false>), (unsigned)cb, kCompactThreads, 0, stream, N, list, use_candidates ? w.cand_n : nullptr, w.rects_in, p.row_begin, p.row_end, nullptr, nullptr,
             BandPretest(), w.compact_flags, counts, counts + cb, w.tickets + 8, w.n_band,
             use_candidates ? (unsigned long long)N : 0ull);
         BSPLAT_LAUNCH_CHECK();
-        bin_compact_scatter_kernel<false><<<(unsigned)(cb < 148 * 4 ? cb : 148 * 4), kCompactThreads, 0, stream>>>(
-            cb, list, w.compact_flags, counts + cb, w.dkeys_alt, w.dkeys, w.perm, w.hist);
+        BSPLAT_LAUNCH_PDL((bin_compact_scatter_kernel<false>), (unsigned)(cb < 148 * 4 ? cb : 148 * 4), kCompactThreads, 0, stream, cb, list, w.compact_flags, counts + cb, w.dkeys_alt, w.dkeys, w.perm, w.hist);
         BSPLAT_LAUNCH_CHECK();
         n_dev = reinterpret_cast<const uint64_t*>(w.n_band);
         vsrc = w.perm;
@@ -1038,8 +1041,7 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
     }
     // after 4 passes the sorted permutation is in w.perm (passes 1 and 3 write w.perm)
     const unsigned grid = (unsigned)ceil_div(N, kScan2Chunk);
-    bin_count_scan2_kernel<<<grid, kScan2Threads, 0, stream>>>(
-        N, reinterpret_cast<const unsigned long long*>(n_dev), w.perm, w.rects_in, p.row_begin, p.row_end, w.offsets,
+    BSPLAT_LAUNCH_PDL((bin_count_scan2_kernel), grid, kScan2Threads, 0, stream, N, reinterpret_cast<const unsigned long long*>(n_dev), w.perm, w.rects_in, p.row_begin, p.row_end, w.offsets,
         w.info, static_cast<unsigned long long*>(w.scan_ws), w.rects, tile_keys_2d(p) ? w.hist + 4 * kRadix : nullptr,
         p.tiles_w);
     BSPLAT_LAUNCH_CHECK();
@@ -1075,12 +1077,10 @@ int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* w
     const int64_t emit_ctas = ceil_div(ceil_div(M, (int64_t)kEmitTask), kEmit2Threads / 32);
     const unsigned emit_grid = (unsigned)(emit_ctas < 148 * 8 ? emit_ctas : 148 * 8);
     if (keys2d)
-        bin_emit2_kernel<true><<<emit_grid, kEmit2Threads, 0, stream>>>(
-            N, compact ? w.n_band : nullptr, w.perm, w.rects, p.tiles_w, w.offsets, tp, w.tkeys, w.ids,
+        BSPLAT_LAUNCH_PDL((bin_emit2_kernel<true>), emit_grid, kEmit2Threads, 0, stream, N, compact ? w.n_band : nullptr, w.perm, w.rects, p.tiles_w, w.offsets, tp, w.tkeys, w.ids,
             w.hist + 4 * kRadix, info_dev, M);
     else
-        bin_emit2_kernel<false><<<emit_grid, kEmit2Threads, 0, stream>>>(
-            N, compact ? w.n_band : nullptr, w.perm, w.rects, p.tiles_w, w.offsets, tp, w.tkeys, w.ids,
+        BSPLAT_LAUNCH_PDL((bin_emit2_kernel<false>), emit_grid, kEmit2Threads, 0, stream, N, compact ? w.n_band : nullptr, w.perm, w.rects, p.tiles_w, w.offsets, tp, w.tkeys, w.ids,
             w.hist + 4 * kRadix, info_dev, M);
     BSPLAT_LAUNCH_CHECK();
     const int64_t tm = sort_tiles_u32(M);

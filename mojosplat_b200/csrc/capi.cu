@@ -573,6 +573,7 @@ extern "C" int bsplat_render_enqueue_band_p2p(int64_t N, const float* means3d, c
         cam_dev = w.cam_dev;
     }
     const bool fast_raster = fast_raster_for(raster_mode, tile_size, channels);
+    const PdlScope pdl_scope(sr == sb);  // two streams = overlapped pipeline: plain launches (common.cuh)
     // the faithful rasterizer reads the stage outputs; the fast one only needs the records of the projection epilogue
     int rc = frame_front(N, means3d, log_scales, quats, opacities, colors, *cam, cam_dev, tile_size, semantics, flags,
                          row0, row1, fast_raster, fast_raster ? nullptr : w.means2d, fast_raster ? nullptr : w.conics,

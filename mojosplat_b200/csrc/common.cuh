@@ -30,6 +30,56 @@
 #define BSPLAT_DASSERT(cond) ((void)0)
 #endif
 
+// Programmatic dependent launch (sm_90+): a kernel launched with BSPLAT_LAUNCH_PDL may become resident while its
+// predecessor in the stream is still draining; it must call pdl_wait() before it touches anything the predecessor
+// wrote (first statement of every kernel launched this way) and pdl_trigger() right after it (so that ITS successor
+// can be staged in turn; after the wait, so that a pre-staged kernel never overtakes two predecessors).  The frame is
+// a chain of ~12 short dependent kernels: this takes the launch / ramp-up latency out of every boundary.
+// BSPLAT_DEBUG=nopdl launches them the plain way (A/B).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#include <cstdlib>
+#include <cstring>
+#include <utility>
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* d = getenv("BSPLAT_DEBUG");
+        return !(d && strstr(d, "nopdl"));
+    }();
+    return on;
+}
+// Per-call switch (thread-local): frames whose binning and rasterization go to two streams (the overlapped pipeline)
+// launch the plain way -- a pre-staged kernel holds registers and shared memory that the OTHER stream's kernels would
+// have used (measured: single frame 0.469 -> 0.453 ms with PDL, overlapped pipeline 2 772 -> 2 740 frames/s).
+inline bool& pdl_call_switch() {
+    static thread_local bool on = true;
+    return on;
+}
+struct PdlScope {
+    bool old;
+    explicit PdlScope(bool on) : old(pdl_call_switch()) { pdl_call_switch() = on; }
+    ~PdlScope() { pdl_call_switch() = old; }
+};
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl_enabled() && pdl_call_switch()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#define BSPLAT_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                       \
+    do {                                                                                                \
+        cudaError_t e_ = launch_pdl(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__);       \
+        if (e_ != cudaSuccess) return (int)e_;                                                          \
+    } while (0)
+#endif
+
 #define BSPLAT_LAUNCH_CHECK()                                  \
     do {                                                       \
         cudaError_t _e = cudaGetLastError();                   \

@@ -80,6 +80,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
                 int32_t* __restrict__ vals_out, const int shift, const int bits_rt,
                 const uint32_t* __restrict__ hist, const int hist_is_scanned, uint32_t* __restrict__ ticket,
                 uint32_t* __restrict__ status, uint32_t* __restrict__ key_counts, const int key_row_stride) {
+    pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
     constexpr int TILE = kSortThreads * ITEMS;
     // BITS > 0: digit width known at compile time (branch-free ballot loop with constant masks)
     const int bits = BITS > 0 ? BITS : bits_rt;
@@ -289,6 +290,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
         s_gbase[tid] = s_bins[tid] + prev - s_local_off[tid];
     }
     __syncthreads();
+    pdl_trigger();  // only the output is left: the next kernel of the stream may be staged now
 
     // ---- contiguous per-digit runs to global ----
     const bool write_keys = keys_out != nullptr, count_keys = key_counts != nullptr;
@@ -330,7 +332,7 @@ int64_t sort_tiles_u64(int64_t M) { return ceil_div(M > 0 ? M : 1, kSortThreads 
 size_t sort_status_words(int64_t n_tiles, int passes) { return (size_t)passes * n_tiles * kRadix; }
 
 #define BSPLAT_ONESWEEP32(B)                                                                              \
-    onesweep_kernel<uint32_t, kSortItems32, B><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(               \
+    BSPLAT_LAUNCH_PDL((onesweep_kernel<uint32_t, kSortItems32, B>), (unsigned)n_tiles, kSortThreads, 0, stream, \
         M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,    \
         key_counts, key_row_stride)
 
@@ -340,8 +342,7 @@ int onesweep_pass_u32(int64_t M, const uint64_t* m_dev, const uint32_t* keys_in,
                       cudaStream_t stream, int key_row_stride) {
     const int64_t n_tiles = sort_tiles_u32(M);
     if (bits == 8 && n_tiles <= 3 * 148) {  // every tile resident at once (3 CTAs per SM): wide look-back window
-        onesweep_kernel<uint32_t, kSortItems32, 8, 64><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
-            M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,
+        BSPLAT_LAUNCH_PDL((onesweep_kernel<uint32_t, kSortItems32, 8, 64>), (unsigned)n_tiles, kSortThreads, 0, stream, M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,
             key_counts, key_row_stride);
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
@@ -421,8 +422,7 @@ extern "C" int bsplat_radix_sort_pairs(int64_t M, uint64_t* keys, uint64_t* keys
     for (int p = 0; p < passes; ++p) {
         const int shift = begin_bit + p * kRadixBits;
         const int bits = (end_bit - shift) < kRadixBits ? (end_bit - shift) : kRadixBits;
-        onesweep_kernel<uint64_t, kSortItems64, 0><<<(unsigned)n_tiles, kSortThreads, 0, stream>>>(
-            M, nullptr, ksrc, kdst, vsrc, vdst, shift, bits, w.hist + (size_t)p * kRadix, 1, w.tickets + p,
+        BSPLAT_LAUNCH_PDL((onesweep_kernel<uint64_t, kSortItems64, 0>), (unsigned)n_tiles, kSortThreads, 0, stream, M, nullptr, ksrc, kdst, vsrc, vdst, shift, bits, w.hist + (size_t)p * kRadix, 1, w.tickets + p,
             w.status + (size_t)p * n_tiles * kRadix, nullptr, 0);
         BSPLAT_LAUNCH_CHECK();
         uint64_t* tk = ksrc; ksrc = kdst; kdst = tk;

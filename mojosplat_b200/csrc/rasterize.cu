@@ -266,6 +266,7 @@ raster_long_compact_kernel(const int64_t N, const float4* __restrict__ rec, cons
                            const int32_t* __restrict__ tile_order, const int n_order,
                            const int32_t* __restrict__ sorted_ids, const int tiles_w,
                            int32_t* __restrict__ surv, uint32_t* __restrict__ scratch, uint32_t* __restrict__ barrier) {
+    pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
     __shared__ int s_pref[kMaxLongSlots + 1];   // exclusive prefix of chunk counts over the long tiles
     __shared__ int s_wsum[kLongThreads / 32];
     __shared__ int s_grp[kLongChunk / 32];      // survivors per (round, warp) group of a chunk
@@ -406,6 +407,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                    float* __restrict__ image, const int vec_store,
                    const unsigned long long* __restrict__ m_dev, const PeerImages peers,
                    const int32_t* __restrict__ surv, const uint32_t* __restrict__ chunk_cnt) {
+    pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
     // staging: with records a ring of kRecStages batches, without one batch; the output tile (16 x 48 floats) reuses it.
     // (Kept as small as possible: what shared memory does not take stays L1, which the record gathers live on.)
     constexpr int kStageRecs = kRec ? kRecStages * kRecBatch : kPairBatch;
@@ -627,6 +629,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
         }
     }
 
+    pdl_trigger();  // only the output is left: the next kernel of the stream may be staged now
     if (kRec) cp_async_wait_all();  // nothing may still be landing in shared memory when it is reused below
     // sync-free frames: no intersections at all => all-zero image (render.py:73-76), decided on the device
     const float bgs = (m_dev != nullptr && *m_dev == 0ull) ? 0.0f : 1.0f;
@@ -778,18 +781,16 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
                                  !(dbg && strstr(dbg, "noprepass"));
             if (prepass) {
                 // one CTA per SM: the grid-wide barrier inside needs every CTA resident
-                raster_long_compact_kernel<<<148, kLongThreads, 0, stream>>>(N, recp, tile_ranges, tile_order, (int)grid,
+                BSPLAT_LAUNCH_PDL((raster_long_compact_kernel), 148, kLongThreads, 0, stream, N, recp, tile_ranges, tile_order, (int)grid,
                                                                              sorted_ids, tiles_w, surv, chunk_cnt,
                                                                              long_barrier);
                 BSPLAT_LAUNCH_CHECK();
             }
             if (mode == BSPLAT_RASTER_FAST_NOCULL)
-                raster_pair_kernel<false, true><<<grid, kPairThreads, 0, stream>>>(
-                    N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
+                BSPLAT_LAUNCH_PDL((raster_pair_kernel<false, true>), grid, kPairThreads, 0, stream, N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
                     tiles_w, image, vec, m_dev, peers, nullptr, nullptr);
             else
-                raster_pair_kernel<true, true><<<grid, kPairThreads, 0, stream>>>(
-                    N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
+                BSPLAT_LAUNCH_PDL((raster_pair_kernel<true, true>), grid, kPairThreads, 0, stream, N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
                     tiles_w, image, vec, m_dev, peers, prepass ? surv : nullptr,
                     prepass ? chunk_cnt : nullptr);
         } else {
@@ -797,12 +798,10 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
                           (reinterpret_cast<uintptr_t>(means2d) & 7u) != 0))
                 return BSPLAT_E_ARG;
             if (mode == BSPLAT_RASTER_FAST_NOCULL)
-                raster_pair_kernel<false, false><<<grid, kPairThreads, 0, stream>>>(
-                    N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W,
+                BSPLAT_LAUNCH_PDL((raster_pair_kernel<false, false>), grid, kPairThreads, 0, stream, N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W,
                     H, tiles_w, image, vec, m_dev, peers, nullptr, nullptr);
             else
-                raster_pair_kernel<true, false><<<grid, kPairThreads, 0, stream>>>(
-                    N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W,
+                BSPLAT_LAUNCH_PDL((raster_pair_kernel<true, false>), grid, kPairThreads, 0, stream, N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W,
                     H, tiles_w, image, vec, m_dev, peers, nullptr, nullptr);
         }
         BSPLAT_LAUNCH_CHECK();
