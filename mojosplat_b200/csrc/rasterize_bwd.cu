@@ -30,6 +30,42 @@ namespace bsplat {
 
 constexpr float kAlphaMin = 1.0f / 255.0f;
 
+// Thread -> pixel of the tile.  Tile sizes that are multiples of 8 give every warp an 8x4 pixel block (a tighter
+// culling box than the 16x2 strip of the row-major order: fewer Gaussians survive the per-warp test); other sizes keep
+// the row-major order (threads past ts*ts idle).
+__device__ __forceinline__ void tile_pixel_of(const int tid, const int ts, int& lx, int& ly) {
+    if ((ts & 7) == 0) {
+        const int w = tid >> 5, l = tid & 31, per_row = ts >> 3;
+        lx = (w % per_row) * 8 + (l & 7);
+        ly = (w / per_row) * 4 + (l >> 3);
+    } else {
+        ly = tid / ts;
+        lx = tid - ly * ts;
+    }
+}
+
+// Warp reduction of P (8 or 16) values per lane in P + log2(32 / P) shuffles instead of 5 P: at every step a lane keeps
+// one half of its values and sends the other half to its partner, so the sums end up SPREAD over the lanes --
+// lane L holds the total of value (L >> (P == 16 ? 1 : 2)) in v[0] -- and P lanes can issue their atomics in one
+// instruction instead of one lane issuing P.
+template <int P>
+__device__ __forceinline__ void warp_reduce_spread(float (&v)[P], const unsigned lane) {
+    static_assert(P == 8 || P == 16, "8 or 16 values");
+    int d = 16;
+#pragma unroll
+    for (int half = P / 2; half >= 1; half >>= 1, d >>= 1) {
+        const bool up = (lane & (unsigned)d) != 0u;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half];
+            const float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+        }
+    }
+#pragma unroll
+    for (; d >= 1; d >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
+}
+
 template <int CH>
 __global__ void __launch_bounds__(1024)
 raster_train_fwd_kernel(const int64_t N, const float* __restrict__ means2d, const float* __restrict__ conics,
@@ -53,7 +89,8 @@ raster_train_fwd_kernel(const int64_t N, const float* __restrict__ means2d, cons
 
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u;
-    const int ly = tid / ts, lx = tid - ly * ts;
+    int lx, ly;
+    tile_pixel_of(tid, ts, lx, ly);
     const int tile = blockIdx.y * tiles_w + blockIdx.x;
     const int i = blockIdx.y * ts + ly;
     const int j = blockIdx.x * ts + lx;
@@ -164,7 +201,8 @@ raster_bwd_kernel(const int64_t N, const float* __restrict__ means2d, const floa
 
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u;
-    const int ly = tid / ts, lx = tid - ly * ts;
+    int lx, ly;
+    tile_pixel_of(tid, ts, lx, ly);
     const int tile = blockIdx.y * tiles_w + blockIdx.x;
     const int i = blockIdx.y * ts + ly;
     const int j = blockIdx.x * ts + lx;
@@ -279,27 +317,25 @@ raster_bwd_kernel(const int64_t N, const float* __restrict__ means2d, const floa
                     v_op = vis * v_alpha;
                 }
             }
+            // spread reduction: lane L ends up with the total of value L >> kShift (colours first, then conic a, b,
+            // c, mean x, y, opacity), and those lanes add it to the gradient arrays in one atomic instruction
+            constexpr int kVals = CH + 6, P = kVals <= 8 ? 8 : 16, kShift = P == 16 ? 1 : 2;
+            float v[P];
 #pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
+            for (int q = 0; q < P; ++q) v[q] = 0.0f;
 #pragma unroll
-                for (int ch = 0; ch < CH; ++ch) v_rgb[ch] += __shfl_xor_sync(0xffffffffu, v_rgb[ch], d);
-                v_ca += __shfl_xor_sync(0xffffffffu, v_ca, d);
-                v_cb += __shfl_xor_sync(0xffffffffu, v_cb, d);
-                v_cc += __shfl_xor_sync(0xffffffffu, v_cc, d);
-                v_mx += __shfl_xor_sync(0xffffffffu, v_mx, d);
-                v_my += __shfl_xor_sync(0xffffffffu, v_my, d);
-                v_op += __shfl_xor_sync(0xffffffffu, v_op, d);
-            }
-            if (lane == 0) {
+            for (int ch = 0; ch < CH; ++ch) v[ch] = v_rgb[ch];
+            v[CH] = v_ca; v[CH + 1] = v_cb; v[CH + 2] = v_cc; v[CH + 3] = v_mx; v[CH + 4] = v_my; v[CH + 5] = v_op;
+            warp_reduce_spread<P>(v, lane);
+            const int which = (int)(lane >> kShift);
+            if ((lane & ((1u << kShift) - 1u)) == 0u && which < kVals) {
                 const int64_t g = s_id[t];
-#pragma unroll
-                for (int ch = 0; ch < CH; ++ch) atomicAdd(g_colors + g * CH + ch, v_rgb[ch]);
-                atomicAdd(g_conics + 3 * g, v_ca);
-                atomicAdd(g_conics + 3 * g + 1, v_cb);
-                atomicAdd(g_conics + 3 * g + 2, v_cc);
-                atomicAdd(g_means2d + 2 * g, v_mx);
-                atomicAdd(g_means2d + 2 * g + 1, v_my);
-                atomicAdd(g_opac + g, v_op);
+                float* dst;
+                if (which < CH) dst = g_colors + g * CH + which;
+                else if (which < CH + 3) dst = g_conics + 3 * g + (which - CH);
+                else if (which < CH + 5) dst = g_means2d + 2 * g + (which - CH - 3);
+                else dst = g_opac + g;
+                atomicAdd(dst, v[0]);
             }
           }
         }
