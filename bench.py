@@ -460,6 +460,13 @@ def run_b200(args, rank, world, local_rank):
         pb[k].record()
     torch.cuda.synchronize(dev)
     proj_alone_ms = float(sum(a.elapsed_time(b) for a, b in zip(pa, pb))) / Ks
+    for k in range(Ks):  # the optional fast-math build of the same kernel (not the default: radii can be one off)
+        flush.zero_()
+        pa[k].record()
+        project_gaussians_cuda(g[0], g[1], g[2], g[3], cams[0], semantics=sem, out=proj_out, fast_math=True)
+        pb[k].record()
+    torch.cuda.synchronize(dev)
+    proj_fast_ms = float(sum(a.elapsed_time(b) for a, b in zip(pa, pb))) / Ks
     backward = None
     if not args.no_extras:
         t = [info["means2d"].clone().requires_grad_(True), info["conics"].clone().requires_grad_(True),
@@ -530,6 +537,11 @@ def run_b200(args, rank, world, local_rank):
         "projection": {"ms": proj_alone_ms, "GB/s": proj_bytes / (proj_alone_ms * 1e-3) / 1e9,
                        "frac_hbm": proj_bytes / (proj_alone_ms * 1e-3) / 1e9 / hbm_peak, "bytes": proj_bytes,
                        "kernel": "project_kernel alone (bsplat_project_fwd: the four stage outputs)"},
+        "projection_fast_math": {"ms": proj_fast_ms, "GB/s": proj_bytes / (proj_fast_ms * 1e-3) / 1e9,
+                                 "frac_hbm": proj_bytes / (proj_fast_ms * 1e-3) / 1e9 / hbm_peak, "bytes": proj_bytes,
+                                 "kernel": "project_kernel, BSPLAT_PROJ_FAST_MATH build (MUFU exp / rcp / sqrt, free "
+                                           "contraction): an option, not what the frames above run -- values within "
+                                           "1e-4, but a radius next to an integer boundary can be one off"},
         "projection_fused": {"ms": stage[0], "GB/s": proj_fused_bytes / (stage[0] * 1e-3) / 1e9,
                              "frac_hbm": proj_fused_bytes / (stage[0] * 1e-3) / 1e9 / hbm_peak,
                              "bytes": proj_fused_bytes,

@@ -60,8 +60,18 @@ for k in range(8):
     b.record()
     torch.cuda.synchronize()
     tf.append(a.elapsed_time(b))
+tq = []
+for k in range(8):
+    flush.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    ms.projection.project_gaussians_cuda(g[0], g[1], g[2], g[3], sc.camera, semantics=sem, out=out, fast_math=True)
+    b.record()
+    torch.cuda.synchronize()
+    tq.append(a.elapsed_time(b))
 print(json.dumps({"config": cfg, "projection_alone_ms": round(float(np.median(tp)), 4),
-                  "projection_alone_fma_build_ms": round(float(np.median(tf)), 4), "semantics": sem, "packed": packed, "debug": os.environ.get("BSPLAT_DEBUG", ""),
+                  "projection_alone_fma_build_ms": round(float(np.median(tf)), 4),
+                  "projection_alone_fast_math_ms": round(float(np.median(tq)), 4), "semantics": sem, "packed": packed, "debug": os.environ.get("BSPLAT_DEBUG", ""),
                   "M": info["n_isect"], "stage_ms": [round(float(x), 4) for x in stage],
                   "frame_ms": round(float(stage.sum()), 4),
                   "standalone_raster_call_ms (tile order + record kernel + raster)": round(float(np.median(ts)), 4),

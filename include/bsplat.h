@@ -60,6 +60,11 @@ extern "C" {
 #define BSPLAT_PROJ_ALLOW_FMA 0x100  /* bsplat_project_fwd: let the compiler contract a*b+c into FMAs (A/B build of
                                         the kernel; faster, radii may then differ from the reference by 1 for a few
                                         Gaussians per million -- the default rounds like the eager torch ops) */
+#define BSPLAT_PROJ_FAST_MATH 0x200  /* bsplat_project_fwd: MUFU-based exp / reciprocal / square root and free FMA
+                                        contraction (third build of the kernel).  Values within 1e-4 + 1e-4 |ref|;
+                                        a radius next to an integer boundary may come out one off, so tile lists
+                                        can differ from the reference's -- an option for callers that want the
+                                        HBM-bound kernel, never the default */
 #define BSPLAT_BIN_PACKED 0x100      /* bsplat_bin2_prepare / bsplat_bin2_finish (pass it to both): compact the
                                         Gaussians that own no tile away before the depth sort (gsplat's packed
                                         layout; identical lists) */
@@ -84,6 +89,7 @@ extern "C" {
 #define BSPLAT_FLAG_NO_BAND_PRETEST 0x1000  /* row-band frames: project every Gaussian instead of only those a
                                              * conservative pre-test cannot rule out of the band (A/B and tests:
                                              * both ways give bit-identical lists and images) */
+#define BSPLAT_FLAG_PROJ_FAST 0x2000        /* the BSPLAT_PROJ_FAST_MATH projection inside a fused frame */
 
 /* Pinhole camera, world->camera. Mirrors mojosplat/utils.py:5-31 (Camera.view_matrix, Ks, H, W,
  * near, far) as a POD. viewmat is row-major 4x4. */

@@ -30,6 +30,8 @@ FLAG_PACKED = 0x400
 FLAG_PROJ_FMA = 0x800
 FLAG_NO_BAND_PRETEST = 0x1000
 PROJ_ALLOW_FMA = 0x100  # or-ed into `semantics` of bsplat_project_fwd
+PROJ_FAST_MATH = 0x200  # ditto: the "within 1e-4" build (radii may be one off at integer boundaries)
+FLAG_PROJ_FAST = 0x2000
 BIN_PACKED = 0x100      # or-ed into `semantics` of bsplat_bin2_prepare / bsplat_bin2_finish
 
 # every symbol include/bsplat.h declares (checked by tests/test_capi_symbols.py)

@@ -20,7 +20,10 @@ int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* w
 int project_fwd_launch(int64_t N, const float* means3d, const float* log_scales, const float* quats,
                        const float* opacities, const bsplat_camera& cam, float eps2d, int semantics,
                        float* means2d, float* conics, float* depths, int32_t* radii, cudaStream_t stream,
-                       const bsplat_camera* cam_dev, const ProjExtra* extra, bool allow_fma);
+                       const bsplat_camera* cam_dev, const ProjExtra* extra, int variant);
+inline int proj_variant_of(int flags) {
+    return (flags & BSPLAT_FLAG_PROJ_FAST) ? 2 : ((flags & BSPLAT_FLAG_PROJ_FMA) ? 1 : 0);
+}
 int rasterize_launch(int64_t N, int channels, const float* means2d, const float* conics, const float* colors,
                      const float* opacities, const float* background_dev, const int32_t* tile_ranges,
                      const int32_t* tile_order, const int32_t* sorted_ids, int W, int H, int tile_size,
@@ -239,7 +242,7 @@ int frame_front(int64_t N, const float* means3d, const float* log_scales, const 
         if (rc != BSPLAT_OK) return rc;
     }
     rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, cam, 0.3f, semantics, o_means2d, o_conics,
-                            o_depths, o_radii, stream, cam_dev, &ex, (flags & BSPLAT_FLAG_PROJ_FMA) != 0);
+                            o_depths, o_radii, stream, cam_dev, &ex, proj_variant_of(flags));
     if (rc != BSPLAT_OK) return rc;
     if (ev_after_projection) BSPLAT_CUDA_TRY(cudaEventRecord(ev_after_projection, stream));
     return bin2_prepare(N, nullptr, nullptr, 0, nullptr, p, w.bin_ws, w.bin_bytes, stream, /*have_prep=*/true, compact,
@@ -307,7 +310,7 @@ extern "C" int bsplat_render_fwd(int64_t N, const float* means3d, const float* l
     bool rec_ready = false;
     if (single_level) {
         rc = project_fwd_launch(N, means3d, log_scales, quats, opacities, *cam, 0.3f, semantics, d_means2d, d_conics,
-                                d_depths, d_radii, stream, nullptr, nullptr, (flags & BSPLAT_FLAG_PROJ_FMA) != 0);
+                                d_depths, d_radii, stream, nullptr, nullptr, proj_variant_of(flags));
         if (rc != BSPLAT_OK) return rc;
         rc = te.record(1, stream);
         if (rc != BSPLAT_OK) return rc;

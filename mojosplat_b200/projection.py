@@ -48,7 +48,7 @@ def project_gaussians(
 
 
 def project_gaussians_cuda(means3d, scales, quats, opacities, camera, semantics=_lib.SEM_TORCH,
-                           out=None, allow_fma=False):
+                           out=None, allow_fma=False, fast_math=False):
     """sm_100a kernel behind the C ABI (include/bsplat.h: bsplat_project_fwd).
     ``allow_fma``: the A/B build with FMA contraction allowed (BSPLAT_PROJ_ALLOW_FMA)."""
     L = _lib.require_device(means3d.device)
@@ -74,7 +74,7 @@ def project_gaussians_cuda(means3d, scales, quats, opacities, camera, semantics=
     cam = _lib.camera_struct(camera)
     with torch.cuda.device(dev):
         rc = L.bsplat_project_fwd(N, _lib.ptr(means3d), _lib.ptr(scales), _lib.ptr(quats), _lib.ptr(op),
-                                  byref(cam), 1, 0.3, semantics | (_lib.PROJ_ALLOW_FMA if allow_fma else 0),
+                                  byref(cam), 1, 0.3, semantics | (_lib.PROJ_ALLOW_FMA if allow_fma else 0) | (_lib.PROJ_FAST_MATH if fast_math else 0),
                                   _lib.ptr(means2d), _lib.ptr(conics),
                                   _lib.ptr(depths), _lib.ptr(radii), _lib.stream_ptr(dev))
     _lib.check(rc, "bsplat_project_fwd")

@@ -95,7 +95,7 @@ _last_M: dict = {}
 
 def render_fused(means3d, scales, quats, opacities, colors, camera, background, tile_size=TILE_SIZE,
                  semantics=_lib.SEM_TORCH, raster_mode="fast", return_aux=False, timing=False,
-                 bin_algo="two_level", packed=False, proj_fma=False):
+                 bin_algo="two_level", packed=False, proj_fma=False, proj_fast=False):
     """One C call per frame (include/bsplat.h: bsplat_render_fwd). Device tensors in, image out.
     ``packed``: gsplat's packed layout -- Gaussians that own no tile are compacted away right after projection
     (same image and lists; only pays under the gsplat rule set, where culled Gaussians own no tile).
@@ -132,6 +132,7 @@ def render_fused(means3d, scales, quats, opacities, colors, camera, background, 
     needed = c_size_t(0)
     flags = RASTER_MODES[raster_mode] | (_lib.FLAG_BIN_SINGLE_LEVEL if bin_algo == "single" else 0)
     flags |= (_lib.FLAG_PACKED if packed else 0) | (_lib.FLAG_PROJ_FMA if proj_fma else 0)
+    flags |= _lib.FLAG_PROJ_FAST if proj_fast else 0
     with torch.cuda.device(dev):
         for _attempt in range(3):
             rc = L.bsplat_render_fwd(N, _lib.ptr(means3d), _lib.ptr(scales), _lib.ptr(quats),

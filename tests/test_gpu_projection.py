@@ -77,6 +77,15 @@ def test_projection_full_size_vs_oracle(cuda_device, cfg, N):
     bad_culled = int((np.abs(out_fma[0] - ref[0]) > 1e-4 + 1e-4 * np.abs(ref[0])).any(-1).sum())
     print(f"\n[projection {cfg}] radii that differ from the oracle: exact build {d_exact}, FMA build {d_fma} of {N}; "
           f"means2d rows of the FMA build outside 1e-4 + 1e-4|ref| (all culled): {bad_culled}")
+    # the fast-math build (BSPLAT_PROJ_FAST_MATH: MUFU exp / rcp / sqrt): an OPTION for callers that want the HBM-bound
+    # kernel.  Visible Gaussians within the float tolerances; radii at most one off, and only next to integer crossings
+    out_fast = [t.cpu().numpy() for t in project_gaussians_cuda(m, s, q, o, cam, fast_math=True)]
+    np.testing.assert_allclose(out_fast[0][vis], ref[0][vis], atol=1e-3, rtol=1e-4)
+    np.testing.assert_allclose(out_fast[1][vis], ref[1][vis], atol=1e-4, rtol=2e-4)
+    np.testing.assert_allclose(out_fast[2], ref[2], atol=1e-4, rtol=1e-4)
+    d_fast = int((out_fast[3] != ref[3]).any(-1).sum())
+    assert np.abs(out_fast[3].astype(np.int64) - ref[3]).max() <= 1 and d_fast <= max(16, N // 2_000), d_fast
+    print(f"[projection {cfg}] fast-math build: {d_fast} of {N} radii one off")
 
 
 def test_projection_gsplat_semantics(cuda_device):
