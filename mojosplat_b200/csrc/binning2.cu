@@ -355,7 +355,6 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
                        const int row_end, uint32_t* __restrict__ offsets, bsplat_bin_info* __restrict__ info,
                        unsigned long long* __restrict__ ws, uint2* __restrict__ rects,
                        uint32_t* __restrict__ hist_xy /* [2][256] or null */, const int tiles_w) {
-    pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
     __shared__ unsigned int s_chunk;
     // 2-D tile keys (hist_xy != null): the digit histograms of the two tile-sort passes are the column and row
     // coverage counts -- a rectangle adds h to each of its w columns and w to each of its h rows, i.e. four updates of
@@ -368,9 +367,12 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
     __shared__ unsigned long long s_prefix;
 
     const int tid = threadIdx.x;
+    // (the ticket counter was zeroed at the start of the frame: drawn, like the shared-memory reset above, before the
+    // wait for the previous kernel of the stream -- programmatic dependent launch, common.cuh)
+    if (tid == 0) s_chunk = atomicAdd(reinterpret_cast<unsigned int*>(ws), 1u);
+    pdl_wait();
     // n_dev: the number of items lives on the device (compacted depth order); the grid is sized by N_host
     const int64_t N = n_dev ? (int64_t)(*n_dev) : N_host;
-    if (tid == 0) s_chunk = atomicAdd(reinterpret_cast<unsigned int*>(ws), 1u);
     __syncthreads();
     const unsigned int chunk = s_chunk;
     unsigned long long* status = ws + 1;
@@ -543,23 +545,24 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
                  uint32_t* __restrict__ tile_keys, int32_t* __restrict__ ids,
                  uint32_t* __restrict__ hist /* [kMaxTilePasses][256] */,
                  bsplat_bin_info* __restrict__ info_dev, const int64_t m_cap) {
-    pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
+    __shared__ uint32_t s_hist[kSep ? 1 : kMaxTilePasses][kRadix];  // kSep: ceil(2^32 / w) for w = 1 .. 256 instead
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    if (kSep) {
+        // s_hist[0][w - 1] = ceil(2^32 / w) (w = 1: 2^32 does not fit -- handled where it is used); filled before the
+        // wait for the previous kernel (programmatic dependent launch)
+        for (int i = tid; i < kRadix; i += kEmit2Threads) s_hist[0][i] = i == 0 ? 0u : 0xffffffffu / (uint32_t)(i + 1) + 1u;
+    } else {
+        for (int i = tid; i < kMaxTilePasses * kRadix; i += kEmit2Threads) (&s_hist[0][0])[i] = 0;
+    }
+    pdl_wait();
     // sync-free frames: the pair buffers hold m_cap entries; if this frame produced more, emit nothing,
     // raise the overflow flag (reserved[1]) and let the later passes see it (they skip too)
     if (info_dev != nullptr && (int64_t)info_dev->n_isect > m_cap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) info_dev->reserved[1] = 1u;
         return;
     }
-    __shared__ uint32_t s_hist[kSep ? 1 : kMaxTilePasses][kRadix];  // kSep: ceil(2^32 / w) for w = 1 .. 256 instead
     const int64_t N = n_dev ? (int64_t)(*n_dev) : N_host;  // compacted depth order: the count is on the device
-    const int tid = threadIdx.x;
-    const uint32_t lane = tid & 31u;
-    if (kSep) {
-        // s_hist[0][w - 1] = ceil(2^32 / w) (w = 1: 2^32 does not fit -- handled where it is used)
-        for (int i = tid; i < kRadix; i += kEmit2Threads) s_hist[0][i] = i == 0 ? 0u : 0xffffffffu / (uint32_t)(i + 1) + 1u;
-    } else {
-        for (int i = tid; i < kMaxTilePasses * kRadix; i += kEmit2Threads) (&s_hist[0][0])[i] = 0;
-    }
     __syncthreads();
     const int top = tp.n - 1;
     const int top_shift = tp.n == 1 ? tp.shift[0] : (tp.n == 2 ? tp.shift[1] : (tp.n == 3 ? tp.shift[2] : tp.shift[3]));
@@ -1031,9 +1034,10 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
     const uint32_t* ksrc = w.dkeys; uint32_t* kdst = w.dkeys_alt;
     int32_t* vdst = w.perm_alt;
     for (int pass = 0; pass < 4; ++pass) {
+        // (the depth histograms come from the kernel in front of pass 0: passes 1-3 may read theirs early)
         rc = onesweep_pass_u32(N, n_dev, ksrc, pass == 3 ? nullptr : kdst, vsrc, vdst, 8 * pass, 8,
                                w.hist + (size_t)pass * kRadix, 0, w.tickets + pass,
-                               w.status_n + (size_t)pass * tn * kRadix, nullptr, stream);
+                               w.status_n + (size_t)pass * tn * kRadix, nullptr, stream, 0, pass > 0);
         if (rc != BSPLAT_OK) return rc;
         // ping-pong: pass 0 writes (dkeys_alt, perm_alt), pass 1 (dkeys, perm), ...; pass 3 ends in perm
         ksrc = kdst; kdst = (kdst == w.dkeys_alt) ? w.dkeys : w.dkeys_alt;
@@ -1092,7 +1096,10 @@ int bin2_finish(int64_t N, int64_t M, bool device_m, const BinParams& p, void* w
         const int rc = onesweep_pass_u32(M, m_dev, ksrc, last ? nullptr : kdst, vsrc, last ? sorted_ids : vdst,
                                          tp.shift[q], tp.bits[q], w.hist + (size_t)(4 + q) * kRadix, 0,
                                          w.tickets + 4 + q, w.status_m + (size_t)q * tm * kRadix,
-                                         last ? w.tile_counts : nullptr, stream, keys2d ? p.tiles_w : 0);
+                                         last ? w.tile_counts : nullptr, stream, keys2d ? p.tiles_w : 0,
+                                         // 2-D keys: histograms from count + scan (two kernels back); linear keys:
+                                         // from the emitter, the kernel in front of pass 0
+                                         (keys2d || q > 0) ? 1 : 0);
         if (rc != BSPLAT_OK) return rc;
         ksrc = kdst; kdst = (kdst == w.tkeys_alt) ? w.tkeys : w.tkeys_alt;
         vsrc = vdst; vdst = (vdst == w.ids_alt) ? w.ids : w.ids_alt;

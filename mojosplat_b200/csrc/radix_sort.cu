@@ -79,8 +79,8 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
                 KeyT* __restrict__ keys_out, const int32_t* __restrict__ vals_in,
                 int32_t* __restrict__ vals_out, const int shift, const int bits_rt,
                 const uint32_t* __restrict__ hist, const int hist_is_scanned, uint32_t* __restrict__ ticket,
-                uint32_t* __restrict__ status, uint32_t* __restrict__ key_counts, const int key_row_stride) {
-    pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
+                uint32_t* __restrict__ status, uint32_t* __restrict__ key_counts, const int key_row_stride,
+                const int hist_early) {
     constexpr int TILE = kSortThreads * ITEMS;
     // BITS > 0: digit width known at compile time (branch-free ballot loop with constant masks)
     const int bits = BITS > 0 ? BITS : bits_rt;
@@ -93,6 +93,17 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
     __shared__ uint32_t s_warp_tot[kSortWarps];
     __shared__ uint32_t s_tile;
 
+    // Programmatic dependent launch: this CTA may be resident while the previous kernel of the stream is still
+    // running.  What does not depend on that kernel happens before the wait: the ticket (its counter was zeroed at
+    // the start of the frame), the shared-memory reset and -- when the caller says the histogram is older than the
+    // previous kernel (hist_early) -- the histogram load.
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const int warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&s_whist[0][0])[i] = 0;
+    const uint32_t h_early = hist_early ? hist[tid] : 0u;
+    pdl_wait();
     // device-side count (sync-free frames): M_host is then the capacity the launch and the buffers were
     // sized for; a count beyond it disables the pass (the emitter has flagged the overflow)
     int64_t M = M_host;
@@ -100,11 +111,6 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
         const int64_t md = (int64_t)(*m_dev);
         M = md <= M_host ? md : 0;
     }
-    const int tid = threadIdx.x;
-    const uint32_t lane = tid & 31u;
-    const int warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&s_whist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
     const int64_t tile_base = (int64_t)tile * TILE;
@@ -116,7 +122,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
     // global digit offsets: either already exclusive-scanned, or a raw histogram scanned here
     // (256-wide block scan; saves a kernel launch per sort)
     {
-        const uint32_t h = hist[tid];
+        const uint32_t h = hist_early ? h_early : hist[tid];
         uint32_t incl = h;
         if (!hist_is_scanned) {
 #pragma unroll
@@ -334,16 +340,16 @@ size_t sort_status_words(int64_t n_tiles, int passes) { return (size_t)passes * 
 #define BSPLAT_ONESWEEP32(B)                                                                              \
     BSPLAT_LAUNCH_PDL((onesweep_kernel<uint32_t, kSortItems32, B>), (unsigned)n_tiles, kSortThreads, 0, stream, \
         M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,    \
-        key_counts, key_row_stride)
+        key_counts, key_row_stride, hist_early)
 
 int onesweep_pass_u32(int64_t M, const uint64_t* m_dev, const uint32_t* keys_in, uint32_t* keys_out,
                       const int32_t* vals_in, int32_t* vals_out, int shift, int bits, const uint32_t* hist,
                       int hist_is_scanned, uint32_t* ticket, uint32_t* status, uint32_t* key_counts,
-                      cudaStream_t stream, int key_row_stride) {
+                      cudaStream_t stream, int key_row_stride, int hist_early) {
     const int64_t n_tiles = sort_tiles_u32(M);
     if (bits == 8 && n_tiles <= 3 * 148) {  // every tile resident at once (3 CTAs per SM): wide look-back window
         BSPLAT_LAUNCH_PDL((onesweep_kernel<uint32_t, kSortItems32, 8, 64>), (unsigned)n_tiles, kSortThreads, 0, stream, M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,
-            key_counts, key_row_stride);
+            key_counts, key_row_stride, hist_early);
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
     }
@@ -423,7 +429,7 @@ extern "C" int bsplat_radix_sort_pairs(int64_t M, uint64_t* keys, uint64_t* keys
         const int shift = begin_bit + p * kRadixBits;
         const int bits = (end_bit - shift) < kRadixBits ? (end_bit - shift) : kRadixBits;
         BSPLAT_LAUNCH_PDL((onesweep_kernel<uint64_t, kSortItems64, 0>), (unsigned)n_tiles, kSortThreads, 0, stream, M, nullptr, ksrc, kdst, vsrc, vdst, shift, bits, w.hist + (size_t)p * kRadix, 1, w.tickets + p,
-            w.status + (size_t)p * n_tiles * kRadix, nullptr, 0);
+            w.status + (size_t)p * n_tiles * kRadix, nullptr, 0, 0);
         BSPLAT_LAUNCH_CHECK();
         uint64_t* tk = ksrc; ksrc = kdst; kdst = tk;
         int32_t* tv = vsrc; vsrc = vdst; vdst = tv;

@@ -30,10 +30,12 @@ size_t sort_status_words(int64_t n_tiles, int passes);
 //   key_counts != nullptr (only valid on the LAST pass of a sort whose keys are fully covered by the
 //   passes): key_counts[key] += number of elements with that key (zeroed by the caller); with key_row_stride > 0
 //   the keys are 2-D (row << 16 | column) and are counted under row * key_row_stride + column
+//   hist_early: the histogram was complete before the PREVIOUS kernel of the stream started (it may then be read
+//   while that kernel is still running: programmatic dependent launch, common.cuh)
 int onesweep_pass_u32(int64_t M, const uint64_t* m_dev, const uint32_t* keys_in, uint32_t* keys_out,
                       const int32_t* vals_in, int32_t* vals_out, int shift, int bits, const uint32_t* hist,
                       int hist_is_scanned, uint32_t* ticket, uint32_t* status, uint32_t* key_counts,
-                      cudaStream_t stream, int key_row_stride = 0);
+                      cudaStream_t stream, int key_row_stride = 0, int hist_early = 0);
 // In-place exclusive scan of `passes` consecutive 256-bin histograms.
 int radix_scan_launch(uint32_t* hist, int passes, cudaStream_t stream);
 
