@@ -196,10 +196,20 @@ __device__ __forceinline__ unsigned int compact_flags(const int64_t N, const int
         }
     } else {
         int32_t gidx[kCompactItems];
+        if (list != nullptr && base + kCompactItems <= N) {  // (a thread's slots are contiguous: 128-bit loads)
+            static_assert(kCompactItems % 4 == 0, "128-bit loads over a thread's slots");
+            const int4* vl = reinterpret_cast<const int4*>(list + base);
 #pragma unroll
-        for (int k = 0; k < kCompactItems; ++k) {
-            const int64_t i = base + k;
-            gidx[k] = (i < N) ? (list ? __ldg(list + i) : (int32_t)i) : -1;
+            for (int v = 0; v < kCompactItems / 4; ++v) {
+                const int4 q = __ldg(vl + v);
+                gidx[4 * v] = q.x; gidx[4 * v + 1] = q.y; gidx[4 * v + 2] = q.z; gidx[4 * v + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kCompactItems; ++k) {
+                const int64_t i = base + k;
+                gidx[k] = (i < N) ? (list ? __ldg(list + i) : (int32_t)i) : -1;
+            }
         }
         uint2 rc[kCompactItems];
 #pragma unroll
@@ -383,12 +393,27 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
     }
     // blocked arrangement: thread t owns slots base + t*kScanItems + k (keeps the scan trivial); all gathers of a
     // thread are issued before the first one is used
+    // A thread's kScanItems slots are contiguous in memory: when all of them are valid, the index loads and the
+    // offset / rectangle stores go as 128-bit accesses (8 scalar accesses per thread, each touching 32 different
+    // sectors per warp, left the kernel waiting on the load / store queue: stall_lg was its top stall reason)
+    static_assert(kScanItems % 4 == 0, "128-bit accesses over a thread's slots");
+    const int64_t slot0 = base + (int64_t)tid * kScanItems;
+    const bool full = slot0 + kScanItems <= N;
     int32_t gi[kScanItems];
     uint2 rc[kScanItems];
+    if (full && perm != nullptr) {
+        const int4* vp = reinterpret_cast<const int4*>(perm + slot0);
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const int64_t jj = base + (int64_t)tid * kScanItems + k;
-        gi[k] = (jj < N) ? (perm ? __ldg(perm + jj) : (int32_t)jj) : -1;
+        for (int v = 0; v < kScanItems / 4; ++v) {
+            const int4 q = __ldg(vp + v);
+            gi[4 * v] = q.x; gi[4 * v + 1] = q.y; gi[4 * v + 2] = q.z; gi[4 * v + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int64_t jj = slot0 + k;
+            gi[k] = (jj < N) ? (perm ? __ldg(perm + jj) : (int32_t)jj) : -1;
+        }
     }
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) rc[k] = gi[k] >= 0 ? __ldg(rects_in + gi[k]) : make_uint2(0u, 0u);
@@ -399,8 +424,14 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
         const int64_t jj = base + (int64_t)tid * kScanItems + k;
         const uint2 cl = clip_rect_rows(rc[k], row_begin, row_end);
         cnt[k] = (cl.y & 0xffffu) * (cl.y >> 16);
-        if (jj < N) rects[jj] = cl;
+        rc[k] = cl;
+        if (!full && jj < N) rects[jj] = cl;
         thread_sum += cnt[k];
+    }
+    if (full) {
+        uint4* vr = reinterpret_cast<uint4*>(rects + slot0);
+#pragma unroll
+        for (int v = 0; v < kScanItems / 2; ++v) vr[v] = make_uint4(rc[2 * v].x, rc[2 * v].y, rc[2 * v + 1].x, rc[2 * v + 1].y);
     }
     const int lane = tid & 31, warp = tid >> 5;
     auto add_coverage = [&]() {
@@ -499,11 +530,20 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
     __syncthreads();
     pdl_trigger();  // only the output is left: the next kernel of the stream may be staged now
     unsigned long long run = s_prefix + thread_excl;
+    if (full) {
+        uint32_t o[kScanItems];
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const int64_t i = base + (int64_t)tid * kScanItems + k;
-        if (i < N) offsets[i] = (uint32_t)run;
-        run += cnt[k];
+        for (int k = 0; k < kScanItems; ++k) { o[k] = (uint32_t)run; run += cnt[k]; }
+        uint4* vo = reinterpret_cast<uint4*>(offsets + slot0);
+#pragma unroll
+        for (int v = 0; v < kScanItems / 4; ++v) vo[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int64_t i = slot0 + k;
+            if (i < N) offsets[i] = (uint32_t)run;
+            run += cnt[k];
+        }
     }
     // the chunk that owns the last slot publishes the total
     if (tid == kScan2Threads - 1 && base + kScan2Chunk >= N) {
