@@ -629,18 +629,32 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
         }
         int64_t jg0 = lo;       // first Gaussian of the current window
         uint32_t cur = S;       // next pair to write
-        while (cur < E) {
-            const int64_t jg = jg0 + lane;
-            const bool have = jg < N;
-            int32_t g = 0;
-            uint2 rc = make_uint2(0u, 0u);
-            uint32_t off = M;   // lanes past N own nothing
-            if (have) {
-                g = perm ? __ldg(perm + jg) : (int32_t)jg;
-                rc = __ldg(rects + jg);
-                off = __ldg(offsets + jg);
+        // the window after the current one is fetched while the current one is expanded (its three loads were the
+        // kernel's largest stall: one task per warp leaves nothing else to hide them behind)
+        int32_t g_nx = 0;
+        uint2 rc_nx = make_uint2(0u, 0u);
+        uint32_t off_nx = M;    // lanes past N own nothing
+        auto fetch_window = [&](const int64_t first) {
+            const int64_t jg = first + lane;
+            g_nx = 0; rc_nx = make_uint2(0u, 0u); off_nx = M;
+            if (jg < N) {
+                g_nx = perm ? __ldg(perm + jg) : (int32_t)jg;
+                rc_nx = __ldg(rects + jg);
+                off_nx = __ldg(offsets + jg);
             }
+        };
+        fetch_window(jg0);
+        while (cur < E) {
+            const int32_t g = g_nx;
+            const uint2 rc = rc_nx;
+            const uint32_t off = off_nx;
+            const bool have = jg0 + lane < N;
+            fetch_window(jg0 + 32);
             const uint32_t w = rc.y & 0xffffu, cnt = w * (rc.y >> 16);
+            // no Gaussian of the window is empty (always true under the torch rules and after a compaction): the owner
+            // of a pair follows from ONE warp-wide OR of "my range starts at pair p0 + j" bits instead of a 5-step
+            // chain of dependent shuffles
+            const bool dense = __ballot_sync(0xffffffffu, have && cnt == 0u) == 0u;
             // kSep: the reciprocal is the integer magic of w (bit pattern carried in the same register)
             const float inv_w = kSep ? __uint_as_float(s_hist[0][(w ? w : 1u) - 1u]) : 1.0f / (float)(w ? w : 1u);
             // pairs covered by this window: [off of lane 0, end of the last live lane)
@@ -652,11 +666,20 @@ bin_emit2_kernel(const int64_t N_host, const unsigned long long* __restrict__ n_
                 const bool valid = pidx < stop;
                 // owner = largest lane l with off_l <= pidx (offsets are non-decreasing; off_{l+1} = off_l + cnt_l)
                 uint32_t ol = 0;
+                if (dense) {
+                    // = (number of lanes whose range starts at or before pidx) - 1: those before p0 by ballot, those
+                    // inside [p0, p0 + 32) by their start bits (distinct, because no range is empty)
+                    const uint32_t rel = off - p0;
+                    const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
+                    const uint32_t before = __popc(__ballot_sync(0xffffffffu, off < p0));
+                    ol = before + __popc(starts & (0xffffffffu >> (31u - lane))) - 1u;
+                } else {
 #pragma unroll
-                for (int step = 16; step >= 1; step >>= 1) {
-                    const uint32_t cand = ol + step;
-                    const uint32_t oc = __shfl_sync(0xffffffffu, off, cand & 31u);
-                    if (oc <= pidx) ol = cand;
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const uint32_t cand = ol + step;
+                        const uint32_t oc = __shfl_sync(0xffffffffu, off, cand & 31u);
+                        if (oc <= pidx) ol = cand;
+                    }
                 }
                 const uint32_t eo = __shfl_sync(0xffffffffu, off, ol);
                 const uint32_t xy = __shfl_sync(0xffffffffu, rc.x, ol);
