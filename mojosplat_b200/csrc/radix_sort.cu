@@ -17,6 +17,26 @@
 // Per pass the kernel moves key+payload in and out once; nothing else touches HBM.
 #include "radix_sort.cuh"
 
+#ifdef BSPLAT_PHASES
+// A/B instrumentation (not in the product build): per CTA, SM clock at the phase boundaries of a pass + the global
+// timer at entry and exit.  Slot = pass (from the ticket address), row = tile.
+__device__ unsigned long long g_phases[8][4096][10];
+#define BSPLAT_PHASE(i)                                                                                  \
+    do {                                                                                                 \
+        if (threadIdx.x == 0 && ph_row < 4096) g_phases[ph_slot][ph_row][i] = (unsigned long long)clock64(); \
+    } while (0)
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+extern "C" int bsplat_debug_phases(void* host_out, size_t bytes) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_phases, bytes < sizeof(g_phases) ? bytes : sizeof(g_phases));
+}
+#else
+#define BSPLAT_PHASE(i)
+#endif
+
 namespace bsplat {
 
 template <typename KeyT>
@@ -100,6 +120,12 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const int warp = tid >> 5;
+#ifdef BSPLAT_PHASES
+    const int ph_slot = (int)(((uintptr_t)ticket >> 2) & 7);
+    uint32_t ph_row = blockIdx.x;  // until the ticket is known
+    const unsigned long long ph_g0 = gtimer();
+    const unsigned long long ph_c0 = clock64();
+#endif
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&s_whist[0][0])[i] = 0;
     const uint32_t h_early = hist_early ? hist[tid] : 0u;
@@ -114,6 +140,11 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
     __syncthreads();
     const uint32_t tile = s_tile;
     const int64_t tile_base = (int64_t)tile * TILE;
+#ifdef BSPLAT_PHASES
+    ph_row = tile;
+    if (tid == 0 && ph_row < 4096) { g_phases[ph_slot][ph_row][8] = ph_g0; g_phases[ph_slot][ph_row][0] = ph_c0; }
+    BSPLAT_PHASE(1);  // after the dependency wait
+#endif
     if (tile_base >= M) return;  // launches sized by capacity: surplus CTAs retire (uniform per CTA)
     const int n_valid = (int)min((int64_t)TILE, M - tile_base);
     const uint32_t digit_mask = (1u << bits) - 1u;
@@ -215,6 +246,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
             __syncwarp();
         }
         __syncthreads();
+        BSPLAT_PHASE(2);  // loaded + ranked
 
         // ---- per-digit: exclusive scan over warps, tile count -> aggregate published immediately ----
         uint32_t run = 0;
@@ -241,6 +273,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
         // s_gbase holds (count, excl) needs: keep count in s_gbase until the look-back rewrites it
         s_gbase[tid] = count;
         __syncthreads();
+        BSPLAT_PHASE(3);  // aggregates published, local scan
 
         // ---- scatter key / payload into shared memory in tile-sorted order ----
 #pragma unroll
@@ -253,6 +286,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
         }
     }
 
+    BSPLAT_PHASE(4);  // thread 0 has scattered its items
     // ---- decoupled look-back for digit `tid` (registers are free: wide window) ----
     if (tid < n_digits) {
         const uint32_t count = s_gbase[tid];
@@ -296,6 +330,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
         s_gbase[tid] = s_bins[tid] + prev - s_local_off[tid];
     }
     __syncthreads();
+    BSPLAT_PHASE(5);  // look-back of every digit done
     pdl_trigger();  // only the output is left: the next kernel of the stream may be staged now
 
     // ---- contiguous per-digit runs to global ----
@@ -329,6 +364,11 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
             }
         }
     }
+#ifdef BSPLAT_PHASES
+    __syncthreads();
+    BSPLAT_PHASE(6);
+    if (tid == 0 && ph_row < 4096) g_phases[ph_slot][ph_row][9] = gtimer();
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
