@@ -228,9 +228,19 @@ int bsplat_rasterize_fwd_train(int64_t N, int32_t channels, const float* means2d
                                const int32_t* tile_ranges, const int32_t* sorted_ids, int64_t M,
                                int32_t width, int32_t height, int32_t tile_size, float* image,
                                float* final_T, int32_t* last_idx, void* stream);
+/* The same through the fast forward kernel (16x16 tiles, RGB): image bit-identical to bsplat_rasterize_fwd's default
+ * mode (within 1e-4 of the faithful arithmetic, like every fast frame); last_idx holds the last list entry the
+ * backward pass has to look at (the entry in front of the one that saturated the pixel, or the end of the tile's
+ * list). tile_order (optional, bsplat_tile_order): heavy tiles first. workspace (optional,
+ * bsplat_rasterize_workspace_bytes(N)): per-Gaussian records + cp.async staging. */
+int bsplat_rasterize_fwd_train_fast(int64_t N, const float* means2d, const float* conics, const float* colors,
+                                    const float* opacities, const float* background, const int32_t* tile_ranges,
+                                    const int32_t* tile_order, const int32_t* sorted_ids, int64_t M, int32_t width,
+                                    int32_t height, float* image, float* final_T, int32_t* last_idx,
+                                    void* workspace, size_t workspace_bytes, void* stream);
 /* Backward of the compositing: ACCUMULATES d loss / d (means2d[N,2], conics[N,3], colors[N,C],
  * opacities[N]) into the caller-zeroed gradient arrays, given grad_image[height, width, C] and the
- * final_T / last_idx of bsplat_rasterize_fwd_train on the same inputs. Threshold tests are piecewise
+ * final_T / last_idx of bsplat_rasterize_fwd_train[_fast] on the same inputs. Threshold tests are piecewise
  * constant; no gradient flows through the 0.999 alpha clamp. (d loss / d background =
  * sum_pixels final_T * grad_image is left to the caller.) */
 int bsplat_rasterize_bwd(int64_t N, int32_t channels, const float* means2d, const float* conics,

@@ -397,7 +397,16 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // kRec: the Gaussians come as prepared records; batches of 128 are gathered by sorted id with cp.async into the two
 // halves of the staging buffer, one batch ahead of the walk (ids two batches ahead), one barrier per batch.
 // !kRec: workspace-free staging of 256 per batch from the raw arrays (same arithmetic, bit-identical image).
-template <bool kCull, bool kRec>
+// kTrain (training-side forward, bsplat_rasterize_fwd_train_fast): the same walk also yields what the backward pass
+// starts from -- per pixel the final transmittance and the list index of the last entry the pixel looked at (the
+// entry in front of the one that saturated it, or the end of the list; entries that failed the alpha test in between
+// fail it again in the backward pass).
+struct TrainOut {
+    float* final_T;
+    int32_t* last_idx;
+};
+
+template <bool kCull, bool kRec, bool kTrain = false>
 __global__ void __launch_bounds__(kPairThreads)
 raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float* __restrict__ means2d, const float* __restrict__ conics,
                    const float* __restrict__ colors, const float* __restrict__ opacities,
@@ -406,7 +415,8 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                    const int32_t* __restrict__ sorted_ids, const int W, const int H, const int tiles_w,
                    float* __restrict__ image, const int vec_store,
                    const unsigned long long* __restrict__ m_dev, const PeerImages peers,
-                   const int32_t* __restrict__ surv, const uint32_t* __restrict__ chunk_cnt) {
+                   const int32_t* __restrict__ surv, const uint32_t* __restrict__ chunk_cnt,
+                   const TrainOut train) {
     pdl_wait();  // (programmatic dependent launch: nothing of the predecessor is read before this)
     // staging: with records a ring of kRecStages batches, without one batch; the output tile (16 x 48 floats) reuses it.
     // (Kept as small as possible: what shared memory does not take stays L1, which the record gathers live on.)
@@ -453,6 +463,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     // negated x per pixel; -inf = finished
     float2 npx2 = make_float2(in0 ? -((float)j + 0.5f) : -INFINITY, in1 ? -((float)j + 0.5f) : -INFINITY);
     const float2 one2 = dup2(1.0f);
+    int32_t stop0 = r1, stop1 = r1;  // kTrain: list position of the entry that saturated the pixel (r1: none did)
 
     constexpr int kBatch = kRec ? kRecBatch : kPairBatch;
     constexpr int kPer = (kBatch + kPairThreads - 1) / kPairThreads;  // staged entries per thread and batch
@@ -591,10 +602,14 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             // compositing of one Gaussian.  Saturation (T (1 - alpha) <= 1e-4, once per pixel): the Gaussian is not
             // added (rasterization.mojo:146-150) and the pixel retires with its T unchanged -- alpha := 0, -x := -inf.
             // Branch-free: a lane that left the walk for a rare path would make its warp walk the chunk twice.
-            auto composite = [&](float2 a2, const float cr, const float cg, const float cb) {
+            auto composite = [&](float2 a2, const float cr, const float cg, const float cb, const int32_t cur) {
                 float2 oma = __fadd2_rn(one2, make_float2(-a2.x, -a2.y));  // 1 - alpha
                 const float2 nT = __fmul2_rn(T2, oma);
                 const bool dead0 = !(nT.x > 1e-4f), dead1 = !(nT.y > 1e-4f);
+                if constexpr (kTrain) {  // (a retired pixel has alpha = 0 from here on: it is never "dead" again)
+                    stop0 = dead0 ? cur : stop0;
+                    stop1 = dead1 ? cur : stop1;
+                }
                 a2.x = dead0 ? 0.0f : a2.x;
                 a2.y = dead1 ? 0.0f : a2.y;
                 npx2.x = dead0 ? -INFINITY : npx2.x;
@@ -621,7 +636,8 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                     BSPLAT_DASSERT(r >= s_g && r + kPairRec <= s_g + kStageRecs * kPairRec && c0 + 31 - (int)b_hi < bs);
                     const float4 p0 = r[0], p1 = r[1];
                     const float cb = reinterpret_cast<const float*>(r + 2)[0];
-                    composite(alpha_of(plain_tag, r, p0, p1), p1.z, p1.w, cb);
+                    composite(alpha_of(plain_tag, r, p0, p1), p1.z, p1.w, cb,
+                              kTrain ? (int32_t)(b0 + c0 + 31 - (int)b_hi) : 0);
                 }
             };
             if (any_special) walk(std::false_type{});
@@ -636,6 +652,10 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     const float bgr = bgs * __ldg(background), bgg = bgs * __ldg(background + 1), bgb = bgs * __ldg(background + 2);
     const float T0 = T2.x, T1 = T2.y, ar0 = acc_r.x, ar1 = acc_r.y, ag0 = acc_g.x, ag1 = acc_g.y, ab0 = acc_b.x,
                 ab1 = acc_b.y;
+    if constexpr (kTrain) {
+        if (in0) { train.final_T[(int64_t)i0 * W + j] = T0; train.last_idx[(int64_t)i0 * W + j] = stop0 - 1; }
+        if (in1) { train.final_T[(int64_t)i1 * W + j] = T1; train.last_idx[(int64_t)i1 * W + j] = stop1 - 1; }
+    }
     const float o0r = fmaf(T0, bgr, ar0), o0g = fmaf(T0, bgg, ag0), o0b = fmaf(T0, bgb, ab0);
     const float o1r = fmaf(T1, bgr, ar1), o1g = fmaf(T1, bgg, ag1), o1b = fmaf(T1, bgb, ab1);
     const bool full_tile = (tile_x * kFastTile + kFastTile <= W) && (tile_y * kFastTile + kFastTile <= H);
@@ -788,21 +808,21 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
             }
             if (mode == BSPLAT_RASTER_FAST_NOCULL)
                 BSPLAT_LAUNCH_PDL((raster_pair_kernel<false, true>), grid, kPairThreads, 0, stream, N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
-                    tiles_w, image, vec, m_dev, peers, nullptr, nullptr);
+                    tiles_w, image, vec, m_dev, peers, nullptr, nullptr, TrainOut{nullptr, nullptr});
             else
                 BSPLAT_LAUNCH_PDL((raster_pair_kernel<true, true>), grid, kPairThreads, 0, stream, N, recp, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W, H,
                     tiles_w, image, vec, m_dev, peers, prepass ? surv : nullptr,
-                    prepass ? chunk_cnt : nullptr);
+                    prepass ? chunk_cnt : nullptr, TrainOut{nullptr, nullptr});
         } else {
             if (N > 0 && (!means2d || !conics || !colors || !opacities ||
                           (reinterpret_cast<uintptr_t>(means2d) & 7u) != 0))
                 return BSPLAT_E_ARG;
             if (mode == BSPLAT_RASTER_FAST_NOCULL)
                 BSPLAT_LAUNCH_PDL((raster_pair_kernel<false, false>), grid, kPairThreads, 0, stream, N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W,
-                    H, tiles_w, image, vec, m_dev, peers, nullptr, nullptr);
+                    H, tiles_w, image, vec, m_dev, peers, nullptr, nullptr, TrainOut{nullptr, nullptr});
             else
                 BSPLAT_LAUNCH_PDL((raster_pair_kernel<true, false>), grid, kPairThreads, 0, stream, N, nullptr, means2d, conics, colors, opacities, bg, tile_ranges, tile_order, first_tile, sorted_ids, W,
-                    H, tiles_w, image, vec, m_dev, peers, nullptr, nullptr);
+                    H, tiles_w, image, vec, m_dev, peers, nullptr, nullptr, TrainOut{nullptr, nullptr});
         }
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
@@ -820,6 +840,40 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
         }
         if (rc != BSPLAT_OK) return rc;
     }
+    return BSPLAT_OK;
+}
+
+// Training-side forward through the pair kernel (16x16 tiles, RGB): image bit-identical to the inference kernel's,
+// plus final_T / last_idx for rasterize_bwd.cu.  rec_ws (optional, raster_workspace_bytes(N)): records + cp.async
+// staging; tile_order (optional): heavy tiles first.
+int rasterize_train_fast_launch(int64_t N, const float* means2d, const float* conics, const float* colors,
+                                const float* opacities, const float* background_dev, const int32_t* tile_ranges,
+                                const int32_t* tile_order, const int32_t* sorted_ids, int W, int H, float* image,
+                                float* final_T, int32_t* last_idx, void* rec_ws, cudaStream_t stream) {
+    if (W <= 0 || H <= 0 || !background_dev || !image || !final_T || !last_idx || !tile_ranges) return BSPLAT_E_ARG;
+    const int tiles_w = (W + kFastTile - 1) / kFastTile, tiles_h = (H + kFastTile - 1) / kFastTile;
+    if (N > 0 && (!means2d || !conics || !colors || !opacities || (reinterpret_cast<uintptr_t>(means2d) & 7u) != 0))
+        return BSPLAT_E_ARG;
+    const int vec = ((reinterpret_cast<uintptr_t>(image) & 15u) == 0 && (W % 4) == 0) ? 1 : 0;
+    const unsigned grid = (unsigned)(tiles_w * tiles_h);
+    PeerImages peers;
+    peers.n = 0;
+    const TrainOut train{final_T, last_idx};
+    const bool have_rec = rec_ws != nullptr && N > 0 && (reinterpret_cast<uintptr_t>(rec_ws) & 15u) == 0;
+    if (have_rec) {
+        float4* recp = static_cast<float4*>(rec_ws);
+        raster_pair_prep_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(N, means2d, conics, colors, opacities,
+                                                                                recp, nullptr, nullptr);
+        BSPLAT_LAUNCH_CHECK();
+        raster_pair_kernel<true, true, true><<<grid, kPairThreads, 0, stream>>>(
+            N, recp, means2d, conics, colors, opacities, background_dev, tile_ranges, tile_order, 0, sorted_ids, W, H,
+            tiles_w, image, vec, nullptr, peers, nullptr, nullptr, train);
+    } else {
+        raster_pair_kernel<true, false, true><<<grid, kPairThreads, 0, stream>>>(
+            N, nullptr, means2d, conics, colors, opacities, background_dev, tile_ranges, tile_order, 0, sorted_ids, W,
+            H, tiles_w, image, vec, nullptr, peers, nullptr, nullptr, train);
+    }
+    BSPLAT_LAUNCH_CHECK();
     return BSPLAT_OK;
 }
 

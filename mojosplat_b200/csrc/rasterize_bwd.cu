@@ -385,6 +385,31 @@ extern "C" int bsplat_rasterize_fwd_train(int64_t N, int32_t channels, const flo
     return BSPLAT_OK;
 }
 
+namespace bsplat {
+int rasterize_train_fast_launch(int64_t N, const float* means2d, const float* conics, const float* colors,
+                                const float* opacities, const float* background_dev, const int32_t* tile_ranges,
+                                const int32_t* tile_order, const int32_t* sorted_ids, int W, int H, float* image,
+                                float* final_T, int32_t* last_idx, void* rec_ws, cudaStream_t stream);
+size_t raster_workspace_bytes(int64_t N);
+}
+
+// The same through the fast forward kernel (16x16 tiles, RGB only): image bit-identical to bsplat_rasterize_fwd's
+// default mode; last_idx holds, per pixel, the last list entry the backward pass has to look at.
+extern "C" int bsplat_rasterize_fwd_train_fast(int64_t N, const float* means2d, const float* conics,
+                                               const float* colors, const float* opacities, const float* background,
+                                               const int32_t* tile_ranges, const int32_t* tile_order,
+                                               const int32_t* sorted_ids, int64_t M, int32_t width, int32_t height,
+                                               float* image, float* final_T, int32_t* last_idx, void* workspace,
+                                               size_t workspace_bytes, void* stream_) {
+    if (N < 0 || M < 0 || width <= 0 || height <= 0) return BSPLAT_E_ARG;
+    if (M > 0 && !sorted_ids) return BSPLAT_E_ARG;
+    if ((height + 15) / 16 > 65535) return BSPLAT_E_ARG;
+    if (workspace && workspace_bytes < raster_workspace_bytes(N)) return BSPLAT_E_WORKSPACE;
+    return rasterize_train_fast_launch(N, means2d, conics, colors, opacities, background, tile_ranges, tile_order,
+                                       sorted_ids, width, height, image, final_T, last_idx, workspace,
+                                       (cudaStream_t)stream_);
+}
+
 extern "C" int bsplat_rasterize_bwd(int64_t N, int32_t channels, const float* means2d, const float* conics,
                                     const float* colors, const float* opacities, const float* background,
                                     const int32_t* tile_ranges, const int32_t* sorted_ids, int64_t M,

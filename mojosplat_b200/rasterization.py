@@ -112,7 +112,8 @@ class _RasterizeFn(torch.autograd.Function):
     """Differentiable compositing (bsplat_rasterize_fwd_train / bsplat_rasterize_bwd)."""
 
     @staticmethod
-    def forward(ctx, means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, H, W, tile_size):
+    def forward(ctx, means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, H, W, tile_size,
+                mode="fast"):
         L = _lib.require_device(means2d.device)
         dev, means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, N, C = _prep(
             means2d, conics, colors, opacities, background, tile_ranges, sorted_ids)
@@ -121,13 +122,29 @@ class _RasterizeFn(torch.autograd.Function):
         image = torch.empty((H, W, C), dtype=torch.float32, device=dev)
         final_T = torch.empty((H, W), dtype=torch.float32, device=dev)
         last_idx = torch.empty((H, W), dtype=torch.int32, device=dev)
+        # the fast forward kernel serves the default shape (16x16 tiles, RGB); everything else, and mode="faithful",
+        # goes through the kernel with the reference's operation order
+        fast = (mode == "fast" and int(tile_size) == 16 and C == 3 and means2d.data_ptr() % 8 == 0 and H > 0 and W > 0)
         with torch.cuda.device(dev):
-            rc = L.bsplat_rasterize_fwd_train(N, C, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
-                                              _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
-                                              _lib.ptr(sorted_ids), sorted_ids.numel(), W, H, int(tile_size),
-                                              _lib.ptr(image), _lib.ptr(final_T), _lib.ptr(last_idx),
-                                              _lib.stream_ptr(dev))
-        _lib.check(rc, "bsplat_rasterize_fwd_train")
+            if fast:
+                th, tw = tile_ranges.shape[0], tile_ranges.shape[1]
+                order = torch.empty((th * tw,), dtype=torch.int32, device=dev)
+                _lib.check(L.bsplat_tile_order(0, order.numel(), _lib.ptr(tile_ranges), _lib.ptr(order),
+                                               _lib.stream_ptr(dev)), "bsplat_tile_order")
+                ws = _lib.workspace.get(dev, "raster_rec", L.bsplat_rasterize_workspace_bytes(N))
+                rc = L.bsplat_rasterize_fwd_train_fast(N, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
+                                                       _lib.ptr(opacities), _lib.ptr(background),
+                                                       _lib.ptr(tile_ranges), _lib.ptr(order), _lib.ptr(sorted_ids),
+                                                       sorted_ids.numel(), W, H, _lib.ptr(image), _lib.ptr(final_T),
+                                                       _lib.ptr(last_idx), _lib.ptr(ws), ws.numel(),
+                                                       _lib.stream_ptr(dev))
+            else:
+                rc = L.bsplat_rasterize_fwd_train(N, C, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
+                                                  _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
+                                                  _lib.ptr(sorted_ids), sorted_ids.numel(), W, H, int(tile_size),
+                                                  _lib.ptr(image), _lib.ptr(final_T), _lib.ptr(last_idx),
+                                                  _lib.stream_ptr(dev))
+        _lib.check(rc, "bsplat_rasterize_fwd_train_fast" if fast else "bsplat_rasterize_fwd_train")
         ctx.save_for_backward(means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, final_T,
                               last_idx)
         ctx.dims = (H, W, int(tile_size))
@@ -151,14 +168,17 @@ class _RasterizeFn(torch.autograd.Function):
                                         _lib.ptr(g_c), _lib.ptr(g_o), _lib.stream_ptr(dev))
         _lib.check(rc, "bsplat_rasterize_bwd")
         g_bg = (final_T.unsqueeze(-1) * grad_image).sum(dim=(0, 1))
-        return g_m, g_k, g_c, g_o, g_bg, None, None, None, None, None
+        return g_m, g_k, g_c, g_o, g_bg, None, None, None, None, None, None
 
 
 def rasterize_gaussians_diff(means2d, conics, colors, opacities, background_color, tile_ranges,
-                             sorted_gaussian_indices, camera, tile_size=16):
+                             sorted_gaussian_indices, camera, tile_size=16, mode="fast"):
     """Differentiable ``rasterize_gaussians`` (additive: the reference is forward-only, render.py:11).
     Gradients flow to means2d, conics, colors, opacities and background_color; the tile lists are
-    treated as constants. Forward values are those of the faithful kernel."""
+    treated as constants. Forward values: ``mode="fast"`` (16x16 tiles, RGB) = the default inference kernel's, bit for
+    bit; ``mode="faithful"`` (and every other shape) = the faithful kernel's."""
+    if mode not in ("fast", "faithful"):
+        raise ValueError(f"Invalid mode: {mode}")
     opac = opacities.reshape(-1)
     return _RasterizeFn.apply(means2d, conics, colors, opac, background_color, tile_ranges,
-                              sorted_gaussian_indices, int(camera.H), int(camera.W), int(tile_size))
+                              sorted_gaussian_indices, int(camera.H), int(camera.W), int(tile_size), mode)

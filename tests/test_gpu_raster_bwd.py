@@ -105,10 +105,72 @@ def test_train_forward_equals_faithful_kernel(cuda_device):
     a = [dev(m2, cuda_device), dev(con, cuda_device), dev(c, cuda_device), dev(o, cuda_device),
          dev(bg, cuda_device), dev(ranges, cuda_device), dev(ids, cuda_device)]
     faithful = rasterization.rasterize_gaussians_cuda(*a, cam, 16, mode="faithful")
-    img = rasterization.rasterize_gaussians_diff(*a, cam, 16)
+    img = rasterization.rasterize_gaussians_diff(*a, cam, 16, mode="faithful")
     assert torch.equal(img, faithful)
     ref = oracle.rasterize(m2, con, c, o, bg, ranges, ids, 96, 96, 16)
     assert image_gate(img.cpu().numpy(), ref)["ok"]
+
+
+def _train_forward_raw(a, H, W, fast, cuda_device):
+    """(image, final_T, last_idx) of the two training-side forward entry points, straight through the C ABI."""
+    from mojosplat_b200 import _lib
+    L = _lib.load()
+    m2, con, c, o, bg, ranges, ids = a
+    N = m2.shape[0]
+    image = torch.empty((H, W, 3), dtype=torch.float32, device=cuda_device)
+    final_T = torch.empty((H, W), dtype=torch.float32, device=cuda_device)
+    last = torch.empty((H, W), dtype=torch.int32, device=cuda_device)
+    sp = _lib.stream_ptr(torch.device(cuda_device))
+    if fast:
+        rc = L.bsplat_rasterize_fwd_train_fast(N, _lib.ptr(m2), _lib.ptr(con), _lib.ptr(c), _lib.ptr(o), _lib.ptr(bg),
+                                               _lib.ptr(ranges), None, _lib.ptr(ids), ids.numel(), W, H,
+                                               _lib.ptr(image), _lib.ptr(final_T), _lib.ptr(last), None, 0, sp)
+    else:
+        rc = L.bsplat_rasterize_fwd_train(N, 3, _lib.ptr(m2), _lib.ptr(con), _lib.ptr(c), _lib.ptr(o), _lib.ptr(bg),
+                                          _lib.ptr(ranges), _lib.ptr(ids), ids.numel(), W, H, 16, _lib.ptr(image),
+                                          _lib.ptr(final_T), _lib.ptr(last), sp)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return image, final_T, last
+
+
+@pytest.mark.parametrize("scene", ["plain", "opaque"])
+def test_fast_train_forward(cuda_device, scene):
+    """The training-side forward through the pair kernel: image == the inference kernel's bit for bit (with and without
+    the record workspace), final transmittance within the float tolerance of the faithful forward's, and last_idx
+    consistent with it: never in front of the faithful 'last composited' index (entries behind it fail the alpha test
+    again in the backward pass), equal to it + 0 wherever the pixel saturated."""
+    if scene == "plain":
+        cam, m2, con, dep, rad, o, c = small_scene(300, 96, 7)
+        HW = 96
+    else:  # opaque stacks: most pixels saturate long before the end of their list
+        N, HW = 80, 64
+        g = torch.Generator().manual_seed(3)
+        m2 = (torch.rand(N, 2, generator=g) * 40 + 12).numpy().astype(np.float32)
+        con = np.tile(np.array([[0.02, 0.0, 0.02]], np.float32), (N, 1))
+        dep = np.arange(N, dtype=np.float32) + 1
+        rad = np.full((N, 2), 40, np.int32)
+        o = np.full(N, 0.95, np.float32)
+        c = torch.rand(N, 3, generator=g).numpy()
+        cam = ms.Camera(R=torch.eye(3), T=torch.zeros(3), H=HW, W=HW, fx=60.0, fy=60.0, cx=32.0, cy=32.0)
+    ids, ranges = oracle.bin_tiles(m2, rad, dep, HW, HW, 16)
+    bg = np.array([0.1, 0.2, 0.3], np.float32)
+    a = [dev(m2, cuda_device), dev(con, cuda_device), dev(c, cuda_device), dev(o, cuda_device),
+         dev(bg, cuda_device), dev(ranges, cuda_device).to(torch.int32).contiguous(),
+         dev(ids, cuda_device).to(torch.int32).contiguous()]
+    infer = rasterization.rasterize_gaussians_cuda(*a, cam, 16)
+    img_ws = rasterization.rasterize_gaussians_diff(*a, cam, 16)          # records + tile order
+    img_raw, T_fast, last_fast = _train_forward_raw(a, HW, HW, True, cuda_device)   # workspace-free staging
+    assert torch.equal(img_ws, infer) and torch.equal(img_raw, infer)
+    img_f, T_f, last_f = _train_forward_raw(a, HW, HW, False, cuda_device)
+    assert float((T_fast - T_f).abs().max()) <= 1e-5
+    r1 = a[5][..., 1].repeat_interleave(16, 0).repeat_interleave(16, 1)[:HW, :HW]
+    saturated = last_fast < r1 - 1
+    assert bool((last_fast >= last_f).all())
+    if scene == "opaque":
+        assert int(saturated.sum()) > 100
+    # and never past the end of the tile's list
+    assert bool((last_fast <= r1 - 1).all())
 
 
 def test_backward_saturated_pixels_and_clamp(cuda_device):
