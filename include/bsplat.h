@@ -346,6 +346,17 @@ int bsplat_render_fwd_host(int64_t N, const float* means3d, const float* log_sca
  * FP32 / SFU denominators of the rasterizer roofline. */
 int bsplat_microbench(int32_t kind, int32_t blocks, int32_t iters, float* out, void* stream);
 
+/* The backward pass in the fast kernel's layout (16x16 tiles, RGB; two pixels per lane, packed FP32, MUFU ex2 / rcp):
+ * same contract as bsplat_rasterize_bwd; gradients agree with it within float rounding (both are checked against
+ * fp64 autograd at 1e-3). workspace: bsplat_rasterize_workspace_bytes(N), 16-byte aligned (the records are rebuilt
+ * here); tile_order optional (bsplat_tile_order). */
+int bsplat_rasterize_bwd_fast(int64_t N, const float* means2d, const float* conics, const float* colors,
+                              const float* opacities, const float* background, const int32_t* tile_ranges,
+                              const int32_t* tile_order, const int32_t* sorted_ids, int64_t M, int32_t width,
+                              int32_t height, const float* final_T, const int32_t* last_idx,
+                              const float* grad_image, float* grad_means2d, float* grad_conics, float* grad_colors,
+                              float* grad_opacities, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -843,6 +843,17 @@ int rasterize_launch(int64_t N, int channels, const float* means2d, const float*
     return BSPLAT_OK;
 }
 
+// the records of all N Gaussians (stage-level callers outside this file: the fast backward pass)
+int raster_records_launch(int64_t N, const float* means2d, const float* conics, const float* colors,
+                          const float* opacities, void* rec_ws, cudaStream_t stream) {
+    if (N <= 0) return BSPLAT_OK;
+    raster_pair_prep_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(N, means2d, conics, colors, opacities,
+                                                                            static_cast<float4*>(rec_ws), nullptr,
+                                                                            nullptr);
+    BSPLAT_LAUNCH_CHECK();
+    return BSPLAT_OK;
+}
+
 // Training-side forward through the pair kernel (16x16 tiles, RGB): image bit-identical to the inference kernel's,
 // plus final_T / last_idx for rasterize_bwd.cu.  rec_ws (optional, raster_workspace_bytes(N)): records + cp.async
 // staging; tile_order (optional): heavy tiles first.

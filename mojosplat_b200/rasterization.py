@@ -148,6 +148,7 @@ class _RasterizeFn(torch.autograd.Function):
         ctx.save_for_backward(means2d, conics, colors, opacities, background, tile_ranges, sorted_ids, final_T,
                               last_idx)
         ctx.dims = (H, W, int(tile_size))
+        ctx.fast = fast
         return image
 
     @staticmethod
@@ -161,12 +162,25 @@ class _RasterizeFn(torch.autograd.Function):
         g_m = torch.zeros_like(means2d); g_k = torch.zeros_like(conics)
         g_c = torch.zeros_like(colors); g_o = torch.zeros_like(opacities)
         with torch.cuda.device(dev):
-            rc = L.bsplat_rasterize_bwd(N, C, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
-                                        _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
-                                        _lib.ptr(sorted_ids), sorted_ids.numel(), W, H, ts, _lib.ptr(final_T),
-                                        _lib.ptr(last_idx), _lib.ptr(grad_image), _lib.ptr(g_m), _lib.ptr(g_k),
-                                        _lib.ptr(g_c), _lib.ptr(g_o), _lib.stream_ptr(dev))
-        _lib.check(rc, "bsplat_rasterize_bwd")
+            if ctx.fast:
+                th, tw = tile_ranges.shape[0], tile_ranges.shape[1]
+                order = torch.empty((th * tw,), dtype=torch.int32, device=dev)
+                _lib.check(L.bsplat_tile_order(0, order.numel(), _lib.ptr(tile_ranges), _lib.ptr(order),
+                                               _lib.stream_ptr(dev)), "bsplat_tile_order")
+                ws = _lib.workspace.get(dev, "raster_rec", L.bsplat_rasterize_workspace_bytes(N))
+                rc = L.bsplat_rasterize_bwd_fast(N, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
+                                                 _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
+                                                 _lib.ptr(order), _lib.ptr(sorted_ids), sorted_ids.numel(), W, H,
+                                                 _lib.ptr(final_T), _lib.ptr(last_idx), _lib.ptr(grad_image),
+                                                 _lib.ptr(g_m), _lib.ptr(g_k), _lib.ptr(g_c), _lib.ptr(g_o),
+                                                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+            else:
+                rc = L.bsplat_rasterize_bwd(N, C, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
+                                            _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
+                                            _lib.ptr(sorted_ids), sorted_ids.numel(), W, H, ts, _lib.ptr(final_T),
+                                            _lib.ptr(last_idx), _lib.ptr(grad_image), _lib.ptr(g_m), _lib.ptr(g_k),
+                                            _lib.ptr(g_c), _lib.ptr(g_o), _lib.stream_ptr(dev))
+        _lib.check(rc, "bsplat_rasterize_bwd_fast" if ctx.fast else "bsplat_rasterize_bwd")
         g_bg = (final_T.unsqueeze(-1) * grad_image).sum(dim=(0, 1))
         return g_m, g_k, g_c, g_o, g_bg, None, None, None, None, None, None
 
