@@ -379,8 +379,8 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
                        const float* __restrict__ final_T, const int32_t* __restrict__ last_idx,
                        const float* __restrict__ grad_image, float* __restrict__ g_means2d,
                        float* __restrict__ g_conics, float* __restrict__ g_colors, float* __restrict__ g_opac) {
-    __shared__ float4 s_rec[kBwdBatch * kPairRec];
-    __shared__ int32_t s_id[kBwdBatch];
+    __shared__ float4 s_rec[2 * kBwdBatch * kPairRec];
+    __shared__ int32_t s_id[2 * kBwdBatch];
     __shared__ int s_max_last;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -420,31 +420,55 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
     const int32_t hi_all = s_max_last;  // furthest entry any pixel of the tile looked at
     if (hi_all < r0) return;
 
-    for (int32_t hi = hi_all; hi >= r0; hi -= kBwdBatch) {
-        __syncthreads();  // previous batch fully consumed
-        {   // staged back to front: slot t holds entry hi - t
-            const int32_t idx = hi - tid;
-            float4 q0, q1, q2;
-            int32_t g = -1;
-            if (idx >= r0) g = __ldg(sorted_ids + idx);
-            if (g >= 0 && (int64_t)g < N) {
-                const float4* src = rec + kPairRec * (int64_t)g;
-                q0 = __ldg(src); q1 = __ldg(src + 1); q2 = __ldg(src + 2);
-            } else {
-                g = -1;
-                pair_record_none(q0, q1, q2);
+    // this thread's record of a batch goes into the other half of the staging ring with cp.async, one batch ahead of
+    // the walk (slot t of batch `hi` holds entry hi - t)
+    auto fetch = [&](const int32_t hi, const int half) {
+        const int32_t idx = hi - tid;
+        int32_t g = -1;
+        if (idx >= r0) g = __ldg(sorted_ids + idx);
+        float4* dst = s_rec + (half * kBwdBatch + tid) * kPairRec;
+        if (g >= 0 && (int64_t)g < N) {
+            const float4* src = rec + kPairRec * (int64_t)g;
+#pragma unroll
+            for (int q = 0; q < kPairRec; ++q) {
+                const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst + q);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + q) : "memory");
             }
-            s_id[tid] = g;
-            s_rec[kPairRec * tid] = q0; s_rec[kPairRec * tid + 1] = q1; s_rec[kPairRec * tid + 2] = q2;
+        } else {
+            g = -1;
+            pair_record_none(dst[0], dst[1], dst[2]);
         }
-        __syncthreads();
+        s_id[half * kBwdBatch + tid] = g;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // loop-invariant roles of the lanes that issue the atomics: lane 4 k adds value k of the spread reduction (colours,
+    // conic a b c, mean x y), lane 1 the opacity gradient -- one predicated RED instruction per Gaussian and warp
+    const int which = lane >> 2;
+    const bool role_mean = which >= 6, role_my = which == 7, role_op = lane == 1;
+    const bool issues = ((lane & 3) == 0) || role_op;
+    float* role_base;
+    int role_stride;
+    float role_scale = 1.0f;
+    if (role_op) { role_base = g_opac; role_stride = 1; }
+    else if (which < 3) { role_base = g_colors + which; role_stride = 3; }
+    else if (which < 6) { role_base = g_conics + (which - 3); role_stride = 3; role_scale = (which == 4) ? 1.0f : 0.5f; }
+    else { role_base = g_means2d + (which - 6); role_stride = 2; }
+
+    fetch(hi_all, 0);
+    int half = 0;
+    for (int32_t hi = hi_all; hi >= r0; hi -= kBwdBatch, half ^= 1) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();  // this batch has landed; everyone is done with the other half
+        if (hi - kBwdBatch >= r0) fetch(hi - kBwdBatch, half ^ 1);  // in flight during the walk below
+        const float4* s_cur = s_rec + half * kBwdBatch * kPairRec;
+        const int32_t* s_idc = s_id + half * kBwdBatch;
         const int bs = min(kBwdBatch, (int)(hi - r0 + 1));
         if (hi - (bs - 1) > warp_last) continue;  // nothing of this batch was looked at by this warp's pixels
         for (int c0 = 0; c0 < bs; c0 += 32) {
             // lane l tests slot c0 + 31 - l: the first slot of the walk is the HIGHEST ballot bit
             const int gi = c0 + 31 - lane;
             bool hit = false, special = false;
-            if (gi < bs && hi - gi <= warp_last) hit = pair_record_hit(s_rec + kPairRec * gi, X0, X1, Y0, Y1, &special);
+            if (gi < bs && hi - gi <= warp_last) hit = pair_record_hit(s_cur + kPairRec * gi, X0, X1, Y0, Y1, &special);
             unsigned mask = __ballot_sync(0xffffffffu, hit);
             while (mask) {
                 unsigned b_hi, below;
@@ -453,7 +477,7 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
                 mask &= below;
                 const int slot = c0 + 31 - (int)b_hi;
                 const int32_t cur = hi - slot;
-                const float4* r = s_rec + kPairRec * slot;
+                const float4* r = s_cur + kPairRec * slot;
                 const float4 p0 = r[0], p1 = r[1];
                 const float2 dx2 = dupb(p0.x - px);
                 const float2 dy2 = __fadd2_rn(dupb(p0.y), npy);
@@ -502,23 +526,16 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
                 const float sx = __shfl_sync(0xffffffffu, v[0], 24), sy = __shfl_sync(0xffffffffu, v[0], 28);
-                const int64_t g = s_id[slot];
-                const int which = lane >> 2;
-                if ((lane & 3) == 0) {
-                    // conic of the record: (a, b, c) = (-2 nA, -nB, -2 nC) / log2e
-                    constexpr float kInv = 1.0f / kLog2e;
-                    const float a = -2.0f * kInv * p0.z, b = -kInv * p0.w, c = -2.0f * kInv * p1.x;
-                    float* dst;
-                    float val = v[0];
-                    if (which < 3) dst = g_colors + 3 * g + which;
-                    else if (which < 6) { dst = g_conics + 3 * g + (which - 3); val = (which == 4) ? val : 0.5f * val; }
-                    else if (which == 6) { dst = g_means2d + 2 * g; val = a * sx + b * sy; }
-                    else { dst = g_means2d + 2 * g + 1; val = b * sx + c * sy; }
-                    atomicAdd(dst, val);
-                } else if (lane == 1) {
-                    // d alpha / d opacity = alpha / opacity  =>  -sum v_sigma / opacity, opacity = 2^L
-                    atomicAdd(g_opac + g, -ss * ex2_approx_b(-p1.y));
-                }
+                const int64_t g = s_idc[slot];
+                // conic of the record: (a, b, c) = (-2 nA, -nB, -2 nC) / log2e;  mean gradient = (a sx + b sy, b sx + c sy)
+                constexpr float kInv = 1.0f / kLog2e;
+                const float cb_ = -kInv * p0.w;
+                const float c_first = role_my ? cb_ : -2.0f * kInv * p0.z;
+                const float c_second = role_my ? -2.0f * kInv * p1.x : cb_;
+                float val = role_mean ? (c_first * sx + c_second * sy) : role_scale * v[0];
+                // d alpha / d opacity = alpha / opacity  =>  -sum v_sigma / opacity, opacity = 2^L
+                val = role_op ? -ss * ex2_approx_b(-p1.y) : val;
+                if (issues) atomicAdd(role_base + g * role_stride, val);
             }
         }
     }

@@ -149,6 +149,7 @@ class _RasterizeFn(torch.autograd.Function):
                               last_idx)
         ctx.dims = (H, W, int(tile_size))
         ctx.fast = fast
+        ctx.order = order if fast else None  # heavy tiles first: reused by the backward pass
         return image
 
     @staticmethod
@@ -163,10 +164,7 @@ class _RasterizeFn(torch.autograd.Function):
         g_c = torch.zeros_like(colors); g_o = torch.zeros_like(opacities)
         with torch.cuda.device(dev):
             if ctx.fast:
-                th, tw = tile_ranges.shape[0], tile_ranges.shape[1]
-                order = torch.empty((th * tw,), dtype=torch.int32, device=dev)
-                _lib.check(L.bsplat_tile_order(0, order.numel(), _lib.ptr(tile_ranges), _lib.ptr(order),
-                                               _lib.stream_ptr(dev)), "bsplat_tile_order")
+                order = ctx.order
                 ws = _lib.workspace.get(dev, "raster_rec", L.bsplat_rasterize_workspace_bytes(N))
                 rc = L.bsplat_rasterize_bwd_fast(N, _lib.ptr(means2d), _lib.ptr(conics), _lib.ptr(colors),
                                                  _lib.ptr(opacities), _lib.ptr(background), _lib.ptr(tile_ranges),
