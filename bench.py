@@ -475,23 +475,32 @@ def run_b200(args, rank, world, local_rank):
         t = [info["means2d"].clone().requires_grad_(True), info["conics"].clone().requires_grad_(True),
              g[4].clone().requires_grad_(True), g[3].clone().requires_grad_(True)]
         gimg = torch.ones((H, W, 3), dtype=torch.float32, device=dev)
-        fw, bw = [], []
-        for k in range(4):
-            for x in t:
-                x.grad = None
-            flush.zero_()
-            e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            e0.record()
-            out = rasterization.rasterize_gaussians_diff(*t, bg, info["tile_ranges"], info["sorted_ids"], cams[0], 16)
-            e1.record()
-            out.backward(gimg)
-            e2.record()
-            torch.cuda.synchronize(dev)
-            if k >= 1:
-                fw.append(e0.elapsed_time(e1)); bw.append(e1.elapsed_time(e2))
+        times = {}
+        for mode in ("fast", "faithful"):
+            fw, bw = [], []
+            for k in range(4):
+                for x in t:
+                    x.grad = None
+                flush.zero_()
+                e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                e0.record()
+                out = rasterization.rasterize_gaussians_diff(*t, bg, info["tile_ranges"], info["sorted_ids"], cams[0],
+                                                             16, mode=mode)
+                e1.record()
+                out.backward(gimg)
+                e2.record()
+                torch.cuda.synchronize(dev)
+                if k >= 1:
+                    fw.append(e0.elapsed_time(e1)); bw.append(e1.elapsed_time(e2))
+            times[mode] = (float(np.mean(fw)), float(np.mean(bw)))
         backward = {"workload": "rasterization forward (training variant: final T, last index) + backward at the "
                                 "timed config (view 0), gradients w.r.t. means2d, conics, colours, opacities",
-                    "forward_train_ms": float(np.mean(fw)), "backward_ms": float(np.mean(bw)),
+                    "forward_train_ms": times["fast"][0], "backward_ms": times["fast"][1],
+                    "kernels": "pair layout (raster_pair_kernel<train> / raster_bwd_pair_kernel: two pixels per lane, "
+                               "packed FP32), the default for 16x16 RGB",
+                    "generic_kernels": {"forward_train_ms": times["faithful"][0], "backward_ms": times["faithful"][1],
+                                        "note": "raster_train_fwd_kernel / raster_bwd_kernel: any tile size, 1-4 "
+                                                "channels, the reference's operation order (mode='faithful')"},
                     "note": "additive (the reference is forward-only, render.py:11); includes the autograd glue"}
         del t, out, gimg
     _, e_all, e_pass = rasterization.rasterize_gaussians_stats(
