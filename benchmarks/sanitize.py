@@ -41,8 +41,10 @@ for cfg, N, sem in [("config1_1k_256", None, "cuda"), ("config3_1m_1080p", 8000 
                                             semantics=semv, packed=packed)
     t = [aux["means2d"].clone().requires_grad_(True), aux["conics"].clone().requires_grad_(True),
          g[4].clone().requires_grad_(True), g[3].clone().requires_grad_(True)]
-    out = rasterization.rasterize_gaussians_diff(*t, bg, aux["tile_ranges"], aux["sorted_ids"], sc.camera, 16)
-    out.sum().backward()
+    for mode in ("fast", "faithful"):  # pair-layout kernels / generic kernels
+        out = rasterization.rasterize_gaussians_diff(*t, bg, aux["tile_ranges"], aux["sorted_ids"], sc.camera, 16,
+                                                     mode=mode)
+        out.sum().backward()
     pipe = OverlappedPipeline(dev, sc.N, sc.camera.W, sc.camera.H, semantics=semv, m_capacity=200 * sc.N + 4096)
     cams = synthetic.orbit_cameras(4, sc.camera.W, sc.camera.H, sc.camera.fx)
     pipe.render(*g, cams, bg); pipe.check()

@@ -477,6 +477,7 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
                 mask &= below;
                 const int slot = c0 + 31 - (int)b_hi;
                 const int32_t cur = hi - slot;
+                BSPLAT_DASSERT(slot >= 0 && slot < bs && cur >= r0 && cur <= hi_all);
                 const float4* r = s_cur + kPairRec * slot;
                 const float4 p0 = r[0], p1 = r[1];
                 const float2 dx2 = dupb(p0.x - px);
@@ -527,6 +528,7 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
                 for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
                 const float sx = __shfl_sync(0xffffffffu, v[0], 24), sy = __shfl_sync(0xffffffffu, v[0], 28);
                 const int64_t g = s_idc[slot];
+                BSPLAT_DASSERT(g >= 0 && g < N);  // (a record that is not a Gaussian never passes the alpha test)
                 // conic of the record: (a, b, c) = (-2 nA, -nB, -2 nC) / log2e;  mean gradient = (a sx + b sy, b sx + c sy)
                 constexpr float kInv = 1.0f / kLog2e;
                 const float cb_ = -kInv * p0.w;

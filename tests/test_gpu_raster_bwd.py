@@ -66,6 +66,8 @@ def small_scene(N, HW, seed, C=3, opacity_lo=0.3):
 @pytest.mark.parametrize("N,HW,ts,C,seed", [(1, 32, 16, 3, 0), (40, 48, 16, 3, 1), (150, 64, 16, 3, 2),
                                             (60, 40, 10, 3, 3), (80, 48, 16, 1, 4), (80, 48, 16, 4, 5),
                                             (400, 32, 16, 3, 6),
+                                            # partial tiles / image width not a multiple of 4 in the pair-layout kernels
+                                            (80, 42, 16, 3, 12), (120, 57, 16, 3, 13),
                                             # tile sizes 31 / 32: > 48 KB of dynamic shared memory (opt-in attribute)
                                             (60, 64, 32, 3, 7), (60, 64, 32, 4, 8), (60, 62, 31, 3, 9),
                                             (60, 64, 32, 2, 10)])
