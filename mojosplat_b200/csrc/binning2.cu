@@ -964,7 +964,7 @@ static Bin2Ws carve_bin2(void* base, int64_t N, int64_t M, int64_t n_tiles) {
     w.compact_status = (unsigned long long*)take((size_t)(ceil_div((int64_t)n, kCompactChunk) + 1) * 8);
     w.cand_n = (unsigned long long*)take(16);
     w.cand_status = (unsigned long long*)take((size_t)(ceil_div((int64_t)n, kCompactChunk) + 1) * 8);
-    w.status_n = (uint32_t*)take(sort_status_words(sort_tiles_u32(N), 4) * 4);
+    w.status_n = (uint32_t*)take(sort_status_words(sort_tiles_u32_depth(N), 4) * 4);
     w.zero_end_n = off;
     w.n_bytes = off;
     w.tkeys = (uint32_t*)take(m * 4); w.tkeys_alt = (uint32_t*)take(m * 4);
@@ -1076,7 +1076,7 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
                                                   compact ? nullptr : w.hist);
         BSPLAT_LAUNCH_CHECK();
     }
-    const int64_t tn = sort_tiles_u32(N);
+    const int64_t tn = sort_tiles_u32_depth(N);
     const uint64_t* n_dev = nullptr;
     const int32_t* vsrc = nullptr;
     if (compact) {
@@ -1100,7 +1100,7 @@ int bin2_prepare(int64_t N, const float* means2d, const void* radii, int radii_i
         // (the depth histograms come from the kernel in front of pass 0: passes 1-3 may read theirs early)
         rc = onesweep_pass_u32(N, n_dev, ksrc, pass == 3 ? nullptr : kdst, vsrc, vdst, 8 * pass, 8,
                                w.hist + (size_t)pass * kRadix, 0, w.tickets + pass,
-                               w.status_n + (size_t)pass * tn * kRadix, nullptr, stream, 0, pass > 0);
+                               w.status_n + (size_t)pass * tn * kRadix, nullptr, stream, 0, pass > 0, 1);
         if (rc != BSPLAT_OK) return rc;
         // ping-pong: pass 0 writes (dkeys_alt, perm_alt), pass 1 (dkeys, perm), ...; pass 3 ends in perm
         ksrc = kdst; kdst = (kdst == w.dkeys_alt) ? w.dkeys : w.dkeys_alt;

@@ -93,24 +93,30 @@ __global__ void __launch_bounds__(kRadix) radix_scan_kernel(uint32_t* __restrict
 // walk back through ALL of them -- tiles / LOOKBACK dependent round trips of ~1 us each bound the pass, so those
 // launches use a 64-wide window (4 round trips instead of 15); the M-scale passes run in waves, find inclusive
 // prefixes a few tiles back and keep the 16-wide window.
-template <typename KeyT, int ITEMS, int BITS, int LOOKBACK = kLookback>
-__global__ void __launch_bounds__(kSortThreads, 3)
+// THREADS: 256 (3 CTAs per SM), or 512 for the depth passes of frames whose tiles are all resident at once anyway
+// (twice the tile, half the tiles: the look-back of such a pass is quadratic in the number of tiles, see above).
+template <typename KeyT, int ITEMS, int BITS, int LOOKBACK = kLookback, int THREADS = kSortThreads>
+__global__ void __launch_bounds__(THREADS, THREADS == kSortThreads ? 3 : 1)
 onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const KeyT* __restrict__ keys_in,
                 KeyT* __restrict__ keys_out, const int32_t* __restrict__ vals_in,
                 int32_t* __restrict__ vals_out, const int shift, const int bits_rt,
                 const uint32_t* __restrict__ hist, const int hist_is_scanned, uint32_t* __restrict__ ticket,
                 uint32_t* __restrict__ status, uint32_t* __restrict__ key_counts, const int key_row_stride,
                 const int hist_early) {
-    constexpr int TILE = kSortThreads * ITEMS;
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
+    static_assert(THREADS >= kRadix && THREADS % 32 == 0, "one thread per digit");
     // BITS > 0: digit width known at compile time (branch-free ballot loop with constant masks)
     const int bits = BITS > 0 ? BITS : bits_rt;
-    __shared__ uint32_t s_whist[kSortWarps][kRadix];
-    __shared__ KeyT s_keys[TILE];
-    __shared__ int32_t s_vals[TILE];
+    __shared__ uint32_t s_whist[WARPS][kRadix];
+    // key / payload exchange buffers: dynamic shared memory (TILE * (sizeof(KeyT) + 4) bytes; > 48 KB for 512 threads)
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    KeyT* s_keys = reinterpret_cast<KeyT*>(s_dyn);
+    int32_t* s_vals = reinterpret_cast<int32_t*>(s_dyn + (size_t)TILE * sizeof(KeyT));
     __shared__ uint32_t s_local_off[kRadix];
     __shared__ uint32_t s_gbase[kRadix];
     __shared__ uint32_t s_bins[kRadix];
-    __shared__ uint32_t s_warp_tot[kSortWarps];
+    __shared__ uint32_t s_warp_tot[kRadix / 32];
     __shared__ uint32_t s_tile;
 
     // Programmatic dependent launch: this CTA may be resident while the previous kernel of the stream is still
@@ -127,8 +133,9 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
     const unsigned long long ph_c0 = clock64();
 #endif
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&s_whist[0][0])[i] = 0;
-    const uint32_t h_early = hist_early ? hist[tid] : 0u;
+    for (int i = tid; i < WARPS * kRadix; i += THREADS) (&s_whist[0][0])[i] = 0;
+    const bool dig = tid < kRadix;  // threads that own a digit (whole warps: 0 .. 7)
+    const uint32_t h_early = (hist_early && dig) ? hist[tid] : 0u;
     pdl_wait();
     // device-side count (sync-free frames): M_host is then the capacity the launch and the buffers were
     // sized for; a count beyond it disables the pass (the emitter has flagged the overflow)
@@ -149,11 +156,11 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
     const int n_valid = (int)min((int64_t)TILE, M - tile_base);
     const uint32_t digit_mask = (1u << bits) - 1u;
     const int n_digits = 1 << bits;
-    uint32_t* my_status = status + (size_t)tile * kRadix + tid;
+    uint32_t* my_status = status + (size_t)tile * kRadix + (dig ? tid : 0);
     // global digit offsets: either already exclusive-scanned, or a raw histogram scanned here
     // (256-wide block scan; saves a kernel launch per sort)
     {
-        const uint32_t h = hist_early ? h_early : hist[tid];
+        const uint32_t h = dig ? (hist_early ? h_early : hist[tid]) : 0u;
         uint32_t incl = h;
         if (!hist_is_scanned) {
 #pragma unroll
@@ -161,15 +168,17 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
                 const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= (uint32_t)d) incl += t;
             }
-            if (lane == 31) s_warp_tot[warp] = incl;
+            if (lane == 31 && dig) s_warp_tot[warp] = incl;
         }
         __syncthreads();
-        uint32_t excl = h;
-        if (!hist_is_scanned) {
-            excl = incl - h;
-            for (int w = 0; w < warp; ++w) excl += s_warp_tot[w];
+        if (dig) {
+            uint32_t excl = h;
+            if (!hist_is_scanned) {
+                excl = incl - h;
+                for (int w = 0; w < warp; ++w) excl += s_warp_tot[w];
+            }
+            s_bins[tid] = excl;
         }
-        s_bins[tid] = excl;
         __syncthreads();  // s_warp_tot is reused below
     }
 
@@ -250,11 +259,13 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
 
         // ---- per-digit: exclusive scan over warps, tile count -> aggregate published immediately ----
         uint32_t run = 0;
+        if (dig) {
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
-            const uint32_t c = s_whist[w][tid];
-            s_whist[w][tid] = run;
-            run += c;
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = s_whist[w][tid];
+                s_whist[w][tid] = run;
+                run += c;
+            }
         }
         // the padding slots of the last tile were counted under the last digit: take them out again
         const uint32_t count = run - ((uint32_t)tid == digit_mask ? (uint32_t)(TILE - n_valid) : 0u);
@@ -265,13 +276,15 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= (uint32_t)d) incl += t;
         }
-        if (lane == 31) s_warp_tot[warp] = incl;
+        if (lane == 31 && dig) s_warp_tot[warp] = incl;
         __syncthreads();
-        uint32_t excl = incl - count;
-        for (int w = 0; w < warp; ++w) excl += s_warp_tot[w];
-        s_local_off[tid] = excl;
-        // s_gbase holds (count, excl) needs: keep count in s_gbase until the look-back rewrites it
-        s_gbase[tid] = count;
+        if (dig) {
+            uint32_t excl = incl - count;
+            for (int w = 0; w < warp; ++w) excl += s_warp_tot[w];
+            s_local_off[tid] = excl;
+            // s_gbase holds (count, excl) needs: keep count in s_gbase until the look-back rewrites it
+            s_gbase[tid] = count;
+        }
         __syncthreads();
         BSPLAT_PHASE(3);  // aggregates published, local scan
 
@@ -337,7 +350,7 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
     const bool write_keys = keys_out != nullptr, count_keys = key_counts != nullptr;
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-        const int j = tid + k * kSortThreads;
+        const int j = tid + k * THREADS;
         if (j < n_valid) {
             const KeyT kk = s_keys[j];
             const uint32_t d = (uint32_t)(kk >> shift) & digit_mask;
@@ -374,21 +387,48 @@ onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const 
 // ------------------------------------------------------------------------------------------
 int64_t sort_tiles_u32(int64_t M) { return ceil_div(M > 0 ? M : 1, kSortThreads * kSortItems32); }
 int64_t sort_tiles_u64(int64_t M) { return ceil_div(M > 0 ? M : 1, kSortThreads * kSortItems64); }
+// Depth passes of frames with at most kSortWideMax Gaussians run 512-thread CTAs over tiles of 8192 pairs, one CTA per
+// SM: every tile of such a pass is resident at once, all tiles publish their aggregates at the same time and each
+// one sums ALL its predecessors (nobody has an inclusive prefix yet), so the look-back costs tiles^2 / 2 status rows
+// in total -- 30 % of the pass's instructions with 245 tiles of 4096, a quarter of that with 123 tiles of 8192.
+// (BSPLAT_DEBUG=nowide: A/B switch.)
+static bool sort_wide_enabled() {
+    static const bool on = [] { const char* d = getenv("BSPLAT_DEBUG"); return !(d && strstr(d, "nowide")); }();
+    return on;
+}
+bool sort_depth_wide(int64_t N) { return sort_wide_enabled() && N > 8192 && N <= kSortWideMax; }
+int64_t sort_tiles_u32_depth(int64_t N) {
+    return sort_depth_wide(N) ? ceil_div(N, (int64_t)kSortWideThreads * kSortItems32) : sort_tiles_u32(N);
+}
 
 size_t sort_status_words(int64_t n_tiles, int passes) { return (size_t)passes * n_tiles * kRadix; }
 
 #define BSPLAT_ONESWEEP32(B)                                                                              \
-    BSPLAT_LAUNCH_PDL((onesweep_kernel<uint32_t, kSortItems32, B>), (unsigned)n_tiles, kSortThreads, 0, stream, \
+    BSPLAT_LAUNCH_PDL((onesweep_kernel<uint32_t, kSortItems32, B>), (unsigned)n_tiles, kSortThreads, kSmem32, stream, \
         M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,    \
         key_counts, key_row_stride, hist_early)
 
 int onesweep_pass_u32(int64_t M, const uint64_t* m_dev, const uint32_t* keys_in, uint32_t* keys_out,
                       const int32_t* vals_in, int32_t* vals_out, int shift, int bits, const uint32_t* hist,
                       int hist_is_scanned, uint32_t* ticket, uint32_t* status, uint32_t* key_counts,
-                      cudaStream_t stream, int key_row_stride, int hist_early) {
+                      cudaStream_t stream, int key_row_stride, int hist_early, int depth_pass) {
+    constexpr size_t kSmem32 = (size_t)kSortThreads * kSortItems32 * (sizeof(uint32_t) + sizeof(int32_t));
+    if (depth_pass && bits == 8 && sort_depth_wide(M)) {
+        constexpr size_t kSmemWide = (size_t)kSortWideThreads * kSortItems32 * (sizeof(uint32_t) + sizeof(int32_t));
+        static const cudaError_t attr = cudaFuncSetAttribute(
+            onesweep_kernel<uint32_t, kSortItems32, 8, 64, kSortWideThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int)kSmemWide);
+        if (attr != cudaSuccess) return (int)attr;
+        BSPLAT_LAUNCH_PDL((onesweep_kernel<uint32_t, kSortItems32, 8, 64, kSortWideThreads>),
+                          (unsigned)sort_tiles_u32_depth(M), kSortWideThreads, kSmemWide, stream, M, m_dev, keys_in, keys_out,
+                          vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status, key_counts, key_row_stride,
+                          hist_early);
+        BSPLAT_LAUNCH_CHECK();
+        return BSPLAT_OK;
+    }
     const int64_t n_tiles = sort_tiles_u32(M);
     if (bits == 8 && n_tiles <= 3 * 148) {  // every tile resident at once (3 CTAs per SM): wide look-back window
-        BSPLAT_LAUNCH_PDL((onesweep_kernel<uint32_t, kSortItems32, 8, 64>), (unsigned)n_tiles, kSortThreads, 0, stream, M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,
+        BSPLAT_LAUNCH_PDL((onesweep_kernel<uint32_t, kSortItems32, 8, 64>), (unsigned)n_tiles, kSortThreads, kSmem32, stream, M, m_dev, keys_in, keys_out, vals_in, vals_out, shift, bits, hist, hist_is_scanned, ticket, status,
             key_counts, key_row_stride, hist_early);
         BSPLAT_LAUNCH_CHECK();
         return BSPLAT_OK;
@@ -468,7 +508,8 @@ extern "C" int bsplat_radix_sort_pairs(int64_t M, uint64_t* keys, uint64_t* keys
     for (int p = 0; p < passes; ++p) {
         const int shift = begin_bit + p * kRadixBits;
         const int bits = (end_bit - shift) < kRadixBits ? (end_bit - shift) : kRadixBits;
-        BSPLAT_LAUNCH_PDL((onesweep_kernel<uint64_t, kSortItems64, 0>), (unsigned)n_tiles, kSortThreads, 0, stream, M, nullptr, ksrc, kdst, vsrc, vdst, shift, bits, w.hist + (size_t)p * kRadix, 1, w.tickets + p,
+        BSPLAT_LAUNCH_PDL((onesweep_kernel<uint64_t, kSortItems64, 0>), (unsigned)n_tiles, kSortThreads,
+                          (size_t)kSortThreads * kSortItems64 * (sizeof(uint64_t) + sizeof(int32_t)), stream, M, nullptr, ksrc, kdst, vsrc, vdst, shift, bits, w.hist + (size_t)p * kRadix, 1, w.tickets + p,
             w.status + (size_t)p * n_tiles * kRadix, nullptr, 0, 0);
         BSPLAT_LAUNCH_CHECK();
         uint64_t* tk = ksrc; ksrc = kdst; kdst = tk;

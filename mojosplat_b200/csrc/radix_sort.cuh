@@ -8,6 +8,8 @@ constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortItems64 = 10;  // 2560 (uint64 key, int32) pairs per CTA
 constexpr int kSortItems32 = 16;  // 4096 (uint32 key, int32) pairs per CTA (80 registers, 3 CTAs per SM)
+constexpr int kSortWideThreads = 512;  // depth passes of small frames: 8192 pairs per CTA, one CTA per SM
+constexpr int64_t kSortWideMax = 148LL * kSortWideThreads * kSortItems32;
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
@@ -19,6 +21,7 @@ constexpr uint32_t kStatMask = (1u << 30) - 1;
 
 int64_t sort_tiles_u32(int64_t M);
 int64_t sort_tiles_u64(int64_t M);
+int64_t sort_tiles_u32_depth(int64_t N);  // tiles of a depth pass (onesweep_pass_u32 with depth_pass != 0)
 size_t sort_status_words(int64_t n_tiles, int passes);
 
 // One pass over (uint32 key, int32 payload) pairs on key bits [shift, shift+bits).
@@ -35,7 +38,7 @@ size_t sort_status_words(int64_t n_tiles, int passes);
 int onesweep_pass_u32(int64_t M, const uint64_t* m_dev, const uint32_t* keys_in, uint32_t* keys_out,
                       const int32_t* vals_in, int32_t* vals_out, int shift, int bits, const uint32_t* hist,
                       int hist_is_scanned, uint32_t* ticket, uint32_t* status, uint32_t* key_counts,
-                      cudaStream_t stream, int key_row_stride = 0, int hist_early = 0);
+                      cudaStream_t stream, int key_row_stride = 0, int hist_early = 0, int depth_pass = 0);
 // In-place exclusive scan of `passes` consecutive 256-bin histograms.
 int radix_scan_launch(uint32_t* hist, int passes, cudaStream_t stream);
 
