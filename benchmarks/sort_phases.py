@@ -46,3 +46,17 @@ for slot in range(8):
     q = [0, len(order) // 4, len(order) // 2, 3 * len(order) // 4, len(order) - 1]
     print("    entry/exit (us since first entry) of tiles at quantiles of entry time:",
           [(round((g0[order[i]] - g0.min()) / 1e3, 1), round((g1[order[i]] - g0.min()) / 1e3, 1)) for i in q])
+
+# count + scan (bin_count_scan2_kernel): thread 0 = the look-back path, first thread of the last warp = the coverage path
+sb = np.zeros((1024, 16), dtype=np.uint64)
+if hasattr(L, "bsplat_debug_scan_phases") and L.bsplat_debug_scan_phases(sb.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(sb.nbytes)) == 0:
+    rows = np.nonzero(sb[:, 7])[0]
+    b = sb[rows].astype(np.int64)
+    print(f"count + scan: {len(rows)} CTAs")
+    for nm, i0, i1 in [("entry->dep wait", 0, 1), ("index loads + gathers + rect stores", 1, 2), ("warp 0 coverage", 2, 3),
+                       ("block scan (barrier)", 3, 4), ("look-back (warp 0)", 4, 5), ("barrier after look-back", 5, 6),
+                       ("offset stores", 6, 7), ("[last warp] gathers -> after block scan", 8, 9),
+                       ("[last warp] coverage", 9, 10), ("[last warp] coverage barrier", 10, 11),
+                       ("[last warp] prefix + flush of the difference arrays", 11, 12)]:
+        d = (b[:, i1] - b[:, i0]) / 1965.0
+        print(f"    {nm:52s} median {np.median(d):6.2f}  p90 {np.percentile(d, 90):6.2f}  max {d.max():6.2f} us")

@@ -356,6 +356,20 @@ bin_compact_scatter_kernel(const int64_t n_chunks, const int32_t* __restrict__ l
 // The clipped rectangles are kept in depth order for the emitter.
 // 1 024 threads x 8 slots per CTA: few chunks keep the look-back chain short (all chunks start together, so the last
 // one walks back through every predecessor, 32 per round trip), many threads keep all gathers of a chunk in flight.
+#ifdef BSPLAT_PHASES
+// A/B instrumentation (make phases; benchmarks/sort_phases.py): SM clock at the phase boundaries of count + scan, per CTA;
+// columns 0-7 thread 0 (warp 0: the look-back path), 8-13 the first thread of the last warp (the coverage path)
+__device__ unsigned long long g_scan_phases[1024][16];
+#define BSPLAT_SPHASE(t, i)                                                                              \
+    do {                                                                                                 \
+        if (threadIdx.x == (t) && ph_row < 1024) g_scan_phases[ph_row][i] = (unsigned long long)clock64(); \
+    } while (0)
+extern "C" int bsplat_debug_scan_phases(void* host_out, size_t bytes) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_scan_phases, bytes < sizeof(g_scan_phases) ? bytes : sizeof(g_scan_phases));
+}
+#else
+#define BSPLAT_SPHASE(t, i)
+#endif
 constexpr int kScan2Threads = 1024;
 constexpr int kScan2Chunk = kScan2Threads * kScanItems;
 
@@ -377,10 +391,15 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
     __shared__ unsigned long long s_prefix;
 
     const int tid = threadIdx.x;
+#ifdef BSPLAT_PHASES
+    unsigned ph_row = blockIdx.x;
+    BSPLAT_SPHASE(0, 0);
+#endif
     // (the ticket counter was zeroed at the start of the frame: drawn, like the shared-memory reset above, before the
     // wait for the previous kernel of the stream -- programmatic dependent launch, common.cuh)
     if (tid == 0) s_chunk = atomicAdd(reinterpret_cast<unsigned int*>(ws), 1u);
     pdl_wait();
+    BSPLAT_SPHASE(0, 1);
     // n_dev: the number of items lives on the device (compacted depth order); the grid is sized by N_host
     const int64_t N = n_dev ? (int64_t)(*n_dev) : N_host;
     __syncthreads();
@@ -434,6 +453,8 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
         for (int v = 0; v < kScanItems / 2; ++v) vr[v] = make_uint4(rc[2 * v].x, rc[2 * v].y, rc[2 * v + 1].x, rc[2 * v + 1].y);
     }
     const int lane = tid & 31, warp = tid >> 5;
+    if (thread_sum == 0xffffffffu) return;  // (never: keeps the loads above in front of the clock reads below)
+    BSPLAT_SPHASE(0, 2); BSPLAT_SPHASE(kScan2Threads - 32, 8);
     auto add_coverage = [&]() {
         // (s_diff was zeroed before the first barrier above; uint32 wrap-around carries the negative steps.)  Runs of
         // identical rectangles in a thread's depth-consecutive slots -- the culled Gaussians that the torch rules clamp
@@ -478,6 +499,7 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
     // warp 0 (which goes into the look-back below) adds its coverage now; the other 31 warps do it while warp 0 waits
     // for its predecessors, so the chunk's aggregate is published without waiting for the histogram work
     if (hist_xy != nullptr && warp == 0) add_coverage();
+    BSPLAT_SPHASE(0, 3);
     unsigned long long incl = thread_sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -494,9 +516,12 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
         block_total += s;
     }
     const unsigned long long thread_excl = warp_excl + incl - thread_sum;
+    BSPLAT_SPHASE(0, 4); BSPLAT_SPHASE(kScan2Threads - 32, 9);
     if (hist_xy != nullptr && warp != 0) {
         add_coverage();
+        BSPLAT_SPHASE(kScan2Threads - 32, 10);
         asm volatile("bar.sync 2, %0;" ::"n"(kScan2Threads - 32));  // warps 1 .. 31: every update is in s_diff
+        BSPLAT_SPHASE(kScan2Threads - 32, 11);
     }
     if (hist_xy != nullptr && tid >= kScan2Threads - 2 * kRadix) {
         // inclusive prefix of the difference arrays = coverage per column (first 256 of these threads) / row (last
@@ -527,7 +552,9 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
         }
         if (lane == 0) s_prefix = prefix;
     }
+    BSPLAT_SPHASE(0, 5); BSPLAT_SPHASE(kScan2Threads - 32, 12);
     __syncthreads();
+    BSPLAT_SPHASE(0, 6);
     pdl_trigger();  // only the output is left: the next kernel of the stream may be staged now
     unsigned long long run = s_prefix + thread_excl;
     if (full) {
@@ -550,6 +577,7 @@ bin_count_scan2_kernel(const int64_t N_host, const unsigned long long* __restric
         offsets[N] = (uint32_t)run;
         info->n_isect = run;
     }
+    BSPLAT_SPHASE(0, 7);
 }
 
 // ---- 3. emission in depth order ------------------------------------------------------------
