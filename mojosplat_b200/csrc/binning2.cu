@@ -992,7 +992,7 @@ static Bin2Ws carve_bin2(void* base, int64_t N, int64_t M, int64_t n_tiles) {
     w.compact_status = (unsigned long long*)take((size_t)(ceil_div((int64_t)n, kCompactChunk) + 1) * 8);
     w.cand_n = (unsigned long long*)take(16);
     w.cand_status = (unsigned long long*)take((size_t)(ceil_div((int64_t)n, kCompactChunk) + 1) * 8);
-    w.status_n = (uint32_t*)take(sort_status_words(sort_tiles_u32_depth(N), 4) * 4);
+    w.status_n = (uint32_t*)take(sort_status_words(sort_tiles_u32(N), 4) * 4);  // (the wide depth passes use fewer)
     w.zero_end_n = off;
     w.n_bytes = off;
     w.tkeys = (uint32_t*)take(m * 4); w.tkeys_alt = (uint32_t*)take(m * 4);

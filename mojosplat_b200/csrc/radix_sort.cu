@@ -391,12 +391,15 @@ int64_t sort_tiles_u64(int64_t M) { return ceil_div(M > 0 ? M : 1, kSortThreads 
 // SM: every tile of such a pass is resident at once, all tiles publish their aggregates at the same time and each
 // one sums ALL its predecessors (nobody has an inclusive prefix yet), so the look-back costs tiles^2 / 2 status rows
 // in total -- 30 % of the pass's instructions with 245 tiles of 4096, a quarter of that with 123 tiles of 8192.
+// Only for frames that own the GPU (one stream, pdl_call_switch()): such a CTA takes the whole register file of an SM,
+// and in the overlapped pipeline it would have to wait until every rasterizer CTA of another frame has left one
+// (measured: 2 790 -> 2 650 frames/s), while the pipeline hides the look-back latency anyway.
 // (BSPLAT_DEBUG=nowide: A/B switch.)
 static bool sort_wide_enabled() {
     static const bool on = [] { const char* d = getenv("BSPLAT_DEBUG"); return !(d && strstr(d, "nowide")); }();
     return on;
 }
-bool sort_depth_wide(int64_t N) { return sort_wide_enabled() && N > 8192 && N <= kSortWideMax; }
+bool sort_depth_wide(int64_t N) { return sort_wide_enabled() && pdl_call_switch() && N > 8192 && N <= kSortWideMax; }
 int64_t sort_tiles_u32_depth(int64_t N) {
     return sort_depth_wide(N) ? ceil_div(N, (int64_t)kSortWideThreads * kSortItems32) : sort_tiles_u32(N);
 }
