@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kRadix) radix_scan_kernel(uint32_t* __restrict
 // THREADS: 256 (3 CTAs per SM), or 512 for the depth passes of frames whose tiles are all resident at once anyway
 // (twice the tile, half the tiles: the look-back of such a pass is quadratic in the number of tiles, see above).
 template <typename KeyT, int ITEMS, int BITS, int LOOKBACK = kLookback, int THREADS = kSortThreads>
-__global__ void __launch_bounds__(THREADS, THREADS == kSortThreads ? 3 : 1)
+__global__ void __launch_bounds__(THREADS, THREADS == kSortThreads ? BSPLAT_SORT_MINB : 1)
 onesweep_kernel(const int64_t M_host, const uint64_t* __restrict__ m_dev, const KeyT* __restrict__ keys_in,
                 KeyT* __restrict__ keys_out, const int32_t* __restrict__ vals_in,
                 int32_t* __restrict__ vals_out, const int shift, const int bits_rt,

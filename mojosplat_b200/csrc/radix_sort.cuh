@@ -7,7 +7,13 @@ namespace bsplat {
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortItems64 = 10;  // 2560 (uint64 key, int32) pairs per CTA
-constexpr int kSortItems32 = 16;  // 4096 (uint32 key, int32) pairs per CTA (80 registers, 3 CTAs per SM)
+#ifndef BSPLAT_SORT_ITEMS32
+#define BSPLAT_SORT_ITEMS32 16
+#endif
+#ifndef BSPLAT_SORT_MINB
+#define BSPLAT_SORT_MINB 3
+#endif
+constexpr int kSortItems32 = BSPLAT_SORT_ITEMS32;  // 4096 (uint32 key, int32) pairs per CTA (80 registers, 3 CTAs per SM)
 constexpr int kSortWideThreads = 512;  // depth passes of small frames: 8192 pairs per CTA, one CTA per SM
 constexpr int64_t kSortWideMax = 148LL * kSortWideThreads * kSortItems32;
 constexpr int kRadixBits = 8;
