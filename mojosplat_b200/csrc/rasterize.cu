@@ -576,7 +576,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             // sigma < 0 test and without the 0.999 clamp
             // alpha of one Gaussian on this lane's two pixels; a failed alpha test gives alpha = 0 (then T (1 - 0) = T and
             // 0 T = 0 exactly: the compositing below needs no select for it)
-            auto alpha_of = [&](auto plain_tag, const float4* r, const float4 p0, const float4 p1) -> float2 {
+            auto alpha_of = [&](auto plain_tag, const float tau, const float4 p0, const float4 p1) -> float2 {
                 constexpr bool kPlain = decltype(plain_tag)::value;
                 const float2 dx = __fadd2_rn(dup2(p0.x), npx2);
                 const float2 dy = __fadd2_rn(dup2(p0.y), npy);
@@ -589,7 +589,6 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                 if (!kPlain) {
                     // sigma >= 0  <=>  power <= L: tested for special Gaussians only (plain ones pass by
                     // construction and must be treated exactly as in the plain walk)
-                    const float tau = reinterpret_cast<const float*>(r + 2)[1];
                     const float Lt = (__float_as_uint(tau) & 1u) ? p1.y : INFINITY;
                     pass0 = pass0 && (pw.x <= Lt);
                     pass1 = pass1 && (pw.y <= Lt);
@@ -625,6 +624,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             // two copies of the walk: chunks whose survivors are all "plain" (the common case) run without the
             // sigma < 0 test and without the 0.999 clamp
             auto walk = [&](auto plain_tag) {
+                constexpr bool kPlain = decltype(plain_tag)::value;
                 while (mask) {
                     // highest set bit = next Gaussian, front to back (bfind -> a single FLO; written in PTX
                     // because nvcc rewrites 31 - clz(x) into a longer clz-based sequence)
@@ -636,7 +636,8 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                     BSPLAT_DASSERT(r >= s_g && r + kPairRec <= s_g + kStageRecs * kPairRec && c0 + 31 - (int)b_hi < bs);
                     const float4 p0 = r[0], p1 = r[1];
                     const float cb = reinterpret_cast<const float*>(r + 2)[0];
-                    composite(alpha_of(plain_tag, r, p0, p1), p1.z, p1.w, cb,
+                    const float tau = kPlain ? 0.0f : reinterpret_cast<const float*>(r + 2)[1];
+                    composite(alpha_of(plain_tag, tau, p0, p1), p1.z, p1.w, cb,
                               kTrain ? (int32_t)(b0 + c0 + 31 - (int)b_hi) : 0);
                 }
             };
