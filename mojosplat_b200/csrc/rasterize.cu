@@ -602,21 +602,21 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             // added (rasterization.mojo:146-150) and the pixel retires with its T unchanged -- alpha := 0, -x := -inf.
             // Branch-free: a lane that left the walk for a rare path would make its warp walk the chunk twice.
             auto composite = [&](float2 a2, const float cr, const float cg, const float cb, const int32_t cur) {
-                float2 oma = __fadd2_rn(one2, make_float2(-a2.x, -a2.y));  // 1 - alpha
-                const float2 nT = __fmul2_rn(T2, oma);
+                // T (1 - alpha) as T - alpha T: alpha T is needed anyway (one packed instruction instead of two)
+                float2 vis2 = __fmul2_rn(a2, T2);
+                const float2 nT = __fadd2_rn(T2, make_float2(-vis2.x, -vis2.y));
                 const bool dead0 = !(nT.x > 1e-4f), dead1 = !(nT.y > 1e-4f);
                 if constexpr (kTrain) {  // (a retired pixel has alpha = 0 from here on: it is never "dead" again)
                     stop0 = dead0 ? cur : stop0;
                     stop1 = dead1 ? cur : stop1;
                 }
-                a2.x = dead0 ? 0.0f : a2.x;
-                a2.y = dead1 ? 0.0f : a2.y;
+                vis2.x = dead0 ? 0.0f : vis2.x;
+                vis2.y = dead1 ? 0.0f : vis2.y;
                 npx2.x = dead0 ? -INFINITY : npx2.x;
                 npx2.y = dead1 ? -INFINITY : npx2.y;
-                oma.x = dead0 ? 1.0f : oma.x;
-                oma.y = dead1 ? 1.0f : oma.y;
-                const float2 vis2 = __fmul2_rn(a2, T2);
-                T2 = __fmul2_rn(T2, oma);
+                // T - (alpha T or 0): the subtraction again with the selected operand instead of two more selects
+                // (the same value as nT where the pixel goes on, T itself where it retired)
+                T2 = __fadd2_rn(T2, make_float2(-vis2.x, -vis2.y));
                 acc_r = __ffma2_rn(dup2(cr), vis2, acc_r);
                 acc_g = __ffma2_rn(dup2(cg), vis2, acc_g);
                 acc_b = __ffma2_rn(dup2(cb), vis2, acc_b);
