@@ -143,10 +143,9 @@ __global__ void __launch_bounds__(1024) raster_faithful_kernel(const int64_t N, 
 //   with A = 0.5 a log2e, B = b log2e, C = 0.5 c log2e, L = log2(opacity), hy = -B/(2C), hx = -B/(2A) (edge
 //   minimisers of the quadratic), tau = L - log2(1/255) (+inf: never cull, -inf: not a Gaussian; lowest bit = special)
 //   power = L - (A dx^2 + B dx dy + C dy^2) as  fma2(fma2(-A, dx, -B dy), dx, fma2(-C dy, dy, L))
-// alpha is zeroed when it fails the threshold, so alpha T = 0 and T - alpha T = T need no selects.  Retirement
-// (saturation) is a factor: alive = 1.0 / 0.0 straight from the comparison T - alpha T > 1e-4 (FSET.BF), multiplied
-// into alpha T -- a retired pixel keeps evaluating and adds exact zeros; no predicate, no select, no sentinel in the
-// inner loop (31 instructions per Gaussian and pixel pair).  Each warp first tests 32 staged Gaussians at once (one per lane) against its 8x8
+// alpha is zeroed when it fails the threshold, so T (1 - alpha) = T and alpha T = 0 need no selects; the walk only
+// branches (rarely) when a pixel saturates.  A finished pixel carries -x = -inf (every later power is -inf or NaN
+// and fails the alpha test by itself -- no flag in the inner loop).  Each warp first tests 32 staged Gaussians at once (one per lane) against its 8x8
 // block with an exact conservative ellipse / rectangle bound and then only walks the survivors (warp ballot);
 // a skipped Gaussian has alpha < 1/255 on all 64 pixels, so the composited result is unchanged.
 // (Three earlier variants -- one pixel per lane, independent warps with per-warp staging, an mbarrier
@@ -173,8 +172,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // packed FP32 pairs: the sm_100 intrinsics on float2 (register pairs; FFMA2 / FADD2 / FMUL2)
 __device__ __forceinline__ float2 dup2(const float v) { return make_float2(v, v); }  // becomes an `R.F32` operand
-__device__ __forceinline__ bool pair_finished(const float2 alive) {  // both pixels retired (or outside the image)
-    return alive.x == 0.0f && alive.y == 0.0f;
+__device__ __forceinline__ bool pair_finished(const float2 npx) {  // both halves are -inf
+    return !(npx.x > -INFINITY) && !(npx.y > -INFINITY);
 }
 
 // Lists longer than kLongTile are mostly Gaussians that cannot touch the tile at all (under the torch binning rules
@@ -399,9 +398,9 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // halves of the staging buffer, one batch ahead of the walk (ids two batches ahead), one barrier per batch.
 // !kRec: workspace-free staging of 256 per batch from the raw arrays (same arithmetic, bit-identical image).
 // kTrain (training-side forward, bsplat_rasterize_fwd_train_fast): the same walk also yields what the backward pass
-// starts from -- per pixel the final transmittance and the list index of the last entry the pixel's warp walked while
-// the pixel was still compositing (never the entry that saturated it; entries in front of it that failed the alpha
-// test fail it again in the backward pass).
+// starts from -- per pixel the final transmittance and the list index of the last entry the pixel looked at (the
+// entry in front of the one that saturated it, or the end of the list; entries that failed the alpha test in between
+// fail it again in the backward pass).
 struct TrainOut {
     float* final_T;
     int32_t* last_idx;
@@ -461,12 +460,10 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     const float TY0 = (float)(tile_y * kFastTile) + 0.5f, TY1 = TY0 + 15.0f;
     float2 T2 = make_float2(1.0f, 1.0f);
     float2 acc_r = make_float2(0.f, 0.f), acc_g = acc_r, acc_b = acc_r;  // {pixel 0, pixel 1} per channel
-    const float2 npx2 = dup2(-((float)j + 0.5f));
-    // 1 while the pixel composites, 0 once it retired (saturation) or if it lies outside the image: a factor of every
-    // contribution, so a retired pixel needs no sentinel and no select -- it keeps evaluating and adds exact zeros
-    float2 alive2 = make_float2(in0 ? 1.0f : 0.0f, in1 ? 1.0f : 0.0f);
+    // negated x per pixel; -inf = finished
+    float2 npx2 = make_float2(in0 ? -((float)j + 0.5f) : -INFINITY, in1 ? -((float)j + 0.5f) : -INFINITY);
     const float2 one2 = dup2(1.0f);
-    float2 last2 = make_float2(-1.0f, -1.0f);  // kTrain: see composite()
+    int32_t stop0 = r1, stop1 = r1;  // kTrain: list position of the entry that saturated the pixel (r1: none did)
 
     constexpr int kBatch = kRec ? kRecBatch : kPairBatch;
     constexpr int kPer = (kBatch + kPairThreads - 1) / kPairThreads;  // staged entries per thread and batch
@@ -506,7 +503,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     }
     int batch = 0;
     for (int32_t b0 = v0; b0 < v1; b0 += kBatch, ++batch) {
-        const bool fin = pair_finished(alive2);
+        const bool fin = pair_finished(npx2);
         const float4* s_rec = s_g;
         if (kRec) {
             cp_async_wait_group<kRecStages - 2>();  // this thread's part of batch `batch` has landed ...
@@ -551,7 +548,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             __syncthreads();
         }
         for (int c0 = 0; c0 < bs; c0 += 32) {
-            if (__all_sync(0xffffffffu, pair_finished(alive2))) break;
+            if (__all_sync(0xffffffffu, pair_finished(npx2))) break;
             unsigned int tword = 0xffffffffu;
             if (long_tile) {
                 tword = s_tmask[c0 >> 5];
@@ -602,23 +599,24 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                 return a2;
             };
             // compositing of one Gaussian.  Saturation (T (1 - alpha) <= 1e-4, once per pixel): the Gaussian is not
-            // added (rasterization.mojo:146-150) and the pixel retires with its T unchanged -- alive := 0.
+            // added (rasterization.mojo:146-150) and the pixel retires with its T unchanged -- alpha := 0, -x := -inf.
             // Branch-free: a lane that left the walk for a rare path would make its warp walk the chunk twice.
             auto composite = [&](float2 a2, const float cr, const float cg, const float cb, const int32_t cur) {
                 // T (1 - alpha) as T - alpha T: alpha T is needed anyway (one packed instruction instead of two)
                 float2 vis2 = __fmul2_rn(a2, T2);
                 const float2 nT = __fadd2_rn(T2, make_float2(-vis2.x, -vis2.y));
-                // 1.0 / 0.0 straight from the comparison (FSET.BF): no predicate, no select
-                const float2 keep = make_float2(nT.x > 1e-4f ? 1.0f : 0.0f, nT.y > 1e-4f ? 1.0f : 0.0f);
-                alive2 = __fmul2_rn(alive2, keep);
-                if constexpr (kTrain) {
-                    // last list entry (relative to the tile's first, as a float: exact below 2^24) after which the
-                    // pixel was still compositing: last += alive (cur - last), two packed instructions for both pixels
-                    const float2 curf = dup2((float)cur);
-                    last2 = __ffma2_rn(alive2, __fadd2_rn(curf, make_float2(-last2.x, -last2.y)), last2);
+                const bool dead0 = !(nT.x > 1e-4f), dead1 = !(nT.y > 1e-4f);
+                if constexpr (kTrain) {  // (a retired pixel has alpha = 0 from here on: it is never "dead" again)
+                    stop0 = dead0 ? cur : stop0;
+                    stop1 = dead1 ? cur : stop1;
                 }
-                vis2 = __fmul2_rn(vis2, alive2);   // alpha T, or an exact 0 for the saturating Gaussian and ever after
-                T2 = __fadd2_rn(T2, make_float2(-vis2.x, -vis2.y));  // = nT where the pixel goes on, T where it retired
+                vis2.x = dead0 ? 0.0f : vis2.x;
+                vis2.y = dead1 ? 0.0f : vis2.y;
+                npx2.x = dead0 ? -INFINITY : npx2.x;
+                npx2.y = dead1 ? -INFINITY : npx2.y;
+                // T - (alpha T or 0): the subtraction again with the selected operand instead of two more selects
+                // (the same value as nT where the pixel goes on, T itself where it retired)
+                T2 = __fadd2_rn(T2, make_float2(-vis2.x, -vis2.y));
                 acc_r = __ffma2_rn(dup2(cr), vis2, acc_r);
                 acc_g = __ffma2_rn(dup2(cg), vis2, acc_g);
                 acc_b = __ffma2_rn(dup2(cb), vis2, acc_b);
@@ -640,7 +638,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                     const float cb = reinterpret_cast<const float*>(r + 2)[0];
                     const float tau = kPlain ? 0.0f : reinterpret_cast<const float*>(r + 2)[1];
                     composite(alpha_of(plain_tag, tau, p0, p1), p1.z, p1.w, cb,
-                              kTrain ? (int32_t)(b0 - r0 + c0 + 31 - (int)b_hi) : 0);
+                              kTrain ? (int32_t)(b0 + c0 + 31 - (int)b_hi) : 0);
                 }
             };
             if (any_special) walk(std::false_type{});
@@ -656,8 +654,8 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     const float T0 = T2.x, T1 = T2.y, ar0 = acc_r.x, ar1 = acc_r.y, ag0 = acc_g.x, ag1 = acc_g.y, ab0 = acc_b.x,
                 ab1 = acc_b.y;
     if constexpr (kTrain) {
-        if (in0) { train.final_T[(int64_t)i0 * W + j] = T0; train.last_idx[(int64_t)i0 * W + j] = r0 + (int32_t)last2.x; }
-        if (in1) { train.final_T[(int64_t)i1 * W + j] = T1; train.last_idx[(int64_t)i1 * W + j] = r0 + (int32_t)last2.y; }
+        if (in0) { train.final_T[(int64_t)i0 * W + j] = T0; train.last_idx[(int64_t)i0 * W + j] = stop0 - 1; }
+        if (in1) { train.final_T[(int64_t)i1 * W + j] = T1; train.last_idx[(int64_t)i1 * W + j] = stop1 - 1; }
     }
     const float o0r = fmaf(T0, bgr, ar0), o0g = fmaf(T0, bgg, ag0), o0b = fmaf(T0, bgb, ab0);
     const float o1r = fmaf(T1, bgr, ar1), o1g = fmaf(T1, bgg, ag1), o1b = fmaf(T1, bgb, ab1);
