@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import mojosplat_b200 as ms
 from mojosplat_b200 import synthetic, rasterization
 dev = torch.device('cuda:0')
