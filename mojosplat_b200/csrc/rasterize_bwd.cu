@@ -408,7 +408,7 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
     // -T_final * sum_ch bg_ch gout_ch: the background's share of d out / d alpha, up to the factor 1 / (1 - alpha)
     const float2 ntfbg = make_float2(-T2.x * (bgr * go_r.x + bgg * go_g.x + bgb * go_b.x),
                                      -T2.y * (bgr * go_r.y + bgg * go_g.y + bgb * go_b.y));
-    float2 buf_r = make_float2(0.f, 0.f), buf_g = buf_r, buf_b = buf_r;
+    float2 behind = make_float2(-ntfbg.x, -ntfbg.y);  // (sum over the Gaussians behind: c alpha T) . gout + T_final bg . gout
 
     if (tid == 0) s_max_last = -1;
     __syncthreads();
@@ -502,15 +502,16 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
                 T2 = __fmul2_rn(T2, ra);  // transmittance in front of this Gaussian
                 const float2 fac = __fmul2_rn(alpha, T2);
                 const float cb = reinterpret_cast<const float*>(r + 2)[0];
-                // d out / d alpha = sum_ch (c T - behind_ch / (1 - alpha)) gout_ch - T_final bg.gout / (1 - alpha)
-                float2 va = __fmul2_rn(ntfbg, ra);
-                const float2 nra = make_float2(-ra.x, -ra.y);
-                va = __ffma2_rn(__ffma2_rn(buf_r, nra, __fmul2_rn(dupb(p1.z), T2)), go_r, va);
-                va = __ffma2_rn(__ffma2_rn(buf_g, nra, __fmul2_rn(dupb(p1.w), T2)), go_g, va);
-                va = __ffma2_rn(__ffma2_rn(buf_b, nra, __fmul2_rn(dupb(cb), T2)), go_b, va);
-                buf_r = __ffma2_rn(dupb(p1.z), fac, buf_r);
-                buf_g = __ffma2_rn(dupb(p1.w), fac, buf_g);
-                buf_b = __ffma2_rn(dupb(cb), fac, buf_b);
+                // d out / d alpha = sum_ch (c_ch T - behind_ch / (1 - alpha)) gout_ch - T_final bg.gout / (1 - alpha)
+                //                 = T (c . gout) - (behind . gout + T_final bg . gout) / (1 - alpha):
+                // only the scalar behind . gout is carried per pixel (plus the constant background term), not the
+                // three channel sums -- 6 packed instructions instead of 13
+                float2 cgo = __fmul2_rn(dupb(p1.z), go_r);
+                cgo = __ffma2_rn(dupb(p1.w), go_g, cgo);
+                cgo = __ffma2_rn(dupb(cb), go_b, cgo);
+                const float2 rb = __fmul2_rn(ra, behind);
+                const float2 va = __ffma2_rn(T2, cgo, make_float2(-rb.x, -rb.y));
+                behind = __ffma2_rn(fac, cgo, behind);
                 const float2 vr = __fmul2_rn(fac, go_r), vg = __fmul2_rn(fac, go_g), vb = __fmul2_rn(fac, go_b);
                 // v_sigma = -alpha v_alpha; no gradient through the clamp
                 float2 vs = __fmul2_rn(make_float2(-araw.x, -araw.y), va);
