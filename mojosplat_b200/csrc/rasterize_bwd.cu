@@ -371,6 +371,23 @@ __device__ __forceinline__ float rcp_approx_b(const float x) {
     return y;
 }
 __device__ __forceinline__ float2 dupb(const float v) { return make_float2(v, v); }
+// shared-memory loads through a 32-bit shared address kept in a register: the compiler otherwise rebuilds the shared
+// window base (S2UR SR_CgaCtaId + UMOV + ULEA) at every use inside the walk
+__device__ __forceinline__ float4 lds_f4(const uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(const uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int32_t lds_i32(const uint32_t addr) {
+    int32_t v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 __global__ void __launch_bounds__(kBwdThreads)
 raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float* __restrict__ background,
@@ -410,6 +427,8 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
                                      -T2.y * (bgr * go_r.y + bgg * go_g.y + bgb * go_b.y));
     float2 behind = make_float2(-ntfbg.x, -ntfbg.y);  // (sum over the Gaussians behind: c alpha T) . gout + T_final bg . gout
 
+    const uint32_t s_rec_addr = (uint32_t)__cvta_generic_to_shared(s_rec);
+    const uint32_t s_id_addr = (uint32_t)__cvta_generic_to_shared(s_id);
     if (tid == 0) s_max_last = -1;
     __syncthreads();
     int warp_last = max(last0, last1);
@@ -461,7 +480,8 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
         __syncthreads();  // this batch has landed; everyone is done with the other half
         if (hi - kBwdBatch >= r0) fetch(hi - kBwdBatch, half ^ 1);  // in flight during the walk below
         const float4* s_cur = s_rec + half * kBwdBatch * kPairRec;
-        const int32_t* s_idc = s_id + half * kBwdBatch;
+        const uint32_t a_cur = s_rec_addr + (uint32_t)(half * kBwdBatch * kPairRec * sizeof(float4));
+        const uint32_t a_idc = s_id_addr + (uint32_t)(half * kBwdBatch * sizeof(int32_t));
         const int bs = min(kBwdBatch, (int)(hi - r0 + 1));
         if (hi - (bs - 1) > warp_last) continue;  // nothing of this batch was looked at by this warp's pixels
         for (int c0 = 0; c0 < bs; c0 += 32) {
@@ -478,8 +498,9 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
                 const int slot = c0 + 31 - (int)b_hi;
                 const int32_t cur = hi - slot;
                 BSPLAT_DASSERT(slot >= 0 && slot < bs && cur >= r0 && cur <= hi_all);
-                const float4* r = s_cur + kPairRec * slot;
-                const float4 p0 = r[0], p1 = r[1];
+                const uint32_t ra_ = a_cur + (uint32_t)slot * (uint32_t)(kPairRec * sizeof(float4));
+                const float4 p0 = lds_f4(ra_), p1 = lds_f4(ra_ + 16u);
+                const float2 p2 = lds_f2(ra_ + 32u);  // {b, tau}
                 const float2 dx2 = dupb(p0.x - px);
                 const float2 dy2 = __fadd2_rn(dupb(p0.y), npy);
                 const float2 nbdy = __fmul2_rn(dupb(p0.w), dy2);
@@ -488,7 +509,7 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
                 const float2 t = __ffma2_rn(dupb(p0.z), dx2, nbdy);
                 const float2 pw = __ffma2_rn(t, dx2, lmc);
                 // sigma >= 0 <=> power <= L: only special Gaussians can fail it (plain ones pass by construction)
-                const float tau = reinterpret_cast<const float*>(r + 2)[1];
+                const float tau = p2.y;
                 const float Lt = (__float_as_uint(tau) & 1u) ? p1.y : INFINITY;
                 const bool pass0 = (pw.x >= kLog2AlphaThreshold) && (pw.x <= Lt) && (cur <= last0);
                 const bool pass1 = (pw.y >= kLog2AlphaThreshold) && (pw.y <= Lt) && (cur <= last1);
@@ -501,7 +522,7 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
                 const float2 ra = make_float2(rcp_approx_b(oma.x), rcp_approx_b(oma.y));  // (alpha = 0: exactly 1)
                 T2 = __fmul2_rn(T2, ra);  // transmittance in front of this Gaussian
                 const float2 fac = __fmul2_rn(alpha, T2);
-                const float cb = reinterpret_cast<const float*>(r + 2)[0];
+                const float cb = p2.x;
                 // d out / d alpha = sum_ch (c_ch T - behind_ch / (1 - alpha)) gout_ch - T_final bg.gout / (1 - alpha)
                 //                 = T (c . gout) - (behind . gout + T_final bg . gout) / (1 - alpha):
                 // only the scalar behind . gout is carried per pixel (plus the constant background term), not the
@@ -528,7 +549,7 @@ raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const fl
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
                 const float sx = __shfl_sync(0xffffffffu, v[0], 24), sy = __shfl_sync(0xffffffffu, v[0], 28);
-                const int64_t g = s_idc[slot];
+                const int64_t g = lds_i32(a_idc + 4u * (uint32_t)slot);
                 BSPLAT_DASSERT(g >= 0 && g < N);  // (a record that is not a Gaussian never passes the alpha test)
                 // conic of the record: (a, b, c) = (-2 nA, -nB, -2 nC) / log2e;  mean gradient = (a sx + b sy, b sx + c sy)
                 constexpr float kInv = 1.0f / kLog2e;
