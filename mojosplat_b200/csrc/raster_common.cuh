@@ -102,4 +102,35 @@ __device__ __forceinline__ bool pair_record_hit(const float4* r, const float X0,
     return pair_cull_hit(p0.x, p0.y, -p0.z, -p0.w, -nC, p2.y, p2.z, p2.w, X0, X1, Y0, Y1);
 }
 
+// The same on a 32-bit shared-memory address held in a register (the walks use these: the compiler otherwise rebuilds
+// the shared window base -- S2UR SR_CgaCtaId + UMOV + ULEA -- at every use).
+__device__ __forceinline__ float4 lds_f4(const uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(const uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(const uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int32_t lds_i32(const uint32_t addr) {
+    int32_t v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ bool pair_record_hit_at(const uint32_t addr, const float X0, const float X1, const float Y0,
+                                                   const float Y1, bool* special) {
+    const float4 p0 = lds_f4(addr);
+    const float nC = lds_f1(addr + 16u);
+    const float4 p2 = lds_f4(addr + 32u);
+    if (special) *special = (__float_as_uint(p2.y) & 1u) != 0u;
+    return pair_cull_hit(p0.x, p0.y, -p0.z, -p0.w, -nC, p2.y, p2.z, p2.w, X0, X1, Y0, Y1);
+}
+
 }  // namespace bsplat

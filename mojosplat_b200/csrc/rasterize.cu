@@ -426,6 +426,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     __shared__ unsigned int s_tmask[(kRec ? kRecBatch : kPairBatch) / 32];  // long tiles without a pre-pass: survivors of the tile-level test
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t s_g_addr = (uint32_t)__cvta_generic_to_shared(s_g);
     const int tile = tile_order ? __ldg(tile_order + blockIdx.x) : first_tile + (int)blockIdx.x;
     const int tile_y = tile / tiles_w, tile_x = tile - tile_y * tiles_w;
     // warp -> 8x8 pixel block; lane -> column (lane & 7), rows (lane >> 3) and (lane >> 3) + 4
@@ -505,6 +506,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
     for (int32_t b0 = v0; b0 < v1; b0 += kBatch, ++batch) {
         const bool fin = pair_finished(npx2);
         const float4* s_rec = s_g;
+        uint32_t a_rec = s_g_addr;  // the same as a 32-bit shared address (see lds_f4)
         if (kRec) {
             cp_async_wait_group<kRecStages - 2>();  // this thread's part of batch `batch` has landed ...
             if (__syncthreads_count(fin) >= kPairThreads) break;  // ... everyone's has; batch - 1 is fully consumed
@@ -514,6 +516,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
             else cp_async_commit();
             id_next = load_ids(b0 + kRecStages * kBatch);
             s_rec = s_g + (batch % kRecStages) * kBatch * kPairRec;
+            a_rec = s_g_addr + (uint32_t)((batch % kRecStages) * kBatch * kPairRec * sizeof(float4));
         } else {
             if (__syncthreads_count(fin) >= kPairThreads) break;
 #pragma unroll
@@ -562,7 +565,7 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                 // walk below needs a single FLO (bfind) per survivor instead of BREV + FLO
                 const int gi = c0 + 31 - lane;
                 if (gi < bs && ((tword >> (31 - lane)) & 1u))
-                    hit = pair_record_hit(s_rec + kPairRec * gi, X0, X1, Y0, Y1, &special);
+                    hit = pair_record_hit_at(a_rec + (uint32_t)(gi * (int)(kPairRec * sizeof(float4))), X0, X1, Y0, Y1, &special);
                 mask = __ballot_sync(0xffffffffu, hit);
                 special = special && hit;
             } else {
@@ -571,7 +574,8 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                 special = true;
             }
             const bool any_special = __any_sync(0xffffffffu, special);
-            const float4* rec_hi = s_rec + kPairRec * (c0 + 31);  // record of ballot bit 0; bit b is 3 b float4 earlier
+            // record of ballot bit 0; bit b is 3 b float4 (48 bytes) earlier
+            const uint32_t a_hi = a_rec + (uint32_t)((c0 + 31) * (int)(kPairRec * sizeof(float4)));
             // two copies of the walk: chunks whose survivors are all "plain" (the common case) run without the
             // sigma < 0 test and without the 0.999 clamp
             // alpha of one Gaussian on this lane's two pixels; a failed alpha test gives alpha = 0 (then T (1 - 0) = T and
@@ -632,11 +636,16 @@ raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float*
                     asm("bfind.u32 %0, %1;" : "=r"(b_hi) : "r"(mask));
                     asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(below) : "r"(b_hi));  // bits below b_hi
                     mask &= below;
-                    const float4* r = rec_hi - kPairRec * (int)b_hi;
-                    BSPLAT_DASSERT(r >= s_g && r + kPairRec <= s_g + kStageRecs * kPairRec && c0 + 31 - (int)b_hi < bs);
-                    const float4 p0 = r[0], p1 = r[1];
-                    const float cb = reinterpret_cast<const float*>(r + 2)[0];
-                    const float tau = kPlain ? 0.0f : reinterpret_cast<const float*>(r + 2)[1];
+                    const uint32_t ra = a_hi - b_hi * (uint32_t)(kPairRec * sizeof(float4));
+                    BSPLAT_DASSERT(ra >= s_g_addr && ra + 48u <= s_g_addr + kStageRecs * 48u && c0 + 31 - (int)b_hi < bs);
+                    const float4 p0 = lds_f4(ra), p1 = lds_f4(ra + 16u);
+                    float cb, tau = 0.0f;
+                    if (kPlain) {
+                        cb = lds_f1(ra + 32u);
+                    } else {
+                        const float2 bt = lds_f2(ra + 32u);
+                        cb = bt.x; tau = bt.y;
+                    }
                     composite(alpha_of(plain_tag, tau, p0, p1), p1.z, p1.w, cb,
                               kTrain ? (int32_t)(b0 + c0 + 31 - (int)b_hi) : 0);
                 }

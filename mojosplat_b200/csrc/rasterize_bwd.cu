@@ -371,23 +371,6 @@ __device__ __forceinline__ float rcp_approx_b(const float x) {
     return y;
 }
 __device__ __forceinline__ float2 dupb(const float v) { return make_float2(v, v); }
-// shared-memory loads through a 32-bit shared address kept in a register: the compiler otherwise rebuilds the shared
-// window base (S2UR SR_CgaCtaId + UMOV + ULEA) at every use inside the walk
-__device__ __forceinline__ float4 lds_f4(const uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float2 lds_f2(const uint32_t addr) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ int32_t lds_i32(const uint32_t addr) {
-    int32_t v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
 
 __global__ void __launch_bounds__(kBwdThreads)
 raster_bwd_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float* __restrict__ background,
