@@ -154,6 +154,9 @@ __global__ void __launch_bounds__(1024) raster_faithful_kernel(const int64_t N, 
 constexpr int kFastTile = 16;
 constexpr int kPairThreads = 128;
 constexpr int kPairBatch = 256;   // staged entries per batch without records
+#ifndef BSPLAT_RASTER_MINB
+#define BSPLAT_RASTER_MINB 9  // resident CTAs per SM the inference kernel is compiled for (A/B on one box: 8 / 9 / 10 -> 2 899 / 2 942 / 2 901 frames/s)
+#endif
 #ifndef BSPLAT_REC_BATCH
 #define BSPLAT_REC_BATCH 128
 #endif
@@ -407,7 +410,7 @@ struct TrainOut {
 };
 
 template <bool kCull, bool kRec, bool kTrain = false>
-__global__ void __launch_bounds__(kPairThreads)
+__global__ void __launch_bounds__(kPairThreads, kTrain ? 8 : BSPLAT_RASTER_MINB)
 raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float* __restrict__ means2d, const float* __restrict__ conics,
                    const float* __restrict__ colors, const float* __restrict__ opacities,
                    const float* __restrict__ background, const int32_t* __restrict__ tile_ranges,
