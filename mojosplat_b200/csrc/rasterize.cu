@@ -155,7 +155,7 @@ constexpr int kFastTile = 16;
 constexpr int kPairThreads = 128;
 constexpr int kPairBatch = 256;   // staged entries per batch without records
 #ifndef BSPLAT_RASTER_MINB
-#define BSPLAT_RASTER_MINB 9  // resident CTAs per SM the inference kernel is compiled for (A/B on one box: 8 / 9 / 10 -> 2 899 / 2 942 / 2 901 frames/s)
+#define BSPLAT_RASTER_MINB 0  // 0: no minimum-blocks bound (ptxas picks 56 registers = 9 CTAs per SM by itself: 154 M instructions).  A/B on one box, pipeline frames/s: bound 8 / 9 / 10 (58 / 53 / 48 registers) 2 899 / 2 942 / 2 901; unbound vs 9: 2 971 vs 2 935
 #endif
 #ifndef BSPLAT_REC_BATCH
 #define BSPLAT_REC_BATCH 128
@@ -410,7 +410,11 @@ struct TrainOut {
 };
 
 template <bool kCull, bool kRec, bool kTrain = false>
+#if BSPLAT_RASTER_MINB > 0
 __global__ void __launch_bounds__(kPairThreads, kTrain ? 8 : BSPLAT_RASTER_MINB)
+#else
+__global__ void __launch_bounds__(kPairThreads)
+#endif
 raster_pair_kernel(const int64_t N, const float4* __restrict__ rec, const float* __restrict__ means2d, const float* __restrict__ conics,
                    const float* __restrict__ colors, const float* __restrict__ opacities,
                    const float* __restrict__ background, const int32_t* __restrict__ tile_ranges,
